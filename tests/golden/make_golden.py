@@ -1,0 +1,88 @@
+"""Generate the committed golden fixtures (run in the dev container, where
+/root/reference exists):
+
+    python tests/golden/make_golden.py
+
+* `speech_kat.npz`   -- the reference's only known-answer test, copied as data:
+  `onnx/input_speech.wav` (first 2296*320 samples, int16), `onnx/hil_speech_quantized.npy`
+  (int16 [8,1,2296], written by test_onnx.py:100) and `onnx/hil_speech_output.wav`
+  (int16, test_onnx.py:139).  Needs the published hil_speech weights at run time.
+* `ref_random_*.npz` -- outputs of the reference's OWN `models/hilcodec/streaming.py`
+  classes (imported through oracle/ref_shim.py) on seeded random weights
+  (`hilcodec_b200.weights.random_weights(cfg, seed)`, reproducible anywhere), one-shot
+  and frame-by-frame, so the CUDA path can be checked on the GPU box where the reference
+  itself cannot be imported.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from hilcodec_b200 import weights as W  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def synth_wav(batch, samples, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (0.1 * torch.randn(batch, 1, samples, generator=g)).clamp(-1, 1)
+
+
+def speech_kat():
+    from scipy.io import wavfile
+
+    onnx = os.path.join(ref_shim.REF, "onnx")
+    _, wav = wavfile.read(os.path.join(onnx, "input_speech.wav"))
+    gold = np.load(os.path.join(onnx, "hil_speech_quantized.npy"))
+    _, out = wavfile.read(os.path.join(onnx, "hil_speech_output.wav"))
+    frames = gold.shape[2]
+    np.savez_compressed(os.path.join(HERE, "speech_kat.npz"),
+                        wav_in=wav[:frames * 320].astype(np.int16),
+                        indices=gold.astype(np.int16),
+                        wav_out=out.astype(np.int16))
+
+
+def ref_random(name, n_q, seed, batch, frames, stream_hops):
+    cfg = W.CodecConfig(num_quantizers=n_q)
+    w = W.random_weights(cfg, seed)
+    model = ref_shim.build_reference_model(w, n_q)
+    x = synth_wav(batch, frames * cfg.hop, 1234 + seed)
+    one = ref_shim.reference_forward(model, x, n_q)
+    out = {
+        "seed": np.int64(seed), "n_q": np.int64(n_q), "x": x.numpy(),
+        "z": one["z"].numpy(), "indices": one["indices"].numpy().astype(np.int16),
+        "q": one["q"].numpy(), "wav": one["wav"].numpy(),
+    }
+    for i, c in enumerate(one["enc_caches"]):
+        out[f"enc_cache{i}"] = c.numpy()
+    for i, c in enumerate(one["dec_caches"]):
+        out[f"dec_cache{i}"] = c.numpy()
+    # chunked streaming run (chunks of `stream_hops` hops): outputs must equal one-shot ones
+    ce, cd = model.initialize_cache(x)
+    zs, ids, ws = [], [], []
+    step = stream_hops * cfg.hop
+    for s in range(0, x.shape[2], step):
+        r = ref_shim.reference_forward(model, x[:, :, s:s + step], n_q, ce, cd)
+        ce, cd = r["enc_caches"], r["dec_caches"]
+        zs.append(r["z"]); ids.append(r["indices"]); ws.append(r["wav"])
+    out["stream_hops"] = np.int64(stream_hops)
+    out["stream_z"] = torch.cat(zs, 1).numpy()
+    out["stream_indices"] = torch.cat(ids, 2).numpy().astype(np.int16)
+    out["stream_wav"] = torch.cat(ws, 2).numpy()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "stream==oneshot idx", np.array_equal(out["stream_indices"], out["indices"]),
+          "wav", float(np.abs(out["stream_wav"] - out["wav"]).max()))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    speech_kat()
+    ref_random("ref_random_speech.npz", 8, 1, batch=2, frames=12, stream_hops=1)
+    ref_random("ref_random_music.npz", 12, 2, batch=3, frames=10, stream_hops=3)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
