@@ -1,0 +1,1011 @@
+// Host side of libhilcodec_b200: model (weights, repacked), state (caches + workspace) and
+// the C ABI declared in include/hilcodec_b200.h.  The layer schedule below restates
+// Encoder.forward (streaming.py:482-517) and Decoder.forward (streaming.py:619-648) as a
+// sequence of kernel launches; see DESIGN.md for the kernel list and data layout.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hilcodec_b200.h"
+#include "common.cuh"
+
+using namespace hil;
+
+// ----------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+
+static int32_t fail(hil_status st, const std::string& msg) {
+    g_err = msg;
+    return (int32_t)st;
+}
+#define HIL_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(HIL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+#define HIL_TRY(expr)                 \
+    do {                              \
+        int32_t r__ = (expr);         \
+        if (r__ != HIL_OK) return r__; \
+    } while (0)
+
+// ----------------------------------------------------------------------------- launch accounting
+// Every kernel launch of the forward path goes through HIL_LAUNCH: it bumps the launch
+// counter bench.py reports as `gpu_launches`, and, while a profile is open
+// (hil_profile_begin .. hil_profile_end), brackets the launch with CUDA events on the launch
+// stream and books its algorithmic FLOPs / bytes under a kernel category.
+namespace {
+
+enum Cat { CAT_GEMM_PW = 0, CAT_GEMM_STFT, CAT_DW, CAT_DWT, CAT_CONV_PRE, CAT_CONV_POST, CAT_RVQ, CAT_MISC, CAT_COUNT };
+
+struct ProfRec {
+    int cat;
+    cudaEvent_t e0, e1;
+    double flops, bytes;
+};
+
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    unsigned long long launches = 0;
+};
+Profiler g_prof;
+
+struct LaunchScope {
+    bool rec = false;
+    ProfRec r{};
+    cudaStream_t st;
+    LaunchScope(int cat, double flops, double bytes, cudaStream_t s) : st(s) {
+        ++g_prof.launches;
+        if (g_prof.on) {
+            rec = true;
+            r.cat = cat; r.flops = flops; r.bytes = bytes;
+            cudaEventCreate(&r.e0);
+            cudaEventCreate(&r.e1);
+            cudaEventRecord(r.e0, st);
+        }
+    }
+    ~LaunchScope() {
+        if (rec) {
+            cudaEventRecord(r.e1, st);
+            g_prof.recs.push_back(r);
+        }
+    }
+};
+
+}  // namespace
+
+#define HIL_LAUNCH(cat, flops, bytes, st, expr)                     \
+    do {                                                            \
+        LaunchScope scope__((cat), (double)(flops), (double)(bytes), (st)); \
+        HIL_CUDA(expr);                                             \
+    } while (0)
+
+
+// ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
+static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                               float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
+                               cudaStream_t st) {
+    const double n = (double)B * T;
+    HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
+               launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
+    return HIL_OK;
+}
+static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,
+                                  long long y_bs, int y_rs, cudaStream_t st) {
+    const double n = (double)B * T;
+    HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M) + 4.0 * W.M * W.K, st,
+               launch_gemm_chlast_in(W, Q, B, T, bias, Y, y_bs, y_rs, st));
+    return HIL_OK;
+}
+static int32_t run_gemm_stft_logmag(const PackedMat& Wd, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
+                                    long long y_bs, int y_rs, cudaStream_t st) {
+    const double n = (double)B * T;
+    HIL_LAUNCH(CAT_GEMM_STFT, 2.0 * Wd.M * Wd.K * n, 4.0 * (n * hop + n * (Wd.M / 2)) + 4.0 * Wd.M * Wd.K, st,
+               launch_gemm_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st));
+    return HIL_OK;
+}
+static int32_t run_wavcat(const float* x, const float* ci, float* co, float* wav_ext, long long w_bs, int B, int T, int P,
+                          cudaStream_t st) {
+    HIL_LAUNCH(CAT_MISC, 0.0, 4.0 * B * (2.0 * (P + T) + P), st, launch_wavcat(x, ci, co, wav_ext, w_bs, B, T, P, st));
+    return HIL_OK;
+}
+static int32_t run_conv_pre(const float* win, long long w_bs, const float* w, const float* bias, float* y, long long y_bs,
+                            int y_rs, int B, int C, int T, int K, cudaStream_t st) {
+    HIL_LAUNCH(CAT_CONV_PRE, 2.0 * B * C * (double)T * K, 4.0 * B * (double)T * (1 + C), st,
+               launch_conv_pre(win, w_bs, w, bias, y, y_bs, y_rs, B, C, T, K, st));
+    return HIL_OK;
+}
+static int32_t run_dwconv(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
+                          const float* bias, const float* skip, float* y, long long y_bs, int y_rs, int B, int C, int T,
+                          int K, int S, int pre, float pre_scale, cudaStream_t st) {
+    const double nin = (double)B * C * T, nout = nin / S;
+    HIL_LAUNCH(CAT_DW, 2.0 * nout * K, 4.0 * (nin + nout * (skip ? 2 : 1)), st,
+               launch_dwconv(x, x_bs, x_rs, ci, co, w, bias, skip, y, y_bs, y_rs, B, C, T, K, S, pre, pre_scale, st));
+    return HIL_OK;
+}
+static int32_t run_dwconv_transpose(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
+                                    float* y, long long y_bs, int y_rs, int B, int C, int T, int S, int pre,
+                                    float pre_scale, cudaStream_t st) {
+    const double nin = (double)B * C * T;
+    HIL_LAUNCH(CAT_DWT, 4.0 * nin * S, 4.0 * (nin + nin * S), st,
+               launch_dwconv_transpose(x, x_bs, x_rs, ci, co, w, y, y_bs, y_rs, B, C, T, S, pre, pre_scale, st));
+    return HIL_OK;
+}
+static int32_t run_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
+                                  const float* bias, float* y, int B, int C, int T, int K, int pre, float pre_scale,
+                                  cudaStream_t st) {
+    HIL_LAUNCH(CAT_CONV_POST, 2.0 * B * C * (double)T * K, 4.0 * B * (double)T * (C + 1), st,
+               launch_conv_post_tanh(x, x_bs, x_rs, ci, co, w, bias, y, B, C, T, K, pre, pre_scale, st));
+    return HIL_OK;
+}
+static int32_t run_l2norm_chlast(const float* x, long long x_bs, int x_rs, float* z, int B, int C, int F, float scale,
+                                 cudaStream_t st) {
+    HIL_LAUNCH(CAT_MISC, 0.0, 8.0 * B * C * (double)F, st, launch_l2norm_chlast(x, x_bs, x_rs, z, B, C, F, scale, st));
+    return HIL_OK;
+}
+static int32_t run_rvq_encode(const float* z, const float* cb, const float* ee, int size, int dim, long long frames, int n,
+                              int64_t* idx, float* qsum, cudaStream_t st) {
+    HIL_LAUNCH(CAT_RVQ, 2.0 * frames * (double)n * size * dim,
+               4.0 * frames * dim * (qsum ? 2 : 1) + 8.0 * frames * n + 4.0 * (double)n * size * dim, st,
+               launch_rvq_encode(z, cb, ee, size, dim, frames, n, idx, qsum, st));
+    return HIL_OK;
+}
+static int32_t run_rvq_decode(const int64_t* idx, const float* cb, int size, int dim, long long frames, int n, float* q,
+                              cudaStream_t st) {
+    HIL_LAUNCH(CAT_RVQ, 0.0, 4.0 * frames * dim * (n + 1) + 8.0 * frames * n, st,
+               launch_rvq_decode(idx, cb, size, dim, frames, n, q, st));
+    return HIL_OK;
+}
+
+// ----------------------------------------------------------------------------- model
+namespace {
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> dims;
+};
+
+struct Dws {  // DWSBlock streaming.py:160-192
+    PackedMat pw;
+    const float* dw_w = nullptr;
+    const float* dw_b = nullptr;
+};
+
+struct EncStage {
+    int C = 0, ratio = 1, n_fft = 0;
+    PackedMat dft, spec_pw;
+    const float* spec_b = nullptr;
+    std::vector<Dws> units;  // 2 per ResBlock
+    PackedMat down_pw;
+    const float* down_w = nullptr;
+    const float* down_b = nullptr;
+};
+
+struct DecStage {
+    int C = 0, ratio = 1;  // C = input channels of the stage
+    const float* up_w = nullptr;
+    PackedMat up_pw;
+    const float* up_b = nullptr;
+    std::vector<Dws> units;
+};
+
+}  // namespace
+
+struct hil_model {
+    hil_config cfg{};
+    bool finalized = false;
+    bool has_enc = false, has_dec = false, has_vq = false;  // sections present (a module may hold only one)
+    std::map<std::string, HostTensor> host;
+    float* arena = nullptr;
+    size_t arena_floats = 0;
+
+    // encoder
+    const float* conv_pre_w = nullptr;
+    const float* conv_pre_b = nullptr;
+    std::vector<EncStage> enc;
+    int n_fft_post = 0;
+    PackedMat post_dft, post_spec_pw;
+    const float* post_spec_b = nullptr;
+    const float* post_dw_w = nullptr;
+    PackedMat post_pw;
+    const float* post_pw_b = nullptr;
+    // decoder
+    PackedMat dec_pre_pw;
+    const float* dec_pre_dw_w = nullptr;
+    const float* dec_pre_dw_b = nullptr;
+    std::vector<DecStage> dec;
+    const float* dec_post_w = nullptr;
+    const float* dec_post_b = nullptr;
+    // quantizer
+    const float* codebooks = nullptr;  // [n_q][size][dim]
+    float* ee = nullptr;               // [n_q][size]
+
+    std::vector<std::vector<int64_t>> enc_cache_shape, dec_cache_shape;  // [C, len]
+    int hop = 1;
+    float enc_post_scale = 1.f, dec_post_scale = 1.f;
+};
+
+struct hil_state {
+    hil_model* m = nullptr;
+    int B = 0;
+    // caches: two generations (ping-pong) per side
+    float* cache_arena = nullptr;
+    std::vector<float*> enc_c[2], dec_c[2];
+    int enc_gen = 0, dec_gen = 0;
+    // workspace (grow-only)
+    float* ws = nullptr;
+    size_t ws_floats = 0;
+    int64_t* idx_dev = nullptr;
+    size_t idx_elems = 0;
+    float* io_dev = nullptr;  // staging for the *_host call
+    size_t io_floats = 0;
+};
+
+namespace {
+
+struct Arena {  // host-side staging of everything that goes to the device weight arena
+    std::vector<float> buf;
+    size_t alloc(size_t n) {
+        const size_t off = (buf.size() + 63) & ~size_t(63);
+        buf.resize(off + n, 0.f);
+        return off;
+    }
+};
+
+struct PendingMat {
+    PackedMat* dst;
+    size_t off;
+};
+
+struct Builder {
+    hil_model* m;
+    Arena arena;
+    std::vector<PendingMat> mats;
+    std::vector<std::pair<const float**, size_t>> ptrs;
+    std::string missing;
+
+    const HostTensor* get(const std::string& name, std::vector<int64_t> dims) {
+        auto it = m->host.find(name);
+        if (it == m->host.end()) {
+            if (missing.empty()) missing = name;
+            return nullptr;
+        }
+        if (it->second.dims != dims) {
+            if (missing.empty()) missing = name + " (wrong shape)";
+            return nullptr;
+        }
+        return &it->second;
+    }
+    void raw(const std::string& name, std::vector<int64_t> dims, const float** dst) {
+        const HostTensor* t = get(name, dims);
+        if (!t) return;
+        const size_t off = arena.alloc(t->data.size());
+        std::memcpy(arena.buf.data() + off, t->data.data(), t->data.size() * sizeof(float));
+        ptrs.push_back({dst, off});
+    }
+    // W[M][K] (reference layout [M,K,1]) -> A[Kp][Mp]
+    void linear(const std::string& name, int M, int K, PackedMat* dst) {
+        const HostTensor* t = get(name, {M, K, 1});
+        if (!t) return;
+        pack(t->data.data(), M, K, choose_tm(M), false, dst);
+    }
+    // DFT basis [2F][1][N] rows [cos; sin] -> interleaved rows (cos_f, sin_f), TM = 6
+    void dft(const std::string& name, int n_fft, PackedMat* dst) {
+        const int F = n_fft / 2 + 1;
+        const HostTensor* t = get(name, {2 * F, 1, n_fft});
+        if (!t) return;
+        pack(t->data.data(), 2 * F, n_fft, 6, true, dst);
+    }
+    void pack(const float* w, int M, int K, int TM, bool interleave, PackedMat* dst) {
+        const int BM = 16 * TM;
+        const int Mp = round_up(M, BM), Kp = round_up(K, 16);
+        const size_t off = arena.alloc((size_t)Mp * Kp);
+        float* a = arena.buf.data() + off;
+        const int F = M / 2;
+        for (int mrow = 0; mrow < M; ++mrow) {
+            const int src = interleave ? ((mrow & 1) ? F + mrow / 2 : mrow / 2) : mrow;
+            for (int k = 0; k < K; ++k) a[(size_t)k * Mp + mrow] = w[(size_t)src * K + k];
+        }
+        dst->M = M; dst->K = K; dst->Mp = Mp; dst->Kp = Kp; dst->TM = TM;
+        mats.push_back({dst, off});
+    }
+};
+
+size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+
+}  // namespace
+
+extern "C" {
+
+int32_t hil_abi_version(void) { return HIL_ABI_VERSION; }
+const char* hil_last_error(void) { return g_err.c_str(); }
+
+void hil_config_default(hil_config* c, int32_t num_quantizers) {
+    std::memset(c, 0, sizeof(*c));
+    c->channels_enc = 64; c->channels_dec = 96; c->n_fft_base = 64;
+    c->n_residual_enc = 2; c->n_residual_dec = 3;
+    c->res_scale_enc = 0.5773502691896258; c->res_scale_dec = 0.5773502691896258;
+    c->n_strides = 4;
+    c->strides[0] = 8; c->strides[1] = 5; c->strides[2] = 4; c->strides[3] = 2;
+    c->kernel_size = 5; c->dim = 128; c->codebook_size = 1024; c->num_quantizers = num_quantizers;
+}
+
+int32_t hil_model_create(const hil_config* cfg, hil_model** out) {
+    if (!cfg || !out) return fail(HIL_ERR_INVALID, "null argument");
+    if (cfg->n_strides < 1 || cfg->n_strides > HIL_MAX_STRIDES) return fail(HIL_ERR_INVALID, "n_strides out of range");
+    if (cfg->kernel_size != 5) return fail(HIL_ERR_INVALID, "only kernel_size=5 is built (both published configs)");
+    if (cfg->dim != 128) return fail(HIL_ERR_INVALID, "only dim=128 is built (both published configs)");
+    if (cfg->num_quantizers < 1 || cfg->codebook_size < 1) return fail(HIL_ERR_INVALID, "bad quantizer config");
+    if (cfg->channels_enc % 4 || cfg->channels_dec % 4) return fail(HIL_ERR_INVALID, "channels must be multiples of 4");
+    for (int i = 0; i < cfg->n_strides; ++i) {
+        const int r = cfg->strides[i];
+        if (!(r == 2 || r == 4 || r == 5 || r == 8 || r == 3 || r == 6))
+            return fail(HIL_ERR_INVALID, "stride not in {2,3,4,5,6,8}");
+    }
+    hil_model* m = new hil_model();
+    m->cfg = *cfg;
+    m->hop = 1;
+    for (int i = 0; i < cfg->n_strides; ++i) m->hop *= cfg->strides[i];
+    *out = m;
+    return HIL_OK;
+}
+
+int32_t hil_model_set_tensor(hil_model* m, const char* name, const float* host, const int64_t* dims, int32_t ndim) {
+    if (!m || !name || !host || !dims || ndim < 1 || ndim > 4) return fail(HIL_ERR_INVALID, "bad argument");
+    if (m->finalized) return fail(HIL_ERR_STATE, "model already finalized");
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (dims[i] < 0) return fail(HIL_ERR_INVALID, "negative dim");
+        t.dims.push_back(dims[i]);
+        n *= (size_t)dims[i];
+    }
+    t.data.assign(host, host + n);
+    m->host[name] = std::move(t);
+    return HIL_OK;
+}
+
+int32_t hil_model_finalize(hil_model* m) {
+    if (!m) return fail(HIL_ERR_INVALID, "null model");
+    if (m->finalized) return HIL_OK;
+    const hil_config& c = m->cfg;
+    Builder b{m};
+    const int k = c.kernel_size;
+    const int ns = c.n_strides;
+    char nm[256];
+    auto N = [&](const char* fmt, int a = 0, int b2 = 0, int c2 = 0) {
+        std::snprintf(nm, sizeof(nm), fmt, a, b2, c2);
+        return std::string(nm);
+    };
+
+    auto has_prefix = [&](const char* pre) {
+        auto it = m->host.lower_bound(pre);
+        return it != m->host.end() && it->first.compare(0, std::strlen(pre), pre) == 0;
+    };
+    m->has_enc = has_prefix("encoder.");
+    m->has_dec = has_prefix("decoder.");
+    m->has_vq = has_prefix("quantizer.");
+    if (!m->has_enc && !m->has_dec && !m->has_vq) return fail(HIL_ERR_MISSING, "no tensors set");
+
+    // ---- encoder (streaming.py:368-456)
+    int C = c.channels_enc;
+    if (m->has_enc) {
+    b.raw("encoder.conv_pre.weight", {C, 1, k}, &m->conv_pre_w);
+    b.raw("encoder.conv_pre.bias", {C}, &m->conv_pre_b);
+    m->enc.resize(ns);
+    m->enc_cache_shape.clear();
+    m->n_fft_post = c.n_fft_base << ns;
+    m->enc_cache_shape.push_back({1, m->n_fft_post - 1});
+    for (int s = 0; s < ns; ++s) {
+        EncStage& st = m->enc[s];
+        st.C = C;
+        st.ratio = c.strides[ns - 1 - s];
+        st.n_fft = c.n_fft_base << s;
+        const int F = st.n_fft / 2 + 1;
+        b.dft(N("encoder.spec_blocks.%d.spec.weight", s), st.n_fft, &st.dft);
+        b.linear(N("encoder.spec_blocks.%d.layer.weight", s), C, F, &st.spec_pw);
+        b.raw(N("encoder.spec_blocks.%d.layer.bias", s), {C}, &st.spec_b);
+        st.units.resize(2 * c.n_residual_enc);
+        for (int j = 0; j < c.n_residual_enc; ++j)
+            for (int u = 0; u < 2; ++u) {
+                Dws& d = st.units[2 * j + u];
+                b.linear(N("encoder.blocks.%d.%d.block.%d.pointwise.1.weight", s, j, u), C, C, &d.pw);
+                b.raw(N("encoder.blocks.%d.%d.block.%d.depthwise.weight", s, j, u), {C, 1, k}, &d.dw_w);
+                b.raw(N("encoder.blocks.%d.%d.block.%d.depthwise.bias", s, j, u), {C}, &d.dw_b);
+                m->enc_cache_shape.push_back({C, k - 1});
+            }
+        b.linear(N("encoder.downsample_pointwise.%d.1.weight", s), 2 * C, C, &st.down_pw);
+        b.raw(N("encoder.downsample_depthwise.%d.weight", s), {2 * C, 1, 2 * st.ratio}, &st.down_w);
+        b.raw(N("encoder.downsample_depthwise.%d.bias", s), {2 * C}, &st.down_b);
+        m->enc_cache_shape.push_back({2 * C, st.ratio});
+        C *= 2;
+    }
+    {
+        const int F = m->n_fft_post / 2 + 1;
+        b.dft("encoder.spec_post.spec.weight", m->n_fft_post, &m->post_dft);
+        b.linear("encoder.spec_post.layer.weight", C, F, &m->post_spec_pw);
+        b.raw("encoder.spec_post.layer.bias", {C}, &m->post_spec_b);
+        b.raw("encoder.conv_post_depthwise.weight", {C, 1, k}, &m->post_dw_w);
+        b.linear("encoder.conv_post_pointwise.weight", c.dim, C, &m->post_pw);
+        b.raw("encoder.conv_post_pointwise.bias", {c.dim}, &m->post_pw_b);
+        m->enc_cache_shape.push_back({C, k - 1});
+    }
+    }  // has_enc
+    // ---- decoder (streaming.py:520-597)
+    C = c.channels_dec << ns;
+    if (m->has_dec) {
+    b.linear("decoder.conv_pre_pointwise.weight", C, c.dim, &m->dec_pre_pw);
+    b.raw("decoder.conv_pre_depthwise.weight", {C, 1, k}, &m->dec_pre_dw_w);
+    b.raw("decoder.conv_pre_depthwise.bias", {C}, &m->dec_pre_dw_b);
+    m->dec_cache_shape.clear();
+    m->dec_cache_shape.push_back({C, k - 1});
+    m->dec.resize(ns);
+    for (int i = 0; i < ns; ++i) {
+        DecStage& st = m->dec[i];
+        st.C = C;
+        st.ratio = c.strides[i];
+        b.raw(N("decoder.upsample_depthwise.%d.weight", i), {C, 1, 2 * st.ratio}, &st.up_w);
+        b.linear(N("decoder.upsample_pointwise.%d.weight", i), C / 2, C, &st.up_pw);
+        b.raw(N("decoder.upsample_pointwise.%d.bias", i), {C / 2}, &st.up_b);
+        m->dec_cache_shape.push_back({C, (2 * st.ratio - 1) / st.ratio});
+        st.units.resize(2 * c.n_residual_dec);
+        for (int j = 0; j < c.n_residual_dec; ++j)
+            for (int u = 0; u < 2; ++u) {
+                Dws& d = st.units[2 * j + u];
+                b.linear(N("decoder.blocks.%d.%d.block.%d.pointwise.1.weight", i, j, u), C / 2, C / 2, &d.pw);
+                b.raw(N("decoder.blocks.%d.%d.block.%d.depthwise.weight", i, j, u), {C / 2, 1, k}, &d.dw_w);
+                b.raw(N("decoder.blocks.%d.%d.block.%d.depthwise.bias", i, j, u), {C / 2}, &d.dw_b);
+                m->dec_cache_shape.push_back({C / 2, k - 1});
+            }
+        C /= 2;
+    }
+    b.raw("decoder.conv_post.weight", {1, C, k}, &m->dec_post_w);
+    b.raw("decoder.conv_post.bias", {1}, &m->dec_post_b);
+    m->dec_cache_shape.push_back({C, k - 1});
+    }  // has_dec
+    // ---- quantizer: one contiguous [n_q][size][dim] block
+    const size_t cb_elems = (size_t)c.codebook_size * c.dim;
+    const size_t cb_off = b.arena.alloc(cb_elems * c.num_quantizers);
+    for (int i = 0; m->has_vq && i < c.num_quantizers; ++i) {
+        const HostTensor* t = b.get(N("quantizer.layers.%d.embed", i), {c.codebook_size, c.dim});
+        if (t) std::memcpy(b.arena.buf.data() + cb_off + cb_elems * i, t->data.data(), cb_elems * sizeof(float));
+    }
+    const size_t ee_off = b.arena.alloc((size_t)c.codebook_size * c.num_quantizers);
+
+    if (!b.missing.empty()) return fail(HIL_ERR_MISSING, "tensor not set: " + b.missing);
+
+    m->arena_floats = b.arena.buf.size();
+    HIL_CUDA(cudaMalloc(&m->arena, m->arena_floats * sizeof(float)));
+    HIL_CUDA(cudaMemcpy(m->arena, b.arena.buf.data(), m->arena_floats * sizeof(float), cudaMemcpyHostToDevice));
+    for (auto& pm : b.mats) pm.dst->A = m->arena + pm.off;
+    for (auto& p : b.ptrs) *p.first = m->arena + p.second;
+    m->codebooks = m->arena + cb_off;
+    m->ee = m->arena + ee_off;
+    if (m->has_vq)
+        HIL_CUDA(launch_codebook_norms(m->codebooks, m->ee, c.num_quantizers, c.codebook_size, c.dim, 0));
+    HIL_CUDA(cudaDeviceSynchronize());
+
+    // Scale layers: python doubles rounded to fp32 when multiplied into fp32 tensors (streaming.py:404-407, :561-564)
+    m->enc_post_scale = (float)std::pow(1.0 + c.n_residual_enc * (double)c.res_scale_enc * (double)c.res_scale_enc, -0.5);
+    m->dec_post_scale = (float)std::pow(1.0 + c.n_residual_dec * (double)c.res_scale_dec * (double)c.res_scale_dec, -0.5);
+    m->host.clear();
+    m->finalized = true;
+    return HIL_OK;
+}
+
+void hil_model_destroy(hil_model* m) {
+    if (!m) return;
+    if (m->arena) cudaFree(m->arena);
+    delete m;
+}
+
+int32_t hil_model_hop(const hil_model* m) { return m ? m->hop : 0; }
+
+int32_t hil_model_num_caches(const hil_model* m, int32_t which) {
+    if (!m || !m->finalized) return 0;
+    return (int32_t)(which == HIL_ENCODER ? m->enc_cache_shape.size() : m->dec_cache_shape.size());
+}
+
+int32_t hil_model_cache_shape(const hil_model* m, int32_t which, int32_t i, int32_t batch, int64_t dims[3]) {
+    if (!m || !m->finalized) return fail(HIL_ERR_STATE, "model not finalized");
+    const auto& v = which == HIL_ENCODER ? m->enc_cache_shape : m->dec_cache_shape;
+    if (i < 0 || i >= (int)v.size()) return fail(HIL_ERR_INVALID, "cache index out of range");
+    dims[0] = batch; dims[1] = v[i][0]; dims[2] = v[i][1];
+    return HIL_OK;
+}
+
+// ----------------------------------------------------------------------------- state
+int32_t hil_state_create(hil_model* m, int32_t batch, hil_state** out) {
+    if (!m || !out || batch < 1) return fail(HIL_ERR_INVALID, "bad argument");
+    if (!m->finalized) return fail(HIL_ERR_STATE, "model not finalized");
+    hil_state* s = new hil_state();
+    s->m = m;
+    s->B = batch;
+    size_t total = 0;
+    auto count = [&](const std::vector<std::vector<int64_t>>& shapes) {
+        for (auto& sh : shapes) total += ((size_t)batch * sh[0] * sh[1] + 63) & ~size_t(63);
+    };
+    count(m->enc_cache_shape);
+    count(m->dec_cache_shape);
+    cudaError_t e = cudaMalloc(&s->cache_arena, 2 * total * sizeof(float));
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(HIL_ERR_NOMEM, std::string("cudaMalloc caches: ") + cudaGetErrorString(e));
+    }
+    size_t off = 0;
+    for (int g = 0; g < 2; ++g) {
+        for (auto& sh : m->enc_cache_shape) {
+            s->enc_c[g].push_back(s->cache_arena + off);
+            off += ((size_t)batch * sh[0] * sh[1] + 63) & ~size_t(63);
+        }
+        for (auto& sh : m->dec_cache_shape) {
+            s->dec_c[g].push_back(s->cache_arena + off);
+            off += ((size_t)batch * sh[0] * sh[1] + 63) & ~size_t(63);
+        }
+    }
+    e = cudaMemset(s->cache_arena, 0, 2 * total * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(s->cache_arena);
+        delete s;
+        return fail(HIL_ERR_CUDA, std::string("cudaMemset caches: ") + cudaGetErrorString(e));
+    }
+    *out = s;
+    return HIL_OK;
+}
+
+int32_t hil_state_reset(hil_state* s, void* stream) {
+    if (!s) return fail(HIL_ERR_INVALID, "null state");
+    cudaStream_t st = (cudaStream_t)stream;
+    const hil_model* m = s->m;
+    for (size_t i = 0; i < m->enc_cache_shape.size(); ++i)
+        HIL_CUDA(cudaMemsetAsync(s->enc_c[s->enc_gen][i], 0,
+                                 (size_t)s->B * m->enc_cache_shape[i][0] * m->enc_cache_shape[i][1] * sizeof(float), st));
+    for (size_t i = 0; i < m->dec_cache_shape.size(); ++i)
+        HIL_CUDA(cudaMemsetAsync(s->dec_c[s->dec_gen][i], 0,
+                                 (size_t)s->B * m->dec_cache_shape[i][0] * m->dec_cache_shape[i][1] * sizeof(float), st));
+    return HIL_OK;
+}
+
+static int32_t cache_ptr(hil_state* s, int32_t which, int32_t i, float** p, size_t* bytes) {
+    if (!s) return fail(HIL_ERR_INVALID, "null state");
+    const hil_model* m = s->m;
+    const auto& shapes = which == HIL_ENCODER ? m->enc_cache_shape : m->dec_cache_shape;
+    if (i < 0 || i >= (int)shapes.size()) return fail(HIL_ERR_INVALID, "cache index out of range");
+    *p = which == HIL_ENCODER ? s->enc_c[s->enc_gen][i] : s->dec_c[s->dec_gen][i];
+    *bytes = (size_t)s->B * shapes[i][0] * shapes[i][1] * sizeof(float);
+    return HIL_OK;
+}
+
+int32_t hil_state_export_cache(hil_state* s, int32_t which, int32_t i, float* dev_dst, void* stream) {
+    float* p;
+    size_t bytes;
+    HIL_TRY(cache_ptr(s, which, i, &p, &bytes));
+    HIL_CUDA(cudaMemcpyAsync(dev_dst, p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HIL_OK;
+}
+
+int32_t hil_state_import_cache(hil_state* s, int32_t which, int32_t i, const float* dev_src, void* stream) {
+    float* p;
+    size_t bytes;
+    HIL_TRY(cache_ptr(s, which, i, &p, &bytes));
+    HIL_CUDA(cudaMemcpyAsync(p, dev_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HIL_OK;
+}
+
+void hil_state_destroy(hil_state* s) {
+    if (!s) return;
+    if (s->cache_arena) cudaFree(s->cache_arena);
+    if (s->ws) cudaFree(s->ws);
+    if (s->idx_dev) cudaFree(s->idx_dev);
+    if (s->io_dev) cudaFree(s->io_dev);
+    delete s;
+}
+
+size_t hil_state_workspace_bytes(const hil_state* s) {
+    return s ? s->ws_floats * sizeof(float) + s->idx_elems * sizeof(int64_t) + s->io_floats * sizeof(float) : 0;
+}
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------- workspace plan
+namespace {
+
+struct Plan {
+    size_t wav_ext = 0, spec = 0, act = 0, lat = 0;  // floats
+    int Wp = 0;
+    size_t total() const { return wav_ext + spec + 3 * act + 2 * lat; }
+};
+
+// Buffer sizes for a chunk of T samples (T multiple of hop) at batch B.
+Plan make_plan(const hil_model* m, int B, int T) {
+    const hil_config& c = m->cfg;
+    Plan p;
+    p.Wp = pitch4(m->n_fft_post - 1 + T);
+    p.wav_ext = (size_t)B * p.Wp;
+    size_t act = 0, spec = 0;
+    int C = c.channels_enc, Ts = T;
+    for (auto& st : m->enc) {
+        const int Tp = pitch4(Ts);
+        spec = max_sz(spec, (size_t)(st.n_fft / 2 + 1) * Tp);
+        act = max_sz(act, (size_t)2 * C * Tp);
+        C *= 2;
+        Ts /= st.ratio;
+    }
+    spec = max_sz(spec, (size_t)(m->n_fft_post / 2 + 1) * pitch4(Ts));
+    act = max_sz(act, (size_t)C * pitch4(Ts));
+    const int F = Ts;
+    C = c.channels_dec << c.n_strides;
+    Ts = F;
+    act = max_sz(act, (size_t)C * pitch4(Ts));
+    for (auto& st : m->dec) {
+        Ts *= st.ratio;
+        act = max_sz(act, (size_t)C * pitch4(Ts));
+        C /= 2;
+    }
+    p.spec = ((size_t)B * spec + 63) & ~size_t(63);
+    p.act = ((size_t)B * act + 63) & ~size_t(63);
+    p.lat = ((size_t)B * F * c.dim + 63) & ~size_t(63);
+    p.wav_ext = (p.wav_ext + 63) & ~size_t(63);
+    return p;
+}
+
+struct Buffers {
+    float *wav_ext, *spec, *h, *a1, *a2, *z, *q;
+    int Wp;
+};
+
+int32_t ensure_workspace(hil_state* s, int B, int T, Buffers* out) {
+    if (B != s->B) return fail(HIL_ERR_STATE, "batch size differs from the one the state was created with");
+    const Plan p = make_plan(s->m, B, T);
+    if (p.total() > s->ws_floats) {
+        // grow-only; the old block may still be in use by queued kernels, so drain first
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return fail(HIL_ERR_CUDA, std::string("sync before workspace growth: ") + cudaGetErrorString(e));
+        if (s->ws) cudaFree(s->ws);
+        s->ws = nullptr;
+        s->ws_floats = 0;
+        e = cudaMalloc(&s->ws, p.total() * sizeof(float));
+        if (e != cudaSuccess) return fail(HIL_ERR_NOMEM, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
+        s->ws_floats = p.total();
+    }
+    float* w = s->ws;
+    out->wav_ext = w; w += p.wav_ext;
+    out->spec = w; w += p.spec;
+    out->h = w; w += p.act;
+    out->a1 = w; w += p.act;
+    out->a2 = w; w += p.act;
+    out->z = w; w += p.lat;
+    out->q = w;
+    out->Wp = p.Wp;
+    return HIL_OK;
+}
+
+// ResBlock.forward streaming.py:252-275 with the folded residual scale:
+//   h <- h + dw5(pw1(ELU(dw5(pw0(ELU(h * pre))))))
+int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, int Ts, float pre_scale,
+                  const float* const* cin, float* const* cout, cudaStream_t st) {
+    const int Tp = pitch4(Ts);
+    const long long bs = (long long)C * Tp;
+    const int pre0 = pre_scale == 1.0f ? PRE_ELU : PRE_SCALE_ELU;
+    HIL_TRY(run_gemm_linear(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, nullptr, nullptr, a1, bs, Tp, st));
+    HIL_TRY(run_dwconv(a1, bs, Tp, cin[0], cout[0], u[0].dw_w, u[0].dw_b, nullptr, a2, bs, Tp, B, C, Ts, 5, 1,
+                           PRE_NONE, 1.f, st));
+    HIL_TRY(run_gemm_linear(u[1].pw, a2, bs, Tp, B, Ts, PRE_ELU, 1.f, nullptr, nullptr, a1, bs, Tp, st));
+    HIL_TRY(run_dwconv(a1, bs, Tp, cin[1], cout[1], u[1].dw_w, u[1].dw_b, h, h, bs, Tp, B, C, Ts, 5, 1, PRE_NONE,
+                           1.f, st));
+    return HIL_OK;
+}
+
+int32_t encode_impl(hil_model* m, const Buffers& w, const float* wav, int B, int T, float* z, const float* const* cin,
+                    float* const* cout, cudaStream_t st) {
+    const hil_config& c = m->cfg;
+    const int Tw = m->n_fft_post - 1;
+    const int Wp = w.Wp;
+    HIL_TRY(run_wavcat(wav, cin[0], cout[0], w.wav_ext, Wp, B, T, Tw, st));
+    int C = c.channels_enc, Ts = T, stride = 1, ci = 1;
+    float *h = w.h, *a1 = w.a1, *a2 = w.a2;
+    {
+        const int Tp = pitch4(Ts);
+        HIL_TRY(run_conv_pre(w.wav_ext + (Tw - (c.kernel_size - 1)), Wp, m->conv_pre_w, m->conv_pre_b, h,
+                                 (long long)C * Tp, Tp, B, C, Ts, c.kernel_size, st));
+    }
+    const double rs2 = (double)c.res_scale_enc * (double)c.res_scale_enc;
+    for (auto& sg : m->enc) {
+        const int Tp = pitch4(Ts);
+        const int F = sg.n_fft / 2 + 1;
+        const long long bs = (long long)C * Tp;
+        // SpecBlock streaming.py:346-365
+        HIL_TRY(run_gemm_stft_logmag(sg.dft, w.wav_ext + (Tw - (sg.n_fft - 1)), Wp, stride, B, Ts, w.spec,
+                                         (long long)F * Tp, Tp, st));
+        HIL_TRY(run_gemm_linear(sg.spec_pw, w.spec, (long long)F * Tp, Tp, B, Ts, PRE_NONE, 1.f, sg.spec_b, h, h, bs,
+                                    Tp, st));
+        for (int j = 0; j < c.n_residual_enc; ++j) {
+            const float pre = (float)std::pow(1.0 + (j + 1) * rs2, -0.5);  // streaming.py:210 with idx=j+1
+            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, pre, cin + ci, cout + ci, st));
+            ci += 2;
+        }
+        // Scale -> ELU -> 1x1 (C -> 2C) -> strided depthwise (streaming.py:506-510)
+        HIL_TRY(run_gemm_linear(sg.down_pw, h, bs, Tp, B, Ts, PRE_SCALE_ELU, m->enc_post_scale, nullptr, nullptr, a1,
+                                    2 * bs, Tp, st));
+        const int Ts2 = Ts / sg.ratio, Tp2 = pitch4(Ts2);
+        HIL_TRY(run_dwconv(a1, 2 * bs, Tp, cin[ci], cout[ci], sg.down_w, sg.down_b, nullptr, h,
+                               (long long)2 * C * Tp2, Tp2, B, 2 * C, Ts, 2 * sg.ratio, sg.ratio, PRE_NONE, 1.f, st));
+        ci += 1;
+        C *= 2;
+        Ts = Ts2;
+        stride *= sg.ratio;
+    }
+    {
+        const int Tp = pitch4(Ts);
+        const int F = m->n_fft_post / 2 + 1;
+        const long long bs = (long long)C * Tp;
+        HIL_TRY(run_gemm_stft_logmag(m->post_dft, w.wav_ext, Wp, stride, B, Ts, w.spec, (long long)F * Tp, Tp, st));
+        HIL_TRY(run_gemm_linear(m->post_spec_pw, w.spec, (long long)F * Tp, Tp, B, Ts, PRE_NONE, 1.f,
+                                    m->post_spec_b, h, h, bs, Tp, st));
+        HIL_TRY(run_dwconv(h, bs, Tp, cin[ci], cout[ci], m->post_dw_w, nullptr, nullptr, a1, bs, Tp, B, C, Ts, 5, 1,
+                               PRE_ELU, 1.f, st));
+        HIL_TRY(run_gemm_linear(m->post_pw, a1, bs, Tp, B, Ts, PRE_NONE, 1.f, m->post_pw_b, nullptr, a2,
+                                    (long long)c.dim * Tp, Tp, st));
+        HIL_TRY(run_l2norm_chlast(a2, (long long)c.dim * Tp, Tp, z, B, c.dim, Ts, (float)std::sqrt((double)c.dim), st));
+    }
+    return HIL_OK;
+}
+
+int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F, float* wav, const float* const* cin,
+                    float* const* cout, cudaStream_t st) {
+    const hil_config& c = m->cfg;
+    int C = c.channels_dec << c.n_strides, Ts = F, ci = 0;
+    float *h = w.h, *a1 = w.a1, *a2 = w.a2;
+    {
+        const int Tp = pitch4(Ts);
+        const long long bs = (long long)C * Tp;
+        HIL_TRY(run_gemm_chlast_in(m->dec_pre_pw, q, B, Ts, nullptr, a1, bs, Tp, st));
+        HIL_TRY(run_dwconv(a1, bs, Tp, cin[ci], cout[ci], m->dec_pre_dw_w, m->dec_pre_dw_b, nullptr, h, bs, Tp, B, C,
+                               Ts, 5, 1, PRE_NONE, 1.f, st));
+        ci += 1;
+    }
+    for (size_t i = 0; i < m->dec.size(); ++i) {
+        DecStage& sg = m->dec[i];
+        const int Tp = pitch4(Ts);
+        const int Ts2 = Ts * sg.ratio, Tp2 = pitch4(Ts2);
+        // (previous stage's Scale) -> ELU -> transposed depthwise -> 1x1 (C -> C/2) (streaming.py:633-637)
+        HIL_TRY(run_dwconv_transpose(h, (long long)C * Tp, Tp, cin[ci], cout[ci], sg.up_w, a1, (long long)C * Tp2,
+                                         Tp2, B, C, Ts, sg.ratio, i == 0 ? PRE_ELU : PRE_SCALE_ELU, m->dec_post_scale, st));
+        ci += 1;
+        HIL_TRY(run_gemm_linear(sg.up_pw, a1, (long long)C * Tp2, Tp2, B, Ts2, PRE_NONE, 1.f, sg.up_b, nullptr, h,
+                                    (long long)(C / 2) * Tp2, Tp2, st));
+        C /= 2;
+        Ts = Ts2;
+        for (int j = 0; j < c.n_residual_dec; ++j) {
+            // deploy-path quirk: pre_scale is 1.0 for every decoder ResBlock (streaming.py:576-583)
+            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, 1.0f, cin + ci, cout + ci, st));
+            ci += 2;
+        }
+    }
+    {
+        const int Tp = pitch4(Ts);
+        HIL_TRY(run_conv_post_tanh(h, (long long)C * Tp, Tp, cin[ci], cout[ci], m->dec_post_w, m->dec_post_b, wav, B,
+                                       C, Ts, c.kernel_size, PRE_SCALE_ELU, m->dec_post_scale, st));
+    }
+    return HIL_OK;
+}
+
+int32_t check_call(hil_model* m, hil_state* s, int B, long long T, bool need_hop_multiple) {
+    if (!m || !s) return fail(HIL_ERR_INVALID, "null model/state");
+    if (!m->finalized) return fail(HIL_ERR_STATE, "model not finalized");
+    if (s->m != m) return fail(HIL_ERR_STATE, "state belongs to another model");
+    if (B != s->B) return fail(HIL_ERR_STATE, "batch size differs from the one the state was created with");
+    if (T <= 0) return fail(HIL_ERR_INVALID, "empty input");
+    if (need_hop_multiple && T % m->hop) return fail(HIL_ERR_INVALID, "T must be a multiple of the hop length");
+    if (T > (1 << 26)) return fail(HIL_ERR_INVALID, "chunk too long");
+    return HIL_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- forward calls
+extern "C" {
+
+int32_t hil_encode_caches(hil_model* m, hil_state* s, const float* wav, int32_t B, int32_t T, float* z,
+                          const float* const* cin, float* const* cout, void* stream) {
+    HIL_TRY(check_call(m, s, B, T, true));
+    if (!wav || !z || !cin || !cout) return fail(HIL_ERR_INVALID, "null pointer");
+    if (!m->has_enc) return fail(HIL_ERR_STATE, "model has no encoder weights");
+    Buffers w;
+    HIL_TRY(ensure_workspace(s, B, T, &w));
+    return encode_impl(m, w, wav, B, T, z, cin, cout, (cudaStream_t)stream);
+}
+
+int32_t hil_encode(hil_model* m, hil_state* s, const float* wav, int32_t B, int32_t T, float* z, void* stream) {
+    HIL_TRY(check_call(m, s, B, T, true));
+    const int g = s->enc_gen;
+    HIL_TRY(hil_encode_caches(m, s, wav, B, T, z, s->enc_c[g].data(), s->enc_c[g ^ 1].data(), stream));
+    s->enc_gen = g ^ 1;
+    return HIL_OK;
+}
+
+int32_t hil_decode_caches(hil_model* m, hil_state* s, const float* q, int32_t B, int32_t F, float* wav,
+                          const float* const* cin, float* const* cout, void* stream) {
+    HIL_TRY(check_call(m, s, B, (long long)F * (m ? m->hop : 1), false));
+    if (!q || !wav || !cin || !cout) return fail(HIL_ERR_INVALID, "null pointer");
+    if (!m->has_dec) return fail(HIL_ERR_STATE, "model has no decoder weights");
+    Buffers w;
+    HIL_TRY(ensure_workspace(s, B, F * m->hop, &w));
+    return decode_impl(m, w, q, B, F, wav, cin, cout, (cudaStream_t)stream);
+}
+
+int32_t hil_decode(hil_model* m, hil_state* s, const float* q, int32_t B, int32_t F, float* wav, void* stream) {
+    HIL_TRY(check_call(m, s, B, (long long)F * (m ? m->hop : 1), false));
+    const int g = s->dec_gen;
+    HIL_TRY(hil_decode_caches(m, s, q, B, F, wav, s->dec_c[g].data(), s->dec_c[g ^ 1].data(), stream));
+    s->dec_gen = g ^ 1;
+    return HIL_OK;
+}
+
+int32_t hil_rvq_encode(hil_model* m, const float* z, int32_t B, int32_t F, int32_t n, int64_t* idx, float* qsum,
+                       void* stream) {
+    if (!m || !m->finalized) return fail(HIL_ERR_STATE, "model not finalized");
+    if (!z || !idx || B < 0 || F < 0) return fail(HIL_ERR_INVALID, "bad argument");
+    if (!m->has_vq) return fail(HIL_ERR_STATE, "model has no codebooks");
+    // assert 1 <= n <= len(self.layers)  (models/hilcodec/vector_quantize.py:213)
+    if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
+    HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, qsum,
+                               (cudaStream_t)stream));
+    return HIL_OK;
+}
+
+int32_t hil_rvq_decode(hil_model* m, const int64_t* idx, int32_t B, int32_t F, int32_t n, float* q, void* stream) {
+    if (!m || !m->finalized) return fail(HIL_ERR_STATE, "model not finalized");
+    if (!idx || !q || B < 0 || F < 0) return fail(HIL_ERR_INVALID, "bad argument");
+    if (!m->has_vq) return fail(HIL_ERR_STATE, "model has no codebooks");
+    if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
+    HIL_TRY(run_rvq_decode(idx, m->codebooks, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, q,
+                               (cudaStream_t)stream));
+    return HIL_OK;
+}
+
+int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav, int32_t B, int32_t T, int32_t n, float* z_out,
+                          int64_t* idx, float* wav_out, void* stream) {
+    HIL_TRY(check_call(m, s, B, T, true));
+    if (!wav || !idx || !wav_out) return fail(HIL_ERR_INVALID, "null pointer");
+    if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
+    if (!m->has_enc || !m->has_dec || !m->has_vq) return fail(HIL_ERR_STATE, "fused forward needs encoder, decoder and codebooks");
+    cudaStream_t st = (cudaStream_t)stream;
+    Buffers w;
+    HIL_TRY(ensure_workspace(s, B, T, &w));
+    const int F = T / m->hop;
+    float* z = z_out ? z_out : w.z;
+    const int ge = s->enc_gen, gd = s->dec_gen;
+    HIL_TRY(encode_impl(m, w, wav, B, T, z, s->enc_c[ge].data(), s->enc_c[ge ^ 1].data(), st));
+    s->enc_gen = ge ^ 1;
+    HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, w.q, st));
+    HIL_TRY(decode_impl(m, w, w.q, B, F, wav_out, s->dec_c[gd].data(), s->dec_c[gd ^ 1].data(), st));
+    s->dec_gen = gd ^ 1;
+    return HIL_OK;
+}
+
+int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host, int32_t B, int32_t T, int32_t n,
+                               int64_t* idx_host, float* wav_out_host, void* stream) {
+    HIL_TRY(check_call(m, s, B, T, true));
+    if (!wav_host || !idx_host || !wav_out_host) return fail(HIL_ERR_INVALID, "null pointer");
+    if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = T / m->hop;
+    const size_t nwav = (size_t)B * T, nidx = (size_t)n * B * F;
+    if (2 * nwav > s->io_floats) {
+        HIL_CUDA(cudaDeviceSynchronize());
+        if (s->io_dev) cudaFree(s->io_dev);
+        s->io_dev = nullptr; s->io_floats = 0;
+        HIL_CUDA(cudaMalloc(&s->io_dev, 2 * nwav * sizeof(float)));
+        s->io_floats = 2 * nwav;
+    }
+    if (nidx > s->idx_elems) {
+        HIL_CUDA(cudaDeviceSynchronize());
+        if (s->idx_dev) cudaFree(s->idx_dev);
+        s->idx_dev = nullptr; s->idx_elems = 0;
+        HIL_CUDA(cudaMalloc(&s->idx_dev, nidx * sizeof(int64_t)));
+        s->idx_elems = nidx;
+    }
+    float* wav_dev = s->io_dev;
+    float* out_dev = s->io_dev + nwav;
+    HIL_CUDA(cudaMemcpyAsync(wav_dev, wav_host, nwav * sizeof(float), cudaMemcpyHostToDevice, st));
+    HIL_TRY(hil_codec_forward(m, s, wav_dev, B, T, n, nullptr, s->idx_dev, out_dev, stream));
+    HIL_CUDA(cudaMemcpyAsync(idx_host, s->idx_dev, nidx * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    HIL_CUDA(cudaMemcpyAsync(wav_out_host, out_dev, nwav * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HIL_CUDA(cudaStreamSynchronize(st));
+    return HIL_OK;
+}
+
+// ----------------------------------------------------------------------------- launch accounting API
+uint64_t hil_launch_count(void) { return g_prof.launches; }
+
+int32_t hil_profile_begin(void) {
+    for (auto& r : g_prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.recs.clear();
+    g_prof.on = true;
+    return HIL_OK;
+}
+
+int32_t hil_profile_end(double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_cat) {
+    g_prof.on = false;
+    if (!ms || !flops || !bytes || !launches || n_cat < CAT_COUNT) return fail(HIL_ERR_INVALID, "need HIL_PROFILE_CATEGORIES slots");
+    HIL_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < n_cat; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    for (auto& r : g_prof.recs) {
+        float t = 0.f;
+        HIL_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat] += 1;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.recs.clear();
+    return HIL_OK;
+}
+
+// ----------------------------------------------------------------------------- operator level
+int32_t hil_op_dwconv(const float* x, const float* cache_in, float* cache_out, const float* w, const float* bias,
+                      const float* skip, float* y, int32_t B, int32_t C, int32_t T, int32_t K, int32_t S, int32_t pre,
+                      float pre_scale, void* stream) {
+    if (!x || !cache_in || !cache_out || !w || !y) return fail(HIL_ERR_INVALID, "null pointer");
+    if (K < S || S < 1 || T < S) return fail(HIL_ERR_INVALID, "bad conv geometry");
+    const int T_out = (T - S) / S + 1;
+    HIL_TRY(run_dwconv(x, (long long)C * T, T, cache_in, cache_out, w, bias, skip, y, (long long)C * T_out, T_out, B,
+                           C, T, K, S, pre, pre_scale, (cudaStream_t)stream));
+    return HIL_OK;
+}
+
+int32_t hil_op_dwconv_transpose(const float* x, const float* cache_in, float* cache_out, const float* w, float* y,
+                                int32_t B, int32_t C, int32_t T, int32_t S, int32_t pre, float pre_scale, void* stream) {
+    if (!x || !cache_in || !cache_out || !w || !y) return fail(HIL_ERR_INVALID, "null pointer");
+    HIL_TRY(run_dwconv_transpose(x, (long long)C * T, T, cache_in, cache_out, w, y, (long long)C * T * S, T * S, B, C,
+                                     T, S, pre, pre_scale, (cudaStream_t)stream));
+    return HIL_OK;
+}
+
+static int32_t upload_packed(const float* w_host, int M, int K, int TM, bool interleave, PackedMat* pm, float** dev) {
+    hil_model dummy;
+    Builder b{&dummy};
+    b.pack(w_host, M, K, TM, interleave, pm);
+    HIL_CUDA(cudaMalloc(dev, b.arena.buf.size() * sizeof(float)));
+    HIL_CUDA(cudaMemcpy(*dev, b.arena.buf.data(), b.arena.buf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    pm->A = *dev + b.mats[0].off;
+    return HIL_OK;
+}
+
+int32_t hil_op_pointwise(const float* x, const float* w_host, const float* bias_dev, const float* residual, float* y,
+                         int32_t B, int32_t M, int32_t K, int32_t T, int32_t pre, float pre_scale, void* stream) {
+    if (!x || !w_host || !y) return fail(HIL_ERR_INVALID, "null pointer");
+    PackedMat pm;
+    float* dev = nullptr;
+    HIL_TRY(upload_packed(w_host, M, K, choose_tm(M), false, &pm, &dev));
+    cudaError_t e = launch_gemm_linear(pm, x, (long long)K * T, T, B, T, pre, pre_scale, bias_dev, residual, y,
+                                       (long long)M * T, T, (cudaStream_t)stream);
+    cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dev);
+    HIL_CUDA(e);
+    HIL_CUDA(e2);
+    return HIL_OK;
+}
+
+int32_t hil_op_stft_logmag(const float* wav_window, const float* w_host, float* y, int32_t B, int32_t n_fft, int32_t hop,
+                           int32_t T, void* stream) {
+    if (!wav_window || !w_host || !y) return fail(HIL_ERR_INVALID, "null pointer");
+    const int F = n_fft / 2 + 1;
+    PackedMat pm;
+    float* dev = nullptr;
+    HIL_TRY(upload_packed(w_host, 2 * F, n_fft, 6, true, &pm, &dev));
+    const long long L = (long long)(T - 1) * hop + n_fft;
+    cudaError_t e = launch_gemm_stft_logmag(pm, wav_window, L, hop, B, T, y, (long long)F * T, T, (cudaStream_t)stream);
+    cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dev);
+    HIL_CUDA(e);
+    HIL_CUDA(e2);
+    return HIL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Shared device helpers and the internal launcher interface of libhilcodec_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hil {
+
+enum Pre { PRE_NONE = 0, PRE_ELU = 1, PRE_SCALE_ELU = 2 };
+
+// nn.ELU(alpha=1): x > 0 ? x : expm1(x)   (streaming.py:168-175 via activation='ELU')
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+__device__ __forceinline__ float apply_pre(float x, int pre, float s) {
+    if (pre == PRE_NONE) return x;
+    if (pre == PRE_SCALE_ELU) x = x * s;
+    return elu1(x);
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int pitch4(int t) { return (t + 3) & ~3; }
+
+// A weight matrix W[M][K] repacked k-major for the GEMM kernels: A[Kp][Mp], zero padded.
+struct PackedMat {
+    const float* A = nullptr;  // device
+    int M = 0, K = 0, Mp = 0, Kp = 0, TM = 8;
+};
+
+// ---- gemm.cu ---------------------------------------------------------------------
+int choose_tm(int M);
+// Y[b][m][t] = sum_k W[m][k] * pre(X[b][k][t]) (+bias[m]) (+R[b][m][t])
+cudaError_t launch_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T,
+                               int pre, float pre_scale, const float* bias, const float* R, float* Y,
+                               long long y_bs, int y_rs, cudaStream_t st);
+// X given channel-last: Q[(b*T+t)*K + k]  (decoder input q [B,F,dim])
+cudaError_t launch_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,
+                                  long long y_bs, int y_rs, cudaStream_t st);
+// DFT-as-conv + magnitude + clamp + log: Wdft packed with rows interleaved (cos_f, sin_f).
+// Y[b][f][t] = log(max(sqrt(re^2+im^2), 1e-5)), re/im = sum_k Wdft[.][k] * wav[b][t*hop + k]
+cudaError_t launch_gemm_stft_logmag(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T,
+                                    float* Y, long long y_bs, int y_rs, cudaStream_t st);
+
+// ---- conv.cu ---------------------------------------------------------------------
+// wav_ext[b][0:P+T] = cat(cache_in[b][0:P], x[b][0:T]); cache_out = last P of it.
+cudaError_t launch_wavcat(const float* x, const float* cache_in, float* cache_out, float* wav_ext, long long w_bs,
+                          int B, int T, int P, cudaStream_t st);
+// conv_pre: y[b][co][t] = bias[co] + sum_k w[co][k] * win[b][t+k]   (1 -> C, dense k taps)
+cudaError_t launch_conv_pre(const float* win, long long w_bs, const float* w, const float* bias, float* y,
+                            long long y_bs, int y_rs, int B, int C, int T, int K, cudaStream_t st);
+// causal depthwise conv, see hil_op_dwconv
+cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                          const float* w, const float* bias, const float* skip, float* y, long long y_bs, int y_rs,
+                          int B, int C, int T, int K, int S, int pre, float pre_scale, cudaStream_t st);
+cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                                    const float* w, float* y, long long y_bs, int y_rs, int B, int C, int T, int S,
+                                    int pre, float pre_scale, cudaStream_t st);
+// decoder conv_post: y[b][t] = tanh(bias + sum_c sum_k w[c][k] * xin[b][c][t+k]), xin = cat(cache, pre(x))
+cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                                  const float* w, const float* bias, float* y, int B, int C, int T, int K, int pre,
+                                  float pre_scale, cudaStream_t st);
+// z[b][f][c] = x[b][c][f] / max(||x[b][:,f]||, 1e-12) * scale
+cudaError_t launch_l2norm_chlast(const float* x, long long x_bs, int x_rs, float* z, int B, int C, int F, float scale,
+                                 cudaStream_t st);
+
+// ---- rvq.cu ----------------------------------------------------------------------
+// codebooks [n_q][size][dim], ee [n_q][size] = sum_k e^2
+cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, int size, int dim, cudaStream_t st);
+cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
+                              int n, int64_t* idx, float* qsum, cudaStream_t st);
+cudaError_t launch_rvq_decode(const int64_t* idx, const float* codebooks, int size, int dim, long long frames, int n,
+                              float* q, cudaStream_t st);
+
+}  // namespace hil

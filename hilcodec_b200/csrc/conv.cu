@@ -1,0 +1,318 @@
+// Bandwidth-bound kernels of the causal conv stacks: wav-history concat, conv_pre (1->C),
+// causal depthwise conv (k5 s1 and strided k=2r s=r), causal transposed depthwise conv,
+// decoder conv_post (C->1) + tanh, and the encoder's L2-norm + channel-last store.
+//
+// Every cached conv follows causal_layers.py:160-165 / :183-188:
+//     xin = cat(cache, x);  cache' = xin[..., -len(cache):];  y = conv(xin)   (no padding)
+// cache_in and cache_out are distinct buffers (ping-pong), so tiles never race on them.
+#include "common.cuh"
+
+namespace hil {
+
+// ------------------------------------------------------------------ wav history concat
+// Encoder.forward streaming.py:486-488
+__global__ void wavcat_kernel(const float* __restrict__ x, const float* __restrict__ cache_in,
+                              float* __restrict__ cache_out, float* __restrict__ wav_ext, long long w_bs, int T, int P) {
+    const int b = blockIdx.y;
+    const int L = P + T;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x) {
+        const float v = j < P ? cache_in[(size_t)b * P + j] : x[(size_t)b * T + (j - P)];
+        wav_ext[b * w_bs + j] = v;
+        if (j >= T) cache_out[(size_t)b * P + (j - T)] = v;
+    }
+}
+
+cudaError_t launch_wavcat(const float* x, const float* cache_in, float* cache_out, float* wav_ext, long long w_bs,
+                          int B, int T, int P, cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    const int L = P + T;
+    dim3 grid(min((L + 255) / 256, 1024), B);
+    wavcat_kernel<<<grid, 256, 0, st>>>(x, cache_in, cache_out, wav_ext, w_bs, T, P);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ conv_pre (1 -> C, k taps)
+// Encoder.forward streaming.py:490 (nn.Conv1d on the last k-1 history samples + chunk)
+template <int K>
+__global__ void conv_pre_kernel(const float* __restrict__ win, long long w_bs, const float* __restrict__ w,
+                                const float* __restrict__ bias, float* __restrict__ y, long long y_bs, int y_rs,
+                                int C, int T) {
+    extern __shared__ float sw[];  // [C][K] + [C]
+    for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * K + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (t0 >= T) return;
+    float xin[K + 3];
+    const float* src = win + b * w_bs + t0;
+#pragma unroll
+    for (int i = 0; i < K + 3; ++i) xin[i] = (t0 + i < T + K - 1) ? src[i] : 0.f;
+    float* dst = y + b * y_bs + t0;
+    const bool vec = (t0 + 3 < T);
+    for (int c = 0; c < C; ++c) {
+        float o[4];
+        const float bv = sw[C * K + c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) a = fmaf(sw[c * K + k], xin[j + k], a);
+            o[j] = a + bv;
+        }
+        float* d = dst + (long long)c * y_rs;
+        if (vec) {
+            *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+            for (int j = 0; j < 4 && t0 + j < T; ++j) d[j] = o[j];
+        }
+    }
+}
+
+cudaError_t launch_conv_pre(const float* win, long long w_bs, const float* w, const float* bias, float* y,
+                            long long y_bs, int y_rs, int B, int C, int T, int K, cudaStream_t st) {
+    if (K != 5 || (y_rs & 3) || (y_bs & 3)) return cudaErrorInvalidValue;
+    if (B == 0 || T == 0) return cudaSuccess;
+    dim3 grid((T + 4 * 128 - 1) / (4 * 128), B);
+    conv_pre_kernel<5><<<grid, 128, (C * 5 + C) * sizeof(float), st>>>(win, w_bs, w, bias, y, y_bs, y_rs, C, T);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ causal depthwise conv
+// generic: one thread per output sample.  y[t'] = bias + sum_k w[k] * xin[t'*S + k]
+template <int K, int S>
+__global__ void dwconv_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
+                              float* __restrict__ cache_out, const float* __restrict__ w,
+                              const float* __restrict__ bias, const float* skip, float* y,
+                              long long y_bs, int y_rs, int C, int T, int T_out, int pre, float pre_scale) {
+    constexpr int P = K - S;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float* xr = x + b * x_bs + (long long)c * x_rs;
+    const float* ci = cache_in + ((size_t)b * C + c) * P;
+    float wk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wk[k] = w[c * K + k];
+    const float bv = bias ? bias[c] : 0.f;
+    for (int to = blockIdx.x * blockDim.x + threadIdx.x; to < T_out; to += gridDim.x * blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = to * S + k;
+            const float v = j < P ? ci[j] : apply_pre(xr[j - P], pre, pre_scale);
+            a = fmaf(wk[k], v, a);
+        }
+        a += bv;
+        const long long o = b * y_bs + (long long)c * y_rs + to;
+        if (skip) a += skip[o];
+        y[o] = a;
+    }
+    // new cache = last P samples of xin
+    if (blockIdx.x == 0 && threadIdx.x < P) {
+        const int j = T + threadIdx.x;  // index into xin (length P+T)
+        cache_out[((size_t)b * C + c) * P + threadIdx.x] = j < P ? ci[j] : apply_pre(xr[j - P], pre, pre_scale);
+    }
+}
+
+// k=5, s=1 specialisation: 4 outputs per thread from two aligned 16-byte loads.
+__global__ void dwconv5_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
+                               float* __restrict__ cache_out, const float* __restrict__ w,
+                               const float* __restrict__ bias, const float* skip, float* y,
+                               long long y_bs, int y_rs, int C, int T, int pre, float pre_scale) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float* xr = x + b * x_bs + (long long)c * x_rs;
+    const float* ci = cache_in + ((size_t)b * C + c) * 4;
+    float wk[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) wk[k] = w[c * 5 + k];
+    const float bv = bias ? bias[c] : 0.f;
+    const int Tq = (T + 3) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Tq; q += gridDim.x * blockDim.x) {
+        const int t0 = q * 4;
+        float xin[8];
+        if (q == 0) {
+            xin[0] = ci[0]; xin[1] = ci[1]; xin[2] = ci[2]; xin[3] = ci[3];
+        } else {
+            const float4 v = *reinterpret_cast<const float4*>(xr + t0 - 4);
+            xin[0] = apply_pre(v.x, pre, pre_scale); xin[1] = apply_pre(v.y, pre, pre_scale);
+            xin[2] = apply_pre(v.z, pre, pre_scale); xin[3] = apply_pre(v.w, pre, pre_scale);
+        }
+        {
+            // the row pitch is a multiple of 4, so this load stays inside the row's storage
+            const float4 v = *reinterpret_cast<const float4*>(xr + t0);
+            xin[4] = apply_pre(v.x, pre, pre_scale); xin[5] = apply_pre(v.y, pre, pre_scale);
+            xin[6] = apply_pre(v.z, pre, pre_scale); xin[7] = apply_pre(v.w, pre, pre_scale);
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) a = fmaf(wk[k], xin[j + k], a);
+            o[j] = a + bv;
+        }
+        const long long off = b * y_bs + (long long)c * y_rs + t0;
+        if (t0 + 3 < T) {
+            if (skip) {
+                const float4 s = *reinterpret_cast<const float4*>(skip + off);
+                o[0] += s.x; o[1] += s.y; o[2] += s.z; o[3] += s.w;
+            }
+            *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+            for (int j = 0; j < 4 && t0 + j < T; ++j) y[off + j] = o[j] + (skip ? skip[off + j] : 0.f);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+        const int j = T + threadIdx.x;
+        cache_out[((size_t)b * C + c) * 4 + threadIdx.x] = j < 4 ? ci[j] : apply_pre(xr[j - 4], pre, pre_scale);
+    }
+}
+
+cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                          const float* w, const float* bias, const float* skip, float* y, long long y_bs, int y_rs,
+                          int B, int C, int T, int K, int S, int pre, float pre_scale, cudaStream_t st) {
+    if (B == 0 || C == 0) return cudaSuccess;
+    if (K < S || C > 65535 || B > 65535) return cudaErrorInvalidValue;
+    const int P = K - S;
+    if (P + T < K) return cudaErrorInvalidValue;
+    const int T_out = (P + T - K) / S + 1;
+    const bool aligned = ((x_rs & 3) == 0) && ((x_bs & 3) == 0) && ((y_rs & 3) == 0) && ((y_bs & 3) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                         (skip == nullptr || (reinterpret_cast<uintptr_t>(skip) & 15) == 0);
+    if (K == 5 && S == 1 && aligned) {
+        const int Tq = (T + 3) / 4;
+        const int threads = Tq >= 128 ? 128 : 32;
+        dim3 grid(min((Tq + threads - 1) / threads, 512), C, B);
+        dwconv5_kernel<<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y, y_bs, y_rs, C, T,
+                                                 pre, pre_scale);
+        return cudaGetLastError();
+    }
+    const int threads = T_out >= 128 ? 128 : 32;
+    dim3 grid(min((T_out + threads - 1) / threads, 512), C, B);
+#define HIL_DW(KK, SS)                                                                                              \
+    if (K == KK && S == SS) {                                                                                       \
+        dwconv_kernel<KK, SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y, y_bs, \
+                                                         y_rs, C, T, T_out, pre, pre_scale);                         \
+        return cudaGetLastError();                                                                                  \
+    }
+    HIL_DW(5, 1) HIL_DW(4, 2) HIL_DW(8, 4) HIL_DW(10, 5) HIL_DW(16, 8) HIL_DW(6, 3) HIL_DW(12, 6) HIL_DW(3, 1) HIL_DW(7, 1)
+#undef HIL_DW
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ causal transposed depthwise
+// conv_transpose1d(cat(cache[1], x), w[C,1,2S], stride S, padding S):
+//   y[n] = xin[n/S + 1] * w[n%S] + xin[n/S] * w[n%S + S],  xin[0] = cache, xin[i+1] = pre(x[i])
+__global__ void dwconvT_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
+                               float* __restrict__ cache_out, const float* __restrict__ w, float* __restrict__ y,
+                               long long y_bs, int y_rs, int C, int T, int S, int pre, float pre_scale) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float* xr = x + b * x_bs + (long long)c * x_rs;
+    const float cprev = cache_in[(size_t)b * C + c];
+    const float* wc = w + (size_t)c * 2 * S;
+    float* yr = y + b * y_bs + (long long)c * y_rs;
+    const int To = T * S;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < To; n += gridDim.x * blockDim.x) {
+        const int i = n / S, r = n - i * S;
+        const float cur = apply_pre(xr[i], pre, pre_scale);
+        const float prev = i == 0 ? cprev : apply_pre(xr[i - 1], pre, pre_scale);
+        // ATen's col2im-style accumulation adds the two taps; fp32 add of two rounded products
+        yr[n] = __fadd_rn(__fmul_rn(cur, wc[r]), __fmul_rn(prev, wc[r + S]));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        cache_out[(size_t)b * C + c] = T > 0 ? apply_pre(xr[T - 1], pre, pre_scale) : cprev;
+}
+
+cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                                    const float* w, float* y, long long y_bs, int y_rs, int B, int C, int T, int S,
+                                    int pre, float pre_scale, cudaStream_t st) {
+    if (B == 0 || C == 0) return cudaSuccess;
+    if (C > 65535 || B > 65535 || S < 1) return cudaErrorInvalidValue;
+    const int To = T * S;
+    const int threads = To >= 256 ? 256 : (To >= 64 ? 64 : 32);
+    dim3 grid(max(1, min((To + threads - 1) / threads, 512)), C, B);
+    dwconvT_kernel<<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, y, y_bs, y_rs, C, T, S, pre,
+                                             pre_scale);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ decoder conv_post + tanh
+// Decoder.forward streaming.py:644-647: ELU -> CausalConv1d(C -> 1, k) -> Tanh
+template <int K>
+__global__ void conv_post_tanh_kernel(const float* __restrict__ x, long long x_bs, int x_rs,
+                                      const float* __restrict__ cache_in, float* __restrict__ cache_out,
+                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                      float* __restrict__ y, int C, int T, int pre, float pre_scale) {
+    constexpr int P = K - 1;
+    extern __shared__ float sw[];  // [C][K]
+    for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* xb = x + b * x_bs;
+    const float* cb = cache_in + (size_t)b * C * P;
+    if (t < T) {
+        float a = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float* xr = xb + (long long)c * x_rs;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int j = t + k;  // index into xin
+                const float v = j < P ? cb[c * P + j] : apply_pre(xr[j - P], pre, pre_scale);
+                a = fmaf(sw[c * K + k], v, a);
+            }
+        }
+        y[(size_t)b * T + t] = tanhf(a + (bias ? bias[0] : 0.f));
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < C * P; i += blockDim.x) {
+            const int c = i / P, jj = i - c * P;
+            const int j = T + jj;
+            cache_out[(size_t)b * C * P + i] =
+                j < P ? cb[c * P + j] : apply_pre(xb[(long long)c * x_rs + (j - P)], pre, pre_scale);
+        }
+    }
+}
+
+cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                                  const float* w, const float* bias, float* y, int B, int C, int T, int K, int pre,
+                                  float pre_scale, cudaStream_t st) {
+    if (K != 5) return cudaErrorInvalidValue;
+    if (B == 0) return cudaSuccess;
+    const int threads = T >= 128 ? 128 : 32;
+    dim3 grid(max(1, (T + threads - 1) / threads), B);
+    conv_post_tanh_kernel<5><<<grid, threads, C * 5 * sizeof(float), st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias,
+                                                                           y, C, T, pre, pre_scale);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ L2 norm + channel-last
+// L2Norm.forward streaming.py:284-285 then x.transpose(1,2) (:517).  One warp per (b, f).
+__global__ void l2norm_chlast_kernel(const float* __restrict__ x, long long x_bs, int x_rs, float* __restrict__ z,
+                                     int C, int F, long long total, float scale) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= total) return;
+    const int b = (int)(wid / F), f = (int)(wid - (long long)b * F);
+    const float* xb = x + b * x_bs + f;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float v = xb[(long long)c * x_rs];
+        ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    float* zr = z + (size_t)wid * C;
+    for (int c = lane; c < C; c += 32) zr[c] = __fmul_rn(__fdiv_rn(xb[(long long)c * x_rs], denom), scale);
+}
+
+cudaError_t launch_l2norm_chlast(const float* x, long long x_bs, int x_rs, float* z, int B, int C, int F, float scale,
+                                 cudaStream_t st) {
+    const long long total = (long long)B * F;
+    if (total == 0) return cudaSuccess;
+    const long long threads = total * 32;
+    l2norm_chlast_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, x_bs, x_rs, z, C, F, total, scale);
+    return cudaGetLastError();
+}
+
+}  // namespace hil

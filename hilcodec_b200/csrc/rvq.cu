@@ -1,0 +1,209 @@
+// Residual vector quantizer: L2 codebook search, residual subtract and in-order dequant sum
+// for all n stages in ONE kernel (the residual never leaves the SM).
+//
+// Replaces ResidualVQ.forward (streaming.py:89-100) with EuclideanCodebook.forward
+// (streaming.py:51-68) per stage, and Dequantizer.forward (streaming.py:148-157).
+//
+//   dist[c] = -((sum_k r_k^2 - 2 * sum_k r_k e_ck) + sum_k e_ck^2);  idx = argmax (first wins)
+//   r <- r - E[idx];   qsum <- qsum + E[idx]   (stage order, fp32)
+//
+// Layout: a CTA owns FT = 32 frames; warp w owns frames 4w..4w+3 (so the per-frame argmax
+// reduction and the residual update are warp-local shuffles); lane l scores codes
+// l, l+32, l+64, l+96 of each 128-code tile staged in shared memory.
+#include "common.cuh"
+
+namespace hil {
+
+constexpr int RVQ_FT = 32;      // frames per CTA
+constexpr int RVQ_CT = 128;     // codes per smem tile
+constexpr int RVQ_DIM = 128;    // vector dimension (fixed by the kernel's lane mapping)
+constexpr int RVQ_PITCH = RVQ_DIM + 4;
+
+__global__ void codebook_norm_kernel(const float* __restrict__ cb, float* __restrict__ ee, long long rows, int dim) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* e = cb + r * dim;
+    float s = 0.f;
+    for (int k = 0; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(e[k], e[k]));
+    ee[r] = s;
+}
+
+cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, int size, int dim, cudaStream_t st) {
+    const long long rows = (long long)n_q * size;
+    if (rows == 0) return cudaSuccess;
+    codebook_norm_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(codebooks, ee, rows, dim);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256, 1)
+rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee,
+                  int size, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum) {
+    extern __shared__ __align__(16) float smem[];
+    float* R = smem;                              // [RVQ_FT][RVQ_PITCH]
+    float* E = smem + RVQ_FT * RVQ_PITCH;         // [RVQ_CT][RVQ_PITCH]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long f0 = (long long)blockIdx.x * RVQ_FT;
+
+    // load residual tile (zero rows past the end)
+    for (int i = tid; i < RVQ_FT * (RVQ_DIM / 4); i += 256) {
+        const int fr = i / (RVQ_DIM / 4), k4 = i - fr * (RVQ_DIM / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f0 + fr < frames) v = *reinterpret_cast<const float4*>(z + (f0 + fr) * RVQ_DIM + k4 * 4);
+        *reinterpret_cast<float4*>(&R[fr * RVQ_PITCH + k4 * 4]) = v;
+    }
+    float4 qacc[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) qacc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    for (int s = 0; s < n; ++s) {
+        const float* cb = codebooks + (size_t)s * size * RVQ_DIM;
+        const float* ees = ee + (size_t)s * size;
+
+        // xx[f] = sum_k r^2 for this warp's 4 frames (lane-strided partials + shuffle tree)
+        float xx[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const float4 v = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]);
+            float p = __fmul_rn(v.x, v.x);
+            p = fmaf(v.y, v.y, p); p = fmaf(v.z, v.z, p); p = fmaf(v.w, v.w, p);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            xx[f] = p;
+        }
+
+        float best[4];
+        int besti[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) { best[f] = -INFINITY; besti[f] = 0x7fffffff; }
+
+        for (int c0 = 0; c0 < size; c0 += RVQ_CT) {
+            __syncthreads();  // previous tile fully consumed
+            for (int i = tid; i < RVQ_CT * (RVQ_DIM / 4); i += 256) {
+                const int cr = i / (RVQ_DIM / 4), k4 = i - cr * (RVQ_DIM / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + cr < size) v = *reinterpret_cast<const float4*>(cb + (size_t)(c0 + cr) * RVQ_DIM + k4 * 4);
+                *reinterpret_cast<float4*>(&E[cr * RVQ_PITCH + k4 * 4]) = v;
+            }
+            __syncthreads();
+
+            float dot[4][4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dot[f][j] = 0.f;
+#pragma unroll 4
+            for (int k4 = 0; k4 < RVQ_DIM / 4; ++k4) {
+                float4 r4[4], e4[4];
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    r4[f] = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + k4 * 4]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    e4[j] = *reinterpret_cast<const float4*>(&E[(lane + 32 * j) * RVQ_PITCH + k4 * 4]);
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float d = dot[f][j];
+                        d = fmaf(r4[f].x, e4[j].x, d);
+                        d = fmaf(r4[f].y, e4[j].y, d);
+                        d = fmaf(r4[f].z, e4[j].z, d);
+                        d = fmaf(r4[f].w, e4[j].w, d);
+                        dot[f][j] = d;
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int code = c0 + lane + 32 * j;
+                if (code < size) {
+                    const float e2 = ees[code];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        // -(xx - 2*dot + ee), evaluated left to right in fp32 like the reference
+                        const float d = -__fadd_rn(__fsub_rn(xx[f], __fmul_rn(2.f, dot[f][j])), e2);
+                        if (d > best[f]) { best[f] = d; besti[f] = code; }  // codes ascend per lane: first max wins
+                    }
+                }
+            }
+        }
+
+        // warp argmax with first-index tie break, then residual / dequant update
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            float bd = best[f];
+            int bi = besti[f];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bi < 0 || bi >= size) bi = 0;  // all-NaN row: torch's max returns the NaN position; keep in range
+            const long long fr = f0 + warp * 4 + f;
+            const float4 e = *reinterpret_cast<const float4*>(cb + (size_t)bi * RVQ_DIM + lane * 4);
+            float4* rp = reinterpret_cast<float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]);
+            float4 r = *rp;
+            r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y); r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
+            *rp = r;
+            qacc[f].x = __fadd_rn(qacc[f].x, e.x); qacc[f].y = __fadd_rn(qacc[f].y, e.y);
+            qacc[f].z = __fadd_rn(qacc[f].z, e.z); qacc[f].w = __fadd_rn(qacc[f].w, e.w);
+            if (lane == 0 && fr < frames) idx[(size_t)s * frames + fr] = bi;
+        }
+        __syncwarp();
+    }
+
+    if (qsum) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const long long fr = f0 + warp * 4 + f;
+            if (fr < frames) *reinterpret_cast<float4*>(qsum + fr * RVQ_DIM + lane * 4) = qacc[f];
+        }
+    }
+}
+
+cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
+                              int n, int64_t* idx, float* qsum, cudaStream_t st) {
+    if (dim != RVQ_DIM) return cudaErrorInvalidValue;
+    if (frames == 0 || n == 0) return cudaSuccess;
+    static bool attr_set = false;
+    const size_t smem = (size_t)(RVQ_FT + RVQ_CT) * RVQ_PITCH * sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)((frames + RVQ_FT - 1) / RVQ_FT);
+    rvq_encode_kernel<<<grid, 256, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum);
+    return cudaGetLastError();
+}
+
+// Dequantizer: q[f][:] = ((0 + E_0[i_0]) + E_1[i_1]) + ...   one thread per 4 dims.
+__global__ void rvq_decode_kernel(const int64_t* __restrict__ idx, const float* __restrict__ codebooks, int size, int dim,
+                                  long long frames, int n, float* __restrict__ q) {
+    const int d4 = dim / 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= frames * d4) return;
+    const long long fr = i / d4;
+    const int k4 = (int)(i - fr * d4);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < n; ++s) {
+        long long id = idx[(size_t)s * frames + fr];
+        if (id < 0 || id >= size) id = 0;  // F.embedding would raise; the host wrapper validates when asked to
+        const float4 e = *reinterpret_cast<const float4*>(codebooks + ((size_t)s * size + id) * dim + k4 * 4);
+        a.x = __fadd_rn(a.x, e.x); a.y = __fadd_rn(a.y, e.y); a.z = __fadd_rn(a.z, e.z); a.w = __fadd_rn(a.w, e.w);
+    }
+    *reinterpret_cast<float4*>(q + fr * dim + k4 * 4) = a;
+}
+
+cudaError_t launch_rvq_decode(const int64_t* idx, const float* codebooks, int size, int dim, long long frames, int n,
+                              float* q, cudaStream_t st) {
+    if (dim & 3) return cudaErrorInvalidValue;
+    const long long total = frames * (dim / 4);
+    if (total == 0) return cudaSuccess;
+    rvq_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(idx, codebooks, size, dim, frames, n, q);
+    return cudaGetLastError();
+}
+
+}  // namespace hil

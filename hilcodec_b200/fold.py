@@ -1,0 +1,90 @@
+"""Load-time weight preparation: fold a *training-format* streaming state dict into the
+deployment tensors the kernels consume.
+
+Restates `HILCodec.remove_weight_reparameterizations` (streaming.py:740-747):
+  * weight_norm removal, w = g * v / ||v||  (norm over all dims but 0; both the legacy
+    `weight_g`/`weight_v` and the `parametrizations.weight.original{0,1}` spellings),
+  * `Encoder.merge_scaling`  (streaming.py:472-480): conv_pre.weight /= wav_std,
+  * `SpecBlock.merge_scaling` (streaming.py:321-344): W/std, bias = -(sum W) * mean/std,
+    both times res_scale * scale_param,
+  * `ResBlock.merge_scaling`  (streaming.py:240-250): last depthwise weight/bias times
+    res_scale * res_scale_param,
+  * `Decoder.merge_scaling`  (streaming.py:609-617): conv_post.weight *= wav_std (bias untouched).
+A dict that is already folded (no reparametrisation keys) passes through unchanged.
+"""
+from __future__ import annotations
+
+import re
+import typing as tp
+from collections import OrderedDict
+
+import torch
+from torch import Tensor
+
+from .weights import WAV_STD, CodecConfig
+
+SPEC_MEANS = [-4.554, -4.315, -4.021, -3.726, -3.477]  # streaming.py:383
+SPEC_STDS = [2.830, 2.837, 2.817, 2.796, 2.871]        # streaming.py:384
+
+
+def _needs_fold(sd: tp.Mapping[str, Tensor]) -> bool:
+    return any(k.endswith(("weight_g", "weight_v", "res_scale_param", "scale_param",
+                           "parametrizations.weight.original0")) for k in sd)
+
+
+def _remove_weight_norm(sd: "OrderedDict[str, Tensor]") -> "OrderedDict[str, Tensor]":
+    out: "OrderedDict[str, Tensor]" = OrderedDict()
+    for k, v in sd.items():
+        if k.endswith("weight_g") or k.endswith("parametrizations.weight.original0"):
+            base = k[:-len("weight_g")] if k.endswith("weight_g") else k[:-len("parametrizations.weight.original0")]
+            vk = base + ("weight_v" if k.endswith("weight_g") else "parametrizations.weight.original1")
+            g, vv = v.float(), sd[vk].float()
+            norm = vv.reshape(vv.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (vv.dim() - 1)))
+            out[base + "weight"] = vv * (g / norm)  # torch._weight_norm(v, g, dim=0)
+        elif k.endswith("weight_v") or k.endswith("parametrizations.weight.original1"):
+            continue
+        else:
+            out[k] = v
+    return out
+
+
+def fold_state_dict(sd: "OrderedDict[str, Tensor]", cfg: CodecConfig, part: str = "") -> "OrderedDict[str, Tensor]":
+    """`part` is "" for a HILCodec-level dict (keys start with encoder./decoder./...),
+    or "encoder" / "decoder" / "quantizer" for a sub-module dict."""
+    sd = OrderedDict((k, torch.as_tensor(v).detach().cpu()) for k, v in sd.items())
+    if not _needs_fold(sd):
+        return sd
+    sd = _remove_weight_norm(sd)
+    enc = "encoder." if part == "" else ("" if part == "encoder" else None)
+    dec = "decoder." if part == "" else ("" if part == "decoder" else None)
+    n_stage = len(cfg.strides)
+
+    def scale_conv(prefix: str, s: Tensor) -> None:
+        sd[prefix + "weight"] = sd[prefix + "weight"].float() * s
+        if prefix + "bias" in sd:
+            sd[prefix + "bias"] = sd[prefix + "bias"].float() * s
+
+    for p, rs in ((enc, cfg.res_scale_enc), (dec, cfg.res_scale_dec)):
+        if p is None:
+            continue
+        for k in [k for k in sd if k.startswith(p) and k.endswith("res_scale_param")]:
+            block = k[:-len("res_scale_param")]
+            scale_conv(block + "block.1.depthwise.", rs * sd.pop(k).float())
+    if enc is not None:
+        if enc + "conv_pre.weight" in sd:
+            sd[enc + "conv_pre.weight"] = sd[enc + "conv_pre.weight"].float() / WAV_STD
+        specs = [(f"{enc}spec_blocks.{i}.", i) for i in range(n_stage)] + [(enc + "spec_post.", n_stage)]
+        for sp, i in specs:
+            if sp + "scale_param" not in sd:
+                continue
+            mean, std = SPEC_MEANS[min(i, 4)], SPEC_STDS[min(i, 4)]
+            w = sd[sp + "layer.weight"].float()
+            bias2 = w.sum((1, 2)) * (-mean / std)
+            w = w / std
+            b = sd[sp + "layer.bias"].float() + bias2 if sp + "layer.bias" in sd else bias2
+            scale = cfg.res_scale_enc * sd.pop(sp + "scale_param").float()
+            sd[sp + "layer.weight"] = w * scale
+            sd[sp + "layer.bias"] = b * scale
+    if dec is not None and dec + "conv_post.weight" in sd:
+        sd[dec + "conv_post.weight"] = sd[dec + "conv_post.weight"].float() * WAV_STD
+    return sd

@@ -1,0 +1,152 @@
+/*
+ * hilcodec_b200 -- C ABI of the B200-native HILCodec encode -> RVQ -> decode path.
+ *
+ * The reference (aask1357/hilcodec) has no FFI layer: its boundary is
+ * torch.nn.Module.forward of models/hilcodec/streaming.py.  Each entry point below
+ * names the reference interface it replaces (file:line relative to the reference
+ * tree).  All `dev` pointers are CUDA device pointers (fp32 NCW-contiguous unless
+ * stated), every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ * never synchronises the host (except the *_host convenience call), returns HIL_OK or
+ * a negative hil_status, and records a message retrievable with hil_last_error()
+ * (thread-local).  One hil_model may be shared between threads after
+ * hil_model_finalize(); a hil_state (workspace + per-stream caches for a fixed batch
+ * size) must not be used from two threads at once.
+ *
+ * Weights are the folded deployment weights, named exactly like the reference's
+ * streaming `state_dict()` keys after `remove_weight_reparameterizations()`
+ * (streaming.py:740-747) with an `encoder.` / `decoder.` prefix, plus
+ * `quantizer.layers.{i}.embed` -- i.e. the initializers of the published ONNX graphs.
+ */
+#ifndef HILCODEC_B200_H
+#define HILCODEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIL_ABI_VERSION 1
+#define HIL_MAX_STRIDES 8
+
+typedef enum hil_status {
+    HIL_OK = 0,
+    HIL_ERR_INVALID = -1,   /* bad argument / shape (the reference raises from ATen or asserts) */
+    HIL_ERR_MISSING = -2,   /* tensor not set before finalize */
+    HIL_ERR_CUDA = -3,      /* CUDA runtime error */
+    HIL_ERR_STATE = -4,     /* model not finalized / state batch mismatch */
+    HIL_ERR_NOMEM = -5
+} hil_status;
+
+/* HILCodec.__init__ kwargs that shape the graph (streaming.py:651-722,
+ * configs/hilcodec_{speech,music}.yaml:2-38). */
+typedef struct hil_config {
+    int32_t channels_enc;      /* 64  */
+    int32_t channels_dec;      /* 96  */
+    int32_t n_fft_base;        /* 64  */
+    int32_t n_residual_enc;    /* 2   */
+    int32_t n_residual_dec;    /* 3   */
+    double res_scale_enc;      /* 0.5773502691896258 (python float; pre/post scales derive from it in double) */
+    double res_scale_dec;      /* 0.5773502691896258 */
+    int32_t n_strides;         /* 4   */
+    int32_t strides[HIL_MAX_STRIDES]; /* 8,5,4,2 (decoder order; encoder uses them reversed) */
+    int32_t kernel_size;       /* 5   */
+    int32_t dim;               /* 128 */
+    int32_t codebook_size;     /* 1024 */
+    int32_t num_quantizers;    /* 8 (hil_speech) / 12 (hil_music) */
+} hil_config;
+
+typedef struct hil_model hil_model;
+typedef struct hil_state hil_state;
+
+enum { HIL_ENCODER = 0, HIL_DECODER = 1 };
+
+int32_t hil_abi_version(void);
+const char* hil_last_error(void);
+void hil_config_default(hil_config* cfg, int32_t num_quantizers);
+
+/* ---- model: replaces streaming.HILCodec(...) construction + load_state_dict ------- */
+int32_t hil_model_create(const hil_config* cfg, hil_model** out);
+/* host fp32 data; dims as in the reference state_dict (e.g. [C,C,1], [C,1,5], [1024,128]) */
+int32_t hil_model_set_tensor(hil_model* m, const char* name, const float* host, const int64_t* dims, int32_t ndim);
+/* uploads + repacks weights for the kernels; after this the model is immutable */
+int32_t hil_model_finalize(hil_model* m);
+void hil_model_destroy(hil_model* m);
+int32_t hil_model_hop(const hil_model* m);      /* Encoder.hop_length streaming.py:390 */
+int32_t hil_model_num_caches(const hil_model* m, int32_t which); /* Encoder.num_cache streaming.py:455 (22) / 30 */
+/* shape [B,C,len] of cache i in the reference's list order (streaming.py:458-470, :599-607) */
+int32_t hil_model_cache_shape(const hil_model* m, int32_t which, int32_t i, int32_t batch, int64_t dims[3]);
+
+/* ---- state: replaces HILCodec.initialize_cache (streaming.py:723-724) ------------- */
+int32_t hil_state_create(hil_model* m, int32_t batch, hil_state** out);
+int32_t hil_state_reset(hil_state* s, void* stream);                 /* zero all caches */
+int32_t hil_state_export_cache(hil_state* s, int32_t which, int32_t i, float* dev_dst, void* stream);
+int32_t hil_state_import_cache(hil_state* s, int32_t which, int32_t i, const float* dev_src, void* stream);
+void hil_state_destroy(hil_state* s);
+size_t hil_state_workspace_bytes(const hil_state* s);
+
+/* ---- the four calls of the deployment flow (scripts/HILCodec Onnx.ipynb cell 3) --- */
+/* Encoder.forward streaming.py:482-517: wav [B,1,T] (T multiple of hop) -> z [B,T/hop,dim];
+ * caches advance inside `s`. */
+int32_t hil_encode(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, int32_t T, float* z_dev, void* stream);
+/* Same, functional list-of-tensors protocol: caches_in[22] are read, caches_out[22] written
+ * (must not alias); `s` only lends its workspace. */
+int32_t hil_encode_caches(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, int32_t T, float* z_dev,
+                          const float* const* caches_in, float* const* caches_out, void* stream);
+/* ResidualVQ.forward streaming.py:89-100 (+ per-stage EuclideanCodebook.forward :51-68):
+ * z [B,F,dim] -> idx [n,B,F] int64; qsum (optional) [B,F,dim] = Dequantizer(idx). */
+int32_t hil_rvq_encode(hil_model* m, const float* z_dev, int32_t B, int32_t F, int32_t n, int64_t* idx_dev,
+                       float* qsum_dev_or_null, void* stream);
+/* Dequantizer.forward streaming.py:148-157: idx [n,B,F] int64 -> q [B,F,dim]. */
+int32_t hil_rvq_decode(hil_model* m, const int64_t* idx_dev, int32_t B, int32_t F, int32_t n, float* q_dev, void* stream);
+/* Decoder.forward streaming.py:619-648: q [B,F,dim] -> wav [B,1,hop*F]. */
+int32_t hil_decode(hil_model* m, hil_state* s, const float* q_dev, int32_t B, int32_t F, float* wav_dev, void* stream);
+int32_t hil_decode_caches(hil_model* m, hil_state* s, const float* q_dev, int32_t B, int32_t F, float* wav_dev,
+                          const float* const* caches_in, float* const* caches_out, void* stream);
+
+/* ---- fused path: what streaming.HILCodec.forward (streaming.py:726-738) means to do - */
+/* wav [B,1,T] -> idx [n,B,T/hop] int64 (+ optional z [B,F,dim]) -> wav_out [B,1,T]. */
+int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, int32_t T, int32_t n,
+                          float* z_dev_or_null, int64_t* idx_dev, float* wav_out_dev, void* stream);
+/* Same with HOST buffers (pinned recommended): H2D copy of wav, forward, D2H copy of idx and
+ * wav_out, all on `stream`, then a stream synchronise.  This is the e2e call bench.py times. */
+int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host, int32_t B, int32_t T, int32_t n,
+                               int64_t* idx_host, float* wav_out_host, void* stream);
+
+/* ---- launch accounting (measurement support for bench.py; not in the reference) ----- */
+/* kernels launched by this library since load (bench.py reports the per-step delta as gpu_launches) */
+uint64_t hil_launch_count(void);
+/* Per-kernel-category timing: between begin and end every launch is bracketed by CUDA events on
+ * its stream.  Categories: 0 pointwise GEMM, 1 STFT GEMM, 2 depthwise conv, 3 transposed
+ * depthwise, 4 conv_pre, 5 conv_post+tanh, 6 RVQ, 7 misc (wav concat, l2norm).
+ * end() synchronises the device and fills summed ms / algorithmic FLOPs / algorithmic bytes /
+ * launch counts per category (arrays of HIL_PROFILE_CATEGORIES). */
+#define HIL_PROFILE_CATEGORIES 8
+int32_t hil_profile_begin(void);
+int32_t hil_profile_end(double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_cat);
+
+/* ---- operator level: the reference's causal primitives, for per-kernel parity tests - */
+/* CausalConv1d.forward causal_layers.py:160-165, depthwise (groups=C).
+ * x [B,C,T], cache_in/out [B,C,K-S], w [C,1,K], bias [C]|NULL, skip [B,C,T_out]|NULL (added),
+ * pre: 0 none, 1 ELU, 2 ELU(x*pre_scale).  y [B,C,T_out], T_out=(K-S+T-K)/S+1. */
+int32_t hil_op_dwconv(const float* x, const float* cache_in, float* cache_out, const float* w, const float* bias,
+                      const float* skip, float* y, int32_t B, int32_t C, int32_t T, int32_t K, int32_t S,
+                      int32_t pre, float pre_scale, void* stream);
+/* CausalConvTranspose1d.forward causal_layers.py:183-188, depthwise K=2S, no bias.
+ * x [B,C,T], cache [B,C,1], w [C,1,2S], y [B,C,S*T]. */
+int32_t hil_op_dwconv_transpose(const float* x, const float* cache_in, float* cache_out, const float* w, float* y,
+                                int32_t B, int32_t C, int32_t T, int32_t S, int32_t pre, float pre_scale, void* stream);
+/* nn.Conv1d(k=1) built by SConv1d causal_layers.py:191-204: y[B,M,T] = W[M,K] * pre(x[B,K,T]) + bias + residual.
+ * w_host is the reference-layout [M,K,1] HOST weight (packed and uploaded inside; test-only convenience). */
+int32_t hil_op_pointwise(const float* x, const float* w_host, const float* bias_dev, const float* residual, float* y,
+                         int32_t B, int32_t M, int32_t K, int32_t T, int32_t pre, float pre_scale, void* stream);
+/* CausalSTFT.forward causal_layers.py:135-144 + clamp/log streaming.py:351:
+ * wav_window [B,1,(T-1)*hop+n_fft], w_host [2F,1,n_fft] HOST -> y [B,F,T] = log(max(|STFT|,1e-5)). */
+int32_t hil_op_stft_logmag(const float* wav_window, const float* w_host, float* y, int32_t B, int32_t n_fft, int32_t hop,
+                           int32_t T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HILCODEC_B200_H */

@@ -1,0 +1,220 @@
+"""Whole-path parity (-m gpu): the CUDA encode -> RVQ -> decode through the drop-in modules
+(which call the C ABI) against the CPU oracle, the committed reference fixtures and the
+reference's golden clip.
+
+Bars (BASELINE.json north_star): VQ indices bit-exact; latents and decoded PCM max-abs-err
+< 1e-4.  Near-tie policy for large batches: a disagreement is tolerated only if the fp64
+relative gap between the two best codes at that decision is < 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hilcodec_b200 import streaming as S
+from hilcodec_b200 import weights as W
+from oracle import hilcodec_oracle as O
+
+from helpers import GOLDEN, index_report, oracle_cfg, params, synth_wav
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _model(w, n_q):
+    return S.HILCodec.from_weights(w, n_q).cuda()
+
+
+@pytest.mark.parametrize("name", ["ref_random_speech.npz", "ref_random_music.npz"])
+def test_reference_fixture_four_call_flow(name):
+    """Committed outputs of the reference's own streaming.py classes (random weights)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    n_q = int(g["n_q"])
+    w = W.random_weights(W.CodecConfig(num_quantizers=n_q), int(g["seed"]))
+    m = _model(w, n_q)
+    x = torch.from_numpy(g["x"]).cuda()
+    ce, cd = m.initialize_cache(x)
+    assert len(ce) == 22 and len(cd) == 30
+    z, ce = m.encoder(x, *ce)
+    idx = m.quantizer(z, n_q)
+    q = m.dequantizer(idx, n_q)
+    y, cd = m.decoder(q, *cd)
+    torch.cuda.synchronize()
+    assert z.shape == g["z"].shape and y.shape == g["wav"].shape and idx.dtype == torch.int64
+    assert np.abs(z.cpu().numpy() - g["z"]).max() < TOL
+    assert np.array_equal(idx.cpu().numpy(), g["indices"].astype(np.int64))
+    assert np.array_equal(q.cpu().numpy(), g["q"])  # gathers + in-order adds: bit-exact
+    assert np.abs(y.cpu().numpy() - g["wav"]).max() < TOL
+    for i, c in enumerate(ce):
+        assert tuple(c.shape) == g[f"enc_cache{i}"].shape
+        assert np.abs(c.cpu().numpy() - g[f"enc_cache{i}"]).max() < TOL, f"enc cache {i}"
+    for i, c in enumerate(cd):
+        assert tuple(c.shape) == g[f"dec_cache{i}"].shape
+        assert np.abs(c.cpu().numpy() - g[f"dec_cache{i}"]).max() < TOL, f"dec cache {i}"
+
+
+@pytest.mark.parametrize("name", ["ref_random_speech.npz", "ref_random_music.npz"])
+def test_reference_fixture_streaming(name):
+    """Chunked calls with the caches handed back and forth as a list of tensors, exactly like
+    scripts/HILCodec Onnx.ipynb cell 3 / test_onnx.py:75-93."""
+    g = np.load(os.path.join(GOLDEN, name))
+    n_q, hops = int(g["n_q"]), int(g["stream_hops"])
+    w = W.random_weights(W.CodecConfig(num_quantizers=n_q), int(g["seed"]))
+    m = _model(w, n_q)
+    x = torch.from_numpy(g["x"]).cuda()
+    ce, cd = m.initialize_cache(x)
+    ids, ws = [], []
+    step = hops * 320
+    for s in range(0, x.shape[2], step):
+        z, ce = m.encoder(x[:, :, s:s + step], *ce)
+        idx = m.quantizer(z, n_q)
+        y, cd = m.decoder(m.dequantizer(idx, n_q), *cd)
+        ids.append(idx)
+        ws.append(y)
+    idx = torch.cat(ids, 2).cpu().numpy()
+    y = torch.cat(ws, 2).cpu().numpy()
+    assert np.array_equal(idx, g["stream_indices"].astype(np.int64))
+    assert np.abs(y - g["stream_wav"]).max() < TOL
+
+
+def test_fused_forward_and_stateful_streaming_match_four_call_flow():
+    n_q = 12
+    w = W.random_weights(W.HIL_MUSIC, 5)
+    m = _model(w, n_q)
+    x = synth_wav(3, 320 * 9, seed=11).cuda()
+    ce, cd = m.initialize_cache(x)
+    z, _ = m.encoder(x, *ce)
+    idx = m.quantizer(z, n_q)
+    y, _ = m.decoder(m.dequantizer(idx, n_q), *cd)
+    idx2, y2 = m.codec_forward(x, n_q)
+    assert torch.equal(idx, idx2) and torch.equal(y, y2)
+    # GPU-resident state, frame by frame (hop 320), must reproduce the one-shot result
+    st = m.new_stream_state(3)
+    ids, ws = [], []
+    for s in range(0, x.shape[2], 320):
+        i3, y3 = m.codec_forward(x[:, :, s:s + 320], n_q, state=st)
+        ids.append(i3)
+        ws.append(y3)
+    assert torch.equal(torch.cat(ids, 2), idx)
+    assert (torch.cat(ws, 2) - y).abs().max().item() < 1e-5
+    # state export -> list of tensors -> import round trip is lossless
+    e1, d1 = st.export()
+    st2 = m.new_stream_state(3)
+    st2.load(e1, d1)
+    e2, d2 = st2.export()
+    assert all(torch.equal(a, b) for a, b in zip(e1 + d1, e2 + d2))
+    # and equals the caches the functional protocol returns after the same audio
+    ce, cd = m.initialize_cache(x)
+    _, ce = m.encoder(x, *ce)
+    for a, b in zip(e1, ce):
+        assert (a - b).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("cfg_name,B,frames", [("hil_speech", 4, 75), ("hil_music", 2, 75)])
+def test_oracle_parity_random_weights(cfg_name, B, frames):
+    cfg = W.CONFIGS[cfg_name]
+    n_q = cfg.num_quantizers
+    w = W.random_weights(cfg, 21)
+    m = _model(w, n_q)
+    x = synth_wav(B, 320 * frames, seed=77)
+    p = params(w)
+    with torch.no_grad():
+        o = O.codec_forward(oracle_cfg(n_q), p, x, n_q)
+    xd = x.cuda()
+    ce, cd = m.initialize_cache(xd)
+    z, _ = m.encoder(xd, *ce)
+    idx, q = m.quantizer.quantize(z, n_q)
+    y, _ = m.decoder(q, *cd)
+    assert (z.cpu() - o["z"]).abs().max().item() < TOL
+    bad, worst = index_report(oracle_cfg(n_q), p, z, idx, o["indices"], n_q)
+    assert bad == 0 or worst < 1e-5, (bad, worst)
+    if bad == 0:
+        assert (y.cpu() - o["wav"]).abs().max().item() < TOL
+    # decoder alone on the oracle's q: isolates decoder parity from index near-ties
+    y2, _ = m.decoder(o["q"].cuda(), *cd)
+    assert (y2.cpu() - o["wav"]).abs().max().item() < TOL
+    # n < num_quantizers and the assert on n (vector_quantize.py:213)
+    idx3 = m.quantizer(z, 3)
+    assert torch.equal(idx3, idx[:3])
+    with pytest.raises(AssertionError):
+        m.quantizer(z, n_q + 1)
+
+
+def test_rvq_bit_exact_given_identical_latents():
+    """Codebook search + residual + dequant on latents shared with the oracle."""
+    cfg = W.HIL_MUSIC
+    w = W.random_weights(cfg, 2)
+    p = params(w)
+    m = _model(w, 12)
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(5, 301, 128, generator=g)
+    z = z / z.norm(dim=2, keepdim=True) * 128 ** 0.5
+    ref = O.rvq_encode(oracle_cfg(12), p, z, 12)
+    idx, qsum = m.quantizer.quantize(z.cuda(), 12)
+    bad, worst = index_report(oracle_cfg(12), p, z, idx, ref, 12)
+    assert bad == 0 or worst < 1e-6, (bad, worst)
+    q_ref = O.rvq_decode(oracle_cfg(12), p, idx.cpu(), 12)
+    assert torch.equal(m.dequantizer(idx, 12).cpu(), q_ref)
+    assert torch.equal(qsum.cpu(), q_ref)
+
+
+@pytest.mark.skipif(not W.have_pretrained("hil_speech"), reason="published weights not extracted")
+def test_golden_clip_full():
+    """The reference's KAT, all 30.6 s: 18 368 / 18 368 indices, PCM within one int16 LSB."""
+    g = np.load(os.path.join(GOLDEN, "speech_kat.npz"))
+    m = S.HILCodec.from_pretrained("hil_speech").cuda()
+    x = torch.from_numpy(g["wav_in"].astype(np.float32) / 32768).view(1, 1, -1).cuda()
+    idx, y = m.codec_forward(x, 8)
+    gold = torch.from_numpy(g["indices"].astype(np.int64))
+    assert idx.shape == gold.shape
+    assert int((idx.cpu() != gold).sum()) == 0
+    ref = g["wav_out"].astype(np.float32) / 32768
+    assert np.abs(y[0, 0].cpu().numpy() - ref).max() <= 1.0 / 32768 + 1e-5
+
+
+@pytest.mark.skipif(not W.have_pretrained("hil_music"), reason="published weights not extracted")
+def test_pretrained_music_vs_oracle():
+    cfg = W.HIL_MUSIC
+    w = W.load_pretrained("hil_music")
+    m = S.HILCodec.from_pretrained("hil_music").cuda()
+    x = synth_wav(2, 24000, seed=1234)
+    p = params(w)
+    with torch.no_grad():
+        o = O.codec_forward(oracle_cfg(12), p, x, 12)
+    xd = x.cuda()
+    ce, cd = m.initialize_cache(xd)
+    z, _ = m.encoder(xd, *ce)
+    idx, q = m.quantizer.quantize(z, 12)
+    y, _ = m.decoder(q, *cd)
+    assert (z.cpu() - o["z"]).abs().max().item() < TOL
+    bad, worst = index_report(oracle_cfg(12), p, z, idx, o["indices"], 12)
+    assert bad == 0 or worst < 1e-5, (bad, worst)
+    y2, _ = m.decoder(o["q"].cuda(), *cd)
+    assert (y2.cpu() - o["wav"]).abs().max().item() < TOL
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 size (64 x 24000): too big for the CPU oracle in a test, so check
+    size-independent properties: batch rows are independent (row b of the batch == the same
+    clip run alone), chunked == one-shot, outputs finite, ||z_t|| = sqrt(128)."""
+    cfg = W.HIL_SPEECH
+    w = W.load_pretrained("hil_speech") if W.have_pretrained("hil_speech") else W.random_weights(cfg, 4)
+    m = _model(w, 8)
+    x = synth_wav(64, 24000, seed=1234).cuda()
+    idx, y = m.codec_forward(x, 8)
+    assert torch.isfinite(y).all() and y.abs().max().item() <= 1.0
+    for b in (0, 17, 63):
+        i1, y1 = m.codec_forward(x[b:b + 1], 8)
+        assert torch.equal(i1[:, 0], idx[:, b])
+        assert (y1[0] - y[b]).abs().max().item() < 1e-5
+    ce, _ = m.initialize_cache(x)
+    z, _ = m.encoder(x, *ce)
+    assert (z.norm(dim=2) - 128 ** 0.5).abs().max().item() < 1e-3
+    st = m.new_stream_state(64)
+    ids = []
+    for s in range(0, 24000, 8000):  # 25-frame chunks
+        i2, _ = m.codec_forward(x[:, :, s:s + 8000], 8, state=st)
+        ids.append(i2)
+    same = (torch.cat(ids, 2) == idx).float().mean().item()
+    assert same > 0.9999, same

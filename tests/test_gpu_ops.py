@@ -1,0 +1,149 @@
+"""Per-kernel parity (-m gpu): each CUDA operator through the C ABI against the torch CPU
+op the reference calls (F.conv1d / F.conv_transpose1d / elu / log ...).  fp32 tolerance is
+written per test; cache outputs are pure copies and must be bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hilcodec_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _pre_ref(x, pre, s):
+    if pre == 0:
+        return x
+    if pre == 2:
+        x = x * s
+    return F.elu(x)
+
+
+@pytest.mark.parametrize("B,Cc,T,K,S,pre,bias,skip", [
+    (2, 64, 256, 5, 1, 0, True, False),
+    (3, 96, 75, 5, 1, 1, True, True),     # T not a multiple of 4 -> scalar path
+    (2, 128, 1, 5, 1, 0, True, False),    # one frame per call: cache shift-mix
+    (1, 32, 2, 5, 1, 2, False, False),
+    (2, 128, 320, 4, 2, 0, True, False),
+    (2, 256, 160, 8, 4, 0, True, False),
+    (2, 64, 40, 10, 5, 0, True, False),
+    (2, 64, 8, 16, 8, 0, True, False),
+    (1, 1024, 4, 5, 1, 1, False, False),
+    (2, 192, 1000, 5, 1, 0, True, True),
+])
+def test_dwconv(B, Cc, T, K, S, pre, bias, skip):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    P = K - S
+    x = torch.randn(B, Cc, T, generator=g)
+    cache = torch.randn(B, Cc, P, generator=g)
+    w = torch.randn(Cc, 1, K, generator=g) / K ** 0.5
+    b = torch.randn(Cc, generator=g) if bias else None
+    xin = torch.cat((cache, _pre_ref(x, pre, 0.77)), 2)
+    y_ref = F.conv1d(xin, w, b, stride=S, groups=Cc)
+    sk = torch.randn_like(y_ref) if skip else None
+    if skip:
+        y_ref = y_ref + sk
+    c_ref = xin[:, :, -P:]
+    xd, cd, wd = x.cuda(), cache.cuda(), w.cuda()
+    bd = b.cuda() if bias else None
+    skd = sk.cuda() if skip else None
+    y = torch.empty(y_ref.shape, device="cuda")
+    co = torch.empty(B, Cc, P, device="cuda")
+    _lib.check(lib.hil_op_dwconv(_ptr(xd), _ptr(cd), _ptr(co), _ptr(wd), _ptr(bd), _ptr(skd), _ptr(y),
+                                 B, Cc, T, K, S, pre, 0.77, _stream()))
+    torch.cuda.synchronize()
+    assert torch.allclose(y.cpu(), y_ref, rtol=1e-5, atol=2e-6), (y.cpu() - y_ref).abs().max()
+    assert torch.allclose(co.cpu(), c_ref, rtol=0, atol=1e-6)
+    if pre == 0:
+        assert torch.equal(co.cpu(), c_ref)
+
+
+@pytest.mark.parametrize("B,Cc,T,S,pre", [(2, 192, 300, 2, 1), (2, 384, 75, 4, 2), (1, 768, 15, 5, 2),
+                                           (3, 1536, 1, 8, 1), (2, 64, 7, 8, 0)])
+def test_dwconv_transpose(B, Cc, T, S, pre):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(S * 100 + T)
+    x = torch.randn(B, Cc, T, generator=g)
+    cache = torch.randn(B, Cc, 1, generator=g)
+    w = torch.randn(Cc, 1, 2 * S, generator=g)
+    xin = torch.cat((cache, _pre_ref(x, pre, 0.7071)), 2)
+    y_ref = F.conv_transpose1d(xin, w, None, stride=S, padding=S, output_padding=0, groups=Cc)
+    assert y_ref.shape[2] == T * S
+    y = torch.empty(B, Cc, T * S, device="cuda")
+    co = torch.empty(B, Cc, 1, device="cuda")
+    _lib.check(lib.hil_op_dwconv_transpose(_ptr(x.cuda()), _ptr(cache.cuda()), _ptr(co), _ptr(w.cuda()), _ptr(y),
+                                           B, Cc, T, S, pre, 0.7071, _stream()))
+    torch.cuda.synchronize()
+    assert torch.allclose(y.cpu(), y_ref, rtol=1e-5, atol=2e-6), (y.cpu() - y_ref).abs().max()
+    assert torch.allclose(co.cpu(), xin[:, :, -1:], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,M,K,T,pre,bias,res", [
+    (2, 64, 64, 512, 1, False, False),
+    (2, 128, 64, 300, 2, False, False),
+    (3, 96, 192, 75, 0, True, False),      # ragged T, flattened columns
+    (2, 64, 33, 640, 0, True, True),       # SpecBlock 1x1: odd K, bias, residual add
+    (1, 1024, 513, 75, 0, True, True),
+    (2, 768, 1536, 40, 0, True, False),
+    (1, 128, 1024, 5, 0, True, False),
+    (4, 192, 192, 1, 1, False, False),     # one column per stream
+    (1, 256, 257, 129, 2, True, True),
+])
+def test_pointwise(B, M, K, T, pre, bias, res):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + K + T)
+    x = torch.randn(B, K, T, generator=g)
+    w = (torch.randn(M, K, 1, generator=g) / K ** 0.5).contiguous()
+    b = torch.randn(M, generator=g) if bias else None
+    r = torch.randn(B, M, T, generator=g) if res else None
+    y_ref = F.conv1d(_pre_ref(x, pre, 0.8660254), w, b)
+    y64 = F.conv1d(_pre_ref(x, pre, 0.8660254).double(), w.double(), b.double() if bias else None)
+    if res:
+        y_ref = y_ref + r
+        y64 = y64 + r.double()
+    y = torch.empty(B, M, T, device="cuda")
+    _lib.check(lib.hil_op_pointwise(_ptr(x.cuda()), _ptr(w), _ptr(b.cuda() if bias else None),
+                                    _ptr(r.cuda() if res else None), _ptr(y), B, M, K, T, pre, 0.8660254, _stream()))
+    torch.cuda.synchronize()
+    err = (y.cpu().double() - y64).abs().max().item()
+    ref_err = (y_ref.double() - y64).abs().max().item()
+    # as accurate as the CPU fp32 result is (both are fp32 accumulations in different orders)
+    assert err <= max(4 * ref_err, 2e-6), (err, ref_err)
+
+
+@pytest.mark.parametrize("B,n_fft,hop,T", [(2, 64, 1, 640), (2, 128, 2, 320), (1, 256, 8, 75),
+                                            (2, 512, 40, 15), (2, 1024, 320, 3), (1, 1024, 320, 1)])
+def test_stft_logmag(B, n_fft, hop, T):
+    from hilcodec_b200.weights import dft_basis
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n_fft + T)
+    L = (T - 1) * hop + n_fft
+    wav = 0.1 * torch.randn(B, 1, L, generator=g)
+    wav[0, 0, : L // 3] = 0.0  # silence: exercises the 1e-5 clamp
+    w = torch.from_numpy(dft_basis(n_fft)).contiguous()
+    s = F.conv1d(wav, w, None, stride=hop)
+    Fr = n_fft // 2 + 1
+    s = s.view(B, 2, Fr, T)
+    y_ref = s.square().sum(1).sqrt().clamp_min(1e-5).log()
+    s64 = F.conv1d(wav.double(), w.double(), None, stride=hop).view(B, 2, Fr, T)
+    y64 = s64.square().sum(1).sqrt().clamp_min(1e-5).log()
+    y = torch.empty(B, Fr, T, device="cuda")
+    _lib.check(lib.hil_op_stft_logmag(_ptr(wav.cuda()), _ptr(w), _ptr(y), B, n_fft, hop, T, _stream()))
+    torch.cuda.synchronize()
+    # log of a magnitude near cancellation amplifies fp32 noise: compare where the fp64
+    # magnitude is well conditioned, and bound everything by the CPU fp32 error itself
+    err = (y.cpu().double() - y64).abs()
+    ref_err = (y_ref.double() - y64).abs()
+    assert err.max().item() <= max(8 * ref_err.max().item(), 1e-4), (err.max().item(), ref_err.max().item())
+    assert torch.median(err).item() < 1e-6

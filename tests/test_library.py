@@ -1,0 +1,81 @@
+"""CPU-side checks of the boundary: the shared library builds, loads and exports every
+symbol include/hilcodec_b200.h declares; host-side argument validation mirrors the
+reference's error behaviour.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from hilcodec_b200 import _lib, build
+from hilcodec_b200 import streaming as S
+from hilcodec_b200 import weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    lib_path = build.build_library()
+    assert os.path.exists(lib_path)
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "hilcodec_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hil_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.hil_abi_version() == 1
+
+
+def test_config_struct_layout_matches_header_defaults():
+    lib = _lib.load()
+    c = _lib.HilConfig()
+    lib.hil_config_default(C.byref(c), 12)
+    assert (c.channels_enc, c.channels_dec, c.n_fft_base) == (64, 96, 64)
+    assert (c.n_residual_enc, c.n_residual_dec) == (2, 3)
+    assert c.res_scale_enc == 0.5773502691896258 and c.res_scale_dec == 0.5773502691896258
+    assert list(c.strides)[:4] == [8, 5, 4, 2] and c.n_strides == 4
+    assert (c.kernel_size, c.dim, c.codebook_size, c.num_quantizers) == (5, 128, 1024, 12)
+
+
+def test_model_create_validates_config_without_gpu():
+    lib = _lib.load()
+    c = _lib.HilConfig()
+    lib.hil_config_default(C.byref(c), 8)
+    c.kernel_size = 7
+    h = C.c_void_p()
+    assert lib.hil_model_create(C.byref(c), C.byref(h)) == -1
+    assert b"kernel_size" in lib.hil_last_error()
+    lib.hil_config_default(C.byref(c), 8)
+    assert lib.hil_model_create(C.byref(c), C.byref(h)) == 0
+    # finalize with nothing set: HIL_ERR_MISSING, no CUDA call made
+    assert lib.hil_model_finalize(h) == -2
+    lib.hil_model_destroy(h)
+
+
+def test_dropin_surface_and_errors():
+    m = S.HILCodec(24000, vq_kwargs=dict(dim=128, codebook_size=1024, num_quantizers=8))
+    w = W.random_weights(W.HIL_SPEECH, 3)
+    r = m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    assert not r.missing_keys and not r.unexpected_keys
+    assert m.encoder.num_cache == 22 and m.decoder.num_cache == 30
+    assert m.encoder.hop_length == 320 and m.encoder.ratios == [2, 4, 5, 8]
+    assert len(m.quantizer.layers) == 8
+    assert m.quantizer.layers[0].embed.shape == (1024, 128)
+    sd = m.state_dict()
+    for k in ("encoder.conv_pre.weight", "encoder.blocks.0.0.block.0.pointwise.1.weight",
+              "decoder.upsample_depthwise.3.weight", "quantizer.layers.7.embed", "dequantizer.layers.7.embed"):
+        assert k in sd
+    assert set(m.encoder.state_dict()) == {k[len("encoder."):] for k in W.tensor_shapes(W.HIL_SPEECH) if k.startswith("encoder.")}
+    # no CPU path: CPU tensors raise instead of silently computing somewhere else
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.encoder(torch.zeros(1, 1, 320))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.quantizer(torch.zeros(1, 1, 128), 8)
+    with pytest.raises(ValueError, match="Unknown norm"):
+        S.HILCodec(24000, norm="layer_norm")
+    with pytest.raises(RuntimeError, match="missing"):
+        S.HILCodec(24000, vq_kwargs=dict(dim=128, num_quantizers=8)).load_state_dict({})
