@@ -49,7 +49,13 @@ class _NativeCodec:
         self.weights: "OrderedDict[str, Tensor]" = OrderedDict()  # folded fp32 CPU tensors
         self._models: tp.Dict[int, int] = {}
         self._states: tp.Dict[tp.Tuple[int, int], int] = {}
-        self._lib = None
+        self._lib_handle = None
+
+    @property
+    def _lib(self):
+        if self._lib_handle is None:
+            self._lib_handle = _lib.load()
+        return self._lib_handle
 
     # -- weights ---------------------------------------------------------------------
     def set_weights(self, w: tp.Mapping[str, tp.Any]) -> None:
@@ -59,7 +65,7 @@ class _NativeCodec:
         self.invalidate()
 
     def invalidate(self) -> None:
-        lib = self._lib
+        lib = self._lib_handle
         if lib is not None:
             for s in self._states.values():
                 lib.hil_state_destroy(s)
@@ -93,7 +99,7 @@ class _NativeCodec:
         h = self._models.get(idx)
         if h is not None:
             return h
-        lib = self._lib = _lib.load()
+        lib = self._lib
         with torch.cuda.device(idx):
             handle = C.c_void_p()
             cfg = self.c_config()

@@ -82,7 +82,8 @@ def test_dwconv_transpose(B, Cc, T, S, pre):
     assert y_ref.shape[2] == T * S
     y = torch.empty(B, Cc, T * S, device="cuda")
     co = torch.empty(B, Cc, 1, device="cuda")
-    _lib.check(lib.hil_op_dwconv_transpose(_ptr(x.cuda()), _ptr(cache.cuda()), _ptr(co), _ptr(w.cuda()), _ptr(y),
+    xd, cd, wd = x.cuda(), cache.cuda(), w.cuda()  # keep the device tensors alive across the call
+    _lib.check(lib.hil_op_dwconv_transpose(_ptr(xd), _ptr(cd), _ptr(co), _ptr(wd), _ptr(y),
                                            B, Cc, T, S, pre, 0.7071, _stream()))
     torch.cuda.synchronize()
     assert torch.allclose(y.cpu(), y_ref, rtol=1e-5, atol=2e-6), (y.cpu() - y_ref).abs().max()
@@ -113,8 +114,11 @@ def test_pointwise(B, M, K, T, pre, bias, res):
         y_ref = y_ref + r
         y64 = y64 + r.double()
     y = torch.empty(B, M, T, device="cuda")
-    _lib.check(lib.hil_op_pointwise(_ptr(x.cuda()), _ptr(w), _ptr(b.cuda() if bias else None),
-                                    _ptr(r.cuda() if res else None), _ptr(y), B, M, K, T, pre, 0.8660254, _stream()))
+    xd = x.cuda()
+    bd = b.cuda() if bias else None
+    rd = r.cuda() if res else None
+    _lib.check(lib.hil_op_pointwise(_ptr(xd), _ptr(w), _ptr(bd), _ptr(rd), _ptr(y), B, M, K, T, pre, 0.8660254,
+                                    _stream()))
     torch.cuda.synchronize()
     err = (y.cpu().double() - y64).abs().max().item()
     ref_err = (y_ref.double() - y64).abs().max().item()
@@ -139,7 +143,8 @@ def test_stft_logmag(B, n_fft, hop, T):
     s64 = F.conv1d(wav.double(), w.double(), None, stride=hop).view(B, 2, Fr, T)
     y64 = s64.square().sum(1).sqrt().clamp_min(1e-5).log()
     y = torch.empty(B, Fr, T, device="cuda")
-    _lib.check(lib.hil_op_stft_logmag(_ptr(wav.cuda()), _ptr(w), _ptr(y), B, n_fft, hop, T, _stream()))
+    wd = wav.cuda()
+    _lib.check(lib.hil_op_stft_logmag(_ptr(wd), _ptr(w), _ptr(y), B, n_fft, hop, T, _stream()))
     torch.cuda.synchronize()
     # log of a magnitude near cancellation amplifies fp32 noise: compare where the fp64
     # magnitude is well conditioned, and bound everything by the CPU fp32 error itself
