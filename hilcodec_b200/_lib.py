@@ -66,6 +66,7 @@ SIGNATURES = {
     "hil_codec_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "hil_codec_forward_host": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "hil_launch_count": (C.c_uint64, []),
+    "hil_set_tensor_cores": (_I, [_I]),
     "hil_profile_begin": (_I, []),
     "hil_profile_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                              C.POINTER(C.c_int64), _I]),

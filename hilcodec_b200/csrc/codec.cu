@@ -4,6 +4,7 @@
 // sequence of kernel launches; see DESIGN.md for the kernel list and data layout.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -86,13 +87,17 @@ struct LaunchScope {
     } while (0)
 
 
+static bool g_use_tc = std::getenv("HILCODEC_DISABLE_TC") == nullptr;  // tensor-core GEMM on unless disabled
+
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                                cudaStream_t st) {
     const double n = (double)B * T;
+    const bool tcore = g_use_tc && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
     HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
-               launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
+               tcore ? launch_gemm_tc(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
+                     : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
     return HIL_OK;
 }
 static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,
@@ -260,7 +265,20 @@ struct Arena {  // host-side staging of everything that goes to the device weigh
 struct PendingMat {
     PackedMat* dst;
     size_t off;
+    size_t off_hi = 0, off_lo = 0;
+    bool tc = false;
 };
+
+// cvt.rna.tf32.f32 on the host: round to nearest, ties away, keep 10 mantissa bits
+float tf32_rna_host(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0x1000u;
+    u &= 0xffffe000u;
+    std::memcpy(&x, &u, 4);
+    return x;
+}
 
 struct Builder {
     hil_model* m;
@@ -312,7 +330,24 @@ struct Builder {
             for (int k = 0; k < K; ++k) a[(size_t)k * Mp + mrow] = w[(size_t)src * K + k];
         }
         dst->M = M; dst->K = K; dst->Mp = Mp; dst->Kp = Kp; dst->TM = TM;
-        mats.push_back({dst, off});
+        PendingMat pm{dst, off};
+        if (!interleave) {  // tensor-core form for the pointwise convs
+            const int Mp128 = round_up(M, 128), Kp32 = round_up(K, 32);
+            pm.off_hi = arena.alloc((size_t)Mp128 * Kp32);
+            pm.off_lo = arena.alloc((size_t)Mp128 * Kp32);
+            pm.tc = true;
+            float* hi = arena.buf.data() + pm.off_hi;
+            float* lo = arena.buf.data() + pm.off_lo;
+            for (int mrow = 0; mrow < M; ++mrow)
+                for (int k = 0; k < K; ++k) {
+                    const float v = w[(size_t)mrow * K + k];
+                    const float h = tf32_rna_host(v);
+                    hi[(size_t)mrow * Kp32 + k] = h;
+                    lo[(size_t)mrow * Kp32 + k] = tf32_rna_host(v - h);
+                }
+            dst->Mp128 = Mp128; dst->Kp32 = Kp32;
+        }
+        mats.push_back(pm);
     }
 };
 
@@ -482,7 +517,10 @@ int32_t hil_model_finalize(hil_model* m) {
     m->arena_floats = b.arena.buf.size();
     HIL_CUDA(cudaMalloc(&m->arena, m->arena_floats * sizeof(float)));
     HIL_CUDA(cudaMemcpy(m->arena, b.arena.buf.data(), m->arena_floats * sizeof(float), cudaMemcpyHostToDevice));
-    for (auto& pm : b.mats) pm.dst->A = m->arena + pm.off;
+    for (auto& pm : b.mats) {
+        pm.dst->A = m->arena + pm.off;
+        if (pm.tc) { pm.dst->A_hi = m->arena + pm.off_hi; pm.dst->A_lo = m->arena + pm.off_lo; }
+    }
     for (auto& p : b.ptrs) *p.first = m->arena + p.second;
     m->codebooks = m->arena + cb_off;
     m->ee = m->arena + ee_off;
@@ -924,6 +962,12 @@ int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host
 // ----------------------------------------------------------------------------- launch accounting API
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 
+int32_t hil_set_tensor_cores(int32_t on) {
+    const int32_t prev = g_use_tc ? 1 : 0;
+    g_use_tc = on != 0;
+    return prev;
+}
+
 int32_t hil_profile_begin(void) {
     for (auto& r : g_prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof.recs.clear();
@@ -974,6 +1018,7 @@ static int32_t upload_packed(const float* w_host, int M, int K, int TM, bool int
     HIL_CUDA(cudaMalloc(dev, b.arena.buf.size() * sizeof(float)));
     HIL_CUDA(cudaMemcpy(*dev, b.arena.buf.data(), b.arena.buf.size() * sizeof(float), cudaMemcpyHostToDevice));
     pm->A = *dev + b.mats[0].off;
+    if (b.mats[0].tc) { pm->A_hi = *dev + b.mats[0].off_hi; pm->A_lo = *dev + b.mats[0].off_lo; }
     return HIL_OK;
 }
 
@@ -983,11 +1028,11 @@ int32_t hil_op_pointwise(const float* x, const float* w_host, const float* bias_
     PackedMat pm;
     float* dev = nullptr;
     HIL_TRY(upload_packed(w_host, M, K, choose_tm(M), false, &pm, &dev));
-    cudaError_t e = launch_gemm_linear(pm, x, (long long)K * T, T, B, T, pre, pre_scale, bias_dev, residual, y,
-                                       (long long)M * T, T, (cudaStream_t)stream);
+    int32_t rc = run_gemm_linear(pm, x, (long long)K * T, T, B, T, pre, pre_scale, bias_dev, residual, y,
+                                 (long long)M * T, T, (cudaStream_t)stream);
     cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(dev);
-    HIL_CUDA(e);
+    HIL_TRY(rc);
     HIL_CUDA(e2);
     return HIL_OK;
 }

@@ -21,8 +21,12 @@ static inline int pitch4(int t) { return (t + 3) & ~3; }
 
 // A weight matrix W[M][K] repacked k-major for the GEMM kernels: A[Kp][Mp], zero padded.
 struct PackedMat {
-    const float* A = nullptr;  // device
+    const float* A = nullptr;  // device, [Kp][Mp] for the FFMA kernels
     int M = 0, K = 0, Mp = 0, Kp = 0, TM = 8;
+    // tensor-core form: row-major [Mp128][Kp32], split w = hi + lo with hi = tf32(w), lo = tf32(w - hi)
+    const float* A_hi = nullptr;
+    const float* A_lo = nullptr;
+    int Mp128 = 0, Kp32 = 0;
 };
 
 // ---- gemm.cu ---------------------------------------------------------------------
@@ -38,6 +42,13 @@ cudaError_t launch_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
 // Y[b][f][t] = log(max(sqrt(re^2+im^2), 1e-5)), re/im = sum_k Wdft[.][k] * wav[b][t*hop + k]
 cudaError_t launch_gemm_stft_logmag(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T,
                                     float* Y, long long y_bs, int y_rs, cudaStream_t st);
+
+// ---- gemm_tc.cu: same contract as launch_gemm_linear, on the tensor pipe (tcgen05, 3xTF32)
+bool gemm_tc_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
+                    long long y_bs, int y_rs);
+cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
+                           cudaStream_t st);
 
 // ---- conv.cu ---------------------------------------------------------------------
 // wav_ext[b][0:P+T] = cat(cache_in[b][0:P], x[b][0:T]); cache_out = last P of it.

@@ -1,0 +1,481 @@
+// Tensor-core (tcgen05 / TMEM / TMA) pointwise GEMM with fp32-level accuracy (3xTF32).
+//
+//   Y[b][m][t] = sum_k W[m][k] * pre(X[b][k][t]) (+bias[m]) (+R[b][m][t])
+//
+// Why 3xTF32: VQ indices must match the fp32 reference bit for bit, and a single TF32 pass
+// (10-bit mantissa) flips indices.  Every operand is split x = hi + lo with
+// hi = tf32(x), lo = tf32(x - hi); D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi accumulates in
+// fp32 in TMEM and drops only the ~2^-22 lo*lo term.
+//
+// Mapping (one persistent CTA per SM, 128 x 128 output tile, BK = 32):
+//   A = weights  [M = Cout rows, K]   K-major, SWIZZLE_128B, hi/lo pre-split at finalize, TMA 2D
+//   B = activations [K rows, N = time] MN-major (time contiguous, NCW), SWIZZLE_128B_ATOM_32B, TMA 3D
+//       boxes of 32 k x 32 t; raw fp32 lands in the B_hi slot, 8 transform warps apply the
+//       ELU prologue + hi/lo split in place (elementwise, so the swizzle is untouched)
+//   D in TMEM: per tile two 128-column accumulators -- "big" (A_hi*B_hi) and "small" (the two
+//       cross terms) -- so the big sum is rounded once per k-step instead of three times (the
+//       tensor core truncates after every accumulate); both are double buffered (4 x 128 = all
+//       512 columns), so the epilogue of tile i overlaps the MMAs of tile i+1.  Lane = Cout
+//       row, column = time: bias is a per-thread scalar.
+//   Epilogue: TMEM -> registers -> (big + small + bias) -> 128B-swizzled smem staging ->
+//       TMA tensor store (or TMA reduce-add when the 1x1 output is added in place to h, the
+//       SpecBlock case); out-of-range rows / columns are clipped by the tensor map.
+// Warp roles: 0 TMA producer | 1 MMA issuer | 2 TMEM alloc | 4-7 epilogue | 8-15 transform.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace hil {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;         // 16 KB: one operand tile
+constexpr int PANEL_BYTES = BK * 32 * 4;        // 4 KB: 32 k-rows x 32 t (one TMA box of B)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
+constexpr int STAGE_TX = 3 * TILE_BYTES;        // bytes TMA writes per stage
+constexpr int NUM_THREADS = 512;
+constexpr int NUM_XFORM = 256;
+constexpr int NUM_EPI = 128;
+constexpr int OUT_BYTES = BM * 32 * 4;           // 16 KB: one 128-row x 32-column output chunk
+constexpr int TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256;
+
+struct Params {
+    int M, K, T, B;
+    int num_m, tiles_t;
+    long long total_tiles;
+    int pre;
+    float pre_scale;
+    const float* bias;
+    int reduce_add;  // 1: Y += tile (TMA reduce), 0: Y = tile
+};
+
+// ------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug becomes a trapped kernel (launch error) instead of a hung GPU.
+// Roles with long waits (producer, epilogue) back off with nanosleep so their polling does not
+// take issue slots from the transform warps sharing the scheduler.
+template <int kSleepNs = 0>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (kSleepNs > 0) __nanosleep(kSleepNs);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout).
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks, 8-row period; K-major A),
+//              1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row period) -- the only layout the
+//                  tensor core accepts for MN-major tf32 operands; TMA writes it with
+//                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+// kind::tf32, D = f32, A K-major, B MN-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ELU for the GEMM prologue: x > 0 ? x : 2^(x*log2(e)) - 1 with ex2.approx (rel. error 2^-22 on
+// the exponential, i.e. <= 2.4e-7 absolute on the result) -- branch free, 5 instructions.  The
+// accurate expm1f costs ~30 instructions per element and made the transform warps the
+// bottleneck of the whole kernel (ncu: 3900 cycles per k-block against 768 of MMA time).
+__device__ __forceinline__ float elu_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.0f;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// ------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t out_base = base + STAGES * STAGE_BYTES;
+    const uint32_t bars = out_base + 2 * OUT_BYTES;
+    // barrier slots (8 bytes each)
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xform_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi);
+        prefetch_tmap(&map_a_lo);
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_y);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xform_bar(s), NUM_XFORM);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), NUM_EPI);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        const uint32_t ncols = TMEM_COLS;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int m_blk = (int)(tile % p.num_m);
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait<32>(empty_bar(s), ph ^ 1);
+                    const uint32_t st = base + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(s), STAGE_TX);
+                    tma_load_2d(&map_a_hi, st, full_bar(s), kb * BK, m_blk * BM);
+                    tma_load_2d(&map_a_lo, st + TILE_BYTES, full_bar(s), kb * BK, m_blk * BM);
+#pragma unroll
+                    for (int pnl = 0; pnl < 4; ++pnl)
+                        tma_load_3d(&map_x, st + 2 * TILE_BYTES + pnl * PANEL_BYTES, full_bar(s), tt * BN + pnl * 32,
+                                    kb * BK, b);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = (int)(it & 1);
+            const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_big = tmem_base + acc * 2 * BN;
+            const uint32_t d_small = d_big + BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(s), ph);
+                mbar_wait(xform_bar(s), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < BK / 8; ++j) {
+                        // A: 8-row groups 1024 B apart; +32 B walks K inside the 128-byte swizzle row.
+                        // B: 32-column panels PANEL_BYTES apart (LBO), 4-row swizzle groups 512 B apart
+                        //    (SBO); one MMA (K = 8) consumes 8 k-rows = 1024 B.
+                        const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
+                        const uint64_t a_lo = make_desc(st + TILE_BYTES + j * 32, 16, 1024, 2);
+                        const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
+                        const uint64_t b_lo = make_desc(st + 3 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
+                        umma_tf32(d_small, a_lo, b_hi, (kb | j) != 0);
+                        umma_tf32(d_small, a_hi, b_lo, 1);
+                        umma_tf32(d_big, a_hi, b_hi, (kb | j) != 0);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (kb == nkb - 1) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================================================================== transform (ELU + hi/lo split)
+        const int xt = threadIdx.x - 256;
+        int s = 0;
+        uint32_t ph = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(s), ph);
+                float4* bh = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 2 * TILE_BYTES);
+                float4* bl = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 3 * TILE_BYTES);
+#pragma unroll
+                for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
+                    const int idx = xt + i * NUM_XFORM;
+                    float4 v = bh[idx];
+                    if (p.pre != PRE_NONE) {  // pre_scale is 1.0 for PRE_ELU (x * 1.0f is exact)
+                        v.x = elu_fast(v.x * p.pre_scale); v.y = elu_fast(v.y * p.pre_scale);
+                        v.z = elu_fast(v.z * p.pre_scale); v.w = elu_fast(v.w * p.pre_scale);
+                    }
+                    float4 h, l;
+                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y);
+                    l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    bh[idx] = h;
+                    bl[idx] = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(xform_bar(s));
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue
+        const int q = warp - 4;
+        const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
+        const bool issuer = (q == 0 && lane == 0);
+        const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
+        long long it = 0;
+        uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = (int)(tile % p.num_m);
+            const long long rest = tile / p.num_m;
+            const int tt = (int)(rest % p.tiles_t);
+            const int b = (int)(rest / p.tiles_t);
+            const int acc = (int)(it & 1);
+            const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait<64>(tfull_bar(acc), acc_ph);
+            tc_fence_after();
+            const int m = m_blk * BM + row;
+            const float bv = (m < p.M && p.bias) ? p.bias[m] : 0.f;
+            const int t0 = tt * BN;
+            const int n_chunks = min(BN / 32, (p.T - t0 + 31) / 32);
+            const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                if (issuer) tma_wait_read<1>();              // the store that used this buffer two chunks ago has drained it
+                epi_bar_sync();
+                uint32_t rb[32], rs[32];
+                tmem_ld32(t_big + c * 32, rb);
+                tmem_ld32(t_big + BN + c * 32, rs);
+                tmem_ld_wait();
+                if (c == n_chunks - 1) {
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(acc));
+                }
+                const uint32_t orow = obuf + row * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float o0 = (__uint_as_float(rb[4 * j + 0]) + __uint_as_float(rs[4 * j + 0])) + bv;
+                    const float o1 = (__uint_as_float(rb[4 * j + 1]) + __uint_as_float(rs[4 * j + 1])) + bv;
+                    const float o2 = (__uint_as_float(rb[4 * j + 2]) + __uint_as_float(rs[4 * j + 2])) + bv;
+                    const float o3 = (__uint_as_float(rb[4 * j + 3]) + __uint_as_float(rs[4 * j + 3])) + bv;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j ^ sw) << 4)), "f"(o0),
+                                 "f"(o1), "f"(o2), "f"(o3)
+                                 : "memory");
+                }
+                fence_proxy_async();
+                epi_bar_sync();
+                if (issuer) {
+                    if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
+                    else tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
+                    tma_commit();
+                }
+            }
+        }
+        if (issuer) tma_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        const uint32_t ncols = TMEM_COLS;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols));
+    }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+
+bool gemm_tc_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
+                    long long y_bs, int y_rs) {
+    if (!W.A_hi || !W.A_lo) return false;
+    if (T < 64) return false;  // short chunks (streaming) go to the flattened-column FFMA kernel
+    if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
+    if (R && (reinterpret_cast<uintptr_t>(R) & 15)) return false;
+    return true;
+}
+
+cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
+                           cudaStream_t st) {
+    using namespace tc;
+    if (B == 0 || T == 0) return cudaSuccess;
+    static int num_sms = 0;
+    static bool attr_set = false;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    CUtensorMap map_hi, map_lo, map_x;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)W.Kp32, (cuuint64_t)W.Mp128};
+        const cuuint64_t strides[1] = {(cuuint64_t)W.Kp32 * 4};
+        const cuuint32_t box[2] = {BK, BM};
+        if (!make_map(&map_hi, W.A_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !make_map(&map_lo, W.A_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)x_rs * 4, (cuuint64_t)x_bs * 4};
+        const cuuint32_t box[3] = {32, BK, 1};
+        if (!make_map(&map_x, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return cudaErrorInvalidValue;
+    }
+    CUtensorMap map_y;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {32, BM, 1};
+        if (!make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidValue;
+    }
+    if (R && R != Y) {  // out-of-place residual: seed Y with R, then accumulate in place
+        for (int b = 0; b < B; ++b) {
+            cudaError_t e = cudaMemcpy2DAsync(Y + (long long)b * y_bs, (size_t)y_rs * 4, R + (long long)b * y_bs,
+                                              (size_t)y_rs * 4, (size_t)T * 4, W.M, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    Params p{};
+    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
+    p.num_m = (W.M + BM - 1) / BM;
+    p.tiles_t = (T + BN - 1) / BN;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
+    return cudaGetLastError();
+}
+
+}  // namespace hil

@@ -122,6 +122,9 @@ uint64_t hil_launch_count(void);
  * depthwise, 4 conv_pre, 5 conv_post+tanh, 6 RVQ, 7 misc (wav concat, l2norm).
  * end() synchronises the device and fills summed ms / algorithmic FLOPs / algorithmic bytes /
  * launch counts per category (arrays of HIL_PROFILE_CATEGORIES). */
+/* 1 (default): pointwise GEMMs run on the tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy);
+ * 0: FP32 FFMA kernels everywhere.  Returns the previous setting.  For A/B measurement. */
+int32_t hil_set_tensor_cores(int32_t on);
 #define HIL_PROFILE_CATEGORIES 8
 int32_t hil_profile_begin(void);
 int32_t hil_profile_end(double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_cat);
