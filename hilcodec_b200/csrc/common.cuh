@@ -16,6 +16,29 @@ __device__ __forceinline__ float apply_pre(float x, int pre, float s) {
     return elu1(x);
 }
 
+// Cheap ELU for the bandwidth-bound kernels and the GEMM transform warps (expm1f is ~30
+// instructions and made them ALU-bound): for -1/16 < x <= 0 a degree-5 Taylor polynomial
+// (relative error < 1e-10), below that 2^(x*log2 e) - 1 with ex2.approx (absolute error
+// <= 2.4e-7).  Branch free, ~11 instructions.
+__device__ __forceinline__ float elu_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    e -= 1.0f;
+    float p = fmaf(x, 1.0f / 120.0f, 1.0f / 24.0f);
+    p = fmaf(x, p, 1.0f / 6.0f);
+    p = fmaf(x, p, 0.5f);
+    p = fmaf(x, p, 1.0f);
+    p *= x;
+    const float neg = x > -0.0625f ? p : e;
+    return x > 0.f ? x : neg;
+}
+
+__device__ __forceinline__ float apply_act_fast(float x, int mode, float s) {
+    if (mode == PRE_NONE) return x;
+    if (mode == PRE_SCALE_ELU) x = x * s;
+    return elu_fast(x);
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int pitch4(int t) { return (t + 3) & ~3; }
 
@@ -57,10 +80,11 @@ cudaError_t launch_wavcat(const float* x, const float* cache_in, float* cache_ou
 // conv_pre: y[b][co][t] = bias[co] + sum_k w[co][k] * win[b][t+k]   (1 -> C, dense k taps)
 cudaError_t launch_conv_pre(const float* win, long long w_bs, const float* w, const float* bias, float* y,
                             long long y_bs, int y_rs, int B, int C, int T, int K, cudaStream_t st);
-// causal depthwise conv, see hil_op_dwconv
+// causal depthwise conv, see hil_op_dwconv; post: activation applied to the stored output (after bias + skip)
 cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                           const float* w, const float* bias, const float* skip, float* y, long long y_bs, int y_rs,
-                          int B, int C, int T, int K, int S, int pre, float pre_scale, cudaStream_t st);
+                          int B, int C, int T, int K, int S, int pre, float pre_scale, int post, float post_scale,
+                          cudaStream_t st);
 cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                                     const float* w, float* y, long long y_bs, int y_rs, int B, int C, int T, int S,
                                     int pre, float pre_scale, cudaStream_t st);

@@ -84,7 +84,8 @@ template <int K, int S>
 __global__ void dwconv_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
                               float* __restrict__ cache_out, const float* __restrict__ w,
                               const float* __restrict__ bias, const float* skip, float* y,
-                              long long y_bs, int y_rs, int C, int T, int T_out, int pre, float pre_scale) {
+                              long long y_bs, int y_rs, int C, int T, int T_out, int pre, float pre_scale, int post,
+                              float post_scale) {
     constexpr int P = K - S;
     const int c = blockIdx.y, b = blockIdx.z;
     const float* xr = x + b * x_bs + (long long)c * x_rs;
@@ -104,7 +105,7 @@ __global__ void dwconv_kernel(const float* __restrict__ x, long long x_bs, int x
         a += bv;
         const long long o = b * y_bs + (long long)c * y_rs + to;
         if (skip) a += skip[o];
-        y[o] = a;
+        y[o] = apply_act_fast(a, post, post_scale);
     }
     // new cache = last P samples of xin
     if (blockIdx.x == 0 && threadIdx.x < P) {
@@ -117,7 +118,8 @@ __global__ void dwconv_kernel(const float* __restrict__ x, long long x_bs, int x
 __global__ void dwconv5_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
                                float* __restrict__ cache_out, const float* __restrict__ w,
                                const float* __restrict__ bias, const float* skip, float* y,
-                               long long y_bs, int y_rs, int C, int T, int pre, float pre_scale) {
+                               long long y_bs, int y_rs, int C, int T, int pre, float pre_scale, int post,
+                               float post_scale) {
     const int c = blockIdx.y, b = blockIdx.z;
     const float* xr = x + b * x_bs + (long long)c * x_rs;
     const float* ci = cache_in + ((size_t)b * C + c) * 4;
@@ -156,9 +158,14 @@ __global__ void dwconv5_kernel(const float* __restrict__ x, long long x_bs, int 
                 const float4 s = *reinterpret_cast<const float4*>(skip + off);
                 o[0] += s.x; o[1] += s.y; o[2] += s.z; o[3] += s.w;
             }
+            if (post != PRE_NONE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = apply_act_fast(o[j], post, post_scale);
+            }
             *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
-            for (int j = 0; j < 4 && t0 + j < T; ++j) y[off + j] = o[j] + (skip ? skip[off + j] : 0.f);
+            for (int j = 0; j < 4 && t0 + j < T; ++j)
+                y[off + j] = apply_act_fast(o[j] + (skip ? skip[off + j] : 0.f), post, post_scale);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < 4) {
@@ -169,7 +176,8 @@ __global__ void dwconv5_kernel(const float* __restrict__ x, long long x_bs, int 
 
 cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                           const float* w, const float* bias, const float* skip, float* y, long long y_bs, int y_rs,
-                          int B, int C, int T, int K, int S, int pre, float pre_scale, cudaStream_t st) {
+                          int B, int C, int T, int K, int S, int pre, float pre_scale, int post, float post_scale,
+                          cudaStream_t st) {
     if (B == 0 || C == 0) return cudaSuccess;
     if (K < S || C > 65535 || B > 65535) return cudaErrorInvalidValue;
     const int P = K - S;
@@ -183,7 +191,7 @@ cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float*
         const int threads = Tq >= 128 ? 128 : 32;
         dim3 grid(min((Tq + threads - 1) / threads, 512), C, B);
         dwconv5_kernel<<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y, y_bs, y_rs, C, T,
-                                                 pre, pre_scale);
+                                                 pre, pre_scale, post, post_scale);
         return cudaGetLastError();
     }
     const int threads = T_out >= 128 ? 128 : 32;
@@ -191,7 +199,7 @@ cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float*
 #define HIL_DW(KK, SS)                                                                                              \
     if (K == KK && S == SS) {                                                                                       \
         dwconv_kernel<KK, SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y, y_bs, \
-                                                         y_rs, C, T, T_out, pre, pre_scale);                         \
+                                                         y_rs, C, T, T_out, pre, pre_scale, post, post_scale);       \
         return cudaGetLastError();                                                                                  \
     }
     HIL_DW(5, 1) HIL_DW(4, 2) HIL_DW(8, 4) HIL_DW(10, 5) HIL_DW(16, 8) HIL_DW(6, 3) HIL_DW(12, 6) HIL_DW(3, 1) HIL_DW(7, 1)
@@ -202,21 +210,51 @@ cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float*
 // ------------------------------------------------------------------ causal transposed depthwise
 // conv_transpose1d(cat(cache[1], x), w[C,1,2S], stride S, padding S):
 //   y[n] = xin[n/S + 1] * w[n%S] + xin[n/S] * w[n%S + S],  xin[0] = cache, xin[i+1] = pre(x[i])
+// One thread owns 4 consecutive INPUT samples (one aligned 16-byte load + the sample before),
+// applies the activation once per input (not once per output) and writes the 4*S outputs they
+// generate as S aligned 16-byte stores.
+template <int S>
 __global__ void dwconvT_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
                                float* __restrict__ cache_out, const float* __restrict__ w, float* __restrict__ y,
-                               long long y_bs, int y_rs, int C, int T, int S, int pre, float pre_scale) {
+                               long long y_bs, int y_rs, int C, int T, int pre, float pre_scale, int vec) {
     const int c = blockIdx.y, b = blockIdx.z;
     const float* xr = x + b * x_bs + (long long)c * x_rs;
     const float cprev = cache_in[(size_t)b * C + c];
-    const float* wc = w + (size_t)c * 2 * S;
+    float wc[2 * S];
+#pragma unroll
+    for (int k = 0; k < 2 * S; ++k) wc[k] = w[(size_t)c * 2 * S + k];
     float* yr = y + b * y_bs + (long long)c * y_rs;
-    const int To = T * S;
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < To; n += gridDim.x * blockDim.x) {
-        const int i = n / S, r = n - i * S;
-        const float cur = apply_pre(xr[i], pre, pre_scale);
-        const float prev = i == 0 ? cprev : apply_pre(xr[i - 1], pre, pre_scale);
-        // ATen's col2im-style accumulation adds the two taps; fp32 add of two rounded products
-        yr[n] = __fadd_rn(__fmul_rn(cur, wc[r]), __fmul_rn(prev, wc[r + S]));
+    const int Tq = (T + 3) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Tq; q += gridDim.x * blockDim.x) {
+        const int i0 = q * 4;
+        float e[5];  // e[0] = xin before i0, e[1..4] = pre(x[i0..i0+3])
+        e[0] = i0 == 0 ? cprev : apply_pre(xr[i0 - 1], pre, pre_scale);
+        if (vec) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + i0);
+            e[1] = apply_pre(v.x, pre, pre_scale); e[2] = apply_pre(v.y, pre, pre_scale);
+            e[3] = apply_pre(v.z, pre, pre_scale); e[4] = apply_pre(v.w, pre, pre_scale);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[1 + j] = i0 + j < T ? apply_pre(xr[i0 + j], pre, pre_scale) : 0.f;
+        }
+        float o[4 * S];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < S; ++r)
+                // two rounded products, one rounded add (col2im-style accumulation)
+                o[j * S + r] = __fadd_rn(__fmul_rn(e[1 + j], wc[r]), __fmul_rn(e[j], wc[r + S]));
+        float* dst = yr + (long long)i0 * S;
+        if (vec && i0 + 3 < T) {
+#pragma unroll
+            for (int k = 0; k < S; ++k)
+                *reinterpret_cast<float4*>(dst + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        } else {
+            const int nvalid = min(4, T - i0) * S;
+#pragma unroll
+            for (int k = 0; k < 4 * S; ++k)
+                if (k < nvalid) dst[k] = o[k];
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         cache_out[(size_t)b * C + c] = T > 0 ? apply_pre(xr[T - 1], pre, pre_scale) : cprev;
@@ -227,12 +265,20 @@ cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
                                     int pre, float pre_scale, cudaStream_t st) {
     if (B == 0 || C == 0) return cudaSuccess;
     if (C > 65535 || B > 65535 || S < 1) return cudaErrorInvalidValue;
-    const int To = T * S;
-    const int threads = To >= 256 ? 256 : (To >= 64 ? 64 : 32);
-    dim3 grid(max(1, min((To + threads - 1) / threads, 512)), C, B);
-    dwconvT_kernel<<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, y, y_bs, y_rs, C, T, S, pre,
-                                             pre_scale);
-    return cudaGetLastError();
+    const int vec = ((x_rs & 3) == 0) && ((x_bs & 3) == 0) && ((y_rs & 3) == 0) && ((y_bs & 3) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const int Tq = (T + 3) / 4;
+    const int threads = Tq >= 128 ? 128 : 32;
+    dim3 grid(max(1, min((Tq + threads - 1) / threads, 512)), C, B);
+#define HIL_DWT(SS)                                                                                                  \
+    if (S == SS) {                                                                                                   \
+        dwconvT_kernel<SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, y, y_bs, y_rs, C, T, pre, \
+                                                     pre_scale, vec);                                                \
+        return cudaGetLastError();                                                                                   \
+    }
+    HIL_DWT(2) HIL_DWT(3) HIL_DWT(4) HIL_DWT(5) HIL_DWT(6) HIL_DWT(8)
+#undef HIL_DWT
+    return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------ decoder conv_post + tanh

@@ -5,7 +5,8 @@
 // Why 3xTF32: VQ indices must match the fp32 reference bit for bit, and a single TF32 pass
 // (10-bit mantissa) flips indices.  Every operand is split x = hi + lo with
 // hi = tf32(x), lo = tf32(x - hi); D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi accumulates in
-// fp32 in TMEM and drops only the ~2^-22 lo*lo term.
+// fp32 in TMEM and drops only the ~2^-22 lo*lo term.  For the activations hi = trunc(x) is what
+// the tensor core reads out of a raw fp32 container, so the raw tile doubles as B_hi.
 //
 // Mapping (one persistent CTA per SM, 128 x 128 output tile, BK = 32):
 //   A = weights  [M = Cout rows, K]   K-major, SWIZZLE_128B, hi/lo pre-split at finalize, TMA 2D
@@ -159,16 +160,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ELU for the GEMM prologue: x > 0 ? x : 2^(x*log2(e)) - 1 with ex2.approx (rel. error 2^-22 on
-// the exponential, i.e. <= 2.4e-7 absolute on the result) -- branch free, 5 instructions.  The
-// accurate expm1f costs ~30 instructions per element and made the transform warps the
-// bottleneck of the whole kernel (ncu: 3900 cycles per k-block against 768 of MMA time).
-__device__ __forceinline__ float elu_fast(float x) {
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-    return x > 0.f ? x : e - 1.0f;
-}
-
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -260,11 +252,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t d_big = tmem_base + acc * 2 * BN;
             const uint32_t d_small = d_big + BN;
             for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t st = base + s * STAGE_BYTES;
                 mbar_wait(full_bar(s), ph);
-                mbar_wait(xform_bar(s), ph);
+                // The tensor core reads only the top 19 bits of a tf32 operand, so the raw fp32 tile
+                // IS the hi operand (hi = trunc(x)); without an activation prologue the two MMAs that
+                // need only hi are issued as soon as TMA lands, and the transform warps (computing
+                // lo = tf32(x - trunc(x))) run underneath them.
+                if (p.pre != PRE_NONE) mbar_wait(xform_bar(s), ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < BK / 8; ++j) {
                         // A: 8-row groups 1024 B apart; +32 B walks K inside the 128-byte swizzle row.
@@ -273,10 +269,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
                         const uint64_t a_lo = make_desc(st + TILE_BYTES + j * 32, 16, 1024, 2);
                         const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
-                        const uint64_t b_lo = make_desc(st + 3 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
-                        umma_tf32(d_small, a_lo, b_hi, (kb | j) != 0);
-                        umma_tf32(d_small, a_hi, b_lo, 1);
                         umma_tf32(d_big, a_hi, b_hi, (kb | j) != 0);
+                        umma_tf32(d_small, a_lo, b_hi, (kb | j) != 0);
+                    }
+                }
+                __syncwarp();
+                if (p.pre == PRE_NONE) {
+                    mbar_wait(xform_bar(s), ph);
+                    tc_fence_after();
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < BK / 8; ++j) {
+                        const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
+                        const uint64_t b_lo = make_desc(st + 3 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
+                        umma_tf32(d_small, a_hi, b_lo, 1);
                     }
                     umma_commit(empty_bar(s));
                     if (kb == nkb - 1) umma_commit(tfull_bar(acc));
@@ -295,20 +302,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(full_bar(s), ph);
                 float4* bh = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 2 * TILE_BYTES);
                 float4* bl = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 3 * TILE_BYTES);
+                if (p.pre == PRE_NONE) {
 #pragma unroll
-                for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
-                    const int idx = xt + i * NUM_XFORM;
-                    float4 v = bh[idx];
-                    if (p.pre != PRE_NONE) {  // pre_scale is 1.0 for PRE_ELU (x * 1.0f is exact)
+                    for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
+                        const int idx = xt + i * NUM_XFORM;
+                        const float4 v = bh[idx];
+                        float4 l;
+                        l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
+                        l.z = tf32_rna(v.z - tf32_trunc(v.z)); l.w = tf32_rna(v.w - tf32_trunc(v.w));
+                        bl[idx] = l;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
+                        const int idx = xt + i * NUM_XFORM;
+                        float4 v = bh[idx];  // pre_scale is 1.0 for PRE_ELU (x * 1.0f is exact)
                         v.x = elu_fast(v.x * p.pre_scale); v.y = elu_fast(v.y * p.pre_scale);
                         v.z = elu_fast(v.z * p.pre_scale); v.w = elu_fast(v.w * p.pre_scale);
+                        float4 l;
+                        l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
+                        l.z = tf32_rna(v.z - tf32_trunc(v.z)); l.w = tf32_rna(v.w - tf32_trunc(v.w));
+                        bh[idx] = v;
+                        bl[idx] = l;
                     }
-                    float4 h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y);
-                    l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                    bh[idx] = h;
-                    bl[idx] = l;
                 }
                 fence_proxy_async();
                 mbar_arrive(xform_bar(s));
