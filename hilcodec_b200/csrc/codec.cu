@@ -88,6 +88,7 @@ struct LaunchScope {
 
 
 static bool g_use_tc = std::getenv("HILCODEC_DISABLE_TC") == nullptr;  // tensor-core GEMM on unless disabled
+static bool g_fuse_dw = std::getenv("HILCODEC_DISABLE_DWS_FUSION") == nullptr;
 
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
@@ -100,6 +101,13 @@ static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_b
                      : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
     return HIL_OK;
 }
+// DWSBlock (ELU/none -> 1x1 -> depthwise k5 + bias [+ skip] [+ activation]): one fused tensor-core kernel
+// when the chunk is long enough, otherwise the pointwise GEMM and the depthwise kernel back to back
+// through `tmp`.
+static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs, int B, int T, int pre, float pre_scale,
+                       const float* dw_w, const float* dw_b, const float* ci, float* co, const float* skip, int post,
+                       float post_scale, float* tmp, float* Y, cudaStream_t st);
+
 static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,
                                   long long y_bs, int y_rs, cudaStream_t st) {
     const double n = (double)B * T;
@@ -135,6 +143,22 @@ static int32_t run_dwconv(const float* x, long long x_bs, int x_rs, const float*
                              post_scale, st));
     return HIL_OK;
 }
+static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs, int B, int T, int pre, float pre_scale,
+                       const float* dw_w, const float* dw_b, const float* ci, float* co, const float* skip, int post,
+                       float post_scale, float* tmp, float* Y, cudaStream_t st) {
+    if (g_use_tc && g_fuse_dw && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
+        const double n = (double)B * T;
+        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
+                   4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
+                   launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, post, post_scale, Y, bs,
+                                     rs, st));
+        return HIL_OK;
+    }
+    HIL_TRY(run_gemm_linear(W, X, bs, rs, B, T, pre, pre_scale, nullptr, nullptr, tmp, bs, rs, st));
+    return run_dwconv(tmp, bs, rs, ci, co, dw_w, dw_b, skip, Y, bs, rs, B, W.M, T, 5, 1, PRE_NONE, 1.f, st, post,
+                      post_scale);
+}
+
 static int32_t run_dwconv_transpose(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
                                     float* y, long long y_bs, int y_rs, int B, int C, int T, int S, int pre,
                                     float pre_scale, cudaStream_t st) {
@@ -737,12 +761,10 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     const int Tp = pitch4(Ts);
     const long long bs = (long long)C * Tp;
     const int pre0 = pre_scale == 1.0f ? PRE_ELU : PRE_SCALE_ELU;
-    HIL_TRY(run_gemm_linear(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, nullptr, nullptr, a1, bs, Tp, st));
-    HIL_TRY(run_dwconv(a1, bs, Tp, cin[0], cout[0], u[0].dw_w, u[0].dw_b, nullptr, a2, bs, Tp, B, C, Ts, 5, 1,
-                       PRE_NONE, 1.f, st, PRE_ELU, 1.f));
-    HIL_TRY(run_gemm_linear(u[1].pw, a2, bs, Tp, B, Ts, PRE_NONE, 1.f, nullptr, nullptr, a1, bs, Tp, st));
-    HIL_TRY(run_dwconv(a1, bs, Tp, cin[1], cout[1], u[1].dw_w, u[1].dw_b, h, h, bs, Tp, B, C, Ts, 5, 1, PRE_NONE,
-                       1.f, st, out_post, out_scale));
+    HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, PRE_ELU, 1.f,
+                    a1, a2, st));
+    HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, PRE_NONE, 1.f, u[1].dw_w, u[1].dw_b, cin[1], cout[1], h, out_post,
+                    out_scale, a1, h, st));
     return HIL_OK;
 }
 
@@ -1045,6 +1067,22 @@ int32_t hil_op_pointwise(const float* x, const float* w_host, const float* bias_
     HIL_TRY(upload_packed(w_host, M, K, choose_tm(M), false, &pm, &dev));
     int32_t rc = run_gemm_linear(pm, x, (long long)K * T, T, B, T, pre, pre_scale, bias_dev, residual, y,
                                  (long long)M * T, T, (cudaStream_t)stream);
+    cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dev);
+    HIL_TRY(rc);
+    HIL_CUDA(e2);
+    return HIL_OK;
+}
+
+int32_t hil_op_dws(const float* x, const float* w_pw_host, const float* w_dw, const float* b_dw, const float* cache_in,
+                   float* cache_out, const float* skip, float* tmp, float* y, int32_t B, int32_t C, int32_t T, int32_t pre,
+                   float pre_scale, int32_t post, float post_scale, void* stream) {
+    if (!x || !w_pw_host || !w_dw || !cache_in || !cache_out || !tmp || !y) return fail(HIL_ERR_INVALID, "null pointer");
+    PackedMat pm;
+    float* dev = nullptr;
+    HIL_TRY(upload_packed(w_pw_host, C, C, choose_tm(C), false, &pm, &dev));
+    int32_t rc = run_dws(pm, x, (long long)C * T, T, B, T, pre, pre_scale, w_dw, b_dw, cache_in, cache_out, skip, post,
+                         post_scale, tmp, y, (cudaStream_t)stream);
     cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(dev);
     HIL_TRY(rc);

@@ -50,6 +50,19 @@ struct Params {
     float pre_scale;
     const float* bias;
     int reduce_add;  // 1: Y += tile (TMA reduce), 0: Y = tile
+    // time tiling: tile tt covers columns [tt * t_step - t_halo, ... + BN)
+    int t_step, t_halo;
+    // fused DWS epilogue (kDw): y = post(bias_dw + dw5(pw) (+ skip)), causal with cache
+    const float* dw_w;       // [M][5]
+    const float* dw_b;       // [M] or null
+    const float* cache_in;   // [B][M][4]
+    float* cache_out;        // [B][M][4]
+    const float* skip;       // same layout as Y, or null (may alias Y)
+    float* Y;
+    long long y_bs;
+    int y_rs;
+    int post;
+    float post_scale;
 };
 
 // ------------------------------------------------------------------------------- PTX helpers
@@ -168,6 +181,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 // ------------------------------------------------------------------------------- kernel
+template <bool kDw>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const Params p) {
@@ -181,7 +195,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (3 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
-    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+    auto sfull_bar = [&](int a) { return bars + 8u * (3 * STAGES + 4 + a); };    // staging buffer filled (kDw)
+    auto sempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + 6 + a); };   // staging buffer drained (kDw)
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 8);
+    constexpr int kNumXform = kDw ? 128 : NUM_XFORM;  // kDw: warps 8-11 transform, warps 12-15 write out
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,12 +213,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(xform_bar(s), NUM_XFORM);
+            mbar_init(xform_bar(s), kNumXform);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), NUM_EPI);
+            mbar_init(sfull_bar(a), NUM_EPI);
+            mbar_init(sempty_bar(a), 128);
         }
         fence_barrier_init();
     }
@@ -233,8 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     tma_load_2d(&map_a_lo, st + TILE_BYTES, full_bar(s), kb * BK, m_blk * BM);
 #pragma unroll
                     for (int pnl = 0; pnl < 4; ++pnl)
-                        tma_load_3d(&map_x, st + 2 * TILE_BYTES + pnl * PANEL_BYTES, full_bar(s), tt * BN + pnl * 32,
-                                    kb * BK, b);
+                        tma_load_3d(&map_x, st + 2 * TILE_BYTES + pnl * PANEL_BYTES, full_bar(s),
+                                    tt * p.t_step - p.t_halo + pnl * 32, kb * BK, b);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -292,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 8 + kNumXform / 32) {
         // ===================================================================== transform (ELU + hi/lo split)
         const int xt = threadIdx.x - 256;
         int s = 0;
@@ -304,8 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 float4* bl = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 3 * TILE_BYTES);
                 if (p.pre == PRE_NONE) {
 #pragma unroll
-                    for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
-                        const int idx = xt + i * NUM_XFORM;
+                    for (int i = 0; i < TILE_BYTES / 16 / kNumXform; ++i) {
+                        const int idx = xt + i * kNumXform;
                         const float4 v = bh[idx];
                         float4 l;
                         l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
@@ -314,8 +333,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
-                        const int idx = xt + i * NUM_XFORM;
+                    for (int i = 0; i < TILE_BYTES / 16 / kNumXform; ++i) {
+                        const int idx = xt + i * kNumXform;
                         float4 v = bh[idx];  // pre_scale is 1.0 for PRE_ELU (x * 1.0f is exact)
                         v.x = elu_fast(v.x * p.pre_scale); v.y = elu_fast(v.y * p.pre_scale);
                         v.z = elu_fast(v.z * p.pre_scale); v.w = elu_fast(v.w * p.pre_scale);
@@ -331,62 +350,217 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ===================================================================== epilogue
-        const int q = warp - 4;
-        const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
-        const bool issuer = (q == 0 && lane == 0);
-        const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
-        long long it = 0;
-        uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        if constexpr (!kDw) {
+            const int q = warp - 4;
+            const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
+            const bool issuer = (q == 0 && lane == 0);
+            const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
+            long long it = 0;
+            uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int m_blk = (int)(tile % p.num_m);
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                const int acc = (int)(it & 1);
+                const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait<64>(tfull_bar(acc), acc_ph);
+                tc_fence_after();
+                const int m = m_blk * BM + row;
+                const float bv = (m < p.M && p.bias) ? p.bias[m] : 0.f;
+                const int t0 = tt * BN;
+                const int n_chunks = min(BN / 32, (p.T - t0 + 31) / 32);
+                const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+    #pragma unroll 1
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                    if (issuer) tma_wait_read<1>();              // the store that used this buffer two chunks ago has drained it
+                    epi_bar_sync();
+                    uint32_t rb[32], rs[32];
+                    tmem_ld32(t_big + c * 32, rb);
+                    tmem_ld32(t_big + BN + c * 32, rs);
+                    tmem_ld_wait();
+                    if (c == n_chunks - 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    const uint32_t orow = obuf + row * 128;
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float o0 = (__uint_as_float(rb[4 * j + 0]) + __uint_as_float(rs[4 * j + 0])) + bv;
+                        const float o1 = (__uint_as_float(rb[4 * j + 1]) + __uint_as_float(rs[4 * j + 1])) + bv;
+                        const float o2 = (__uint_as_float(rb[4 * j + 2]) + __uint_as_float(rs[4 * j + 2])) + bv;
+                        const float o3 = (__uint_as_float(rb[4 * j + 3]) + __uint_as_float(rs[4 * j + 3])) + bv;
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j ^ sw) << 4)), "f"(o0),
+                                     "f"(o1), "f"(o2), "f"(o3)
+                                     : "memory");
+                    }
+                    fence_proxy_async();
+                    epi_bar_sync();
+                    if (issuer) {
+                        if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
+                        else tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
+                        tma_commit();
+                    }
+                }
+            }
+            if (issuer) tma_wait_all();
+
+        } else {
+            // ---- fused DWS epilogue, part 1 (warps 4-7): pointwise tile -> causal depthwise k5 + bias.
+            // The tile holds 128 pointwise columns for times [t0-4, t0+124); each thread owns one
+            // channel row and slides the 5-tap window along it in registers (the 4 halo columns come
+            // from this tile, or from cache_in at the start of the chunk).  Results go to a swizzled
+            // smem staging buffer that the write-out warps (12-15) drain.
+            const int q = warp - 4;
+            const int row = q * 32 + lane;
+            const uint32_t sw = (uint32_t)(row & 7);
+            long long it = 0;
+            uint32_t g = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int m_blk = (int)(tile % p.num_m);
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                const int acc = (int)(it & 1);
+                const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+                const int m = m_blk * BM + row;
+                const bool row_ok = m < p.M;
+                float wk[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) wk[k] = row_ok ? p.dw_w[m * 5 + k] : 0.f;
+                const float bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                const int tcol0 = tt * p.t_step - p.t_halo;       // time of tile column 0
+                const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
+                const bool has_tail = row_ok && (tcol0 + BN > p.T - 4);  // tile holds some of the last 4 columns
+                float carry[4] = {0.f, 0.f, 0.f, 0.f};
+                if (tt == 0 && row_ok) {
+                    const float4 cv = *reinterpret_cast<const float4*>(p.cache_in + ((size_t)b * p.M + m) * 4);
+                    carry[0] = cv.x; carry[1] = cv.y; carry[2] = cv.z; carry[3] = cv.w;
+                }
+                mbar_wait<64>(tfull_bar(acc), acc_ph);
+                tc_fence_after();
+                const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+#pragma unroll 1
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                    uint32_t rb[32], rs[32];
+                    tmem_ld32(t_big + c * 32, rb);
+                    tmem_ld32(t_big + BN + c * 32, rs);
+                    tmem_ld_wait();
+                    if (c == n_chunks - 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    float v[36];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[4 + j] = __uint_as_float(rb[j]) + __uint_as_float(rs[j]);
+                    // columns 0..3 of the first tile are times -4..-1: the cache handed in by the caller
+                    if (c == 0 && tt == 0) { v[4] = carry[0]; v[5] = carry[1]; v[6] = carry[2]; v[7] = carry[3]; }
+                    v[0] = carry[0]; v[1] = carry[1]; v[2] = carry[2]; v[3] = carry[3];
+                    if (has_tail) {  // new cache = pointwise outputs at times T-4..T-1 (each time is owned by one tile)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = c * 32 + j;
+                            const int t = tcol0 + col;
+                            if (col >= p.t_halo && t >= p.T - 4 && t < p.T)
+                                p.cache_out[((size_t)b * p.M + m) * 4 + (t - (p.T - 4))] = v[4 + j];
+                        }
+                    }
+                    mbar_wait<20>(sempty_bar(g & 1), ((g >> 1) & 1) ^ 1);   // write-out warps drained this buffer
+                    const uint32_t orow = obuf + row * 128;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = j4 * 4 + e;  // output i of this chunk uses v[i..i+4]
+                            float a = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[i + k], a);
+                            o[e] = a + bv;
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j4 ^ sw) << 4)),
+                                     "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3])
+                                     : "memory");
+                    }
+                    carry[0] = v[32]; carry[1] = v[33]; carry[2] = v[34]; carry[3] = v[35];
+                    mbar_arrive(sfull_bar(g & 1));
+                }
+            }
+        }
+    } else if (kDw && warp >= 12) {
+        // ===================================================================== fused DWS epilogue, part 2: write-out
+        // Coalesced 16-byte stores of the staged depthwise outputs; the residual skip is read
+        // coalesced here and the stage-end activation applied.  Output i of chunk c is time
+        // tcol0 + 32c + i (i = 0..3 of chunk 0 belong to the previous tile).
+        const int te = threadIdx.x - 384;  // 0..127
+        uint32_t g = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int m_blk = (int)(tile % p.num_m);
             const long long rest = tile / p.num_m;
             const int tt = (int)(rest % p.tiles_t);
             const int b = (int)(rest / p.tiles_t);
-            const int acc = (int)(it & 1);
-            const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
-            mbar_wait<64>(tfull_bar(acc), acc_ph);
-            tc_fence_after();
-            const int m = m_blk * BM + row;
-            const float bv = (m < p.M && p.bias) ? p.bias[m] : 0.f;
-            const int t0 = tt * BN;
-            const int n_chunks = min(BN / 32, (p.T - t0 + 31) / 32);
-            const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+            const int tcol0 = tt * p.t_step - p.t_halo;
+            const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
 #pragma unroll 1
             for (int c = 0; c < n_chunks; ++c, ++g) {
                 const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
-                if (issuer) tma_wait_read<1>();              // the store that used this buffer two chunks ago has drained it
-                epi_bar_sync();
-                uint32_t rb[32], rs[32];
-                tmem_ld32(t_big + c * 32, rb);
-                tmem_ld32(t_big + BN + c * 32, rs);
-                tmem_ld_wait();
-                if (c == n_chunks - 1) {
-                    tc_fence_before();
-                    mbar_arrive(tempty_bar(acc));
-                }
-                const uint32_t orow = obuf + row * 128;
+                mbar_wait<20>(sfull_bar(g & 1), (g >> 1) & 1);
+                float4 o[8];
+                long long off[8];
+                bool ok[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float o0 = (__uint_as_float(rb[4 * j + 0]) + __uint_as_float(rs[4 * j + 0])) + bv;
-                    const float o1 = (__uint_as_float(rb[4 * j + 1]) + __uint_as_float(rs[4 * j + 1])) + bv;
-                    const float o2 = (__uint_as_float(rb[4 * j + 2]) + __uint_as_float(rs[4 * j + 2])) + bv;
-                    const float o3 = (__uint_as_float(rb[4 * j + 3]) + __uint_as_float(rs[4 * j + 3])) + bv;
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j ^ sw) << 4)), "f"(o0),
-                                 "f"(o1), "f"(o2), "f"(o3)
-                                 : "memory");
+                for (int k8 = 0; k8 < 8; ++k8) {
+                    const int idx = te + k8 * 128;
+                    const int r = idx >> 3, f4 = idx & 7;
+                    const int mr = m_blk * BM + r;
+                    const int t = tcol0 + c * 32 + f4 * 4;
+                    ok[k8] = !((c == 0 && f4 * 4 < p.t_halo) || mr >= p.M || t >= p.T);
+                    off[k8] = (long long)b * p.y_bs + (long long)mr * p.y_rs + t;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(o[k8].x), "=f"(o[k8].y), "=f"(o[k8].z), "=f"(o[k8].w)
+                                 : "r"(obuf + r * 128 + (((uint32_t)f4 ^ (uint32_t)(r & 7)) << 4)));
                 }
-                fence_proxy_async();
-                epi_bar_sync();
-                if (issuer) {
-                    if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
-                    else tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
-                    tma_commit();
+                mbar_arrive(sempty_bar(g & 1));  // staging values are in registers now
+                const bool full = (tcol0 + c * 32 + 32 <= p.T);  // every float4 of the chunk is entirely inside T
+                if (full) {
+                    if (p.skip) {
+                        float4 sk[8];
+#pragma unroll
+                        for (int k8 = 0; k8 < 8; ++k8)
+                            sk[k8] = ok[k8] ? *reinterpret_cast<const float4*>(p.skip + off[k8]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k8 = 0; k8 < 8; ++k8) {
+                            o[k8].x += sk[k8].x; o[k8].y += sk[k8].y; o[k8].z += sk[k8].z; o[k8].w += sk[k8].w;
+                        }
+                    }
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        if (!ok[k8]) continue;
+                        if (p.post != PRE_NONE) {
+                            o[k8].x = apply_act_fast(o[k8].x, p.post, p.post_scale);
+                            o[k8].y = apply_act_fast(o[k8].y, p.post, p.post_scale);
+                            o[k8].z = apply_act_fast(o[k8].z, p.post, p.post_scale);
+                            o[k8].w = apply_act_fast(o[k8].w, p.post, p.post_scale);
+                        }
+                        *reinterpret_cast<float4*>(p.Y + off[k8]) = o[k8];
+                    }
+                } else {
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        if (!ok[k8]) continue;
+                        const int t = tcol0 + c * 32 + ((te + k8 * 128) & 7) * 4;
+                        const float ov[4] = {o[k8].x, o[k8].y, o[k8].z, o[k8].w};
+                        for (int e = 0; e < 4 && t + e < p.T; ++e)
+                            p.Y[off[k8] + e] =
+                                apply_act_fast(ov[e] + (p.skip ? p.skip[off[k8] + e] : 0.f), p.post, p.post_scale);
+                    }
                 }
             }
         }
-        if (issuer) tma_wait_all();
     }
 
     tc_fence_before();
@@ -437,11 +611,9 @@ bool gemm_tc_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs
     return true;
 }
 
-cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
-                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
-                           cudaStream_t st) {
+static cudaError_t tc_common(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, CUtensorMap* map_hi,
+                             CUtensorMap* map_lo, CUtensorMap* map_x, int* num_sms_out) {
     using namespace tc;
-    if (B == 0 || T == 0) return cudaSuccess;
     static int num_sms = 0;
     static bool attr_set = false;
     if (!num_sms) {
@@ -450,26 +622,39 @@ cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, i
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    CUtensorMap map_hi, map_lo, map_x;
+    *num_sms_out = num_sms;
     {
         const cuuint64_t dims[2] = {(cuuint64_t)W.Kp32, (cuuint64_t)W.Mp128};
         const cuuint64_t strides[1] = {(cuuint64_t)W.Kp32 * 4};
         const cuuint32_t box[2] = {BK, BM};
-        if (!make_map(&map_hi, W.A_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
-            !make_map(&map_lo, W.A_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+        if (!make_map(map_hi, W.A_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !make_map(map_lo, W.A_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
             return cudaErrorInvalidValue;
     }
     {
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)x_rs * 4, (cuuint64_t)x_bs * 4};
         const cuuint32_t box[3] = {32, BK, 1};
-        if (!make_map(&map_x, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return cudaErrorInvalidValue;
+        if (!make_map(map_x, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return cudaErrorInvalidValue;
     }
-    CUtensorMap map_y;
+    return cudaSuccess;
+}
+
+cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
+                           cudaStream_t st) {
+    using namespace tc;
+    if (B == 0 || T == 0) return cudaSuccess;
+    CUtensorMap map_hi, map_lo, map_x, map_y;
+    int num_sms = 0;
+    cudaError_t e = tc_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
+    if (e != cudaSuccess) return e;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
@@ -478,19 +663,46 @@ cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, i
     }
     if (R && R != Y) {  // out-of-place residual: seed Y with R, then accumulate in place
         for (int b = 0; b < B; ++b) {
-            cudaError_t e = cudaMemcpy2DAsync(Y + (long long)b * y_bs, (size_t)y_rs * 4, R + (long long)b * y_bs,
-                                              (size_t)y_rs * 4, (size_t)T * 4, W.M, cudaMemcpyDeviceToDevice, st);
+            e = cudaMemcpy2DAsync(Y + (long long)b * y_bs, (size_t)y_rs * 4, R + (long long)b * y_bs, (size_t)y_rs * 4,
+                                  (size_t)T * 4, W.M, cudaMemcpyDeviceToDevice, st);
             if (e != cudaSuccess) return e;
         }
     }
     Params p{};
     p.M = W.M; p.K = W.K; p.T = T; p.B = B;
     p.num_m = (W.M + BM - 1) / BM;
-    p.tiles_t = (T + BN - 1) / BN;
+    p.t_step = BN; p.t_halo = 0;
+    p.tiles_t = (T + p.t_step - 1) / p.t_step;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
+    gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
+    return cudaGetLastError();
+}
+
+// Fused DWSBlock (streaming.py:189-192): y = post(dw5(W * pre(x)) + b_dw (+ skip)), with the causal
+// cache of the depthwise conv (the last 4 pointwise outputs) read from cache_in / written to cache_out.
+cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                              float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
+                              float* cache_out, const float* skip, int post, float post_scale, float* Y, long long y_bs,
+                              int y_rs, cudaStream_t st) {
+    using namespace tc;
+    if (B == 0 || T == 0) return cudaSuccess;
+    CUtensorMap map_hi, map_lo, map_x;
+    int num_sms = 0;
+    cudaError_t e = tc_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
+    if (e != cudaSuccess) return e;
+    Params p{};
+    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
+    p.num_m = (W.M + BM - 1) / BM;
+    p.t_step = BN - 4; p.t_halo = 4;
+    p.tiles_t = (T + p.t_step - 1) / p.t_step;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out; p.skip = skip;
+    p.Y = Y; p.y_bs = y_bs; p.y_rs = y_rs; p.post = post; p.post_scale = post_scale;
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    gemm_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, p);
     return cudaGetLastError();
 }
 

@@ -144,6 +144,12 @@ int32_t hil_op_dwconv_transpose(const float* x, const float* cache_in, float* ca
  * w_host is the reference-layout [M,K,1] HOST weight (packed and uploaded inside; test-only convenience). */
 int32_t hil_op_pointwise(const float* x, const float* w_host, const float* bias_dev, const float* residual, float* y,
                          int32_t B, int32_t M, int32_t K, int32_t T, int32_t pre, float pre_scale, void* stream);
+/* DWSBlock.forward streaming.py:189-192 (+ the ResBlock tail :268-274 when skip is given):
+ * y[B,C,T] = post( dw5( W_pw[C,C] * pre(x[B,C,T]) ; cache[B,C,4] ) + b_dw + skip ).  One fused tensor-core
+ * kernel for T >= 64, otherwise pointwise GEMM + depthwise kernel through tmp[B,C,T].  w_pw_host is HOST. */
+int32_t hil_op_dws(const float* x, const float* w_pw_host, const float* w_dw, const float* b_dw, const float* cache_in,
+                   float* cache_out, const float* skip, float* tmp, float* y, int32_t B, int32_t C, int32_t T, int32_t pre,
+                   float pre_scale, int32_t post, float post_scale, void* stream);
 /* CausalSTFT.forward causal_layers.py:135-144 + clamp/log streaming.py:351:
  * wav_window [B,1,(T-1)*hop+n_fft], w_host [2F,1,n_fft] HOST -> y [B,F,T] = log(max(|STFT|,1e-5)). */
 int32_t hil_op_stft_logmag(const float* wav_window, const float* w_host, float* y, int32_t B, int32_t n_fft, int32_t hop,
