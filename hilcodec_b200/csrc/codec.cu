@@ -146,12 +146,11 @@ static int32_t run_dwconv(const float* x, long long x_bs, int x_rs, const float*
 static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs, int B, int T, int pre, float pre_scale,
                        const float* dw_w, const float* dw_b, const float* ci, float* co, const float* skip, int post,
                        float post_scale, float* tmp, float* Y, cudaStream_t st) {
-    if (g_use_tc && g_fuse_dw && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
+    if (g_use_tc && g_fuse_dw && post == PRE_NONE && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
         const double n = (double)B * T;
         HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
                    4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
-                   launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, post, post_scale, Y, bs,
-                                     rs, st));
+                   launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st));
         return HIL_OK;
     }
     HIL_TRY(run_gemm_linear(W, X, bs, rs, B, T, pre, pre_scale, nullptr, nullptr, tmp, bs, rs, st));
@@ -751,20 +750,17 @@ int32_t ensure_workspace(hil_state* s, int B, int T, Buffers* out) {
 
 // ResBlock.forward streaming.py:252-275 with the folded residual scale:
 //   h <- h + dw5(pw1(ELU(dw5(pw0(ELU(h * pre))))))
-// The inner ELU is applied by the first depthwise kernel when it stores (its only consumer is
-// pw1), and when `out_post` is set the block's output is stored as ELU(h * out_scale): that is
-// the Scale -> ELU every stage ends with (streaming.py:506-507, :643 + :633 / :644), whose only
-// consumer is the next resampling layer.
+// Two fused DWS kernels; the second accumulates into h in place (TMA reduce-add).  Activations
+// are applied by the consumer (GEMM transform warps / resampling kernels).
 int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, int Ts, float pre_scale,
-                  const float* const* cin, float* const* cout, cudaStream_t st, int out_post = PRE_NONE,
-                  float out_scale = 1.f) {
+                  const float* const* cin, float* const* cout, cudaStream_t st) {
     const int Tp = pitch4(Ts);
     const long long bs = (long long)C * Tp;
     const int pre0 = pre_scale == 1.0f ? PRE_ELU : PRE_SCALE_ELU;
-    HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, PRE_ELU, 1.f,
-                    a1, a2, st));
-    HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, PRE_NONE, 1.f, u[1].dw_w, u[1].dw_b, cin[1], cout[1], h, out_post,
-                    out_scale, a1, h, st));
+    HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, PRE_NONE,
+                    1.f, a1, a2, st));
+    HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, PRE_ELU, 1.f, u[1].dw_w, u[1].dw_b, cin[1], cout[1], h, PRE_NONE, 1.f, a1,
+                    h, st));
     return HIL_OK;
 }
 
@@ -793,14 +789,12 @@ int32_t encode_impl(hil_model* m, const Buffers& w, const float* wav, int B, int
                                     Tp, st));
         for (int j = 0; j < c.n_residual_enc; ++j) {
             const float pre = (float)std::pow(1.0 + (j + 1) * rs2, -0.5);  // streaming.py:210 with idx=j+1
-            const bool last = j == c.n_residual_enc - 1;
-            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, pre, cin + ci, cout + ci, st,
-                              last ? PRE_SCALE_ELU : PRE_NONE, m->enc_post_scale));
+            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, pre, cin + ci, cout + ci, st));
             ci += 2;
         }
-        // Scale -> ELU (done by the last ResBlock's store) -> 1x1 (C -> 2C) -> strided depthwise (streaming.py:506-510)
-        HIL_TRY(run_gemm_linear(sg.down_pw, h, bs, Tp, B, Ts, c.n_residual_enc > 0 ? PRE_NONE : PRE_SCALE_ELU,
-                                m->enc_post_scale, nullptr, nullptr, a1, 2 * bs, Tp, st));
+        // Scale -> ELU -> 1x1 (C -> 2C) -> strided depthwise (streaming.py:506-510)
+        HIL_TRY(run_gemm_linear(sg.down_pw, h, bs, Tp, B, Ts, PRE_SCALE_ELU, m->enc_post_scale, nullptr, nullptr, a1,
+                                2 * bs, Tp, st));
         const int Ts2 = Ts / sg.ratio, Tp2 = pitch4(Ts2);
         HIL_TRY(run_dwconv(a1, 2 * bs, Tp, cin[ci], cout[ci], sg.down_w, sg.down_b, nullptr, h,
                                (long long)2 * C * Tp2, Tp2, B, 2 * C, Ts, 2 * sg.ratio, sg.ratio, PRE_NONE, 1.f, st));
@@ -839,16 +833,15 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
                            Ts, 5, 1, PRE_NONE, 1.f, st, PRE_ELU, 1.f));
         ci += 1;
     }
-    const bool act_at_store = c.n_residual_dec > 0;  // stage outputs are stored as ELU(h * scale)
+
     for (size_t i = 0; i < m->dec.size(); ++i) {
         DecStage& sg = m->dec[i];
         const int Tp = pitch4(Ts);
         const int Ts2 = Ts * sg.ratio, Tp2 = pitch4(Ts2);
-        // (previous stage's Scale -> ELU, already applied by the producer's store) -> transposed
-        // depthwise -> 1x1 (C -> C/2) (streaming.py:633-637)
+        // (previous stage's Scale) -> ELU -> transposed depthwise -> 1x1 (C -> C/2) (streaming.py:633-637);
+        // stage 0's ELU was applied by conv_pre_depthwise's store
         HIL_TRY(run_dwconv_transpose(h, (long long)C * Tp, Tp, cin[ci], cout[ci], sg.up_w, a1, (long long)C * Tp2, Tp2,
-                                     B, C, Ts, sg.ratio, (i == 0 || act_at_store) ? PRE_NONE : PRE_SCALE_ELU,
-                                     m->dec_post_scale, st));
+                                     B, C, Ts, sg.ratio, i == 0 ? PRE_NONE : PRE_SCALE_ELU, m->dec_post_scale, st));
         ci += 1;
         HIL_TRY(run_gemm_linear(sg.up_pw, a1, (long long)C * Tp2, Tp2, B, Ts2, PRE_NONE, 1.f, sg.up_b, nullptr, h,
                                     (long long)(C / 2) * Tp2, Tp2, st));
@@ -856,16 +849,14 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
         Ts = Ts2;
         for (int j = 0; j < c.n_residual_dec; ++j) {
             // deploy-path quirk: pre_scale is 1.0 for every decoder ResBlock (streaming.py:576-583)
-            const bool last = j == c.n_residual_dec - 1;
-            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, 1.0f, cin + ci, cout + ci, st,
-                              last ? PRE_SCALE_ELU : PRE_NONE, m->dec_post_scale));
+            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, 1.0f, cin + ci, cout + ci, st));
             ci += 2;
         }
     }
     {
         const int Tp = pitch4(Ts);
         HIL_TRY(run_conv_post_tanh(h, (long long)C * Tp, Tp, cin[ci], cout[ci], m->dec_post_w, m->dec_post_b, wav, B, C,
-                                   Ts, c.kernel_size, act_at_store ? PRE_NONE : PRE_SCALE_ELU, m->dec_post_scale, st));
+                                   Ts, c.kernel_size, PRE_SCALE_ELU, m->dec_post_scale, st));
     }
     return HIL_OK;
 }

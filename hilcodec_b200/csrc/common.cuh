@@ -73,11 +73,10 @@ cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, i
                            float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                            cudaStream_t st);
 
-// fused DWSBlock: y = post(dw5(W * pre(x)) + b_dw (+ skip)); same usability conditions as launch_gemm_tc
+// fused DWSBlock: y = dw5(W * pre(x)) + b_dw (+ skip); same usability conditions as launch_gemm_tc
 cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
-                              float* cache_out, const float* skip, int post, float post_scale, float* Y, long long y_bs,
-                              int y_rs, cudaStream_t st);
+                              float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
 // ---- conv.cu ---------------------------------------------------------------------
 // wav_ext[b][0:P+T] = cat(cache_in[b][0:P], x[b][0:T]); cache_out = last P of it.

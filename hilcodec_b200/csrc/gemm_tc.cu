@@ -52,17 +52,11 @@ struct Params {
     int reduce_add;  // 1: Y += tile (TMA reduce), 0: Y = tile
     // time tiling: tile tt covers columns [tt * t_step - t_halo, ... + BN)
     int t_step, t_halo;
-    // fused DWS epilogue (kDw): y = post(bias_dw + dw5(pw) (+ skip)), causal with cache
+    // fused DWS epilogue (kDw): y (+)= bias_dw + dw5(pw), causal with cache; (+)= when reduce_add
     const float* dw_w;       // [M][5]
     const float* dw_b;       // [M] or null
     const float* cache_in;   // [B][M][4]
     float* cache_out;        // [B][M][4]
-    const float* skip;       // same layout as Y, or null (may alias Y)
-    float* Y;
-    long long y_bs;
-    int y_rs;
-    int post;
-    float post_scale;
 };
 
 // ------------------------------------------------------------------------------- PTX helpers
@@ -184,7 +178,8 @@ __device__ __forceinline__ float tf32_rna(float x) {
 template <bool kDw>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const Params p) {
+               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+               const __grid_constant__ CUtensorMap map_y28, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t out_base = base + STAGES * STAGE_BYTES;
@@ -198,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     auto sfull_bar = [&](int a) { return bars + 8u * (3 * STAGES + 4 + a); };    // staging buffer filled (kDw)
     auto sempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + 6 + a); };   // staging buffer drained (kDw)
     const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 8);
-    constexpr int kNumXform = kDw ? 128 : NUM_XFORM;  // kDw: warps 8-11 transform, warps 12-15 write out
+    constexpr int kNumXform = NUM_XFORM;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -409,13 +404,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             if (issuer) tma_wait_all();
 
         } else {
-            // ---- fused DWS epilogue, part 1 (warps 4-7): pointwise tile -> causal depthwise k5 + bias.
+            // ---- fused DWS epilogue: pointwise tile -> causal depthwise k5 + bias -> TMA store / reduce-add.
             // The tile holds 128 pointwise columns for times [t0-4, t0+124); each thread owns one
             // channel row and slides the 5-tap window along it in registers (the 4 halo columns come
-            // from this tile, or from cache_in at the start of the chunk).  Results go to a swizzled
-            // smem staging buffer that the write-out warps (12-15) drain.
+            // from this tile, or from cache_in at the start of the chunk).  Chunk 0 yields 28 outputs
+            // (dense 112-byte rows, box-28 tensor map), chunks 1-3 yield 32 (128B-swizzled rows).
+            // With a residual skip the output is accumulated in place (h += ...) by TMA reduce-add.
             const int q = warp - 4;
             const int row = q * 32 + lane;
+            const bool issuer = (q == 0 && lane == 0);
             const uint32_t sw = (uint32_t)(row & 7);
             long long it = 0;
             uint32_t g = 0;
@@ -469,8 +466,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 p.cache_out[((size_t)b * p.M + m) * 4 + (t - (p.T - 4))] = v[4 + j];
                         }
                     }
-                    mbar_wait<20>(sempty_bar(g & 1), ((g >> 1) & 1) ^ 1);   // write-out warps drained this buffer
-                    const uint32_t orow = obuf + row * 128;
+                    if (issuer) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
+                    epi_bar_sync();
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float o[4];
@@ -482,84 +479,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[i + k], a);
                             o[e] = a + bv;
                         }
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j4 ^ sw) << 4)),
-                                     "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3])
+                        uint32_t dst;
+                        if (c == 0) {
+                            if (j4 == 0) continue;   // outputs 0..3 of chunk 0 belong to the previous tile
+                            dst = obuf + row * 112 + (j4 - 1) * 16;
+                        } else {
+                            dst = obuf + row * 128 + (((uint32_t)j4 ^ sw) << 4);
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                                     "f"(o[3])
                                      : "memory");
                     }
                     carry[0] = v[32]; carry[1] = v[33]; carry[2] = v[34]; carry[3] = v[35];
-                    mbar_arrive(sfull_bar(g & 1));
-                }
-            }
-        }
-    } else if (kDw && warp >= 12) {
-        // ===================================================================== fused DWS epilogue, part 2: write-out
-        // Coalesced 16-byte stores of the staged depthwise outputs; the residual skip is read
-        // coalesced here and the stage-end activation applied.  Output i of chunk c is time
-        // tcol0 + 32c + i (i = 0..3 of chunk 0 belong to the previous tile).
-        const int te = threadIdx.x - 384;  // 0..127
-        uint32_t g = 0;
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int m_blk = (int)(tile % p.num_m);
-            const long long rest = tile / p.num_m;
-            const int tt = (int)(rest % p.tiles_t);
-            const int b = (int)(rest / p.tiles_t);
-            const int tcol0 = tt * p.t_step - p.t_halo;
-            const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
-#pragma unroll 1
-            for (int c = 0; c < n_chunks; ++c, ++g) {
-                const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
-                mbar_wait<20>(sfull_bar(g & 1), (g >> 1) & 1);
-                float4 o[8];
-                long long off[8];
-                bool ok[8];
-#pragma unroll
-                for (int k8 = 0; k8 < 8; ++k8) {
-                    const int idx = te + k8 * 128;
-                    const int r = idx >> 3, f4 = idx & 7;
-                    const int mr = m_blk * BM + r;
-                    const int t = tcol0 + c * 32 + f4 * 4;
-                    ok[k8] = !((c == 0 && f4 * 4 < p.t_halo) || mr >= p.M || t >= p.T);
-                    off[k8] = (long long)b * p.y_bs + (long long)mr * p.y_rs + t;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(o[k8].x), "=f"(o[k8].y), "=f"(o[k8].z), "=f"(o[k8].w)
-                                 : "r"(obuf + r * 128 + (((uint32_t)f4 ^ (uint32_t)(r & 7)) << 4)));
-                }
-                mbar_arrive(sempty_bar(g & 1));  // staging values are in registers now
-                const bool full = (tcol0 + c * 32 + 32 <= p.T);  // every float4 of the chunk is entirely inside T
-                if (full) {
-                    if (p.skip) {
-                        float4 sk[8];
-#pragma unroll
-                        for (int k8 = 0; k8 < 8; ++k8)
-                            sk[k8] = ok[k8] ? *reinterpret_cast<const float4*>(p.skip + off[k8]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int k8 = 0; k8 < 8; ++k8) {
-                            o[k8].x += sk[k8].x; o[k8].y += sk[k8].y; o[k8].z += sk[k8].z; o[k8].w += sk[k8].w;
-                        }
-                    }
-#pragma unroll
-                    for (int k8 = 0; k8 < 8; ++k8) {
-                        if (!ok[k8]) continue;
-                        if (p.post != PRE_NONE) {
-                            o[k8].x = apply_act_fast(o[k8].x, p.post, p.post_scale);
-                            o[k8].y = apply_act_fast(o[k8].y, p.post, p.post_scale);
-                            o[k8].z = apply_act_fast(o[k8].z, p.post, p.post_scale);
-                            o[k8].w = apply_act_fast(o[k8].w, p.post, p.post_scale);
-                        }
-                        *reinterpret_cast<float4*>(p.Y + off[k8]) = o[k8];
-                    }
-                } else {
-#pragma unroll
-                    for (int k8 = 0; k8 < 8; ++k8) {
-                        if (!ok[k8]) continue;
-                        const int t = tcol0 + c * 32 + ((te + k8 * 128) & 7) * 4;
-                        const float ov[4] = {o[k8].x, o[k8].y, o[k8].z, o[k8].w};
-                        for (int e = 0; e < 4 && t + e < p.T; ++e)
-                            p.Y[off[k8] + e] =
-                                apply_act_fast(ov[e] + (p.skip ? p.skip[off[k8] + e] : 0.f), p.post, p.post_scale);
+                    fence_proxy_async();
+                    epi_bar_sync();
+                    if (issuer) {
+                        const CUtensorMap* mp = c == 0 ? &map_y28 : &map_y;
+                        const int tc = c == 0 ? tcol0 + p.t_halo : tcol0 + c * 32;
+                        if (p.reduce_add) tma_reduce_add_3d(mp, obuf, tc, m_blk * BM, b);
+                        else tma_store_3d(mp, obuf, tc, m_blk * BM, b);
+                        tma_commit();
                     }
                 }
             }
+            if (issuer) tma_wait_all();
         }
     }
 
@@ -676,7 +619,7 @@ cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, i
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
+    gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     return cudaGetLastError();
 }
 
@@ -684,14 +627,29 @@ cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, i
 // cache of the depthwise conv (the last 4 pointwise outputs) read from cache_in / written to cache_out.
 cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
-                              float* cache_out, const float* skip, int post, float post_scale, float* Y, long long y_bs,
-                              int y_rs, cudaStream_t st) {
+                              float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st) {
     using namespace tc;
     if (B == 0 || T == 0) return cudaSuccess;
-    CUtensorMap map_hi, map_lo, map_x;
+    CUtensorMap map_hi, map_lo, map_x, map_y, map_y28;
     int num_sms = 0;
     cudaError_t e = tc_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
     if (e != cudaSuccess) return e;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {32, BM, 1};
+        const cuuint32_t box28[3] = {28, BM, 1};
+        if (!make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !make_map(&map_y28, Y, 3, dims, strides, box28, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return cudaErrorInvalidValue;
+    }
+    if (skip && skip != Y) {  // out-of-place residual: seed Y with the skip, then accumulate in place
+        for (int b = 0; b < B; ++b) {
+            e = cudaMemcpy2DAsync(Y + (long long)b * y_bs, (size_t)y_rs * 4, skip + (long long)b * y_bs, (size_t)y_rs * 4,
+                                  (size_t)T * 4, W.M, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
     Params p{};
     p.M = W.M; p.K = W.K; p.T = T; p.B = B;
     p.num_m = (W.M + BM - 1) / BM;
@@ -699,10 +657,10 @@ cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs
     p.tiles_t = (T + p.t_step - 1) / p.t_step;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f;
-    p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out; p.skip = skip;
-    p.Y = Y; p.y_bs = y_bs; p.y_rs = y_rs; p.post = post; p.post_scale = post_scale;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out;
+    p.reduce_add = skip ? 1 : 0;
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, p);
+    gemm_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
     return cudaGetLastError();
 }
 
