@@ -275,10 +275,8 @@ def main_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_checksum = float(y_host.abs().sum())  # the device->host result is really read on the host
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    from hilcodec_b200 import sharding
+    ms, ms_e2e = sharding.reduce_max([ms, ms_e2e], device=dev)  # a multi-GPU step is as slow as its slowest rank
 
     # ---- per-category kernel timing (separate pass, CUDA events around every launch)
     n_cat = len(CATEGORIES)

@@ -152,3 +152,37 @@ def test_stft_logmag(B, n_fft, hop, T):
     ref_err = (y_ref.double() - y64).abs()
     assert err.max().item() <= max(8 * ref_err.max().item(), 1e-4), (err.max().item(), ref_err.max().item())
     assert torch.median(err).item() < 1e-6
+
+
+@pytest.mark.parametrize("B,Cc,T,skip,pre", [
+    (2, 96, 2400, True, 1),     # fused tensor-core kernel, in-place residual (TMA reduce-add)
+    (3, 64, 1000, False, 2),    # ragged last tile, pre-scale + ELU prologue
+    (1, 192, 248, False, 0),    # exactly two 124-column tiles
+    (2, 384, 130, True, 1),     # multi row-tile, second tile nearly empty
+    (2, 128, 75, False, 1),     # T not a multiple of 4 -> unfused FFMA + depthwise fallback
+    (4, 96, 8, True, 1),        # short chunk (streaming) fallback
+])
+def test_dws_block(B, Cc, T, skip, pre):
+    """DWSBlock (ELU -> 1x1 -> depthwise k5 + bias) plus the ResBlock's residual add."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(Cc + T)
+    x = torch.randn(B, Cc, T, generator=g)
+    w = (torch.randn(Cc, Cc, 1, generator=g) / Cc ** 0.5).contiguous()
+    wd = torch.randn(Cc, 1, 5, generator=g) / 5 ** 0.5
+    bd = torch.randn(Cc, generator=g)
+    cache = torch.randn(B, Cc, 4, generator=g)
+    sk = torch.randn(B, Cc, T, generator=g) if skip else None
+    pw = F.conv1d(_pre_ref(x, pre, 0.8660254).double(), w.double())
+    xin = torch.cat((cache.double(), pw), 2)
+    ref = F.conv1d(xin, wd.double(), bd.double(), groups=Cc)
+    if skip:
+        ref = ref + sk.double()
+    xd, wdd, bdd, cd = x.cuda(), wd.cuda(), bd.cuda(), cache.cuda()
+    y = sk.cuda() if skip else torch.empty(B, Cc, T, device="cuda")   # residual accumulates in place, like h
+    tmp = torch.empty(B, Cc, T, device="cuda")
+    co = torch.empty(B, Cc, 4, device="cuda")
+    _lib.check(lib.hil_op_dws(_ptr(xd), _ptr(w), _ptr(wdd), _ptr(bdd), _ptr(cd), _ptr(co), _ptr(y if skip else None),
+                              _ptr(tmp), _ptr(y), B, Cc, T, pre, 0.8660254, 0, 1.0, _stream()))
+    torch.cuda.synchronize()
+    assert (y.cpu().double() - ref).abs().max().item() < 2e-5
+    assert (co.cpu().double() - xin[:, :, -4:]).abs().max().item() < 1e-5
