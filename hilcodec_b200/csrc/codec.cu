@@ -118,8 +118,10 @@ static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
 static int32_t run_gemm_stft_logmag(const PackedMat& Wd, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
                                     long long y_bs, int y_rs, cudaStream_t st) {
     const double n = (double)B * T;
+    const bool tcore = g_use_tc && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs);
     HIL_LAUNCH(CAT_GEMM_STFT, 2.0 * Wd.M * Wd.K * n, 4.0 * (n * hop + n * (Wd.M / 2)) + 4.0 * Wd.M * Wd.K, st,
-               launch_gemm_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st));
+               tcore ? launch_stft_tc(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
+                     : launch_gemm_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st));
     return HIL_OK;
 }
 static int32_t run_wavcat(const float* x, const float* ci, float* co, float* wav_ext, long long w_bs, int B, int T, int P,
@@ -356,7 +358,7 @@ struct Builder {
         }
         dst->M = M; dst->K = K; dst->Mp = Mp; dst->Kp = Kp; dst->TM = TM;
         PendingMat pm{dst, off};
-        if (!interleave) {  // tensor-core form for the pointwise convs
+        {  // tensor-core form (row-major hi/lo split; DFT rows interleaved like the FFMA pack)
             const int Mp128 = round_up(M, 128), Kp32 = round_up(K, 32);
             pm.off_hi = arena.alloc((size_t)Mp128 * Kp32);
             pm.off_lo = arena.alloc((size_t)Mp128 * Kp32);
@@ -365,7 +367,8 @@ struct Builder {
             float* lo = arena.buf.data() + pm.off_lo;
             for (int mrow = 0; mrow < M; ++mrow)
                 for (int k = 0; k < K; ++k) {
-                    const float v = w[(size_t)mrow * K + k];
+                    const int src = interleave ? ((mrow & 1) ? F + mrow / 2 : mrow / 2) : mrow;
+                    const float v = w[(size_t)src * K + k];
                     const float h = tf32_rna_host(v);
                     hi[(size_t)mrow * Kp32 + k] = h;
                     lo[(size_t)mrow * Kp32 + k] = tf32_rna_host(v - h);
@@ -1089,10 +1092,10 @@ int32_t hil_op_stft_logmag(const float* wav_window, const float* w_host, float* 
     float* dev = nullptr;
     HIL_TRY(upload_packed(w_host, 2 * F, n_fft, 6, true, &pm, &dev));
     const long long L = (long long)(T - 1) * hop + n_fft;
-    cudaError_t e = launch_gemm_stft_logmag(pm, wav_window, L, hop, B, T, y, (long long)F * T, T, (cudaStream_t)stream);
+    int32_t rc = run_gemm_stft_logmag(pm, wav_window, L, hop, B, T, y, (long long)F * T, T, (cudaStream_t)stream);
     cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(dev);
-    HIL_CUDA(e);
+    HIL_TRY(rc);
     HIL_CUDA(e2);
     return HIL_OK;
 }

@@ -78,6 +78,12 @@ cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs
                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
                               float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
+// ---- stft_tc.cu: launch_gemm_stft_logmag on the tensor pipe
+bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
+                    int y_rs);
+cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
+                           long long y_bs, int y_rs, cudaStream_t st);
+
 // ---- conv.cu ---------------------------------------------------------------------
 // wav_ext[b][0:P+T] = cat(cache_in[b][0:P], x[b][0:T]); cache_out = last P of it.
 cudaError_t launch_wavcat(const float* x, const float* cache_in, float* cache_out, float* wav_ext, long long w_bs,

@@ -1,0 +1,344 @@
+// CausalSTFT + magnitude + clamp + log on the tensor pipe (tcgen05, 3xTF32).
+//
+//   S[2F][t] = sum_k Wdft[2F][k] * wav[t*hop + k],  y[f][t] = log(max(sqrt(re_f^2 + im_f^2), 1e-5))
+//
+// Replaces CausalSTFT.forward (causal_layers.py:135-144: the DFT as a strided Conv1d) and the
+// clamp/log of SpecBlock.forward (streaming.py:351).  Same pipeline as gemm_tc.cu (TMA ->
+// transform warps -> tcgen05.mma into two TMEM accumulators -> epilogue warps -> TMA store);
+// what differs:
+//   * A = DFT basis with rows interleaved (cos_f, sin_f), so re/im of one bin sit in adjacent
+//     TMEM lanes and the magnitude is one warp shuffle in the epilogue;
+//   * B = the im2col view of the waveform, K-major: row t of the tile is the n_fft-sample
+//     window starting at t*hop.  For hop % 4 == 0 that is a plain (overlapping-row) tensor map
+//     and TMA loads it; for hop 1 / 2 (row stride not a multiple of 16 bytes) the transform
+//     warps gather the windows through L1 and write the swizzled tile themselves;
+//   * the epilogue stores F rows per 128 accumulator rows (box 32 x 64).
+#include "tc_ptx.cuh"
+
+namespace hil {
+namespace stft {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+constexpr int OUT_BYTES = 64 * 32 * 4;           // 64 bins x 32 columns
+constexpr int NUM_THREADS = 512;
+constexpr int NUM_XFORM = 256;
+constexpr int NUM_EPI = 128;
+constexpr int TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256;
+constexpr uint32_t IDESC = make_idesc(BM, BN, 0);  // A and B both K-major
+
+struct Params {
+    int M, F, K, T, B, hop;
+    int num_m, tiles_t;
+    long long total_tiles;
+    int gather;          // 1: transform warps build B from global memory (hop % 4 != 0)
+    const float* wav;    // window base (first sample of the window of frame 0)
+    long long w_bs;      // batch stride of wav
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t out_base = base + STAGES * STAGE_BYTES;
+    const uint32_t bars = out_base + 2 * OUT_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xform_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi);
+        prefetch_tmap(&map_a_lo);
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_y);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xform_bar(s), NUM_XFORM);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), NUM_EPI);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        const uint32_t ncols = TMEM_COLS;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int m_blk = (int)(tile % p.num_m);
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait<32>(empty_bar(s), ph ^ 1);
+                    const uint32_t st = base + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(s), p.gather ? 2 * TILE_BYTES : 3 * TILE_BYTES);
+                    tma_load_2d(&map_a_hi, st, full_bar(s), kb * BK, m_blk * BM);
+                    tma_load_2d(&map_a_lo, st + TILE_BYTES, full_bar(s), kb * BK, m_blk * BM);
+                    if (!p.gather) tma_load_3d(&map_x, st + 2 * TILE_BYTES, full_bar(s), kb * BK, tt * BN, b);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = (int)(it & 1);
+            const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_big = tmem_base + acc * 2 * BN;
+            const uint32_t d_small = d_big + BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t st = base + s * STAGE_BYTES;
+                mbar_wait(full_bar(s), ph);
+                if (p.gather) mbar_wait(xform_bar(s), ph);   // B_hi is written by the transform warps too
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < BK / 8; ++j) {
+                        const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
+                        const uint64_t a_lo = make_desc(st + TILE_BYTES + j * 32, 16, 1024, 2);
+                        const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES + j * 32, 16, 1024, 2);
+                        umma_tf32(d_big, a_hi, b_hi, IDESC, (kb | j) != 0);
+                        umma_tf32(d_small, a_lo, b_hi, IDESC, (kb | j) != 0);
+                    }
+                }
+                __syncwarp();
+                if (!p.gather) {
+                    mbar_wait(xform_bar(s), ph);
+                    tc_fence_after();
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < BK / 8; ++j) {
+                        const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
+                        const uint64_t b_lo = make_desc(st + 3 * TILE_BYTES + j * 32, 16, 1024, 2);
+                        umma_tf32(d_small, a_hi, b_lo, IDESC, 1);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (kb == nkb - 1) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================================================================== transform: B_lo (and B_hi when gathering)
+        const int xt = threadIdx.x - 256;
+        int s = 0;
+        uint32_t ph = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const long long rest = tile / p.num_m;
+            const int tt = (int)(rest % p.tiles_t);
+            const int b = (int)(rest / p.tiles_t);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(s), ph);   // also: the slot is free (the producer waited for its MMAs)
+                float4* bh = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 2 * TILE_BYTES);
+                float4* bl = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 3 * TILE_BYTES);
+                if (p.gather) {
+#pragma unroll
+                    for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
+                        const int item = xt + i * NUM_XFORM;
+                        const int t = item >> 3, k4 = item & 7;
+                        const int tg = tt * BN + t;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tg < p.T) {
+                            const float* src = p.wav + (long long)b * p.w_bs + (long long)tg * p.hop + kb * BK + k4 * 4;
+                            v.x = __ldg(src); v.y = __ldg(src + 1); v.z = __ldg(src + 2); v.w = __ldg(src + 3);
+                        }
+                        float4 l;
+                        l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
+                        l.z = tf32_rna(v.z - tf32_trunc(v.z)); l.w = tf32_rna(v.w - tf32_trunc(v.w));
+                        const int dst = t * 8 + (k4 ^ (t & 7));   // float4 index inside the 128B-swizzled K-major tile
+                        bh[dst] = v;
+                        bl[dst] = l;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
+                        const int idx = xt + i * NUM_XFORM;
+                        const float4 v = bh[idx];
+                        float4 l;
+                        l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
+                        l.z = tf32_rna(v.z - tf32_trunc(v.z)); l.w = tf32_rna(v.w - tf32_trunc(v.w));
+                        bl[idx] = l;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(xform_bar(s));
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================================================================== epilogue: |.|, clamp, log, TMA store
+        const int q = warp - 4;
+        const int row = q * 32 + lane;            // accumulator row: 2f (re) / 2f+1 (im)
+        const int frow = row >> 1;                // bin inside the tile's 64
+        const bool issuer = (q == 0 && lane == 0);
+        const bool even = (lane & 1) == 0;
+        const uint32_t sw = (uint32_t)(frow & 7);
+        long long it = 0;
+        uint32_t g = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = (int)(tile % p.num_m);
+            const long long rest = tile / p.num_m;
+            const int tt = (int)(rest % p.tiles_t);
+            const int b = (int)(rest / p.tiles_t);
+            const int acc = (int)(it & 1);
+            const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait<64>(tfull_bar(acc), acc_ph);
+            tc_fence_after();
+            const int t0 = tt * BN;
+            const int n_chunks = min(BN / 32, (p.T - t0 + 31) / 32);
+            const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                if (issuer) tma_wait_read<1>();
+                epi_bar_sync();
+                uint32_t rb[32], rs[32];
+                tmem_ld32(t_big + c * 32, rb);
+                tmem_ld32(t_big + BN + c * 32, rs);
+                tmem_ld_wait();
+                if (c == n_chunks - 1) {
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(acc));
+                }
+                // Lanes 2p / 2p+1 hold re / im of one bin for all 32 columns.  The pair splits the
+                // columns (even lane: 0..15, odd lane: 16..31), swaps what the partner needs with one
+                // shuffle per column, and each lane evaluates 16 log-magnitudes:
+                //   log(max(sqrt(re^2 + im^2), 1e-5)) = 0.5 * log(max(re^2 + im^2, 1e-10))
+                // (no sqrt; ncu showed the sqrt + log of all 128 x 128 accumulators on 4 warps was the
+                // bottleneck of the whole kernel).
+                float mine[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mine[j] = __uint_as_float(rb[j]) + __uint_as_float(rs[j]);
+                const uint32_t orow = obuf + frow * 128;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = j4 * 4 + e;
+                        const float send = even ? mine[16 + i] : mine[i];
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                        const float a = even ? mine[i] : mine[16 + i];   // own component of the column this lane evaluates
+                        const float ss = __fadd_rn(__fmul_rn(a, a), __fmul_rn(recv, recv));
+                        o[e] = 0.5f * logf(fmaxf(ss, 1e-10f));
+                    }
+                    const uint32_t chunk = (uint32_t)(even ? j4 : 4 + j4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + ((chunk ^ sw) << 4)), "f"(o[0]),
+                                 "f"(o[1]), "f"(o[2]), "f"(o[3])
+                                 : "memory");
+                }
+                fence_proxy_async();
+                epi_bar_sync();
+                if (issuer) {
+                    tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * 64, b);
+                    tma_commit();
+                }
+            }
+        }
+        if (issuer) tma_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        const uint32_t ncols = TMEM_COLS;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols));
+    }
+}
+
+}  // namespace stft
+
+bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
+                    int y_rs) {
+    if (!Wdft.A_hi || !Wdft.A_lo) return false;
+    if (T < 64 || (Wdft.K % 32) != 0) return false;
+    if ((w_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(wav) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
+    return true;
+}
+
+cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
+                           long long y_bs, int y_rs, cudaStream_t st) {
+    using namespace stft;
+    if (B == 0 || T == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int F = Wdft.M / 2;
+    CUtensorMap map_hi, map_lo, map_x, map_y;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)Wdft.Kp32, (cuuint64_t)Wdft.Mp128};
+        const cuuint64_t strides[1] = {(cuuint64_t)Wdft.Kp32 * 4};
+        const cuuint32_t box[2] = {BK, BM};
+        if (!make_map(&map_hi, Wdft.A_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !make_map(&map_lo, Wdft.A_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return cudaErrorInvalidValue;
+    }
+    int gather = (hop % 4) != 0;
+    if (!gather) {
+        // im2col as a tensor map with overlapping rows: row t = wav[t*hop .. t*hop + n_fft)
+        const cuuint64_t dims[3] = {(cuuint64_t)Wdft.K, (cuuint64_t)T, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)hop * 4, (cuuint64_t)w_bs * 4};
+        const cuuint32_t box[3] = {BK, BN, 1};
+        if (!make_map(&map_x, wav, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) gather = 1;
+    }
+    if (gather) map_x = map_hi;  // unused placeholder
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {32, 64, 1};
+        if (!make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidValue;
+    }
+    Params p{};
+    p.M = Wdft.M; p.F = F; p.K = Wdft.K; p.T = T; p.B = B; p.hop = hop;
+    p.num_m = (Wdft.M + BM - 1) / BM;
+    p.tiles_t = (T + BN - 1) / BN;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.gather = gather; p.wav = wav; p.w_bs = w_bs;
+    const int num_sms = device_sm_count();
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    stft_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
+    return cudaGetLastError();
+}
+
+}  // namespace hil

@@ -127,7 +127,10 @@ def test_pointwise(B, M, K, T, pre, bias, res):
 
 
 @pytest.mark.parametrize("B,n_fft,hop,T", [(2, 64, 1, 640), (2, 128, 2, 320), (1, 256, 8, 75),
-                                            (2, 512, 40, 15), (2, 1024, 320, 3), (1, 1024, 320, 1)])
+                                            (2, 512, 40, 15), (2, 1024, 320, 3), (1, 1024, 320, 1),
+                                            # tensor-core kernel (T >= 64, 16-byte aligned rows)
+                                            (2, 64, 1, 1000), (2, 128, 2, 500), (2, 256, 8, 300),
+                                            (2, 512, 40, 132), (3, 1024, 320, 76), (1, 1024, 320, 64)])
 def test_stft_logmag(B, n_fft, hop, T):
     from hilcodec_b200.weights import dft_basis
     lib = _lib.load()
@@ -150,8 +153,10 @@ def test_stft_logmag(B, n_fft, hop, T):
     # magnitude is well conditioned, and bound everything by the CPU fp32 error itself
     err = (y.cpu().double() - y64).abs()
     ref_err = (y_ref.double() - y64).abs()
-    assert err.max().item() <= max(8 * ref_err.max().item(), 1e-4), (err.max().item(), ref_err.max().item())
-    assert torch.median(err).item() < 1e-6
+    # (the tensor-core kernel's 3xTF32 DFT is ~2-3x the fp32 rounding error; the worst element sits where
+    # the magnitude nearly cancels and the log amplifies it)
+    assert err.max().item() <= max(16 * ref_err.max().item(), 1e-4), (err.max().item(), ref_err.max().item())
+    assert torch.median(err).item() < 5e-6  # 3xTF32 on the tensor-core path: ~2e-6 on the log-magnitude
 
 
 @pytest.mark.parametrize("B,Cc,T,skip,pre", [
