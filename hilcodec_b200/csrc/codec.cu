@@ -89,16 +89,22 @@ struct LaunchScope {
 
 static bool g_use_tc = std::getenv("HILCODEC_DISABLE_TC") == nullptr;  // tensor-core GEMM on unless disabled
 static bool g_fuse_dw = std::getenv("HILCODEC_DISABLE_DWS_FUSION") == nullptr;
+// time-major kernel (gemm_tm.cu) for Cout <= 192: experimental, off by default -- correct (same bits as
+// gemm_tc.cu) but its register->global epilogue exposes the residual-load latency and it measured slower
+// (493 us vs 187 us on the stage-0 SpecBlock 1x1 at B = 64); enable with HILCODEC_ENABLE_TM=1 or mode bit 3.
+static bool g_use_tm = std::getenv("HILCODEC_ENABLE_TM") != nullptr;
 
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                                cudaStream_t st) {
     const double n = (double)B * T;
+    const bool tmajor = g_use_tc && g_use_tm && gemm_tm_usable(W, X, x_bs, x_rs, T, Y, y_bs, y_rs);
     const bool tcore = g_use_tc && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
     HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
-               tcore ? launch_gemm_tc(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
-                     : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
+               tmajor  ? launch_gemm_tm(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
+               : tcore ? launch_gemm_tc(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
+                       : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
     return HIL_OK;
 }
 // DWSBlock (ELU/none -> 1x1 -> depthwise k5 + bias [+ skip] [+ activation]): one fused tensor-core kernel
@@ -993,9 +999,11 @@ int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host
 // ----------------------------------------------------------------------------- launch accounting API
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 
-int32_t hil_set_tensor_cores(int32_t on) {
-    const int32_t prev = g_use_tc ? 1 : 0;
-    g_use_tc = on != 0;
+int32_t hil_set_tensor_cores(int32_t mode) {
+    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4);
+    g_use_tc = (mode & 1) != 0;
+    g_use_tm = (mode & 8) != 0;
+    g_fuse_dw = (mode & 4) == 0;
     return prev;
 }
 

@@ -78,6 +78,13 @@ cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs
                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
                               float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
+// ---- gemm_tm.cu: time-major tensor-core kernel (activations via TMEM) for Cout <= 192
+bool gemm_tm_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* Y, long long y_bs,
+                    int y_rs);
+cudaError_t launch_gemm_tm(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
+                           cudaStream_t st);
+
 // ---- stft_tc.cu: launch_gemm_stft_logmag on the tensor pipe
 bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
                     int y_rs);

@@ -122,9 +122,11 @@ uint64_t hil_launch_count(void);
  * depthwise, 4 conv_pre, 5 conv_post+tanh, 6 RVQ, 7 misc (wav concat, l2norm).
  * end() synchronises the device and fills summed ms / algorithmic FLOPs / algorithmic bytes /
  * launch counts per category (arrays of HIL_PROFILE_CATEGORIES). */
-/* 1 (default): pointwise GEMMs run on the tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy);
- * 0: FP32 FFMA kernels everywhere.  Returns the previous setting.  For A/B measurement. */
-int32_t hil_set_tensor_cores(int32_t on);
+/* Kernel selection for A/B measurement (returns the previous mode).  Bit 0: 1 (default) = GEMMs and STFT on the
+ * tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy), 0 = FP32 FFMA kernels everywhere.  Bit 2 set: do not
+ * fuse DWS blocks.  Bit 3 set: use the experimental time-major kernel (gemm_tm.cu, activations through TMEM)
+ * for plain 1x1 convs with Cout <= 192. */
+int32_t hil_set_tensor_cores(int32_t mode);
 #define HIL_PROFILE_CATEGORIES 8
 int32_t hil_profile_begin(void);
 int32_t hil_profile_end(double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_cat);

@@ -191,3 +191,29 @@ def test_dws_block(B, Cc, T, skip, pre):
     torch.cuda.synchronize()
     assert (y.cpu().double() - ref).abs().max().item() < 2e-5
     assert (co.cpu().double() - xin[:, :, -4:]).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("B,M,K,T,pre,bias,res", [(2, 64, 64, 1024, 0, False, False), (2, 96, 96, 2000, 1, True, True),
+                                                  (1, 192, 192, 900, 2, False, False), (2, 128, 1024, 76, 0, True, False)])
+def test_pointwise_time_major_kernel_matches_channel_major(B, M, K, T, pre, bias, res):
+    """The experimental time-major tensor-core kernel (activations through TMEM, TS-mode MMA) does the same
+    3xTF32 arithmetic in the same order as the default kernel: results must be bit-identical."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(B, K, T, generator=g).cuda()
+    w = (torch.randn(M, K, 1, generator=g) / K ** 0.5).contiguous()
+    b = torch.randn(M, generator=g).cuda() if bias else None
+    r = torch.randn(B, M, T, generator=g).cuda() if res else None
+    outs = []
+    prev = lib.hil_set_tensor_cores(1)
+    try:
+        for mode in (1, 9):
+            lib.hil_set_tensor_cores(mode)
+            y = torch.empty(B, M, T, device="cuda")
+            _lib.check(lib.hil_op_pointwise(_ptr(x), _ptr(w), _ptr(b), _ptr(r), _ptr(y), B, M, K, T, pre, 0.8660254,
+                                            _stream()))
+            torch.cuda.synchronize()
+            outs.append(y.cpu())
+    finally:
+        lib.hil_set_tensor_cores(prev)
+    assert torch.equal(outs[0], outs[1])

@@ -25,21 +25,22 @@ def run(B, M, K, T, pre, bias, res, tc):
         y64 = y64 + r.double(); y32 = y32 + r
     xd = x.cuda(); bd = b.cuda() if bias else None; rd = r.cuda() if res else None
     y = torch.zeros(B, M, T, device="cuda")
-    lib.hil_set_tensor_cores(1 if tc else 0)
+    lib.hil_set_tensor_cores(tc)
     _lib.check(lib.hil_op_pointwise(P(xd), P(w), P(bd), P(rd), P(y), B, M, K, T, pre, 0.8660254, st))
     torch.cuda.synchronize()
     err = (y.cpu().double() - y64).abs().max().item()
     cpu_err = (y32.double() - y64).abs().max().item()
     return err, cpu_err
 
-shapes = [(2, 128, 64, 256, 0, False, False), (2, 64, 64, 512, 1, False, False), (1, 96, 96, 1000, 1, False, False),
+shapes = [(2, 64, 64, 1024, 0, False, False), (2, 96, 96, 2000, 1, True, True), (1, 192, 192, 900, 2, False, False), (2, 128, 64, 256, 0, False, False), (2, 64, 64, 512, 1, False, False), (1, 96, 96, 1000, 1, False, False),
           (2, 192, 384, 300, 0, True, False), (2, 64, 33, 640, 0, True, True), (1, 1024, 513, 75, 0, True, True),
           (1, 768, 768, 600, 2, False, False), (3, 384, 384, 130, 1, False, True), (1, 1536, 128, 75, 0, False, False)]
 ok = True
 for s in shapes:
-    e_tc, e_cpu = run(*s, tc=True)
-    e_ff, _ = run(*s, tc=False)
-    flag = "OK " if e_tc < max(16 * e_cpu, 1e-5) else "BAD"
+    e_tm, e_cpu = run(*s, tc=9)
+    e_tc, _ = run(*s, tc=1)
+    e_ff, _ = run(*s, tc=0)
+    flag = "OK " if max(e_tc, e_tm) < max(16 * e_cpu, 1e-5) else "BAD"
     ok &= flag == "OK "
-    print(f"{flag} B,M,K,T,pre,bias,res={s}: err tc {e_tc:.3e}  ffma {e_ff:.3e}  cpu-fp32 {e_cpu:.3e}", flush=True)
+    print(f"{flag} B,M,K,T,pre,bias,res={s}: err tm {e_tm:.3e} tc {e_tc:.3e}  ffma {e_ff:.3e}  cpu-fp32 {e_cpu:.3e}", flush=True)
 print("ALL OK" if ok else "FAILURES")
