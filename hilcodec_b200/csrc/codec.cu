@@ -996,6 +996,32 @@ int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host
     return HIL_OK;
 }
 
+// ----------------------------------------------------------------------------- bitstream
+static int index_bits(const hil_model* m) {
+    int bits = 0;
+    while ((1 << bits) < m->cfg.codebook_size) ++bits;
+    return bits < 1 ? 1 : bits;
+}
+
+int32_t hil_bitstream_bytes_per_frame(const hil_model* m, int32_t n) {
+    if (!m || n < 1 || n > m->cfg.num_quantizers) return 0;
+    return (n * index_bits(m) + 7) / 8;
+}
+
+int32_t hil_pack_indices(hil_model* m, const int64_t* idx, int32_t B, int32_t F, int32_t n, uint8_t* out, void* stream) {
+    if (!m || !idx || !out || B < 0 || F < 0) return fail(HIL_ERR_INVALID, "bad argument");
+    if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
+    HIL_CUDA(launch_pack_indices(idx, (long long)B * F, n, index_bits(m), out, (cudaStream_t)stream));
+    return HIL_OK;
+}
+
+int32_t hil_unpack_indices(hil_model* m, const uint8_t* in, int32_t B, int32_t F, int32_t n, int64_t* idx, void* stream) {
+    if (!m || !idx || !in || B < 0 || F < 0) return fail(HIL_ERR_INVALID, "bad argument");
+    if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
+    HIL_CUDA(launch_unpack_indices(in, (long long)B * F, n, index_bits(m), idx, (cudaStream_t)stream));
+    return HIL_OK;
+}
+
 // ----------------------------------------------------------------------------- launch accounting API
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 

@@ -122,4 +122,8 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
 cudaError_t launch_rvq_decode(const int64_t* idx, const float* codebooks, int size, int dim, long long frames, int n,
                               float* q, cudaStream_t st);
 
+// ---- bitpack.cu: indices [n][frames] int64 <-> frame-major bitstream, `bits` per index, LSB first
+cudaError_t launch_pack_indices(const int64_t* idx, long long frames, int n, int bits, uint8_t* out, cudaStream_t st);
+cudaError_t launch_unpack_indices(const uint8_t* in, long long frames, int n, int bits, int64_t* idx, cudaStream_t st);
+
 }  // namespace hil

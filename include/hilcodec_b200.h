@@ -114,6 +114,14 @@ int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav_dev, int3
 int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host, int32_t B, int32_t T, int32_t n,
                                int64_t* idx_host, float* wav_out_host, void* stream);
 
+/* ---- bitstream (the reference stores indices as int16 .npy, test_onnx.py:99) ------- */
+/* ceil(n * log2(codebook_size) / 8): 10 bytes per frame at n = 8, 15 at n = 12 */
+int32_t hil_bitstream_bytes_per_frame(const hil_model* m, int32_t n);
+/* idx [n,B,F] int64 -> frame-major bytes [B*F][bytes_per_frame]; the n indices of a frame are concatenated
+ * LSB first, log2(codebook_size) bits each.  Both pointers are device pointers. */
+int32_t hil_pack_indices(hil_model* m, const int64_t* idx_dev, int32_t B, int32_t F, int32_t n, uint8_t* out_dev, void* stream);
+int32_t hil_unpack_indices(hil_model* m, const uint8_t* in_dev, int32_t B, int32_t F, int32_t n, int64_t* idx_dev, void* stream);
+
 /* ---- launch accounting (measurement support for bench.py; not in the reference) ----- */
 /* kernels launched by this library since load (bench.py reports the per-step delta as gpu_launches) */
 uint64_t hil_launch_count(void);

@@ -228,3 +228,32 @@ def test_full_size_properties_config2():
     p = params(w)
     bad, worst = index_report(oracle_cfg(8), p, z, idx, idc.cpu(), 8)
     assert bad == 0 or worst < 1e-5, (bad, worst)
+
+
+def test_config4_streaming_30s_clip():
+    """BASELINE config 4: hil_music, one 30 s stream fed hop by hop (hop = 320: 2250 sequential frames; the
+    config's "hop=300" is AudioDec's hop and cannot be fed to HILCodec) with the per-layer
+    caches resident on the GPU, against the one-shot result of the same clip."""
+    cfg = W.HIL_MUSIC
+    w = W.load_pretrained("hil_music") if W.have_pretrained("hil_music") else W.random_weights(cfg, 8)
+    m = _model(w, 12)
+    frames = 2250
+    x = synth_wav(1, 320 * frames, seed=30).cuda()
+    idx, y = m.codec_forward(x, 12)
+    st = m.new_stream_state(1)
+    ids, ws = [], []
+    for f in range(frames):
+        i1, y1 = m.codec_forward(x[:, :, f * 320:(f + 1) * 320], 12, state=st)
+        ids.append(i1)
+        ws.append(y1)
+    ids = torch.cat(ids, 2)
+    ws = torch.cat(ws, 2)
+    same = (ids == idx).float().mean().item()
+    assert same > 0.999, same
+    p = params(w)
+    ce, _ = m.initialize_cache(x)
+    z, _ = m.encoder(x, *ce)
+    bad, worst = index_report(oracle_cfg(12), p, z, idx, ids.cpu(), 12)
+    assert bad == 0 or worst < 1e-5, (bad, worst)
+    if bad == 0:
+        assert (ws - y).abs().max().item() < 5e-5
