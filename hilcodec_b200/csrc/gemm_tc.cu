@@ -58,6 +58,7 @@ struct Params {
 };
 
 constexpr uint32_t IDESC = make_idesc(BM, BN, 1);  // kind::tf32, D = f32, A K-major, B MN-major
+constexpr uint32_t IDESC_N256 = make_idesc(BM, 2 * BN, 1);
 
 // ------------------------------------------------------------------------------- kernel
 template <bool kDw>
@@ -153,12 +154,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t st = base + s * STAGE_BYTES;
                 mbar_wait(full_bar(s), ph);
-                // The tensor core reads only the top 19 bits of a tf32 operand, so the raw fp32 tile
-                // IS the hi operand (hi = trunc(x)); without an activation prologue the two MMAs that
-                // need only hi are issued as soon as TMA lands, and the transform warps (computing
-                // lo = tf32(x - trunc(x))) run underneath them.
-                if (p.pre != PRE_NONE) mbar_wait(xform_bar(s), ph);
+                mbar_wait(xform_bar(s), ph);
                 tc_fence_after();
+                // The tensor core reads only the top 19 bits of a tf32 operand, so the raw fp32 tile IS the
+                // hi operand (hi = trunc(x)).  B_hi and B_lo sit back to back in the stage (8 panels of 32
+                // columns), so ONE N = 256 MMA computes A_hi*[B_hi | B_lo] into the adjacent [big | small]
+                // accumulators and a second N = 128 MMA adds A_lo*B_hi to `small`: A_hi is read from shared
+                // memory once per k-step instead of twice (shared-memory bandwidth is what bounds this kernel).
                 if (lane == 0) {
 #pragma unroll
                     for (int j = 0; j < BK / 8; ++j) {
@@ -167,22 +169,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         //    (SBO); one MMA (K = 8) consumes 8 k-rows = 1024 B.
                         const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
                         const uint64_t a_lo = make_desc(st + TILE_BYTES + j * 32, 16, 1024, 2);
-                        const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
-                        umma_tf32(d_big, a_hi, b_hi, IDESC, (kb | j) != 0);
-                        umma_tf32(d_small, a_lo, b_hi, IDESC, (kb | j) != 0);
-                    }
-                }
-                __syncwarp();
-                if (p.pre == PRE_NONE) {
-                    mbar_wait(xform_bar(s), ph);
-                    tc_fence_after();
-                }
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < BK / 8; ++j) {
-                        const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
-                        const uint64_t b_lo = make_desc(st + 3 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
-                        umma_tf32(d_small, a_hi, b_lo, IDESC, 1);
+                        const uint64_t b_hl = make_desc(st + 2 * TILE_BYTES + j * 1024, PANEL_BYTES, 512, 1);
+                        umma_tf32(d_big, a_hi, b_hl, IDESC_N256, (kb | j) != 0);
+                        umma_tf32(d_small, a_lo, b_hl, IDESC, 1);
                     }
                     umma_commit(empty_bar(s));
                     if (kb == nkb - 1) umma_commit(tfull_bar(acc));
