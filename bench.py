@@ -311,13 +311,15 @@ def main_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get("dram_bytes_per_launch_avg")
     except Exception:
         pass
     pw = cats.get("pointwise_gemm", {"tflops": 0.0, "ms_per_step": 0.0, "launches_per_step": 0})
+    if traffic is not None:
+        traffic = traffic * pw["launches_per_step"]   # ncu DRAM bytes of the category's launches in one step
     dominant = max(cats, key=lambda k: cats[k]["ms_per_step"]) if cats else None
     roofline = {
-        "bound": "tensor", "kernel": "pointwise 1x1-conv GEMM (all launches of the step)",
+        "bound": "tensor", "kernel": "tc::gemm_tc_kernel: pointwise 1x1-conv / fused DWS-block GEMMs (all launches of the step)",
         "achieved": pw["tflops"], "peak": bf16_peak, "unit": "TFLOP/s",
         "frac": pw["tflops"] / bf16_peak if bf16_peak else None, "traffic": traffic,
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",

@@ -64,6 +64,7 @@ SIGNATURES = {
     "hil_decode": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "hil_decode_caches": (_I, [_P, _P, _P, _I, _I, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "hil_codec_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "hil_codec_forward_graph": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "hil_codec_forward_host": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "hil_bitstream_bytes_per_frame": (_I, [_P, _I]),
     "hil_pack_indices": (_I, [_P, _P, _I, _I, _I, _P, _P]),

@@ -31,6 +31,7 @@ constexpr int NUM_EPI = 128;
 constexpr int TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256;
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0);  // A and B both K-major
+constexpr uint32_t IDESC_N256 = make_idesc(BM, 2 * BN, 0);
 
 struct Params {
     int M, F, K, T, B, hop;
@@ -123,29 +124,18 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t st = base + s * STAGE_BYTES;
                 mbar_wait(full_bar(s), ph);
-                if (p.gather) mbar_wait(xform_bar(s), ph);   // B_hi is written by the transform warps too
+                mbar_wait(xform_bar(s), ph);
                 tc_fence_after();
                 if (lane == 0) {
 #pragma unroll
                     for (int j = 0; j < BK / 8; ++j) {
+                        // B_hi (rows 0..127) and B_lo (rows 128..255) are adjacent K-major tiles: one N = 256 MMA
+                        // computes A_hi*[B_hi | B_lo] into [big | small], a second N = 128 MMA adds A_lo*B_hi.
                         const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
                         const uint64_t a_lo = make_desc(st + TILE_BYTES + j * 32, 16, 1024, 2);
-                        const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES + j * 32, 16, 1024, 2);
-                        umma_tf32(d_big, a_hi, b_hi, IDESC, (kb | j) != 0);
-                        umma_tf32(d_small, a_lo, b_hi, IDESC, (kb | j) != 0);
-                    }
-                }
-                __syncwarp();
-                if (!p.gather) {
-                    mbar_wait(xform_bar(s), ph);
-                    tc_fence_after();
-                }
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < BK / 8; ++j) {
-                        const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
-                        const uint64_t b_lo = make_desc(st + 3 * TILE_BYTES + j * 32, 16, 1024, 2);
-                        umma_tf32(d_small, a_hi, b_lo, IDESC, 1);
+                        const uint64_t b_hl = make_desc(st + 2 * TILE_BYTES + j * 32, 16, 1024, 2);
+                        umma_tf32(d_big, a_hi, b_hl, IDESC_N256, (kb | j) != 0);
+                        umma_tf32(d_small, a_lo, b_hl, IDESC, 1);
                     }
                     umma_commit(empty_bar(s));
                     if (kb == nkb - 1) umma_commit(tfull_bar(acc));

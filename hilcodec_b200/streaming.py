@@ -600,6 +600,35 @@ class StreamState:
     def reset(self) -> None:
         _lib.check(self._lib.hil_state_reset(self._h, _stream_ptr(self.device)))
 
+    @torch.no_grad()
+    def step(self, x: Tensor, n: int) -> tp.Tuple[Tensor, Tensor]:
+        """One streaming chunk through the CUDA-graph executor (`hil_codec_forward_graph`).  The chunk is copied
+        into a buffer owned by this state and the results are returned as views of state-owned buffers that the
+        next `step` overwrites (clone them to keep them): fixed pointers are what lets the graph be replayed."""
+        _require_cuda(x, "x")
+        B, _, T = x.shape
+        if B != self.batch:
+            raise ValueError(f"state was created for batch {self.batch}, got {B}")
+        hop = self._core.cfg.hop
+        if T % hop or T == 0:
+            raise ValueError(f"T={T} must be a positive multiple of the hop length {hop}")
+        assert 1 <= n <= self._core.cfg.num_quantizers, "n must satisfy 1 <= n <= num_quantizers"
+        key = (T, n)
+        bufs = self._io.get(key) if hasattr(self, "_io") else None
+        if bufs is None:
+            if not hasattr(self, "_io"):
+                self._io = {}
+            bufs = (torch.empty(B, 1, T, dtype=torch.float32, device=self.device),
+                    torch.empty(n, B, T // hop, dtype=torch.int64, device=self.device),
+                    torch.empty(B, 1, T, dtype=torch.float32, device=self.device))
+            self._io[key] = bufs
+        xin, idx, y = bufs
+        with torch.cuda.device(self.device):
+            xin.copy_(x)
+            _lib.check(self._lib.hil_codec_forward_graph(self._core.model(self.device), self._h, xin.data_ptr(), B, T, n,
+                                                         idx.data_ptr(), y.data_ptr(), _stream_ptr(self.device)))
+        return idx, y
+
     def export(self) -> tp.Tuple[tp.List[Tensor], tp.List[Tensor]]:
         out = []
         for which in (_lib.HIL_ENCODER, _lib.HIL_DECODER):

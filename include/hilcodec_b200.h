@@ -109,6 +109,11 @@ int32_t hil_decode_caches(hil_model* m, hil_state* s, const float* q_dev, int32_
 /* wav [B,1,T] -> idx [n,B,T/hop] int64 (+ optional z [B,F,dim]) -> wav_out [B,1,T]. */
 int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, int32_t T, int32_t n,
                           float* z_dev_or_null, int64_t* idx_dev, float* wav_out_dev, void* stream);
+/* Streaming executor: same contract as hil_codec_forward, but the launches of one step are captured into a CUDA
+ * graph (keyed by the buffer pointers, T, n and the cache generation) and replayed on later calls -- a hop-sized
+ * chunk is ~115 dependent launches and otherwise launch-latency bound.  Keep wav/idx/wav_out pointers fixed. */
+int32_t hil_codec_forward_graph(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, int32_t T, int32_t n,
+                                int64_t* idx_dev, float* wav_out_dev, void* stream);
 /* Same with HOST buffers (pinned recommended): H2D copy of wav, forward, D2H copy of idx and
  * wav_out, all on `stream`, then a stream synchronise.  This is the e2e call bench.py times. */
 int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host, int32_t B, int32_t T, int32_t n,

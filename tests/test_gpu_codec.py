@@ -257,3 +257,22 @@ def test_config4_streaming_30s_clip():
     assert bad == 0 or worst < 1e-5, (bad, worst)
     if bad == 0:
         assert (ws - y).abs().max().item() < 5e-5
+
+
+def test_graph_streaming_executor_matches_eager():
+    """CUDA-graph replay of the per-frame step (hil_codec_forward_graph) == the eager stateful path."""
+    n_q = 12
+    w = W.random_weights(W.HIL_MUSIC, 12)
+    m = _model(w, n_q)
+    x = synth_wav(2, 320 * 40, seed=5).cuda()
+    st_e = m.new_stream_state(2)
+    st_g = m.new_stream_state(2)
+    for f in range(40):
+        chunk = x[:, :, f * 320:(f + 1) * 320]
+        ie, ye = m.codec_forward(chunk, n_q, state=st_e)
+        ig, yg = st_g.step(chunk, n_q)
+        assert torch.equal(ie, ig), f
+        assert torch.equal(ye, yg), f
+    ee, de = st_e.export()
+    eg, dg = st_g.export()
+    assert all(torch.equal(a, b) for a, b in zip(ee + de, eg + dg))
