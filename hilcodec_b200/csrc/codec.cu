@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "../../include/hilcodec_b200.h"
 #include "common.cuh"
 
@@ -93,6 +95,9 @@ static bool g_fuse_dw = std::getenv("HILCODEC_DISABLE_DWS_FUSION") == nullptr;
 // gemm_tc.cu) but its register->global epilogue exposes the residual-load latency and it measured slower
 // (493 us vs 187 us on the stage-0 SpecBlock 1x1 at B = 64); enable with HILCODEC_ENABLE_TM=1 or mode bit 3.
 static bool g_use_tm = std::getenv("HILCODEC_ENABLE_TM") != nullptr;
+// fp16-split tensor-core kernel (gemm_h.cu, kind::f16 at twice the tf32 rate, decoupled load / operand rings):
+// mode bit 4 (16) of hil_set_tensor_cores, or HILCODEC_GEMM=tf32 to fall back to gemm_tc.cu.
+static bool g_use_h = []() { const char* e = std::getenv("HILCODEC_GEMM"); return !(e && std::strcmp(e, "tf32") == 0); }();
 
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
@@ -101,8 +106,10 @@ static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_b
     const double n = (double)B * T;
     const bool tmajor = g_use_tc && g_use_tm && gemm_tm_usable(W, X, x_bs, x_rs, T, Y, y_bs, y_rs);
     const bool tcore = g_use_tc && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
+    const bool hcore = g_use_tc && g_use_h && gemm_h_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
     HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
                tmajor  ? launch_gemm_tm(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
+               : hcore ? launch_gemm_h(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
                : tcore ? launch_gemm_tc(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
                        : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
     return HIL_OK;
@@ -158,7 +165,9 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
         const double n = (double)B * T;
         HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
                    4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
-                   launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st));
+                   (g_use_h && gemm_h_usable(W, X, bs, rs, T, skip, Y, bs, rs))
+                       ? launch_gemm_h_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st)
+                       : launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st));
         return HIL_OK;
     }
     HIL_TRY(run_gemm_linear(W, X, bs, rs, B, T, pre, pre_scale, nullptr, nullptr, tmp, bs, rs, st));
@@ -309,6 +318,7 @@ struct PendingMat {
     PackedMat* dst;
     size_t off;
     size_t off_hi = 0, off_lo = 0;
+    size_t off_hh = 0, off_hl = 0;  // fp16-split form (offsets in floats)
     bool tc = false;
 };
 
@@ -390,6 +400,27 @@ struct Builder {
                     lo[(size_t)mrow * Kp32 + k] = tf32_rna_host(v - h);
                 }
             dst->Mp128 = Mp128; dst->Kp32 = Kp32;
+            // fp16-split form (gemm_h.cu): w * 2^s = hh + hl * 2^-11, all scalings exact powers of two
+            float wmax = 0.f;
+            for (size_t i = 0; i < (size_t)M * K; ++i) wmax = std::fmax(wmax, std::fabs(w[i]));
+            int ex = 0;
+            if (wmax > 0.f) std::frexp(wmax, &ex);               // wmax in [2^(ex-1), 2^ex)
+            const float up = wmax > 0.f ? std::ldexp(1.0f, 14 - ex) : 1.0f;
+            dst->h_inv_scale = 1.0f / up;
+            const size_t halves = (size_t)Mp128 * Kp32;
+            pm.off_hh = arena.alloc(halves / 2);
+            pm.off_hl = arena.alloc(halves / 2);
+            uint16_t* hh = reinterpret_cast<uint16_t*>(arena.buf.data() + pm.off_hh);
+            uint16_t* hl = reinterpret_cast<uint16_t*>(arena.buf.data() + pm.off_hl);
+            for (int mrow = 0; mrow < M; ++mrow)
+                for (int k = 0; k < K; ++k) {
+                    const int src = interleave ? ((mrow & 1) ? F + mrow / 2 : mrow / 2) : mrow;
+                    const float v = w[(size_t)src * K + k] * up;
+                    const __half h = __float2half_rn(v);
+                    const __half l = __float2half_rn((v - __half2float(h)) * 2048.0f);
+                    hh[(size_t)mrow * Kp32 + k] = __half_as_ushort(h);
+                    hl[(size_t)mrow * Kp32 + k] = __half_as_ushort(l);
+                }
         }
         mats.push_back(pm);
     }
@@ -563,7 +594,11 @@ int32_t hil_model_finalize(hil_model* m) {
     HIL_CUDA(cudaMemcpy(m->arena, b.arena.buf.data(), m->arena_floats * sizeof(float), cudaMemcpyHostToDevice));
     for (auto& pm : b.mats) {
         pm.dst->A = m->arena + pm.off;
-        if (pm.tc) { pm.dst->A_hi = m->arena + pm.off_hi; pm.dst->A_lo = m->arena + pm.off_lo; }
+        if (pm.tc) {
+            pm.dst->A_hi = m->arena + pm.off_hi; pm.dst->A_lo = m->arena + pm.off_lo;
+            pm.dst->H_hi = reinterpret_cast<const uint16_t*>(m->arena + pm.off_hh);
+            pm.dst->H_lo = reinterpret_cast<const uint16_t*>(m->arena + pm.off_hl);
+        }
     }
     for (auto& p : b.ptrs) *p.first = m->arena + p.second;
     m->codebooks = m->arena + cb_off;
@@ -1106,10 +1141,11 @@ int32_t hil_unpack_indices(hil_model* m, const uint8_t* in, int32_t B, int32_t F
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 
 int32_t hil_set_tensor_cores(int32_t mode) {
-    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4);
+    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0);
     g_use_tc = (mode & 1) != 0;
     g_use_tm = (mode & 8) != 0;
     g_fuse_dw = (mode & 4) == 0;
+    g_use_h = (mode & 16) != 0;
     return prev;
 }
 
@@ -1163,7 +1199,11 @@ static int32_t upload_packed(const float* w_host, int M, int K, int TM, bool int
     HIL_CUDA(cudaMalloc(dev, b.arena.buf.size() * sizeof(float)));
     HIL_CUDA(cudaMemcpy(*dev, b.arena.buf.data(), b.arena.buf.size() * sizeof(float), cudaMemcpyHostToDevice));
     pm->A = *dev + b.mats[0].off;
-    if (b.mats[0].tc) { pm->A_hi = *dev + b.mats[0].off_hi; pm->A_lo = *dev + b.mats[0].off_lo; }
+    if (b.mats[0].tc) {
+        pm->A_hi = *dev + b.mats[0].off_hi; pm->A_lo = *dev + b.mats[0].off_lo;
+        pm->H_hi = reinterpret_cast<const uint16_t*>(*dev + b.mats[0].off_hh);
+        pm->H_lo = reinterpret_cast<const uint16_t*>(*dev + b.mats[0].off_hl);
+    }
     return HIL_OK;
 }
 

@@ -50,6 +50,11 @@ struct PackedMat {
     const float* A_hi = nullptr;
     const float* A_lo = nullptr;
     int Mp128 = 0, Kp32 = 0;
+    // fp16-split form for gemm_h.cu, row-major [Mp128][Kp32] halves: w * 2^s = H_hi + H_lo * 2^-11,
+    // h_inv_scale = 2^-s (s chosen per matrix so that max|w * 2^s| lies in [2^13, 2^14))
+    const uint16_t* H_hi = nullptr;
+    const uint16_t* H_lo = nullptr;
+    float h_inv_scale = 1.f;
 };
 
 // ---- gemm.cu ---------------------------------------------------------------------
@@ -72,6 +77,16 @@ bool gemm_tc_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs
 cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                            float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                            cudaStream_t st);
+
+// ---- gemm_h.cu: the same two contracts with fp16 hi/lo splits (tcgen05 kind::f16, 2x the tf32 rate)
+bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
+                   long long y_bs, int y_rs);
+cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                          float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
+                          cudaStream_t st);
+cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                             float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
+                             float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
 // fused DWSBlock: y = dw5(W * pre(x)) + b_dw (+ skip); same usability conditions as launch_gemm_tc
 cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,

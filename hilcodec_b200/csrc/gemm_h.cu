@@ -1,0 +1,546 @@
+// Tensor-core pointwise GEMM with fp32-level accuracy from fp16 hi/lo splits (tcgen05 kind::f16).
+//
+//   Y[b][m][t] = sum_k W[m][k] * pre(X[b][k][t]) (+bias[m]) (+R[b][m][t])          (launch_gemm_h)
+//   Y = dw5(W * pre(X)) + b_dw (+ skip), the whole DWSBlock (streaming.py:189-192)   (launch_gemm_h_dw)
+//
+// Same arithmetic idea as gemm_tc.cu (3 MMAs per product, lo*lo dropped) but every operand is a
+// pair of fp16 numbers instead of a pair of tf32 numbers: an fp16 significand has the same 11 bits
+// as tf32, the MMA runs at twice the tf32 rate and reads half the shared-memory bytes.
+//   weights      w * 2^s = a_hi + a_lo * 2^-11   (s per matrix, so that max|w * 2^s| is in [2^13, 2^14);
+//                                                 split once at hil_model_finalize)
+//   activations  x       = b_hi + b_lo * 2^-11   (b_hi = fp16_rn(x), b_lo = fp16_rn((x - b_hi) * 2^11);
+//                                                 requires |x| < 65504, otherwise the result is NaN)
+//   big   += a_hi * b_hi                      (TMEM accumulator 0, fp32)
+//   small += a_hi * b_lo + a_lo * b_hi        (TMEM accumulator 1, fp32, carries the 2^11 scale)
+//   y      = (big + small * 2^-11) * 2^-s
+// The 2^11 scale keeps both lo parts in the normal fp16 range, so nothing is lost to fp16
+// subnormals; all scalings are powers of two (exact).
+//
+// Pipeline (one persistent CTA per SM, 128 x 128 output tile, BK = 32, 512 threads).  The ablation in
+// profiles/r1_gemm_tc_ablation.md showed gemm_tc.cu is bound by the LATENCY of one serial chain per
+// smem stage (HBM load -> transform -> MMA -> release, 3 stages in flight), so here the rings are
+// decoupled:
+//   raw ring  (6 x 16 KB): fp32 activation boxes [32 k][128 t] straight from TMA (no swizzle)
+//   op ring   (3 x 32 KB): A_hi | A_lo (fp16, K-major, SWIZZLE_64B, TMA from the pre-split weights)
+//                          B_hi | B_lo (fp16, MN-major, SWIZZLE_128B, written by the transform warps)
+// warp 0  X producer (TMA)      warp 3  A producer (TMA)      warp 1  MMA issuer
+// warp 2  TMEM allocator        warps 4-7 epilogue            warps 8-15 transform (ELU prologue + split)
+// Per k-block two k16 steps of { A_hi x [B_hi | B_lo] (N = 256) -> [big | small]; A_lo x B_hi (N = 128) ->
+// small }.  Epilogues are the ones of gemm_tc.cu (TMEM -> registers -> swizzled staging -> TMA store /
+// reduce-add; optional fused causal depthwise k5).
+#include <cuda_fp16.h>
+
+#include "tc_ptx.cuh"
+
+namespace hil {
+namespace th {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int RAW_STAGES = 6;
+constexpr int OP_STAGES = 3;
+constexpr int RAW_BYTES = BK * BN * 4;            // 16 KB fp32 activation box
+constexpr int A_TILE = BM * BK * 2;               // 8 KB
+constexpr int B_TILE = BK * BN * 2;               // 8 KB
+constexpr int OP_BYTES = 2 * A_TILE + 2 * B_TILE; // 32 KB: A_hi, A_lo, B_hi, B_lo
+constexpr int B_PANEL = 8 * 128 * (BK / 8);       // 4 KB: 64 columns x 32 k (4 swizzle atoms of 8 k-rows x 128 B)
+constexpr int NUM_THREADS = 512;
+constexpr int NUM_XFORM_WARPS = 8;
+constexpr int NUM_EPI = 128;
+constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
+constexpr int TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)RAW_STAGES * RAW_BYTES + (size_t)OP_STAGES * OP_BYTES + 2 * OUT_BYTES + 256;
+constexpr float LO_SCALE = 2048.f;                // 2^11
+
+struct Params {
+    int M, K, T, B;
+    int num_m, tiles_t;
+    long long total_tiles;
+    int pre;
+    float pre_scale;
+    float c_big, c_small;   // 2^-s and 2^-s * 2^-11
+    const float* bias;
+    int reduce_add;         // 1: Y += tile (TMA reduce), 0: Y = tile
+    int t_step, t_halo;     // tile tt covers columns [tt * t_step - t_halo, ... + BN)
+    const float* dw_w;      // [M][5]
+    const float* dw_b;      // [M] or null
+    const float* cache_in;  // [B][M][4]
+    float* cache_out;       // [B][M][4]
+};
+
+// kind::f16, A = B = fp16, D = f32, A K-major, B MN-major (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+constexpr uint32_t IDESC_N128 = make_idesc_f16(BM, BN);
+constexpr uint32_t IDESC_N256 = make_idesc_f16(BM, 2 * BN);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {
+    const __half2 h = __floats2half2_rn(lo_elem, hi_elem);   // .x (low 16 bits) = first element in memory
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+
+// ------------------------------------------------------------------------------- kernel
+template <bool kDw>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+              const __grid_constant__ CUtensorMap map_y28, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t raw_base = base;
+    const uint32_t op_base = raw_base + RAW_STAGES * RAW_BYTES;
+    const uint32_t out_base = op_base + OP_STAGES * OP_BYTES;
+    const uint32_t bars = out_base + 2 * OUT_BYTES;
+    auto raw_full = [&](int r) { return bars + 8u * r; };
+    auto raw_empty = [&](int r) { return bars + 8u * (RAW_STAGES + r); };
+    auto a_full = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };
+    auto b_ready = [&](int s) { return bars + 8u * (2 * RAW_STAGES + OP_STAGES + s); };
+    auto op_empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * RAW_STAGES + 3 * OP_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * RAW_STAGES + 3 * OP_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * RAW_STAGES + 3 * OP_STAGES + 4);
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi);
+        prefetch_tmap(&map_a_lo);
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_y);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int r = 0; r < RAW_STAGES; ++r) {
+            mbar_init(raw_full(r), 1);
+            mbar_init(raw_empty(r), NUM_XFORM_WARPS);
+        }
+        for (int s = 0; s < OP_STAGES; ++s) {
+            mbar_init(a_full(s), 1);
+            mbar_init(b_ready(s), NUM_XFORM_WARPS);
+            mbar_init(op_empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), NUM_EPI);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        const uint32_t ncols = TMEM_COLS;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================================================================== X producer (raw ring)
+        if (lane == 0) {
+            int r = 0;
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait<32>(raw_empty(r), ph ^ 1);
+                    mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
+                    tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
+                    if (++r == RAW_STAGES) { r = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================================================================== A producer (op ring)
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int m_blk = (int)(tile % p.num_m);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait<32>(op_empty(s), ph ^ 1);
+                    const uint32_t st = op_base + s * OP_BYTES;
+                    mbar_arrive_expect_tx(a_full(s), 2 * A_TILE);
+                    tma_load_2d(&map_a_hi, st, a_full(s), kb * BK, m_blk * BM);
+                    tma_load_2d(&map_a_lo, st + A_TILE, a_full(s), kb * BK, m_blk * BM);
+                    if (++s == OP_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = (int)(it & 1);
+            const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_big = tmem_base + acc * 2 * BN;
+            const uint32_t d_small = d_big + BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t st = op_base + s * OP_BYTES;
+                mbar_wait(a_full(s), ph);
+                mbar_wait(b_ready(s), ph);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j) {
+                        // A (K-major, SWIZZLE_64B): 8-row groups 512 B apart; +32 B walks one k16 step inside the
+                        //   64-byte swizzle row.
+                        // B (MN-major, SWIZZLE_128B): 64-column panels B_PANEL apart (LBO) -- B_hi p0, p1, B_lo p0,
+                        //   p1 back to back -- 8-k-row atoms 1024 B apart (SBO); one k16 step = 2 atoms = 2 KB.
+                        const uint64_t a_hi = make_desc(st + j * 32, 16, 512, 4);
+                        const uint64_t a_lo = make_desc(st + A_TILE + j * 32, 16, 512, 4);
+                        const uint64_t b_hl = make_desc(st + 2 * A_TILE + j * 2048, B_PANEL, 1024, 2);
+                        umma_f16(d_big, a_hi, b_hl, IDESC_N256, (kb | j) != 0);
+                        umma_f16(d_small, a_lo, b_hl, IDESC_N128, 1);
+                    }
+                    umma_commit(op_empty(s));
+                    if (kb == nkb - 1) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++s == OP_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================================================================== transform: raw fp32 -> B_hi / B_lo fp16
+        // Warp w converts k-rows 4w .. 4w+3 of the box; a lane owns 4 consecutive columns of a row: one
+        // conflict-free LDS.128, two STS.64 into the 128B-swizzled MN-major atoms.
+        const int xw = warp - 8;
+        const uint32_t panel = (uint32_t)(lane >> 4);     // 64-column panel
+        const uint32_t chunk = (uint32_t)((lane >> 1) & 7);  // 16-byte chunk (8 columns) inside the 128-byte row
+        const uint32_t half8 = (uint32_t)(lane & 1) * 8u;
+        int r = 0, s = 0;
+        uint32_t rph = 0, sph = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(raw_full(r), rph);
+                mbar_wait(op_empty(s), sph ^ 1);
+                const float4* src = reinterpret_cast<const float4*>(gen_base + (raw_base - base) + r * RAW_BYTES);
+                const uint32_t bhi = op_base + s * OP_BYTES + 2 * A_TILE + panel * B_PANEL;
+                float4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = src[(xw * 4 + q) * (BN / 4) + lane];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t k = (uint32_t)(xw * 4 + q);
+                    float4 x = v[q];
+                    if (p.pre != PRE_NONE) {   // pre_scale is 1.0 for PRE_ELU (x * 1.0f is exact)
+                        x.x = elu_fast(x.x * p.pre_scale); x.y = elu_fast(x.y * p.pre_scale);
+                        x.z = elu_fast(x.z * p.pre_scale); x.w = elu_fast(x.w * p.pre_scale);
+                    }
+                    const uint32_t h01 = pack_h2(x.x, x.y), h23 = pack_h2(x.z, x.w);
+                    const float2 f01 = unpack_h2(h01), f23 = unpack_h2(h23);
+                    const uint32_t l01 = pack_h2((x.x - f01.x) * LO_SCALE, (x.y - f01.y) * LO_SCALE);
+                    const uint32_t l23 = pack_h2((x.z - f23.x) * LO_SCALE, (x.w - f23.y) * LO_SCALE);
+                    const uint32_t dst = bhi + (k >> 3) * 1024u + (k & 7u) * 128u + ((chunk ^ (k & 7u)) << 4) + half8;
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h01), "r"(h23) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + (uint32_t)B_TILE), "r"(l01), "r"(l23) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(b_ready(s));
+                    mbar_arrive(raw_empty(r));
+                }
+                if (++r == RAW_STAGES) { r = 0; rph ^= 1; }
+                if (++s == OP_STAGES) { s = 0; sph ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================================================================== epilogue
+        const int q = warp - 4;
+        const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
+        const bool issuer = (q == 0 && lane == 0);
+        const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
+        const float c_big = p.c_big, c_small = p.c_small;
+        long long it = 0;
+        uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
+        if constexpr (!kDw) {
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int m_blk = (int)(tile % p.num_m);
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                const int acc = (int)(it & 1);
+                const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait<64>(tfull_bar(acc), acc_ph);
+                tc_fence_after();
+                const int m = m_blk * BM + row;
+                const float bv = (m < p.M && p.bias) ? p.bias[m] : 0.f;
+                const int t0 = tt * BN;
+                const int n_chunks = min(BN / 32, (p.T - t0 + 31) / 32);
+                const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+#pragma unroll 1
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                    if (issuer) tma_wait_read<1>();          // the store that used this buffer two chunks ago has drained it
+                    epi_bar_sync();
+                    uint32_t rb[32], rs[32];
+                    tmem_ld32(t_big + c * 32, rb);
+                    tmem_ld32(t_big + BN + c * 32, rs);
+                    tmem_ld_wait();
+                    if (c == n_chunks - 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    const uint32_t orow = obuf + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            o[e] = fmaf(__uint_as_float(rs[4 * j + e]), c_small, __uint_as_float(rb[4 * j + e]) * c_big) + bv;
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j ^ sw) << 4)), "f"(o[0]),
+                                     "f"(o[1]), "f"(o[2]), "f"(o[3])
+                                     : "memory");
+                    }
+                    fence_proxy_async();
+                    epi_bar_sync();
+                    if (issuer) {
+                        if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
+                        else tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
+                        tma_commit();
+                    }
+                }
+            }
+            if (issuer) tma_wait_all();
+        } else {
+            // ---- fused DWS epilogue (see gemm_tc.cu): the tile holds 128 pointwise columns for times
+            // [t0-4, t0+124); each thread owns one channel row and slides the 5-tap window along it in registers.
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int m_blk = (int)(tile % p.num_m);
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                const int acc = (int)(it & 1);
+                const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+                const int m = m_blk * BM + row;
+                const bool row_ok = m < p.M;
+                float wk[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) wk[k] = row_ok ? p.dw_w[m * 5 + k] : 0.f;
+                const float bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                const int tcol0 = tt * p.t_step - p.t_halo;       // time of tile column 0
+                const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
+                const bool has_tail = row_ok && (tcol0 + BN > p.T - 4);  // tile holds some of the last 4 columns
+                float carry[4] = {0.f, 0.f, 0.f, 0.f};
+                if (tt == 0 && row_ok) {
+                    const float4 cv = *reinterpret_cast<const float4*>(p.cache_in + ((size_t)b * p.M + m) * 4);
+                    carry[0] = cv.x; carry[1] = cv.y; carry[2] = cv.z; carry[3] = cv.w;
+                }
+                mbar_wait<64>(tfull_bar(acc), acc_ph);
+                tc_fence_after();
+                const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+#pragma unroll 1
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                    uint32_t rb[32], rs[32];
+                    tmem_ld32(t_big + c * 32, rb);
+                    tmem_ld32(t_big + BN + c * 32, rs);
+                    tmem_ld_wait();
+                    if (c == n_chunks - 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    float v[36];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[4 + j] = fmaf(__uint_as_float(rs[j]), c_small, __uint_as_float(rb[j]) * c_big);
+                    // columns 0..3 of the first tile are times -4..-1: the cache handed in by the caller
+                    if (c == 0 && tt == 0) { v[4] = carry[0]; v[5] = carry[1]; v[6] = carry[2]; v[7] = carry[3]; }
+                    v[0] = carry[0]; v[1] = carry[1]; v[2] = carry[2]; v[3] = carry[3];
+                    if (has_tail) {  // new cache = pointwise outputs at times T-4..T-1 (each time is owned by one tile)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = c * 32 + j;
+                            const int t = tcol0 + col;
+                            if (col >= p.t_halo && t >= p.T - 4 && t < p.T)
+                                p.cache_out[((size_t)b * p.M + m) * 4 + (t - (p.T - 4))] = v[4 + j];
+                        }
+                    }
+                    if (issuer) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
+                    epi_bar_sync();
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = j4 * 4 + e;  // output i of this chunk uses v[i..i+4]
+                            float a = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[i + k], a);
+                            o[e] = a + bv;
+                        }
+                        uint32_t dst;
+                        if (c == 0) {
+                            if (j4 == 0) continue;   // outputs 0..3 of chunk 0 belong to the previous tile
+                            dst = obuf + row * 112 + (j4 - 1) * 16;
+                        } else {
+                            dst = obuf + row * 128 + (((uint32_t)j4 ^ sw) << 4);
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                                     "f"(o[3])
+                                     : "memory");
+                    }
+                    carry[0] = v[32]; carry[1] = v[33]; carry[2] = v[34]; carry[3] = v[35];
+                    fence_proxy_async();
+                    epi_bar_sync();
+                    if (issuer) {
+                        const CUtensorMap* mp = c == 0 ? &map_y28 : &map_y;
+                        const int tc0 = c == 0 ? tcol0 + p.t_halo : tcol0 + c * 32;
+                        if (p.reduce_add) tma_reduce_add_3d(mp, obuf, tc0, m_blk * BM, b);
+                        else tma_store_3d(mp, obuf, tc0, m_blk * BM, b);
+                        tma_commit();
+                    }
+                }
+            }
+            if (issuer) tma_wait_all();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        const uint32_t ncols = TMEM_COLS;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols));
+    }
+}
+
+}  // namespace th
+
+// ------------------------------------------------------------------------------- host side
+bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
+                   long long y_bs, int y_rs) {
+    if (!W.H_hi || !W.H_lo) return false;
+    if (T < 64) return false;  // short chunks (streaming) go to the flattened-column FFMA kernel
+    if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
+    if (R && (reinterpret_cast<uintptr_t>(R) & 15)) return false;
+    return true;
+}
+
+static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, CUtensorMap* map_hi,
+                             CUtensorMap* map_lo, CUtensorMap* map_x, int* num_sms_out) {
+    using namespace th;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(gemm_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    *num_sms_out = tc::device_sm_count();
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)W.Kp32, (cuuint64_t)W.Mp128};
+        const cuuint64_t strides[1] = {(cuuint64_t)W.Kp32 * 2};
+        const cuuint32_t box[2] = {BK, BM};
+        if (!tc::make_map_dt(map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !tc::make_map_dt(map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)x_rs * 4, (cuuint64_t)x_bs * 4};
+        const cuuint32_t box[3] = {BN, BK, 1};
+        if (!tc::make_map(map_x, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
+}
+
+static cudaError_t seed_residual(const float* R, float* Y, long long y_bs, int y_rs, int B, int M, int T, cudaStream_t st) {
+    for (int b = 0; b < B; ++b) {   // out-of-place residual: seed Y with R, then accumulate in place
+        cudaError_t e = cudaMemcpy2DAsync(Y + (long long)b * y_bs, (size_t)y_rs * 4, R + (long long)b * y_bs, (size_t)y_rs * 4,
+                                          (size_t)T * 4, M, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre, float pre_scale,
+                          const float* bias, const float* R, float* Y, long long y_bs, int y_rs, cudaStream_t st) {
+    using namespace th;
+    if (B == 0 || T == 0) return cudaSuccess;
+    CUtensorMap map_hi, map_lo, map_x, map_y;
+    int num_sms = 0;
+    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
+    if (e != cudaSuccess) return e;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {32, BM, 1};
+        if (!tc::make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidValue;
+    }
+    if (R && R != Y) {
+        e = seed_residual(R, Y, y_bs, y_rs, B, W.M, T, st);
+        if (e != cudaSuccess) return e;
+    }
+    Params p{};
+    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
+    p.num_m = (W.M + BM - 1) / BM;
+    p.t_step = BN; p.t_halo = 0;
+    p.tiles_t = (T + p.t_step - 1) / p.t_step;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
+    p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                             float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in, float* cache_out,
+                             const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st) {
+    using namespace th;
+    if (B == 0 || T == 0) return cudaSuccess;
+    CUtensorMap map_hi, map_lo, map_x, map_y, map_y28;
+    int num_sms = 0;
+    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
+    if (e != cudaSuccess) return e;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {32, BM, 1};
+        const cuuint32_t box28[3] = {28, BM, 1};
+        if (!tc::make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !tc::make_map(&map_y28, Y, 3, dims, strides, box28, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return cudaErrorInvalidValue;
+    }
+    if (skip && skip != Y) {
+        e = seed_residual(skip, Y, y_bs, y_rs, B, W.M, T, st);
+        if (e != cudaSuccess) return e;
+    }
+    Params p{};
+    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
+    p.num_m = (W.M + BM - 1) / BM;
+    p.t_step = BN - 4; p.t_halo = 4;
+    p.tiles_t = (T + p.t_step - 1) / p.t_step;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out;
+    p.reduce_add = skip ? 1 : 0;
+    p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
+    return cudaGetLastError();
+}
+
+}  // namespace hil

@@ -144,14 +144,18 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-inline bool make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                     const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+inline bool make_map_dt(CUtensorMap* map, CUtensorMapDataType dtype, const void* ptr, int rank, const cuuint64_t* dims,
+                        const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint32_t estr[3] = {1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
-              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    return fn(map, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+    return make_map_dt(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ptr, rank, dims, strides_bytes, box, swizzle);
 }
 
 inline int device_sm_count() {
