@@ -28,6 +28,8 @@
 // Per k-block two k16 steps of { A_hi x [B_hi | B_lo] (N = 256) -> [big | small]; A_lo x B_hi (N = 128) ->
 // small }.  Epilogues are the ones of gemm_tc.cu (TMEM -> registers -> swizzled staging -> TMA store /
 // reduce-add; optional fused causal depthwise k5).
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 
 #include "tc_ptx.cuh"
@@ -58,6 +60,7 @@ struct Params {
     int num_m, tiles_t;
     long long total_tiles;
     int pre;
+    int elu_poly;           // 1: elu_fast in the transform (HILCODEC_ELU_POLY=1), 0: ex2-only ELU on the packed pipe
     float pre_scale;
     float c_big, c_small;   // 2^-s and 2^-s * 2^-11
     const float* bias;
@@ -90,6 +93,64 @@ __device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+
+// Transform of 4 consecutive activations: optional ELU prologue, then the fp16 hi/lo split, on the packed
+// fp32 pipe (FMUL2 / FADD2 / FFMA2: ~7 issue slots per element instead of ~20 with scalar code and elu_fast).
+//   ELU(x) = x > 0 ? x : 2^(x log2 e) - 1 with ex2.approx: absolute error <= 2.4e-7, the bound elu_fast already
+//   has below -1/16 (its near-zero polynomial only buys relative accuracy for |x| < 1/16, which the GEMM that
+//   consumes the value cannot see: the error enters the dot product in absolute terms).
+//   x - fp16(x) is exact in fp32 and the 2^11 scaling is a power of two, so the split is bit-identical to the
+//   scalar form  lo = fp16_rn((x - hi) * 2^11).
+template <int kPre, bool kPoly = false>
+__device__ __forceinline__ void split4(float4 x, float s, uint32_t& h01, uint32_t& h23, uint32_t& l01, uint32_t& l23) {
+    float r0 = x.x, r1 = x.y, r2 = x.z, r3 = x.w;
+    if (kPre != PRE_NONE && kPoly) {   // HILCODEC_ELU_POLY=1: elu_fast (polynomial near zero), for A/B accuracy checks
+        r0 = elu_fast(r0 * s); r1 = elu_fast(r1 * s); r2 = elu_fast(r2 * s); r3 = elu_fast(r3 * s);
+    } else if (kPre != PRE_NONE) {
+        f32x2 a = pk2(r0, r1), b = pk2(r2, r3);
+        if (kPre == PRE_SCALE_ELU) {
+            const f32x2 s2 = pk2(s, s);
+            a = fmul2(a, s2);
+            b = fmul2(b, s2);
+            upk2(a, r0, r1);
+            upk2(b, r2, r3);
+        }
+        const f32x2 l2e = pk2(1.4426950408889634f, 1.4426950408889634f), m1 = pk2(-1.f, -1.f);
+        float t0, t1, t2, t3;
+        upk2(fmul2(a, l2e), t0, t1);
+        upk2(fmul2(b, l2e), t2, t3);
+        float e0, e1, e2, e3;
+        upk2(fadd2(pk2(ex2_approx(t0), ex2_approx(t1)), m1), e0, e1);
+        upk2(fadd2(pk2(ex2_approx(t2), ex2_approx(t3)), m1), e2, e3);
+        r0 = r0 > 0.f ? r0 : e0;
+        r1 = r1 > 0.f ? r1 : e1;
+        r2 = r2 > 0.f ? r2 : e2;
+        r3 = r3 > 0.f ? r3 : e3;
+    }
+    h01 = pack_h2(r0, r1);
+    h23 = pack_h2(r2, r3);
+    const float2 f01 = unpack_h2(h01), f23 = unpack_h2(h23);
+    const f32x2 m1 = pk2(-1.f, -1.f), sc = pk2(LO_SCALE, LO_SCALE);
+    float d0, d1, d2, d3;
+    upk2(fmul2(ffma2(pk2(f01.x, f01.y), m1, pk2(r0, r1)), sc), d0, d1);
+    upk2(fmul2(ffma2(pk2(f23.x, f23.y), m1, pk2(r2, r3)), sc), d2, d3);
+    l01 = pack_h2(d0, d1);
+    l23 = pack_h2(d2, d3);
+}
+
+// rows 4*xw .. 4*xw+3 of a [32 k][128 t] box -> B_hi / B_lo (MN-major, SWIZZLE_128B atoms of 8 k-rows x 128 B)
+template <int kPre, bool kPoly = false>
+__device__ __forceinline__ void xform_rows(const float4 (&v)[4], float s, int xw, uint32_t bhi, uint32_t chunk, uint32_t half8) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t k = (uint32_t)(xw * 4 + q);
+        uint32_t h01, h23, l01, l23;
+        split4<kPre, kPoly>(v[q], s, h01, h23, l01, l23);
+        const uint32_t dst = bhi + (k >> 3) * 1024u + (k & 7u) * 128u + ((chunk ^ (k & 7u)) << 4) + half8;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h01), "r"(h23) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + (uint32_t)B_TILE), "r"(l01), "r"(l23) : "memory");
+    }
+}
 
 // ------------------------------------------------------------------------------- kernel
 template <bool kDw>
@@ -238,22 +299,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 float4 v[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[q] = src[(xw * 4 + q) * (BN / 4) + lane];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t k = (uint32_t)(xw * 4 + q);
-                    float4 x = v[q];
-                    if (p.pre != PRE_NONE) {   // pre_scale is 1.0 for PRE_ELU (x * 1.0f is exact)
-                        x.x = elu_fast(x.x * p.pre_scale); x.y = elu_fast(x.y * p.pre_scale);
-                        x.z = elu_fast(x.z * p.pre_scale); x.w = elu_fast(x.w * p.pre_scale);
-                    }
-                    const uint32_t h01 = pack_h2(x.x, x.y), h23 = pack_h2(x.z, x.w);
-                    const float2 f01 = unpack_h2(h01), f23 = unpack_h2(h23);
-                    const uint32_t l01 = pack_h2((x.x - f01.x) * LO_SCALE, (x.y - f01.y) * LO_SCALE);
-                    const uint32_t l23 = pack_h2((x.z - f23.x) * LO_SCALE, (x.w - f23.y) * LO_SCALE);
-                    const uint32_t dst = bhi + (k >> 3) * 1024u + (k & 7u) * 128u + ((chunk ^ (k & 7u)) << 4) + half8;
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h01), "r"(h23) : "memory");
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + (uint32_t)B_TILE), "r"(l01), "r"(l23) : "memory");
-                }
+                if (p.pre == PRE_NONE) xform_rows<PRE_NONE>(v, 1.0f, xw, bhi, chunk, half8);
+                else if (p.elu_poly) xform_rows<PRE_SCALE_ELU, true>(v, p.pre_scale, xw, bhi, chunk, half8);
+                else if (p.pre == PRE_ELU) xform_rows<PRE_ELU>(v, 1.0f, xw, bhi, chunk, half8);
+                else xform_rows<PRE_SCALE_ELU>(v, p.pre_scale, xw, bhi, chunk, half8);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -270,7 +319,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
         const bool issuer = (q == 0 && lane == 0);
         const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
-        const float c_big = p.c_big, c_small = p.c_small;
+        const float c_big = p.c_big;                        // 2^-s; c_small = c_big * 2^-11
+        const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE), cb2 = pk2(c_big, c_big);
         long long it = 0;
         uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
         if constexpr (!kDw) {
@@ -285,6 +335,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 tc_fence_after();
                 const int m = m_blk * BM + row;
                 const float bv = (m < p.M && p.bias) ? p.bias[m] : 0.f;
+                const f32x2 bv2 = pk2(bv, bv);
                 const int t0 = tt * BN;
                 const int n_chunks = min(BN / 32, (p.T - t0 + 31) / 32);
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
@@ -304,10 +355,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     const uint32_t orow = obuf + row * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
+                        // (big + small * 2^-11) * 2^-s + bias: two packed FMAs per pair; bit-identical to
+                        // fmaf(small, c_small, big * c_big) + bias because every scale is a power of two
                         float o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            o[e] = fmaf(__uint_as_float(rs[4 * j + e]), c_small, __uint_as_float(rb[4 * j + e]) * c_big) + bv;
+                        upk2(ffma2(ffma2(pk2(__uint_as_float(rs[4 * j]), __uint_as_float(rs[4 * j + 1])), lo2,
+                                         pk2(__uint_as_float(rb[4 * j]), __uint_as_float(rb[4 * j + 1]))), cb2, bv2), o[0], o[1]);
+                        upk2(ffma2(ffma2(pk2(__uint_as_float(rs[4 * j + 2]), __uint_as_float(rs[4 * j + 3])), lo2,
+                                         pk2(__uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3]))), cb2, bv2), o[2], o[3]);
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j ^ sw) << 4)), "f"(o[0]),
                                      "f"(o[1]), "f"(o[2]), "f"(o[3])
                                      : "memory");
@@ -334,17 +388,20 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
                 const int m = m_blk * BM + row;
                 const bool row_ok = m < p.M;
+                // The window slides over u = (big + small * 2^-11) = pointwise / c_big, with the taps pre-multiplied
+                // by c_big (powers of two: the products are unchanged); the caches hold true-scale values.
                 float wk[5];
 #pragma unroll
-                for (int k = 0; k < 5; ++k) wk[k] = row_ok ? p.dw_w[m * 5 + k] : 0.f;
+                for (int k = 0; k < 5; ++k) wk[k] = row_ok ? p.dw_w[m * 5 + k] * c_big : 0.f;
                 const float bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                const float c_inv = 1.0f / c_big;
                 const int tcol0 = tt * p.t_step - p.t_halo;       // time of tile column 0
                 const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
                 const bool has_tail = row_ok && (tcol0 + BN > p.T - 4);  // tile holds some of the last 4 columns
                 float carry[4] = {0.f, 0.f, 0.f, 0.f};
                 if (tt == 0 && row_ok) {
                     const float4 cv = *reinterpret_cast<const float4*>(p.cache_in + ((size_t)b * p.M + m) * 4);
-                    carry[0] = cv.x; carry[1] = cv.y; carry[2] = cv.z; carry[3] = cv.w;
+                    carry[0] = cv.x * c_inv; carry[1] = cv.y * c_inv; carry[2] = cv.z * c_inv; carry[3] = cv.w * c_inv;
                 }
                 mbar_wait<64>(tfull_bar(acc), acc_ph);
                 tc_fence_after();
@@ -362,7 +419,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     }
                     float v[36];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[4 + j] = fmaf(__uint_as_float(rs[j]), c_small, __uint_as_float(rb[j]) * c_big);
+                    for (int j = 0; j < 32; j += 2)
+                        upk2(ffma2(pk2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), lo2,
+                                   pk2(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]))), v[4 + j], v[5 + j]);
                     // columns 0..3 of the first tile are times -4..-1: the cache handed in by the caller
                     if (c == 0 && tt == 0) { v[4] = carry[0]; v[5] = carry[1]; v[6] = carry[2]; v[7] = carry[3]; }
                     v[0] = carry[0]; v[1] = carry[1]; v[2] = carry[2]; v[3] = carry[3];
@@ -372,7 +431,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                             const int col = c * 32 + j;
                             const int t = tcol0 + col;
                             if (col >= p.t_halo && t >= p.T - 4 && t < p.T)
-                                p.cache_out[((size_t)b * p.M + m) * 4 + (t - (p.T - 4))] = v[4 + j];
+                                p.cache_out[((size_t)b * p.M + m) * 4 + (t - (p.T - 4))] = v[4 + j] * c_big;
                         }
                     }
                     if (issuer) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
@@ -383,10 +442,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int i = j4 * 4 + e;  // output i of this chunk uses v[i..i+4]
-                            float a = 0.f;
+                            float a = bv;
 #pragma unroll
                             for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[i + k], a);
-                            o[e] = a + bv;
+                            o[e] = a;
                         }
                         uint32_t dst;
                         if (c == 0) {
@@ -435,6 +494,11 @@ bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs,
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
     if (R && (reinterpret_cast<uintptr_t>(R) & 15)) return false;
     return true;
+}
+
+static int elu_poly_env() {
+    static const int v = []() { const char* e = std::getenv("HILCODEC_ELU_POLY"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v;
 }
 
 static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, CUtensorMap* map_hi,
@@ -501,6 +565,7 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     return cudaGetLastError();
@@ -538,6 +603,7 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out;
     p.reduce_add = skip ? 1 : 0;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
     return cudaGetLastError();
