@@ -99,6 +99,10 @@ static bool g_use_tm = std::getenv("HILCODEC_ENABLE_TM") != nullptr;
 // mode bit 4 (16) of hil_set_tensor_cores, or HILCODEC_GEMM=tf32 to fall back to gemm_tc.cu.
 static bool g_use_h = []() { const char* e = std::getenv("HILCODEC_GEMM"); return !(e && std::strcmp(e, "tf32") == 0); }();
 
+// whole-ResBlock kernel (gemm_rb.cu) for C <= 256 and chunks of >= 128 samples; mode bit 5 (32) of
+// hil_set_tensor_cores or HILCODEC_FUSE_RESBLOCK=0 keep the two fused-DWS launches per ResBlock.
+static bool g_fuse_rb = []() { const char* e = std::getenv("HILCODEC_FUSE_RESBLOCK"); return !(e && e[0] == '0'); }();
+
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
@@ -173,6 +177,19 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
     HIL_TRY(run_gemm_linear(W, X, bs, rs, B, T, pre, pre_scale, nullptr, nullptr, tmp, bs, rs, st));
     return run_dwconv(tmp, bs, rs, ci, co, dw_w, dw_b, skip, Y, bs, rs, B, W.M, T, 5, 1, PRE_NONE, 1.f, st, post,
                       post_scale);
+}
+
+// ResBlock.forward streaming.py:252-275 as ONE tensor-core kernel (+ the halo gather in front of it)
+static int32_t run_resblock(const PackedMat& W0, const PackedMat& W1, float* h, long long bs, int rs, int B, int T, int pre,
+                            float pre_scale, const float* dw0_w, const float* dw0_b, const float* dw1_w, const float* dw1_b,
+                            const float* c0i, float* c0o, const float* c1i, float* c1o, float* halo, cudaStream_t st) {
+    const double n = (double)B * T, C = W0.M;
+    const double halo_bytes = 4.0 * (double)resblock_h_halo_floats(W0.M, T, B);
+    HIL_LAUNCH(CAT_MISC, 0.0, 2.0 * halo_bytes, st, launch_resblock_halo(h, bs, rs, B, W0.M, T, halo, st));
+    HIL_LAUNCH(CAT_GEMM_PW, 2.0 * (2.0 * C * C * n + 10.0 * C * n), 8.0 * n * C + halo_bytes + 8.0 * C * C, st,
+               launch_resblock_h(W0, W1, h, bs, rs, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0i, c0o, c1i, c1o, halo,
+                                 st));
+    return HIL_OK;
 }
 
 static int32_t run_dwconv_transpose(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
@@ -816,6 +833,10 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     const int Tp = pitch4(Ts);
     const long long bs = (long long)C * Tp;
     const int pre0 = pre_scale == 1.0f ? PRE_ELU : PRE_SCALE_ELU;
+    if (g_use_tc && g_use_h && g_fuse_dw && g_fuse_rb && resblock_h_usable(u[0].pw, u[1].pw, h, bs, Tp, Ts))
+        // a1 holds the halo columns (8 per tile: always smaller than an activation buffer)
+        return run_resblock(u[0].pw, u[1].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, u[1].dw_w, u[1].dw_b,
+                            cin[0], cout[0], cin[1], cout[1], a1, st);
     HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, PRE_NONE,
                     1.f, a1, a2, st));
     HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, PRE_ELU, 1.f, u[1].dw_w, u[1].dw_b, cin[1], cout[1], h, PRE_NONE, 1.f, a1,
@@ -1141,11 +1162,12 @@ int32_t hil_unpack_indices(hil_model* m, const uint8_t* in, int32_t B, int32_t F
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 
 int32_t hil_set_tensor_cores(int32_t mode) {
-    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0);
+    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32);
     g_use_tc = (mode & 1) != 0;
     g_use_tm = (mode & 8) != 0;
     g_fuse_dw = (mode & 4) == 0;
     g_use_h = (mode & 16) != 0;
+    g_fuse_rb = (mode & 32) == 0;
     return prev;
 }
 
@@ -1233,6 +1255,40 @@ int32_t hil_op_dws(const float* x, const float* w_pw_host, const float* w_dw, co
                          post_scale, tmp, y, (cudaStream_t)stream);
     cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(dev);
+    HIL_TRY(rc);
+    HIL_CUDA(e2);
+    return HIL_OK;
+}
+
+int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, const float* dw0_w, const float* dw0_b,
+                        const float* dw1_w, const float* dw1_b, const float* c0_in, float* c0_out, const float* c1_in,
+                        float* c1_out, float* tmp1, float* tmp2, int32_t B, int32_t C, int32_t T, int32_t pre, float pre_scale,
+                        int32_t fused, void* stream) {
+    if (!h || !w0_host || !w1_host || !dw0_w || !dw1_w || !c0_in || !c0_out || !c1_in || !c1_out || !tmp1 || !tmp2)
+        return fail(HIL_ERR_INVALID, "null pointer");
+    PackedMat pm0, pm1;
+    float *dev0 = nullptr, *dev1 = nullptr;
+    HIL_TRY(upload_packed(w0_host, C, C, choose_tm(C), false, &pm0, &dev0));
+    int32_t rc = upload_packed(w1_host, C, C, choose_tm(C), false, &pm1, &dev1);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long bs = (long long)C * T;
+    if (rc == HIL_OK) {
+        if (fused) {
+            if (!g_use_tc || !g_use_h || !resblock_h_usable(pm0, pm1, h, bs, T, T))
+                rc = fail(HIL_ERR_INVALID, "fused ResBlock kernel not usable for this shape / mode");
+            else
+                rc = run_resblock(pm0, pm1, h, bs, T, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in,
+                                  c1_out, tmp1, st);
+        } else {
+            rc = run_dws(pm0, h, bs, T, B, T, pre, pre_scale, dw0_w, dw0_b, c0_in, c0_out, nullptr, PRE_NONE, 1.f, tmp1, tmp2,
+                         st);
+            if (rc == HIL_OK)
+                rc = run_dws(pm1, tmp2, bs, T, B, T, PRE_ELU, 1.f, dw1_w, dw1_b, c1_in, c1_out, h, PRE_NONE, 1.f, tmp1, h, st);
+        }
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(dev0);
+    if (dev1) cudaFree(dev1);
     HIL_TRY(rc);
     HIL_CUDA(e2);
     return HIL_OK;

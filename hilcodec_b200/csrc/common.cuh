@@ -88,6 +88,15 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
                              float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
                              float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
+// ---- gemm_rb.cu: whole ResBlock (two DWSBlocks + residual add) in one kernel, h updated in place (C <= 256)
+bool resblock_h_usable(const PackedMat& W0, const PackedMat& W1, const float* h, long long bs, int rs, int T);
+size_t resblock_h_halo_floats(int C, int T, int B);
+cudaError_t launch_resblock_halo(const float* h, long long bs, int rs, int B, int C, int T, float* halo, cudaStream_t st);
+cudaError_t launch_resblock_h(const PackedMat& W0, const PackedMat& W1, float* h, long long bs, int rs, int B, int T, int pre,
+                              float pre_scale, const float* dw0_w, const float* dw0_b, const float* dw1_w, const float* dw1_b,
+                              const float* c0_in, float* c0_out, const float* c1_in, float* c1_out, const float* halo,
+                              cudaStream_t st);
+
 // fused DWSBlock: y = dw5(W * pre(x)) + b_dw (+ skip); same usability conditions as launch_gemm_tc
 cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,

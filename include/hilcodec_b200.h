@@ -138,7 +138,8 @@ uint64_t hil_launch_count(void);
 /* Kernel selection for A/B measurement (returns the previous mode).  Bit 0: 1 (default) = GEMMs and STFT on the
  * tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy), 0 = FP32 FFMA kernels everywhere.  Bit 2 set: do not
  * fuse DWS blocks.  Bit 3 set: use the experimental time-major kernel (gemm_tm.cu, activations through TMEM)
- * for plain 1x1 convs with Cout <= 192. */
+ * for plain 1x1 convs with Cout <= 192.  Bit 4 set (default): fp16-split tensor-core kernels (gemm_h.cu, kind::f16)
+ * instead of 3xTF32.  Bit 5 set: do not fuse whole ResBlocks (gemm_rb.cu). */
 int32_t hil_set_tensor_cores(int32_t mode);
 #define HIL_PROFILE_CATEGORIES 8
 int32_t hil_profile_begin(void);
@@ -165,6 +166,15 @@ int32_t hil_op_pointwise(const float* x, const float* w_host, const float* bias_
 int32_t hil_op_dws(const float* x, const float* w_pw_host, const float* w_dw, const float* b_dw, const float* cache_in,
                    float* cache_out, const float* skip, float* tmp, float* y, int32_t B, int32_t C, int32_t T, int32_t pre,
                    float pre_scale, int32_t post, float post_scale, void* stream);
+/* ResBlock.forward streaming.py:252-275 with the residual scale folded into the second depthwise conv
+ * (merge_scaling :240-250):  h[B,C,T] <- h + dw5_1(W1 * ELU(dw5_0(W0 * pre(h)) + b0)) + b1, in place.
+ * c0/c1 [B,C,4] are the caches of the two depthwise convs (in -> out).  fused = 1: the one-kernel path
+ * (C <= 256, C % 32 == 0, T >= 128; tmp1 receives the halo columns), fused = 0: two hil_op_dws-style launches
+ * through tmp1/tmp2 [B,C,T].  w0_host / w1_host are HOST [C,C,1] weights. */
+int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, const float* dw0_w, const float* dw0_b,
+                        const float* dw1_w, const float* dw1_b, const float* c0_in, float* c0_out, const float* c1_in,
+                        float* c1_out, float* tmp1, float* tmp2, int32_t B, int32_t C, int32_t T, int32_t pre, float pre_scale,
+                        int32_t fused, void* stream);
 /* CausalSTFT.forward causal_layers.py:135-144 + clamp/log streaming.py:351:
  * wav_window [B,1,(T-1)*hop+n_fft], w_host [2F,1,n_fft] HOST -> y [B,F,T] = log(max(|STFT|,1e-5)). */
 int32_t hil_op_stft_logmag(const float* wav_window, const float* w_host, float* y, int32_t B, int32_t n_fft, int32_t hop,

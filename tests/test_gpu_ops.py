@@ -217,3 +217,55 @@ def test_pointwise_time_major_kernel_matches_channel_major(B, M, K, T, pre, bias
     finally:
         lib.hil_set_tensor_cores(prev)
     assert (outs[0] - outs[1]).abs().max().item() < 1e-5 * max(1.0, outs[0].abs().max().item())
+
+
+def _resblock_ref(x, w0, w1, d0w, d0b, d1w, d1b, c0, c1, pre, pre_scale):
+    """ResBlock.forward streaming.py:252-275 (merged scaling) in fp64, with both depthwise caches."""
+    C = x.shape[1]
+    a = _pre_ref(x, pre, pre_scale).double()
+    p0 = torch.cat((c0.double(), F.conv1d(a, w0.double())), 2)
+    a = F.elu(F.conv1d(p0, d0w.double(), d0b.double(), groups=C))
+    p1 = torch.cat((c1.double(), F.conv1d(a, w1.double())), 2)
+    y = x.double() + F.conv1d(p1, d1w.double(), d1b.double(), groups=C)
+    return y, p0[:, :, -4:], p1[:, :, -4:]
+
+
+@pytest.mark.parametrize("B,Cc,T,pre", [
+    (2, 96, 2400, 1),     # decoder stage 3 shape: one m-block, 128-column tiles (120 outputs each), 20 tiles
+    (1, 64, 1000, 2),     # encoder stage 0: half-empty m-block, ragged last tile, scaled ELU prologue
+    (3, 128, 128, 1),     # shortest chunk the fused kernel takes: two tiles, the second one 8 columns wide
+    (2, 128, 364, 1),     # three full tiles and a 4-column one
+    (1, 192, 1500, 1),    # decoder stage 2: two m-blocks, 64-column tiles (56 outputs each)
+    (2, 256, 300, 2),     # encoder stage 2: both m-blocks full
+    (1, 32, 200, 1),
+])
+def test_resblock_fused(B, Cc, T, pre):
+    """gemm_rb.cu (whole ResBlock in one kernel, h updated in place) against the fp64 reference and against the two
+    fused-DWS launches it replaces: same arithmetic, so the two CUDA paths must agree bit for bit."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(Cc * 31 + T)
+    x = torch.randn(B, Cc, T, generator=g)
+    w0 = (torch.randn(Cc, Cc, 1, generator=g) / Cc ** 0.5).contiguous()
+    w1 = (torch.randn(Cc, Cc, 1, generator=g) / Cc ** 0.5).contiguous()
+    d0w = torch.randn(Cc, 1, 5, generator=g) / 5 ** 0.5
+    d1w = 0.57735 * torch.randn(Cc, 1, 5, generator=g) / 5 ** 0.5
+    d0b, d1b = torch.randn(Cc, generator=g), torch.randn(Cc, generator=g)
+    c0, c1 = torch.randn(B, Cc, 4, generator=g), torch.randn(B, Cc, 4, generator=g)
+    y_ref, c0_ref, c1_ref = _resblock_ref(x, w0, w1, d0w, d0b, d1w, d1b, c0, c1, pre, 0.8660254)
+    dev = [t.cuda() for t in (d0w, d0b, d1w, d1b, c0, c1)]
+    outs = []
+    for fused in (1, 0):
+        h = x.cuda().clone()
+        c0o, c1o = torch.zeros(B, Cc, 4, device="cuda"), torch.zeros(B, Cc, 4, device="cuda")
+        t1, t2 = torch.zeros(B, Cc, T, device="cuda"), torch.zeros(B, Cc, T, device="cuda")
+        _lib.check(lib.hil_op_resblock(_ptr(h), _ptr(w0), _ptr(w1), _ptr(dev[0]), _ptr(dev[1]), _ptr(dev[2]), _ptr(dev[3]),
+                                       _ptr(dev[4]), _ptr(c0o), _ptr(dev[5]), _ptr(c1o), _ptr(t1), _ptr(t2),
+                                       B, Cc, T, pre, 0.8660254, fused, _stream()))
+        torch.cuda.synchronize()
+        outs.append((h.cpu(), c0o.cpu(), c1o.cpu()))
+    for h, c0o, c1o in outs:
+        assert (h.double() - y_ref).abs().max().item() < 3e-5
+        assert (c0o.double() - c0_ref).abs().max().item() < 1e-5
+        assert (c1o.double() - c1_ref).abs().max().item() < 1e-5
+    assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0] - outs[1][0]).abs().max()
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
