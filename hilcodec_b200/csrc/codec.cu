@@ -2,6 +2,7 @@
 // the C ABI declared in include/hilcodec_b200.h.  The layer schedule below restates
 // Encoder.forward (streaming.py:482-517) and Decoder.forward (streaming.py:619-648) as a
 // sequence of kernel launches; see DESIGN.md for the kernel list and data layout.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -103,6 +104,10 @@ static bool g_use_h = []() { const char* e = std::getenv("HILCODEC_GEMM"); retur
 // hil_set_tensor_cores or HILCODEC_FUSE_RESBLOCK=0 keep the two fused-DWS launches per ResBlock.
 static bool g_fuse_rb = []() { const char* e = std::getenv("HILCODEC_FUSE_RESBLOCK"); return !(e && e[0] == '0'); }();
 
+// decoder upsampling layers (transposed depthwise conv -> 1x1) as one kernel: mode bit 6 (64) of
+// hil_set_tensor_cores or HILCODEC_FUSE_UPSAMPLE=0 keep the two launches.
+static bool g_fuse_up = []() { const char* e = std::getenv("HILCODEC_FUSE_UPSAMPLE"); return e && e[0] == '1'; }();   // WIP: off until green
+
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
@@ -200,6 +205,23 @@ static int32_t run_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
                launch_dwconv_transpose(x, x_bs, x_rs, ci, co, w, y, y_bs, y_rs, B, C, T, S, pre, pre_scale, st));
     return HIL_OK;
 }
+// act -> CausalConvTranspose1d (depthwise) -> 1x1 + bias: one tensor-core kernel when usable, else the two kernels
+// through `tmp` [B][K][S*T_in].
+static int32_t run_upsample(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T_in, int S, int pre,
+                            float pre_scale, const float* up_w, const float* ci, float* co, const float* bias, float* tmp,
+                            float* Y, long long y_bs, int y_rs, bool allow_fused, cudaStream_t st) {
+    const int K = W.K, T = S * T_in;
+    if (allow_fused && g_use_tc && g_use_h && g_fuse_up && gemm_h_up_usable(W, x, x_bs, x_rs, T_in, S, pre, Y, y_bs, y_rs)) {
+        const double n = (double)B * T;
+        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * K * n + 4.0 * K * n, 4.0 * ((double)B * K * T_in + n * W.M) + 4.0 * W.M * K, st,
+                   launch_gemm_h_up(W, x, x_bs, x_rs, B, T_in, S, pre, pre_scale, up_w, ci, co, bias, Y, y_bs, y_rs, st));
+        return HIL_OK;
+    }
+    const int Tp2 = pitch4(T);
+    HIL_TRY(run_dwconv_transpose(x, x_bs, x_rs, ci, co, up_w, tmp, (long long)K * Tp2, Tp2, B, K, T_in, S, pre, pre_scale, st));
+    return run_gemm_linear(W, tmp, (long long)K * Tp2, Tp2, B, T, PRE_NONE, 1.f, bias, nullptr, Y, y_bs, y_rs, st);
+}
+
 static int32_t run_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
                                   const float* bias, float* y, int B, int C, int T, int K, int pre, float pre_scale,
                                   cudaStream_t st) {
@@ -833,7 +855,12 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     const int Tp = pitch4(Ts);
     const long long bs = (long long)C * Tp;
     const int pre0 = pre_scale == 1.0f ? PRE_ELU : PRE_SCALE_ELU;
-    if (g_use_tc && g_use_h && g_fuse_dw && g_fuse_rb && resblock_h_usable(u[0].pw, u[1].pw, h, bs, Tp, Ts))
+    // C <= 128 only by default: with two m-blocks the kernel works on 64-column tiles and re-streams both weight
+    // matrices from L2 for every 56 outputs, which measured slower than two fused-DWS launches (HILCODEC_RB_WIDE=1
+    // enables it for 128 < C <= 256)
+    static const bool rb_wide = std::getenv("HILCODEC_RB_WIDE") != nullptr;
+    if (g_use_tc && g_use_h && g_fuse_dw && g_fuse_rb && (C <= 128 || rb_wide) &&
+        resblock_h_usable(u[0].pw, u[1].pw, h, bs, Tp, Ts))
         // a1 holds the halo columns (8 per tile: always smaller than an activation buffer)
         return run_resblock(u[0].pw, u[1].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, u[1].dw_w, u[1].dw_b,
                             cin[0], cout[0], cin[1], cout[1], a1, st);
@@ -920,11 +947,12 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
         const int Ts2 = Ts * sg.ratio, Tp2 = pitch4(Ts2);
         // (previous stage's Scale) -> ELU -> transposed depthwise -> 1x1 (C -> C/2) (streaming.py:633-637);
         // stage 0's ELU was applied by conv_pre_depthwise's store
-        HIL_TRY(run_dwconv_transpose(h, (long long)C * Tp, Tp, cin[ci], cout[ci], sg.up_w, a1, (long long)C * Tp2, Tp2,
-                                     B, C, Ts, sg.ratio, i == 0 ? PRE_NONE : PRE_SCALE_ELU, m->dec_post_scale, st));
+        // fused: h (low rate) -> a2 (the 1x1 output cannot overwrite its own input), then the buffers swap roles
+        HIL_TRY(run_upsample(sg.up_pw, h, (long long)C * Tp, Tp, B, Ts, sg.ratio, i == 0 ? PRE_NONE : PRE_SCALE_ELU,
+                             m->dec_post_scale, sg.up_w, cin[ci], cout[ci], sg.up_b, a1, a2, (long long)(C / 2) * Tp2, Tp2,
+                             true, st));
         ci += 1;
-        HIL_TRY(run_gemm_linear(sg.up_pw, a1, (long long)C * Tp2, Tp2, B, Ts2, PRE_NONE, 1.f, sg.up_b, nullptr, h,
-                                    (long long)(C / 2) * Tp2, Tp2, st));
+        std::swap(h, a2);
         C /= 2;
         Ts = Ts2;
         for (int j = 0; j < c.n_residual_dec; ++j) {
@@ -1162,12 +1190,13 @@ int32_t hil_unpack_indices(hil_model* m, const uint8_t* in, int32_t B, int32_t F
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 
 int32_t hil_set_tensor_cores(int32_t mode) {
-    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32);
+    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32) | (g_fuse_up ? 0 : 64);
     g_use_tc = (mode & 1) != 0;
     g_use_tm = (mode & 8) != 0;
     g_fuse_dw = (mode & 4) == 0;
     g_use_h = (mode & 16) != 0;
     g_fuse_rb = (mode & 32) == 0;
+    g_fuse_up = (mode & 64) == 0;
     return prev;
 }
 
@@ -1289,6 +1318,32 @@ int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, co
     cudaError_t e2 = cudaStreamSynchronize(st);
     cudaFree(dev0);
     if (dev1) cudaFree(dev1);
+    HIL_TRY(rc);
+    HIL_CUDA(e2);
+    return HIL_OK;
+}
+
+int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out, const float* w_up, const float* w_pw_host,
+                        const float* bias, float* tmp, float* y, int32_t B, int32_t K, int32_t M, int32_t T_in, int32_t S,
+                        int32_t pre, float pre_scale, int32_t fused, void* stream) {
+    if (!x || !cache_in || !cache_out || !w_up || !w_pw_host || !tmp || !y) return fail(HIL_ERR_INVALID, "null pointer");
+    PackedMat pm;
+    float* dev = nullptr;
+    HIL_TRY(upload_packed(w_pw_host, M, K, choose_tm(M), false, &pm, &dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = S * T_in;
+    int32_t rc;
+    if (fused && !(g_use_tc && g_use_h && gemm_h_up_usable(pm, x, (long long)K * T_in, T_in, T_in, S, pre, y, (long long)M * T, T)))
+        rc = fail(HIL_ERR_INVALID, "fused upsampling kernel not usable for this shape / mode");
+    else {
+        const bool keep = g_fuse_up;
+        g_fuse_up = true;
+        rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp, y,
+                          (long long)M * T, T, fused != 0, st);
+        g_fuse_up = keep;
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(dev);
     HIL_TRY(rc);
     HIL_CUDA(e2);
     return HIL_OK;

@@ -88,6 +88,13 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
                              float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
                              float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
+// upsampling layer: act -> causal transposed depthwise conv (stride S, kernel 2S) -> 1x1 conv + bias, one kernel
+bool gemm_h_up_usable(const PackedMat& W, const float* x, long long x_bs, int x_rs, int T_in, int S, int pre, const float* Y,
+                      long long y_bs, int y_rs);
+cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T_in, int S, int pre,
+                             float pre_scale, const float* up_w, const float* cache_in, float* cache_out, const float* bias,
+                             float* Y, long long y_bs, int y_rs, cudaStream_t st);
+
 // ---- gemm_rb.cu: whole ResBlock (two DWSBlocks + residual add) in one kernel, h updated in place (C <= 256)
 bool resblock_h_usable(const PackedMat& W0, const PackedMat& W1, const float* h, long long bs, int rs, int T);
 size_t resblock_h_halo_floats(int C, int T, int B);

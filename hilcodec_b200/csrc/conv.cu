@@ -174,6 +174,81 @@ __global__ void dwconv5_kernel(const float* __restrict__ x, long long x_bs, int 
     }
 }
 
+// strided specialisation (encoder downsampling, k = 2r, s = r): 4 outputs per thread from aligned 16-byte loads.
+// The 4 outputs to0 .. to0+3 read xin[to0*S .. to0*S + 3S + K - 1]; in x coordinates (xin = cat(cache[P], x)) that is
+// x[to0*S - P .. to0*S + 4S - 1], fetched as NV float4 starting at the 16-byte boundary a0 = to0*S - ceil4(P).
+template <int K, int S>
+__global__ void dwconv_strided4_kernel(const float* __restrict__ x, long long x_bs, int x_rs,
+                                       const float* __restrict__ cache_in, float* __restrict__ cache_out,
+                                       const float* __restrict__ w, const float* __restrict__ bias, const float* skip,
+                                       float* y, long long y_bs, int y_rs, int C, int T, int T_out, int pre, float pre_scale,
+                                       int post, float post_scale) {
+    constexpr int P = K - S;
+    constexpr int P4 = (P + 3) & ~3;
+    constexpr int D = P4 - P;
+    constexpr int NV = (P4 + 4 * S) / 4;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float* xr = x + b * x_bs + (long long)c * x_rs;
+    const float* ci = cache_in + ((size_t)b * C + c) * P;
+    float wk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wk[k] = w[c * K + k];
+    const float bv = bias ? bias[c] : 0.f;
+    const int Tq = (T_out + 3) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Tq; q += gridDim.x * blockDim.x) {
+        const int to0 = q * 4;
+        const int a0 = to0 * S - P4;
+        float buf[4 * NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = a0 + 4 * i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j >= 0) {
+                if (j + 3 < x_rs) {   // the row pitch is a multiple of 4: the load stays inside the row's storage
+                    v = *reinterpret_cast<const float4*>(xr + j);
+                    if (pre != PRE_NONE) {
+                        v.x = apply_pre(v.x, pre, pre_scale); v.y = apply_pre(v.y, pre, pre_scale);
+                        v.z = apply_pre(v.z, pre, pre_scale); v.w = apply_pre(v.w, pre, pre_scale);
+                    }
+                }
+            } else {                  // history: x index j' < 0 is cache[P + j'] (only the first group of a row)
+                float t[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t[e] = (j + e >= -P) ? ci[P + j + e] : 0.f;
+                v = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            buf[4 * i] = v.x; buf[4 * i + 1] = v.y; buf[4 * i + 2] = v.z; buf[4 * i + 3] = v.w;
+        }
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) a = fmaf(wk[k], buf[D + e * S + k], a);
+            o[e] = a + bv;
+        }
+        const long long off = b * y_bs + (long long)c * y_rs + to0;
+        if (to0 + 3 < T_out) {
+            if (skip) {
+                const float4 sk = *reinterpret_cast<const float4*>(skip + off);
+                o[0] += sk.x; o[1] += sk.y; o[2] += sk.z; o[3] += sk.w;
+            }
+            if (post != PRE_NONE) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = apply_act_fast(o[e], post, post_scale);
+            }
+            *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+            for (int e = 0; e < 4 && to0 + e < T_out; ++e)
+                y[off + e] = apply_act_fast(o[e] + (skip ? skip[off + e] : 0.f), post, post_scale);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < P) {
+        const int j = T + threadIdx.x;  // index into xin (length P+T)
+        cache_out[((size_t)b * C + c) * P + threadIdx.x] = j < P ? ci[j] : apply_pre(xr[j - P], pre, pre_scale);
+    }
+}
+
 cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                           const float* w, const float* bias, const float* skip, float* y, long long y_bs, int y_rs,
                           int B, int C, int T, int K, int S, int pre, float pre_scale, int post, float post_scale,
@@ -193,6 +268,20 @@ cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float*
         dwconv5_kernel<<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y, y_bs, y_rs, C, T,
                                                  pre, pre_scale, post, post_scale);
         return cudaGetLastError();
+    }
+    if (aligned && K == 2 * S && T % S == 0 && T_out >= 16) {
+        const int Tq = (T_out + 3) / 4;
+        const int threads = Tq >= 128 ? 128 : 32;
+        dim3 grid(min((Tq + threads - 1) / threads, 512), C, B);
+#define HIL_DWS4(KK, SS)                                                                                                  \
+    if (K == KK && S == SS) {                                                                                            \
+        dwconv_strided4_kernel<KK, SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y,   \
+                                                                 y_bs, y_rs, C, T, T_out, pre, pre_scale, post,          \
+                                                                 post_scale);                                            \
+        return cudaGetLastError();                                                                                       \
+    }
+        HIL_DWS4(4, 2) HIL_DWS4(8, 4) HIL_DWS4(10, 5) HIL_DWS4(16, 8)
+#undef HIL_DWS4
     }
     const int threads = T_out >= 128 ? 128 : 32;
     dim3 grid(min((T_out + threads - 1) / threads, 512), C, B);

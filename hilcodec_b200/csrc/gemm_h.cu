@@ -69,7 +69,23 @@ struct Params {
     const float* dw_b;      // [M] or null
     const float* cache_in;  // [B][M][4]
     float* cache_out;       // [B][M][4]
+    // kUp > 0: the B operand is the transposed depthwise conv of a low-rate tensor, computed in the transform
+    int t_in;               // low-rate length (T = kUp * t_in)
+    const float* up_w;      // [K][2 * kUp]
+    const float* up_ci;     // [B][K]: activated last input of the previous chunk
+    float* up_co;           // [B][K]
 };
+
+// columns of the low-rate input a 128-column output tile needs (one before its first column) + alignment slack
+#ifndef HIL_UP_NI_ALIGN
+#define HIL_UP_NI_ALIGN 8
+#endif
+// first low-rate column of tile tt's box: one before the tile's first input, rounded down to a 16-byte boundary
+// (every TMA load in this library starts on one; an unaligned start raised "illegal instruction").  up_ni's
+// padding (>= 3 columns beyond BN / S + 2) covers the shift.
+template <int S>
+__device__ __forceinline__ int up_box_start(int tt) { return ((tt * BN) / S - 1) & ~3; }
+constexpr int up_ni(int S) { return ((BN / S + 2 + (BN % S ? 1 : 0)) + HIL_UP_NI_ALIGN - 1) & ~(HIL_UP_NI_ALIGN - 1); }
 
 constexpr uint32_t IDESC_N128 = make_idesc_f16(BM, BN);
 constexpr uint32_t IDESC_N256 = make_idesc_f16(BM, 2 * BN);
@@ -88,8 +104,83 @@ __device__ __forceinline__ void xform_rows(const float4 (&v)[4], float s, int xw
     }
 }
 
+// Upsample variant: B[k][n] = CausalConvTranspose1d(act(x))[k][n] (causal_layers.py:183-188, depthwise, kernel 2S,
+// stride S) evaluated on the fly from the low-rate box x[k][i_start ..]:
+//     B[k][n] = e[n/S] * w[k][n%S] + e[n/S - 1] * w[k][n%S + S],   e[i] = act(x[k][i]),  e[-1] = cache
+// (two rounded products and one rounded add, like dwconvT_kernel), then the fp16 hi/lo split.  A lane owns 4
+// consecutive output columns of 4 k-rows, which touch x[i0-1], x[i0] and -- unless S is a multiple of 4 -- x[i0+1].
+template <int S, int kPre>
+__device__ __forceinline__ void xform_rows_up(const float* raw, const float (&wreg)[4][8], int xw, int lane, uint32_t bhi,
+                                              uint32_t chunk, uint32_t half8, float s, int n_abs0, int i_start, int k0, int K,
+                                              const float* ci, float* co, int t_in) {
+    constexpr int NI = up_ni(S);
+    constexpr bool kNeedC = (S % 4) != 0;
+    const int i0 = n_abs0 / S;
+    const int r0 = n_abs0 - i0 * S;
+    const int li = i0 - i_start;
+    const int n_last = S * t_in - 1;                       // the column whose "current" input is x[t_in - 1]
+    const bool owns_last = co != nullptr && n_abs0 <= n_last && n_last < n_abs0 + 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int kr = xw * 4 + q;
+        const int k = k0 + kr;
+        const float* xr = raw + kr * NI + li;
+        float ea = xr[-1], eb = xr[0], ec = kNeedC ? xr[1] : 0.f;
+        if (kPre != PRE_NONE) {
+            ea = ea * s; eb = eb * s; ec = ec * s;
+            const float ta = ex2_approx(ea * 1.4426950408889634f) - 1.0f, tb = ex2_approx(eb * 1.4426950408889634f) - 1.0f;
+            ea = ea > 0.f ? ea : ta;
+            eb = eb > 0.f ? eb : tb;
+            if (kNeedC) {
+                const float tcv = ex2_approx(ec * 1.4426950408889634f) - 1.0f;
+                ec = ec > 0.f ? ec : tcv;
+            }
+        }
+        if (i0 == 0) ea = k < K ? __ldg(ci + k) : 0.f;       // x[-1] is the cache (already activated)
+        float u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool next = kNeedC && (r0 + j >= S);       // this column already belongs to input i0 + 1
+            const float cur = next ? ec : eb, prev = next ? eb : ea;
+            u[j] = __fadd_rn(__fmul_rn(cur, wreg[q][j]), __fmul_rn(prev, wreg[q][4 + j]));
+        }
+        if (owns_last && k < K) co[k] = (n_last / S == i0) ? eb : ec;
+        uint32_t h01, h23, l01, l23;
+        split4<PRE_NONE>(make_float4(u[0], u[1], u[2], u[3]), 1.0f, h01, h23, l01, l23);
+        const uint32_t kk = (uint32_t)kr;
+        const uint32_t dst = bhi + (kk >> 3) * 1024u + (kk & 7u) * 128u + ((chunk ^ (kk & 7u)) << 4) + half8;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h01), "r"(h23) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + (uint32_t)B_TILE), "r"(l01), "r"(l23) : "memory");
+    }
+}
+
+// taps of the 4 output columns n_abs0 .. n_abs0+3 for the 4 k-rows of this warp: wreg[q][j] = w[k][(n%S)],
+// wreg[q][4+j] = w[k][(n%S) + S]
+template <int S>
+__device__ __forceinline__ void load_up_taps(const float* w, int k0, int K, int xw, int n_abs0, float (&wreg)[4][8]) {
+    const int r0 = n_abs0 % S;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = k0 + xw * 4 + q;
+        const float* wr = w + (size_t)(k < K ? k : 0) * 2 * S;
+        if constexpr (S % 4 == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(wr + r0)), b = __ldg(reinterpret_cast<const float4*>(wr + r0 + S));
+            wreg[q][0] = a.x; wreg[q][1] = a.y; wreg[q][2] = a.z; wreg[q][3] = a.w;
+            wreg[q][4] = b.x; wreg[q][5] = b.y; wreg[q][6] = b.z; wreg[q][7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int r = r0 + j;
+                if (r >= S) r -= S;
+                wreg[q][j] = __ldg(wr + r);
+                wreg[q][4 + j] = __ldg(wr + r + S);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- kernel
-template <bool kDw>
+template <bool kDw, int kUp = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
@@ -156,8 +247,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const int b = (int)(rest / p.tiles_t);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait<32>(raw_empty(r), ph ^ 1);
-                    mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
-                    tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
+                    if constexpr (kUp > 0) {   // low-rate box: the inputs of the tile's columns and the one before
+                        mbar_arrive_expect_tx(raw_full(r), BK * up_ni(kUp) * 4);
+                        tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), up_box_start<kUp>(tt), kb * BK, b);
+                    } else {
+                        mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
+                        tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
+                    }
                     if (++r == RAW_STAGES) { r = 0; ph ^= 1; }
                 }
             }
@@ -227,18 +323,37 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         int r = 0, s = 0;
         uint32_t rph = 0, sph = 0;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            [[maybe_unused]] const int m_blk = (int)(tile % p.num_m);
+            [[maybe_unused]] const long long rest = tile / p.num_m;
+            [[maybe_unused]] const int tt = (int)(rest % p.tiles_t);
+            [[maybe_unused]] const int b = (int)(rest / p.tiles_t);
             for (int kb = 0; kb < nkb; ++kb) {
+                [[maybe_unused]] float wreg[4][8];
+                if constexpr (kUp > 0)   // taps first: their latency hides behind the wait for the activation box
+                    load_up_taps<kUp>(p.up_w, kb * BK, p.K, xw, tt * BN + 4 * lane, wreg);
                 mbar_wait(raw_full(r), rph);
                 mbar_wait(op_empty(s), sph ^ 1);
-                const float4* src = reinterpret_cast<const float4*>(gen_base + (raw_base - base) + r * RAW_BYTES);
                 const uint32_t bhi = op_base + s * OP_BYTES + 2 * A_TILE + panel * B_PANEL;
-                float4 v[4];
+                if constexpr (kUp > 0) {
+                    const float* raw = reinterpret_cast<const float*>(gen_base + (raw_base - base) + r * RAW_BYTES);
+                    const float* ci = p.up_ci + (size_t)b * p.K;
+                    float* co = m_blk == 0 ? p.up_co + (size_t)b * p.K : nullptr;
+                    if (p.pre == PRE_NONE)
+                        xform_rows_up<kUp, PRE_NONE>(raw, wreg, xw, lane, bhi, chunk, half8, 1.0f, tt * BN + 4 * lane,
+                                                     up_box_start<kUp>(tt), kb * BK, p.K, ci, co, p.t_in);
+                    else
+                        xform_rows_up<kUp, PRE_SCALE_ELU>(raw, wreg, xw, lane, bhi, chunk, half8, p.pre_scale, tt * BN + 4 * lane,
+                                                          up_box_start<kUp>(tt), kb * BK, p.K, ci, co, p.t_in);
+                } else {
+                    const float4* src = reinterpret_cast<const float4*>(gen_base + (raw_base - base) + r * RAW_BYTES);
+                    float4 v[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = src[(xw * 4 + q) * (BN / 4) + lane];
-                if (p.pre == PRE_NONE) xform_rows<PRE_NONE>(v, 1.0f, xw, bhi, chunk, half8);
-                else if (p.elu_poly) xform_rows<PRE_SCALE_ELU, true>(v, p.pre_scale, xw, bhi, chunk, half8);
-                else if (p.pre == PRE_ELU) xform_rows<PRE_ELU>(v, 1.0f, xw, bhi, chunk, half8);
-                else xform_rows<PRE_SCALE_ELU>(v, p.pre_scale, xw, bhi, chunk, half8);
+                    for (int q = 0; q < 4; ++q) v[q] = src[(xw * 4 + q) * (BN / 4) + lane];
+                    if (p.pre == PRE_NONE) xform_rows<PRE_NONE>(v, 1.0f, xw, bhi, chunk, half8);
+                    else if (p.elu_poly) xform_rows<PRE_SCALE_ELU, true>(v, p.pre_scale, xw, bhi, chunk, half8);
+                    else if (p.pre == PRE_ELU) xform_rows<PRE_ELU>(v, 1.0f, xw, bhi, chunk, half8);
+                    else xform_rows<PRE_SCALE_ELU>(v, p.pre_scale, xw, bhi, chunk, half8);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -505,6 +620,79 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     return cudaGetLastError();
+}
+
+// Upsampling layer of the decoder in one kernel (streaming.py:633-637): act -> CausalConvTranspose1d (depthwise,
+// kernel 2S, stride S, cache [B,K,1]) -> 1x1 conv + bias.  x [B][K][T_in] (low rate) -> Y [B][M][S * T_in].
+bool gemm_h_up_usable(const PackedMat& W, const float* x, long long x_bs, int x_rs, int T_in, int S, int pre, const float* Y,
+                      long long y_bs, int y_rs) {
+    if (!W.H_hi || !W.H_lo) return false;
+    if (S != 2 && S != 4 && S != 5 && S != 8) return false;
+    if (pre != PRE_NONE && pre != PRE_SCALE_ELU) return false;
+    if ((long long)S * T_in < 128 || (W.K & 31)) return false;
+    if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
+    return true;
+}
+
+template <int S>
+static cudaError_t launch_up(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T_in, int pre,
+                             float pre_scale, const float* up_w, const float* ci, float* co, const float* bias, float* Y,
+                             long long y_bs, int y_rs, cudaStream_t st) {
+    using namespace th;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int T = S * T_in;
+    CUtensorMap map_hi, map_lo, map_x, map_y;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)W.Kp32, (cuuint64_t)W.Mp128};
+        const cuuint64_t strides[1] = {(cuuint64_t)W.Kp32 * 2};
+        const cuuint32_t box[2] = {BK, BM};
+        if (!tc::make_map_dt(&map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !tc::make_map_dt(&map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T_in, (cuuint64_t)W.K, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)x_rs * 4, (cuuint64_t)x_bs * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)up_ni(S), BK, 1};
+        if (!tc::make_map(&map_x, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {32, BM, 1};
+        if (!tc::make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidValue;
+    }
+    Params p{};
+    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
+    p.num_m = (W.M + BM - 1) / BM;
+    p.t_step = BN; p.t_halo = 0;
+    p.tiles_t = (T + BN - 1) / BN;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = 0;
+    p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.elu_poly = 0;
+    p.t_in = T_in; p.up_w = up_w; p.up_ci = ci; p.up_co = co;
+    const int num_sms = tc::device_sm_count();
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    gemm_h_kernel<false, S><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T_in, int S, int pre,
+                             float pre_scale, const float* up_w, const float* cache_in, float* cache_out, const float* bias,
+                             float* Y, long long y_bs, int y_rs, cudaStream_t st) {
+    if (B == 0 || T_in == 0) return cudaSuccess;
+#define HIL_UP(SS) \
+    if (S == SS) return launch_up<SS>(W, x, x_bs, x_rs, B, T_in, pre, pre_scale, up_w, cache_in, cache_out, bias, Y, y_bs, y_rs, st);
+    HIL_UP(2) HIL_UP(4) HIL_UP(5) HIL_UP(8)
+#undef HIL_UP
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,

@@ -21,7 +21,8 @@
 // Geometry: C <= 128: one 128-row m-block, BN = 128;  128 < C <= 256: two m-blocks, BN = 64 -- either way an
 // accumulator (big | small) fills 256 TMEM columns, D1 and D2 fill the 512.
 // Warp roles (512 threads, 1 CTA/SM): 0 X producer (TMA), 1 MMA issuer, 2 TMEM allocator, 3 weight producer
-// (TMA, W0 then W1 pieces through one ring), 4-7 epilogue E1 + E2, 8-15 transform (ELU + split of the input tile).
+// (TMA, W0 then W1 pieces through one ring), 8-15 workers: transform (ELU + split of the input tile) and E1, two warps
+// per TMEM lane quarter; 4-7 epilogue E2.  E2 of tile i overlaps the transform / G1 / E1 of tile i+1.
 // Arithmetic is the one of gemm_h.cu, instruction for instruction, so the result is bit-identical to the two
 // fused-DWS launches it replaces (tests/test_gpu_ops.py::test_resblock_fused).
 #include <cstdlib>
@@ -138,12 +139,13 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
     auto a_empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + 2 * B_STAGES + A_STAGES + s); };
     constexpr int NB = 2 * RAW_STAGES + 2 * B_STAGES + 2 * A_STAGES;
     const uint32_t d1_full = bars + 8u * NB, d1_empty = bars + 8u * (NB + 1), b2_ready = bars + 8u * (NB + 2),
-                   d2_full = bars + 8u * (NB + 3);
-    const uint32_t tmem_slot = bars + 8u * (NB + 4);
+                   d2_full = bars + 8u * (NB + 3), d2_empty = bars + 8u * (NB + 4);
+    const uint32_t tmem_slot = bars + 8u * (NB + 5);
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.nkb;
+    const uint32_t n_my = (uint32_t)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a0_hi); prefetch_tmap(&map_a0_lo); prefetch_tmap(&map_a1_hi); prefetch_tmap(&map_a1_lo);
@@ -163,9 +165,10 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             mbar_init(a_empty(s), 1);
         }
         mbar_init(d1_full, 1);
-        mbar_init(d1_empty, NUM_EPI);
-        mbar_init(b2_ready, NUM_EPI);
+        mbar_init(d1_empty, NUM_XFORM_WARPS * 32);
+        mbar_init(b2_ready, NUM_XFORM_WARPS * 32);
         mbar_init(d2_full, 1);
+        mbar_init(d2_empty, NUM_EPI);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -197,98 +200,104 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             }
         }
     } else if (warp == 3) {
-        // ===================================================================== weight producer: W0 pieces, then W1 pieces
+        // ===================================================================== weight producer (same order as the MMA issuer)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                for (int g = 0; g < 2; ++g) {
-                    const CUtensorMap* mh = g == 0 ? &map_a0_hi : &map_a1_hi;
-                    const CUtensorMap* ml = g == 0 ? &map_a0_lo : &map_a1_lo;
-                    for (int kb = 0; kb < nkb; ++kb)
-                        for (int mb = 0; mb < p.num_m; ++mb) {
-                            mbar_wait<32>(a_empty(s), ph ^ 1);
-                            const uint32_t st = a_base + s * A_PIECE;
-                            mbar_arrive_expect_tx(a_full(s), A_PIECE);
-                            tma_load_2d(mh, st, a_full(s), kb * BK, mb * BM);
-                            tma_load_2d(ml, st + A_TILE, a_full(s), kb * BK, mb * BM);
-                            if (++s == A_STAGES) { s = 0; ph ^= 1; }
-                        }
-                }
+            auto pieces = [&](const CUtensorMap* mh, const CUtensorMap* ml) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    for (int mb = 0; mb < p.num_m; ++mb) {
+                        mbar_wait<32>(a_empty(s), ph ^ 1);
+                        const uint32_t st = a_base + s * A_PIECE;
+                        mbar_arrive_expect_tx(a_full(s), A_PIECE);
+                        tma_load_2d(mh, st, a_full(s), kb * BK, mb * BM);
+                        tma_load_2d(ml, st + A_TILE, a_full(s), kb * BK, mb * BM);
+                        if (++s == A_STAGES) { s = 0; ph ^= 1; }
+                    }
+            };
+            for (uint32_t it = 0; it < n_my; ++it) {
+                pieces(&map_a0_hi, &map_a0_lo);
+                pieces(&map_a1_hi, &map_a1_lo);
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
+        // Issue order per tile: G1(i), G2(i).  (Putting G1(i+1) in front of G2(i) measured slower: G2(i) then waits for
+        // the whole transform of tile i+1, and E1(i+1) cannot write B2 before G2(i) has read it.)
         int sb = 0, sa = 0;
         uint32_t phb = 0, pha = 0;
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            // ---- G1: D1 = W0 * B(tile).  D1 is free once E1 of the previous tile has read it.
+        auto issue_kblock = [&](uint32_t bst, uint32_t d_base, int kb) {   // all m-blocks of one k-block
+            for (int mb = 0; mb < p.num_m; ++mb) {
+                mbar_wait(a_full(sa), pha);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t ast = a_base + sa * A_PIECE;
+                    const uint32_t d_big = d_base + mb * 2 * BN;
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j) {
+                        // A (K-major, SWIZZLE_64B) and B (MN-major, SWIZZLE_128B panels) descriptors as in gemm_h.cu
+                        const uint64_t a_hi = make_desc(ast + j * 32, 16, 512, 4);
+                        const uint64_t a_lo = make_desc(ast + A_TILE + j * 32, 16, 512, 4);
+                        const uint64_t b_hl = make_desc(bst + j * 2048, B_PANEL, 1024, 2);
+                        umma_f16(d_big, a_hi, b_hl, G::IDESC_2N, (kb | j) != 0);
+                        umma_f16(d_big + BN, a_lo, b_hl, G::IDESC_N, 1);
+                    }
+                    umma_commit(a_empty(sa));
+                }
+                __syncwarp();
+                if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
+            }
+        };
+        auto g1 = [&](uint32_t it) {   // D1 = W0 * B(tile it); D1 is free once E1 of tile it-1 has read it
             mbar_wait(d1_empty, (it & 1) ^ 1);
             tc_fence_after();
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(b_ready(sb), phb);
-                const uint32_t bst = b_base + sb * G::B_STAGE;
-                for (int mb = 0; mb < p.num_m; ++mb) {
-                    mbar_wait(a_full(sa), pha);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t ast = a_base + sa * A_PIECE;
-                        const uint32_t d_big = tmem_base + mb * 2 * BN;
-#pragma unroll
-                        for (int j = 0; j < BK / 16; ++j) {
-                            const uint64_t a_hi = make_desc(ast + j * 32, 16, 512, 4);
-                            const uint64_t a_lo = make_desc(ast + A_TILE + j * 32, 16, 512, 4);
-                            const uint64_t b_hl = make_desc(bst + j * 2048, B_PANEL, 1024, 2);
-                            umma_f16(d_big, a_hi, b_hl, G::IDESC_2N, (kb | j) != 0);
-                            umma_f16(d_big + BN, a_lo, b_hl, G::IDESC_N, 1);
-                        }
-                        umma_commit(a_empty(sa));
-                    }
-                    __syncwarp();
-                    if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
-                }
+                issue_kblock(b_base + sb * G::B_STAGE, tmem_base, kb);
                 if (lane == 0) umma_commit(b_empty(sb));
                 __syncwarp();
                 if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
             }
             if (lane == 0) umma_commit(d1_full);
             __syncwarp();
-            // ---- G2: D2 = W1 * B2.  B2 is written by E1 of this tile; E1 runs after E2 of the previous tile in
-            // the same warps, so D2 is free as well.
+        };
+        auto g2 = [&](uint32_t it) {   // D2 = W1 * B2(tile it); D2 is free once E2 of tile it-1 has read it
             mbar_wait(b2_ready, it & 1);
+            mbar_wait(d2_empty, (it & 1) ^ 1);
             tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb) {
-                const uint32_t bst = b2_base + kb * G::B_STAGE;
-                for (int mb = 0; mb < p.num_m; ++mb) {
-                    mbar_wait(a_full(sa), pha);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t ast = a_base + sa * A_PIECE;
-                        const uint32_t d_big = tmem_base + 256 + mb * 2 * BN;
-#pragma unroll
-                        for (int j = 0; j < BK / 16; ++j) {
-                            const uint64_t a_hi = make_desc(ast + j * 32, 16, 512, 4);
-                            const uint64_t a_lo = make_desc(ast + A_TILE + j * 32, 16, 512, 4);
-                            const uint64_t b_hl = make_desc(bst + j * 2048, B_PANEL, 1024, 2);
-                            umma_f16(d_big, a_hi, b_hl, G::IDESC_2N, (kb | j) != 0);
-                            umma_f16(d_big + BN, a_lo, b_hl, G::IDESC_N, 1);
-                        }
-                        umma_commit(a_empty(sa));
-                    }
-                    __syncwarp();
-                    if (++sa == A_STAGES) { sa = 0; pha ^= 1; }
-                }
-            }
+            for (int kb = 0; kb < nkb; ++kb) issue_kblock(b2_base + kb * G::B_STAGE, tmem_base + 256, kb);
             if (lane == 0) umma_commit(d2_full);
             __syncwarp();
+        };
+        for (uint32_t it = 0; it < n_my; ++it) {
+            g1(it);
+            g2(it);
         }
     } else if (warp >= 8) {
-        // ===================================================================== transform: raw fp32 tile -> B_hi / B_lo
+        // ===================================================================== workers: transform of tile i, then E1 of tile i
+        // Transform: raw fp32 tile -> B_hi / B_lo of the first GEMM.  E1: D1 -> depthwise-0 -> ELU -> split -> B2, two
+        // warps per TMEM lane quarter (warp % 4), each owning half of the tile's columns, so E1 -- the longest serial
+        // stage -- runs 8 warps wide while the epilogue warps drain the previous tile (E2).
         const int xw = warp - 8;
+        const int q = warp & 3;                              // TMEM lane quarter this warp may read
+        const int half = xw >> 2;                            // which half of the tile's columns
+        constexpr int CH = BN / 64;                          // 32-column chunks per half and m-block
+        const int row = q * 32 + lane;
+        const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE);
+        const float c_big0 = p.c_big0, c_inv0 = 1.0f / p.c_big0;
+        float wk0h[5], bv0h = 0.f;
+        auto load_taps = [&](int mb, float (&wk)[5], float& bv) {
+            const int m = mb * BM + row;
+            const bool ok = m < p.C;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) wk[k] = ok ? __ldg(p.dw0_w + m * 5 + k) * c_big0 : 0.f;
+            bv = (ok && p.dw0_b) ? __ldg(p.dw0_b + m) : 0.f;
+        };
+        if constexpr (NUM_M == 1 && RB_HOIST) load_taps(0, wk0h, bv0h);
         int r = 0, s = 0;
         uint32_t rph = 0, sph = 0;
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(raw_full(r), rph);
                 mbar_wait(b_empty(s), sph ^ 1);
@@ -306,47 +315,21 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                 if (++r == RAW_STAGES) { r = 0; rph ^= 1; }
                 if (++s == B_STAGES) { s = 0; sph ^= 1; }
             }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================================================================== epilogue: E1 then E2 of every tile
-        const int q = warp - 4;
-        const int row = q * 32 + lane;                      // row inside an m-block = TMEM lane
-        const bool issuer = (q == 0 && lane == 0);
-        const uint32_t sw = (uint32_t)(row & 7);
-        const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE);
-        const float c_big0 = p.c_big0, c_big1 = p.c_big1;
-        const float c_inv0 = 1.0f / c_big0, c_inv1 = 1.0f / c_big1;
-        // depthwise taps (pre-multiplied by the weight scale 2^-s, see gemm_h.cu) and biases of this thread's row(s);
-        // the tile always spans all channels, so they never change: loaded once when there is one m-block, re-read
-        // per tile (L1 hits) when there are two and the registers are needed elsewhere
-        auto load_taps = [&](int mb, const float* w, const float* bias, float scale, float (&wk)[5], float& bv) {
-            const int m = mb * BM + row;
-            const bool ok = m < p.C;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) wk[k] = ok ? __ldg(w + m * 5 + k) * scale : 0.f;
-            bv = (ok && bias) ? __ldg(bias + m) : 0.f;
-        };
-        float wk0h[5], wk1h[5], bv0h = 0.f, bv1h = 0.f;
-        if constexpr (NUM_M == 1 && RB_HOIST) {
-            load_taps(0, p.dw0_w, p.dw0_b, c_big0, wk0h, bv0h);
-            load_taps(0, p.dw1_w, p.dw1_b, c_big1, wk1h, bv1h);
-        }
-        uint32_t it = 0;
-        uint32_t g = 0;                                      // running staging-chunk counter -> buffer parity
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+
+            // ---------------------------------------------------------------- E1: D1 -> dw0 -> ELU -> split -> B2
             const int tt = (int)(tile % p.tiles_t);
             const int b = (int)(tile / p.tiles_t);
             const int tcol0 = tt * G::VAL - HALO;            // time of tile column 0
             const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
             const bool has_tail = tcol0 + BN > p.T - 4;      // the tile holds some of the last 4 time steps
-
-            // ---------------------------------------------------------------- E1: D1 -> dw0 -> ELU -> split -> B2
-            mbar_wait<32>(d1_full, it & 1);
+            const int c_begin = half * CH, c_end = min(c_begin + CH, n_chunks);
+            mbar_wait(d1_full, it & 1);
             tc_fence_after();
+            bool b2_free = false;                            // G2 of the previous tile must have read B2 before it is rewritten
 #pragma unroll 1
             for (int mb = 0; mb < NUM_M; ++mb) {
                 const int mrow0 = mb * BM + q * 32;
-                if (mrow0 >= p.C) continue;                  // warp-uniform (C % 32 == 0): these rows are weight padding
+                if (mrow0 >= p.C || c_begin >= c_end) continue;   // warp-uniform: weight-padding rows / nothing in this half
                 const int m = mrow0 + lane;
                 float wk[5], bv;
                 if constexpr (NUM_M == 1 && RB_HOIST) {
@@ -354,15 +337,23 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                     for (int k = 0; k < 5; ++k) wk[k] = wk0h[k];
                     bv = bv0h;
                 } else {
-                    load_taps(mb, p.dw0_w, p.dw0_b, c_big0, wk, bv);
+                    load_taps(mb, wk, bv);
                 }
-                float carry[4] = {0.f, 0.f, 0.f, 0.f};
                 const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + mb * 2 * BN;
+                float carry[4] = {0.f, 0.f, 0.f, 0.f};
+                if (c_begin > 0) {   // the 4 pointwise columns in front of this half
+                    uint32_t cb[4], cs[4];
+                    tmem_ld4(t_d + c_begin * 32 - 4, cb);
+                    tmem_ld4(t_d + BN + c_begin * 32 - 4, cs);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) carry[j] = fmaf(__uint_as_float(cs[j]), 1.0f / LO_SCALE, __uint_as_float(cb[j]));
+                }
                 // row k = m of B2: k-block m / 32 = mb * 4 + q, row-in-block = lane
                 const uint32_t b2row = b2_base + (uint32_t)(mb * 4 + q) * G::B_STAGE + (uint32_t)(lane >> 3) * 1024u +
                                        (uint32_t)(lane & 7) * 128u;
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     uint32_t rb[32], rs[32];
                     tmem_ld32(t_d + c * 32, rb);
                     tmem_ld32(t_d + BN + c * 32, rs);
@@ -399,6 +390,10 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                         }
                         uint32_t hi[4], lo[4];
                         elu_split8(o, hi, lo);
+                        if (!b2_free) {
+                            mbar_wait(d2_full, (it & 1) ^ 1);
+                            b2_free = true;
+                        }
                         const uint32_t g8 = (uint32_t)(c * 4 + j8);   // 8-column group inside the tile
                         const uint32_t dst = b2row + (g8 >> 3) * B_PANEL + (((g8 & 7u) ^ (uint32_t)(lane & 7)) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
@@ -415,8 +410,31 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             mbar_arrive(d1_empty);
             fence_proxy_async();
             mbar_arrive(b2_ready);
-
-            // ---------------------------------------------------------------- E2: D2 -> dw1 -> h += (TMA reduce-add)
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================================================================== epilogue E2: D2 -> dw1 -> h += (TMA reduce-add)
+        const int q = warp - 4;
+        const int row = q * 32 + lane;                      // row inside an m-block = TMEM lane
+        const uint32_t sw = (uint32_t)(row & 7);
+        const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE);
+        const float c_big1 = p.c_big1, c_inv1 = 1.0f / p.c_big1;
+        float wk1h[5], bv1h = 0.f;
+        auto load_taps = [&](int mb, float (&wk)[5], float& bv) {
+            const int m = mb * BM + row;
+            const bool ok = m < p.C;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) wk[k] = ok ? __ldg(p.dw1_w + m * 5 + k) * c_big1 : 0.f;
+            bv = (ok && p.dw1_b) ? __ldg(p.dw1_b + m) : 0.f;
+        };
+        if constexpr (NUM_M == 1 && RB_HOIST) load_taps(0, wk1h, bv1h);
+        uint32_t it = 0;
+        uint32_t g = 0;                                      // running staging-chunk counter -> buffer parity
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int tt = (int)(tile % p.tiles_t);
+            const int b = (int)(tile / p.tiles_t);
+            const int tcol0 = tt * G::VAL - HALO;
+            const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
+            const bool has_tail = tcol0 + BN > p.T - 4;
             mbar_wait<32>(d2_full, it & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -431,13 +449,14 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                     for (int k = 0; k < 5; ++k) wk[k] = wk1h[k];
                     bv = bv1h;
                 } else {
-                    load_taps(mb, p.dw1_w, p.dw1_b, c_big1, wk, bv);
+                    load_taps(mb, wk, bv);
                 }
                 float carry[4] = {0.f, 0.f, 0.f, 0.f};
                 const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + mb * 2 * BN;
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c, ++g) {
-                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                    // every warp stages and stores its own 32-row slab (no barrier between the epilogue warps)
+                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES + q * (OUT_BYTES / 4);
                     float v[36];
                     if (warp_ok) {
                         uint32_t rb[32], rs[32];
@@ -463,9 +482,14 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                             }
                         }
                     }
-                    if (issuer) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
-                    epi_bar_sync();
-                    if (warp_ok) {
+                    if (mb == p.num_m - 1 && c == n_chunks - 1) {   // last TMEM read of this tile: D2 may be overwritten
+                        tc_fence_before();
+                        mbar_arrive(d2_empty);
+                    }
+                    if (!warp_ok) continue;           // nothing to store for weight-padding rows (g advances for all warps)
+                    if (lane == 0) tma_wait_read<1>();   // this warp's store from two chunks ago has drained the buffer
+                    __syncwarp();
+                    {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
                             if (c == 0 && j4 < 2) continue;   // tile columns 0..7 are halo: they belong to the left neighbour
@@ -478,7 +502,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                                 for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[i + k], a);
                                 o[e] = a;
                             }
-                            const uint32_t dst = c == 0 ? obuf + row * 96 + (j4 - 2) * 16 : obuf + row * 128 + (((uint32_t)j4 ^ sw) << 4);
+                            const uint32_t dst = c == 0 ? obuf + lane * 96 + (j4 - 2) * 16 : obuf + lane * 128 + (((uint32_t)j4 ^ sw) << 4);
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]),
                                          "f"(o[3])
                                          : "memory");
@@ -486,17 +510,16 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                         carry[0] = v[32]; carry[1] = v[33]; carry[2] = v[34]; carry[3] = v[35];
                     }
                     fence_proxy_async();
-                    epi_bar_sync();
-                    if (issuer) {
-                        if (c == 0) tma_reduce_add_3d(&map_y24, obuf, tcol0 + HALO, mb * BM, b);
-                        else tma_reduce_add_3d(&map_y, obuf, tcol0 + c * 32, mb * BM, b);
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (c == 0) tma_reduce_add_3d(&map_y24, obuf, tcol0 + HALO, mrow0, b);
+                        else tma_reduce_add_3d(&map_y, obuf, tcol0 + c * 32, mrow0, b);
                         tma_commit();
                     }
                 }
             }
-            tc_fence_before();   // orders this tile's TMEM reads before the arrivals of the next tile's E1
         }
-        if (issuer) tma_wait_all();
+        if (lane == 0) tma_wait_all();
     }
 
     tc_fence_before();
@@ -580,8 +603,8 @@ static cudaError_t launch_rb(const PackedMat& W0, const PackedMat& W1, float* h,
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)rs * 4, (cuuint64_t)bs * 4};
         const cuuint32_t box_x[3] = {(cuuint32_t)G::VAL, BK, 1};
-        const cuuint32_t box_y[3] = {32, BM, 1};
-        const cuuint32_t box_y24[3] = {24, BM, 1};
+        const cuuint32_t box_y[3] = {32, 32, 1};      // one epilogue warp's slab: 32 rows x 32 (24) columns
+        const cuuint32_t box_y24[3] = {24, 32, 1};
         if (!tc::make_map(&mx, h, 3, dims, strides, box_x, CU_TENSOR_MAP_SWIZZLE_NONE) ||
             !tc::make_map(&my, h, 3, dims, strides, box_y, CU_TENSOR_MAP_SWIZZLE_128B) ||
             !tc::make_map(&my24, h, 3, dims, strides, box_y24, CU_TENSOR_MAP_SWIZZLE_NONE))

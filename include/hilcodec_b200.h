@@ -139,7 +139,8 @@ uint64_t hil_launch_count(void);
  * tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy), 0 = FP32 FFMA kernels everywhere.  Bit 2 set: do not
  * fuse DWS blocks.  Bit 3 set: use the experimental time-major kernel (gemm_tm.cu, activations through TMEM)
  * for plain 1x1 convs with Cout <= 192.  Bit 4 set (default): fp16-split tensor-core kernels (gemm_h.cu, kind::f16)
- * instead of 3xTF32.  Bit 5 set: do not fuse whole ResBlocks (gemm_rb.cu). */
+ * instead of 3xTF32.  Bit 5 set: do not fuse whole ResBlocks (gemm_rb.cu).  Bit 6 set: do not fuse the decoder's
+ * upsampling layers (transposed depthwise conv -> 1x1). */
 int32_t hil_set_tensor_cores(int32_t mode);
 #define HIL_PROFILE_CATEGORIES 8
 int32_t hil_profile_begin(void);
@@ -175,6 +176,13 @@ int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, co
                         const float* dw1_w, const float* dw1_b, const float* c0_in, float* c0_out, const float* c1_in,
                         float* c1_out, float* tmp1, float* tmp2, int32_t B, int32_t C, int32_t T, int32_t pre, float pre_scale,
                         int32_t fused, void* stream);
+/* Decoder upsampling layer, streaming.py:633-637: pre(x) -> CausalConvTranspose1d (causal_layers.py:183-188,
+ * depthwise, kernel 2S, stride S, cache [B,K,1]) -> nn.Conv1d(k=1) + bias.  x [B,K,T_in] -> y [B,M,S*T_in].
+ * fused = 1: one tensor-core kernel (S in {2,4,5,8}, K % 32 == 0, S*T_in >= 128, pre 0 or 2), fused = 0:
+ * hil_op_dwconv_transpose + hil_op_pointwise through tmp [B,K,S*T_in].  w_pw_host is a HOST [M,K,1] weight. */
+int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out, const float* w_up, const float* w_pw_host,
+                        const float* bias, float* tmp, float* y, int32_t B, int32_t K, int32_t M, int32_t T_in, int32_t S,
+                        int32_t pre, float pre_scale, int32_t fused, void* stream);
 /* CausalSTFT.forward causal_layers.py:135-144 + clamp/log streaming.py:351:
  * wav_window [B,1,(T-1)*hop+n_fft], w_host [2F,1,n_fft] HOST -> y [B,F,T] = log(max(|STFT|,1e-5)). */
 int32_t hil_op_stft_logmag(const float* wav_window, const float* w_host, float* y, int32_t B, int32_t n_fft, int32_t hop,

@@ -38,6 +38,10 @@ def _pre_ref(x, pre, s):
     (2, 256, 160, 8, 4, 0, True, False),
     (2, 64, 40, 10, 5, 0, True, False),
     (2, 64, 8, 16, 8, 0, True, False),
+    (2, 512, 600, 10, 5, 0, True, False),   # vectorised strided kernel, stride 5 (unaligned history)
+    (1, 1024, 600, 16, 8, 0, True, False),  # 75 outputs: ragged last group of 4
+    (2, 128, 1000, 4, 2, 1, False, True),   # activation + skip through the vectorised kernel
+    (1, 256, 72, 8, 4, 0, True, False),     # 18 outputs
     (1, 1024, 4, 5, 1, 1, False, False),
     (2, 192, 1000, 5, 1, 0, True, True),
 ])
@@ -269,3 +273,44 @@ def test_resblock_fused(B, Cc, T, pre):
         assert (c1o.double() - c1_ref).abs().max().item() < 1e-5
     assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0] - outs[1][0]).abs().max()
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.parametrize("B,K,M,T_in,S,pre", [
+    (2, 192, 96, 300, 2, 2),     # decoder stage 3: 192 -> 96, x2, scaled-ELU prologue
+    (1, 384, 192, 200, 4, 2),    # stage 2: two row tiles
+    (2, 768, 384, 60, 5, 2),     # stage 1: stride 5 (tiles do not start on an input boundary)
+    (1, 1536, 768, 40, 8, 0),    # stage 0: no activation (applied by the producer), six row tiles
+    (3, 64, 32, 68, 2, 2),       # ragged: 136 output columns, second tile 8 wide
+])
+def test_upsample_fused(B, K, M, T_in, S, pre):
+    """Decoder upsampling layer (act -> CausalConvTranspose1d depthwise -> 1x1 + bias) as one tensor-core kernel,
+    against the fp64 reference and the two-kernel path."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(K + 7 * S + T_in)
+    x = torch.randn(B, K, T_in, generator=g)
+    if (T_in % 4) != 0:
+        pytest.skip("dense-row operator entry needs T_in % 4 == 0")
+    cache = torch.randn(B, K, 1, generator=g)
+    wu = torch.randn(K, 1, 2 * S, generator=g) / (2 * S) ** 0.5
+    wp = (torch.randn(M, K, 1, generator=g) / K ** 0.5).contiguous()
+    bias = torch.randn(M, generator=g)
+    xin = torch.cat((cache, _pre_ref(x, pre, 0.7071)), 2).double()
+    u = F.conv_transpose1d(xin, wu.double(), None, stride=S, padding=S, output_padding=0, groups=K)
+    y_ref = F.conv1d(u, wp.double(), bias.double())
+    T = S * T_in
+    assert y_ref.shape[2] == T
+    xd, cd, wud, bd = x.cuda(), cache.cuda(), wu.cuda(), bias.cuda()
+    outs = []
+    for fused in (1, 0):
+        y = torch.zeros(B, M, T, device="cuda")
+        co = torch.zeros(B, K, 1, device="cuda")
+        tmp = torch.zeros(B, K, T, device="cuda")
+        _lib.check(lib.hil_op_upsample(_ptr(xd), _ptr(cd), _ptr(co), _ptr(wud), _ptr(wp), _ptr(bd), _ptr(tmp), _ptr(y),
+                                       B, K, M, T_in, S, pre, 0.7071, fused, _stream()))
+        torch.cuda.synchronize()
+        outs.append((y.cpu(), co.cpu()))
+    scale = max(1.0, y_ref.abs().max().item())
+    for y, co in outs:
+        assert (y.double() - y_ref).abs().max().item() < 2e-5 * scale
+        assert (co.double() - xin[:, :, -1:]).abs().max().item() < 1e-6
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5 * scale
