@@ -106,7 +106,10 @@ static bool g_fuse_rb = []() { const char* e = std::getenv("HILCODEC_FUSE_RESBLO
 
 // decoder upsampling layers (transposed depthwise conv -> 1x1) as one kernel: mode bit 6 (64) of
 // hil_set_tensor_cores or HILCODEC_FUSE_UPSAMPLE=0 keep the two launches.
-static bool g_fuse_up = []() { const char* e = std::getenv("HILCODEC_FUSE_UPSAMPLE"); return e && e[0] == '1'; }();   // WIP: off until green
+static bool g_fuse_up = []() { const char* e = std::getenv("HILCODEC_FUSE_UPSAMPLE"); return !(e && e[0] == '0'); }();
+// The fused kernel recomputes the transposed conv once per 128-row output tile; with more than two row tiles
+// (Cout > 256: decoder stages 0 and 1) that costs more than the HBM traffic it saves (measured), unless forced.
+static const bool g_fuse_up_wide = std::getenv("HILCODEC_FUSE_UPSAMPLE_WIDE") != nullptr;
 
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
@@ -170,13 +173,16 @@ static int32_t run_dwconv(const float* x, long long x_bs, int x_rs, const float*
 static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs, int B, int T, int pre, float pre_scale,
                        const float* dw_w, const float* dw_b, const float* ci, float* co, const float* skip, int post,
                        float post_scale, float* tmp, float* Y, cudaStream_t st) {
-    if (g_use_tc && g_fuse_dw && post == PRE_NONE && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
+    const bool hcore = g_use_h && gemm_h_usable(W, X, bs, rs, T, skip, Y, bs, rs);
+    // store-side ELU (post == PRE_ELU, no skip) exists in the fp16-split kernel only
+    const bool post_ok = post == PRE_NONE || (post == PRE_ELU && !skip && hcore);
+    if (g_use_tc && g_fuse_dw && post_ok && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
         const double n = (double)B * T;
         HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
                    4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
-                   (g_use_h && gemm_h_usable(W, X, bs, rs, T, skip, Y, bs, rs))
-                       ? launch_gemm_h_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st)
-                       : launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st));
+                   hcore ? launch_gemm_h_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st,
+                                            post == PRE_ELU)
+                         : launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st));
         return HIL_OK;
     }
     HIL_TRY(run_gemm_linear(W, X, bs, rs, B, T, pre, pre_scale, nullptr, nullptr, tmp, bs, rs, st));
@@ -209,9 +215,11 @@ static int32_t run_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
 // through `tmp` [B][K][S*T_in].
 static int32_t run_upsample(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T_in, int S, int pre,
                             float pre_scale, const float* up_w, const float* ci, float* co, const float* bias, float* tmp,
-                            float* Y, long long y_bs, int y_rs, bool allow_fused, cudaStream_t st) {
+                            float* Y, long long y_bs, int y_rs, bool allow_fused, cudaStream_t st,
+                            bool allow_fused_wide = false) {
     const int K = W.K, T = S * T_in;
-    if (allow_fused && g_use_tc && g_use_h && g_fuse_up && gemm_h_up_usable(W, x, x_bs, x_rs, T_in, S, pre, Y, y_bs, y_rs)) {
+    if (allow_fused && g_use_tc && g_use_h && g_fuse_up && (W.M <= 256 || g_fuse_up_wide || allow_fused_wide) &&
+        gemm_h_up_usable(W, x, x_bs, x_rs, T_in, S, pre, Y, y_bs, y_rs)) {
         const double n = (double)B * T;
         HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * K * n + 4.0 * K * n, 4.0 * ((double)B * K * T_in + n * W.M) + 4.0 * W.M * K, st,
                    launch_gemm_h_up(W, x, x_bs, x_rs, B, T_in, S, pre, pre_scale, up_w, ci, co, bias, Y, y_bs, y_rs, st));
@@ -864,9 +872,11 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
         // a1 holds the halo columns (8 per tile: always smaller than an activation buffer)
         return run_resblock(u[0].pw, u[1].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, u[1].dw_w, u[1].dw_b,
                             cin[0], cout[0], cin[1], cout[1], a1, st);
-    HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, PRE_NONE,
+    // the ELU between the two blocks is applied when the first one stores (once per element) rather than in the
+    // second one's GEMM transform (once per element and 128-row output tile)
+    HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, PRE_ELU,
                     1.f, a1, a2, st));
-    HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, PRE_ELU, 1.f, u[1].dw_w, u[1].dw_b, cin[1], cout[1], h, PRE_NONE, 1.f, a1,
+    HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, PRE_NONE, 1.f, u[1].dw_w, u[1].dw_b, cin[1], cout[1], h, PRE_NONE, 1.f, a1,
                     h, st));
     return HIL_OK;
 }
@@ -1309,10 +1319,10 @@ int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, co
                 rc = run_resblock(pm0, pm1, h, bs, T, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in,
                                   c1_out, tmp1, st);
         } else {
-            rc = run_dws(pm0, h, bs, T, B, T, pre, pre_scale, dw0_w, dw0_b, c0_in, c0_out, nullptr, PRE_NONE, 1.f, tmp1, tmp2,
+            rc = run_dws(pm0, h, bs, T, B, T, pre, pre_scale, dw0_w, dw0_b, c0_in, c0_out, nullptr, PRE_ELU, 1.f, tmp1, tmp2,
                          st);
             if (rc == HIL_OK)
-                rc = run_dws(pm1, tmp2, bs, T, B, T, PRE_ELU, 1.f, dw1_w, dw1_b, c1_in, c1_out, h, PRE_NONE, 1.f, tmp1, h, st);
+                rc = run_dws(pm1, tmp2, bs, T, B, T, PRE_NONE, 1.f, dw1_w, dw1_b, c1_in, c1_out, h, PRE_NONE, 1.f, tmp1, h, st);
         }
     }
     cudaError_t e2 = cudaStreamSynchronize(st);
@@ -1339,7 +1349,7 @@ int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out,
         const bool keep = g_fuse_up;
         g_fuse_up = true;
         rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp, y,
-                          (long long)M * T, T, fused != 0, st);
+                          (long long)M * T, T, fused != 0, st, true);
         g_fuse_up = keep;
     }
     cudaError_t e2 = cudaStreamSynchronize(st);

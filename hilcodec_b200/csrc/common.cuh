@@ -33,6 +33,19 @@ __device__ __forceinline__ float elu_fast(float x) {
     return x > 0.f ? x : neg;
 }
 
+// ELU with ex2.approx only (absolute error <= 2.4e-7, 6 instructions): the form the tensor-core transforms use
+// (gemm_h.cu); also used where the activation feeds a long dot product (decoder conv_post).
+__device__ __forceinline__ float elu_ex2(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.0f;
+}
+__device__ __forceinline__ float apply_act_ex2(float x, int mode, float s) {
+    if (mode == PRE_NONE) return x;
+    if (mode == PRE_SCALE_ELU) x = x * s;
+    return elu_ex2(x);
+}
+
 __device__ __forceinline__ float apply_act_fast(float x, int mode, float s) {
     if (mode == PRE_NONE) return x;
     if (mode == PRE_SCALE_ELU) x = x * s;
@@ -86,7 +99,8 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
                           cudaStream_t st);
 cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                              float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
-                             float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
+                             float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st,
+                             int post_elu = 0);
 
 // upsampling layer: act -> causal transposed depthwise conv (stride S, kernel 2S) -> 1x1 conv + bias, one kernel
 bool gemm_h_up_usable(const PackedMat& W, const float* x, long long x_bs, int x_rs, int T_in, int S, int pre, const float* Y,

@@ -378,51 +378,59 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, long long x_b
                                       const float* __restrict__ w, const float* __restrict__ bias,
                                       float* __restrict__ y, int C, int T, int pre, float pre_scale, int vec) {
     constexpr int P = K - 1;
+    constexpr int NO = 8;          // outputs per thread: P + NO activations feed NO * K MACs per channel
+    static_assert(P == 4, "the vector path loads the 4 history samples as one float4");
     extern __shared__ float sw[];  // [C][K]
     for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
     const int b = blockIdx.y;
-    const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // 4 outputs per thread: activations are evaluated
-    const float* xb = x + b * x_bs;                               // once per input sample, not once per tap
+    const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * NO;
+    const float* xb = x + b * x_bs;
     const float* cb = cache_in + (size_t)b * C * P;
     if (t0 < T) {
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        float a[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) a[o] = 0.f;
+        const bool full = vec && (t0 + NO <= x_rs);   // both float4 loads stay inside the row's storage
         for (int c = 0; c < C; ++c) {
             const float* xr = xb + (long long)c * x_rs;
-            float xin[P + 4];  // xin index j <-> time t0 - P + j
+            float xin[P + NO];  // xin index j <-> time t0 - P + j
             if (t0 == 0) {
 #pragma unroll
                 for (int j = 0; j < P; ++j) xin[j] = cb[c * P + j];
             } else if (vec) {
                 const float4 v = *reinterpret_cast<const float4*>(xr + t0 - 4);
-                xin[0] = apply_act_fast(v.x, pre, pre_scale); xin[1] = apply_act_fast(v.y, pre, pre_scale);
-                xin[2] = apply_act_fast(v.z, pre, pre_scale); xin[3] = apply_act_fast(v.w, pre, pre_scale);
+                xin[0] = apply_act_ex2(v.x, pre, pre_scale); xin[1] = apply_act_ex2(v.y, pre, pre_scale);
+                xin[2] = apply_act_ex2(v.z, pre, pre_scale); xin[3] = apply_act_ex2(v.w, pre, pre_scale);
             } else {
 #pragma unroll
-                for (int j = 0; j < P; ++j) xin[j] = apply_act_fast(xr[t0 - P + j], pre, pre_scale);
+                for (int j = 0; j < P; ++j) xin[j] = apply_act_ex2(xr[t0 - P + j], pre, pre_scale);
             }
-            if (vec) {
-                const float4 v = *reinterpret_cast<const float4*>(xr + t0);
-                xin[P + 0] = apply_act_fast(v.x, pre, pre_scale); xin[P + 1] = apply_act_fast(v.y, pre, pre_scale);
-                xin[P + 2] = apply_act_fast(v.z, pre, pre_scale); xin[P + 3] = apply_act_fast(v.w, pre, pre_scale);
+            if (full) {
+#pragma unroll
+                for (int h = 0; h < NO / 4; ++h) {
+                    const float4 v = *reinterpret_cast<const float4*>(xr + t0 + 4 * h);
+                    xin[P + 4 * h + 0] = apply_act_ex2(v.x, pre, pre_scale); xin[P + 4 * h + 1] = apply_act_ex2(v.y, pre, pre_scale);
+                    xin[P + 4 * h + 2] = apply_act_ex2(v.z, pre, pre_scale); xin[P + 4 * h + 3] = apply_act_ex2(v.w, pre, pre_scale);
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xin[P + j] = t0 + j < T ? apply_act_fast(xr[t0 + j], pre, pre_scale) : 0.f;
+                for (int j = 0; j < NO; ++j) xin[P + j] = t0 + j < T ? apply_act_ex2(xr[t0 + j], pre, pre_scale) : 0.f;
             }
 #pragma unroll
-            for (int o = 0; o < 4; ++o)
+            for (int o = 0; o < NO; ++o)
 #pragma unroll
                 for (int k = 0; k < K; ++k) a[o] = fmaf(sw[c * K + k], xin[o + k], a[o]);
         }
         const float bv = bias ? bias[0] : 0.f;
-        for (int o = 0; o < 4 && t0 + o < T; ++o) y[(size_t)b * T + t0 + o] = tanhf(a[o] + bv);
+        for (int o = 0; o < NO && t0 + o < T; ++o) y[(size_t)b * T + t0 + o] = tanhf(a[o] + bv);
     }
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < C * P; i += blockDim.x) {
             const int c = i / P, jj = i - c * P;
             const int j = T + jj;
             cache_out[(size_t)b * C * P + i] =
-                j < P ? cb[c * P + j] : apply_act_fast(xb[(long long)c * x_rs + (j - P)], pre, pre_scale);
+                j < P ? cb[c * P + j] : apply_act_ex2(xb[(long long)c * x_rs + (j - P)], pre, pre_scale);
         }
     }
 }
@@ -432,7 +440,7 @@ cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, cons
                                   float pre_scale, cudaStream_t st) {
     if (K != 5) return cudaErrorInvalidValue;
     if (B == 0) return cudaSuccess;
-    const int Tq = (T + 3) / 4;
+    const int Tq = (T + 7) / 8;
     const int threads = Tq >= 128 ? 128 : 32;
     const int vec = ((x_rs & 3) == 0) && ((x_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     dim3 grid(max(1, (Tq + threads - 1) / threads), B);

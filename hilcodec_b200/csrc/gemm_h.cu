@@ -64,6 +64,7 @@ struct Params {
     float c_big, c_small;   // 2^-s and 2^-s * 2^-11
     const float* bias;
     int reduce_add;         // 1: Y += tile (TMA reduce), 0: Y = tile
+    int post_elu;           // fused DWS only: store ELU(y) (the consumer then needs no activation prologue)
     int t_step, t_halo;     // tile tt covers columns [tt * t_step - t_halo, ... + BN)
     const float* dw_w;      // [M][5]
     const float* dw_b;      // [M] or null
@@ -154,17 +155,17 @@ __device__ __forceinline__ void xform_rows_up(const float* raw, const float (&wr
     }
 }
 
-// taps of the 4 output columns n_abs0 .. n_abs0+3 for the 4 k-rows of this warp: wreg[q][j] = w[k][(n%S)],
-// wreg[q][4+j] = w[k][(n%S) + S]
+// taps of the 4 output columns n_abs0 .. n_abs0+3 for the 4 k-rows of this warp, from the k-block's tap slice
+// [32][2S] that the producer copied into the raw stage behind the activation box (global loads here put an L2
+// round trip on every k-block's critical path): wreg[q][j] = w[k][n%S], wreg[q][4+j] = w[k][n%S + S]
 template <int S>
-__device__ __forceinline__ void load_up_taps(const float* w, int k0, int K, int xw, int n_abs0, float (&wreg)[4][8]) {
+__device__ __forceinline__ void load_up_taps(const float* wsm, int xw, int n_abs0, float (&wreg)[4][8]) {
     const int r0 = n_abs0 % S;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int k = k0 + xw * 4 + q;
-        const float* wr = w + (size_t)(k < K ? k : 0) * 2 * S;
+        const float* wr = wsm + (xw * 4 + q) * 2 * S;
         if constexpr (S % 4 == 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(wr + r0)), b = __ldg(reinterpret_cast<const float4*>(wr + r0 + S));
+            const float4 a = *reinterpret_cast<const float4*>(wr + r0), b = *reinterpret_cast<const float4*>(wr + r0 + S);
             wreg[q][0] = a.x; wreg[q][1] = a.y; wreg[q][2] = a.z; wreg[q][3] = a.w;
             wreg[q][4] = b.x; wreg[q][5] = b.y; wreg[q][6] = b.z; wreg[q][7] = b.w;
         } else {
@@ -172,8 +173,8 @@ __device__ __forceinline__ void load_up_taps(const float* w, int k0, int K, int 
             for (int j = 0; j < 4; ++j) {
                 int r = r0 + j;
                 if (r >= S) r -= S;
-                wreg[q][j] = __ldg(wr + r);
-                wreg[q][4 + j] = __ldg(wr + r + S);
+                wreg[q][j] = wr[r];
+                wreg[q][4 + j] = wr[r + S];
             }
         }
     }
@@ -248,8 +249,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait<32>(raw_empty(r), ph ^ 1);
                     if constexpr (kUp > 0) {   // low-rate box: the inputs of the tile's columns and the one before
-                        mbar_arrive_expect_tx(raw_full(r), BK * up_ni(kUp) * 4);
+                        constexpr uint32_t XB = BK * up_ni(kUp) * 4, WB = BK * 2 * kUp * 4;   // activation box, tap slice
+                        mbar_arrive_expect_tx(raw_full(r), XB + WB);
                         tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), up_box_start<kUp>(tt), kb * BK, b);
+                        bulk_load(raw_base + r * RAW_BYTES + XB, p.up_w + (size_t)kb * BK * 2 * kUp, WB, raw_full(r));
                     } else {
                         mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
                         tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
@@ -328,14 +331,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             [[maybe_unused]] const int tt = (int)(rest % p.tiles_t);
             [[maybe_unused]] const int b = (int)(rest / p.tiles_t);
             for (int kb = 0; kb < nkb; ++kb) {
-                [[maybe_unused]] float wreg[4][8];
-                if constexpr (kUp > 0)   // taps first: their latency hides behind the wait for the activation box
-                    load_up_taps<kUp>(p.up_w, kb * BK, p.K, xw, tt * BN + 4 * lane, wreg);
                 mbar_wait(raw_full(r), rph);
                 mbar_wait(op_empty(s), sph ^ 1);
                 const uint32_t bhi = op_base + s * OP_BYTES + 2 * A_TILE + panel * B_PANEL;
                 if constexpr (kUp > 0) {
                     const float* raw = reinterpret_cast<const float*>(gen_base + (raw_base - base) + r * RAW_BYTES);
+                    float wreg[4][8];
+                    load_up_taps<kUp>(raw + BK * up_ni(kUp), xw, tt * BN + 4 * lane, wreg);
                     const float* ci = p.up_ci + (size_t)b * p.K;
                     float* co = m_blk == 0 ? p.up_co + (size_t)b * p.K : nullptr;
                     if (p.pre == PRE_NONE)
@@ -498,6 +500,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                             for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[i + k], a);
                             o[e] = a;
                         }
+                        if (p.post_elu) elu4(o[0], o[1], o[2], o[3]);
                         uint32_t dst;
                         if (c == 0) {
                             if (j4 == 0) continue;   // outputs 0..3 of chunk 0 belong to the previous tile
@@ -697,7 +700,8 @@ cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs,
 
 cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                              float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in, float* cache_out,
-                             const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st) {
+                             const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st, int post_elu) {
+    if (post_elu && skip) return cudaErrorInvalidValue;   // the activation cannot follow an in-place accumulation
     using namespace th;
     if (B == 0 || T == 0) return cudaSuccess;
     CUtensorMap map_hi, map_lo, map_x, map_y, map_y28;
@@ -726,6 +730,7 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f;
     p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out;
     p.reduce_add = skip ? 1 : 0;
+    p.post_elu = post_elu;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);

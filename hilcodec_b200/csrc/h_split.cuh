@@ -40,6 +40,21 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(
 //   consumes the value cannot see: the error enters the dot product in absolute terms).
 //   x - fp16(x) is exact in fp32 and the 2^11 scaling is a power of two, so the split is bit-identical to the
 //   scalar form  lo = fp16_rn((x - hi) * 2^11).
+// ELU of 4 values on the packed pipe: x > 0 ? x : 2^(x log2 e) - 1 (the function split4<PRE_ELU> applies)
+__device__ __forceinline__ void elu4(float& r0, float& r1, float& r2, float& r3) {
+    const f32x2 l2e = pk2(1.4426950408889634f, 1.4426950408889634f), m1 = pk2(-1.f, -1.f);
+    float t0, t1, t2, t3;
+    upk2(fmul2(pk2(r0, r1), l2e), t0, t1);
+    upk2(fmul2(pk2(r2, r3), l2e), t2, t3);
+    float e0, e1, e2, e3;
+    upk2(fadd2(pk2(ex2_approx(t0), ex2_approx(t1)), m1), e0, e1);
+    upk2(fadd2(pk2(ex2_approx(t2), ex2_approx(t3)), m1), e2, e3);
+    r0 = r0 > 0.f ? r0 : e0;
+    r1 = r1 > 0.f ? r1 : e1;
+    r2 = r2 > 0.f ? r2 : e2;
+    r3 = r3 > 0.f ? r3 : e3;
+}
+
 template <int kPre, bool kPoly = false>
 __device__ __forceinline__ void split4(float4 x, float s, uint32_t& h01, uint32_t& h23, uint32_t& l01, uint32_t& l23) {
     float r0 = x.x, r1 = x.y, r2 = x.z, r3 = x.w;
@@ -54,17 +69,7 @@ __device__ __forceinline__ void split4(float4 x, float s, uint32_t& h01, uint32_
             upk2(a, r0, r1);
             upk2(b, r2, r3);
         }
-        const f32x2 l2e = pk2(1.4426950408889634f, 1.4426950408889634f), m1 = pk2(-1.f, -1.f);
-        float t0, t1, t2, t3;
-        upk2(fmul2(a, l2e), t0, t1);
-        upk2(fmul2(b, l2e), t2, t3);
-        float e0, e1, e2, e3;
-        upk2(fadd2(pk2(ex2_approx(t0), ex2_approx(t1)), m1), e0, e1);
-        upk2(fadd2(pk2(ex2_approx(t2), ex2_approx(t3)), m1), e2, e3);
-        r0 = r0 > 0.f ? r0 : e0;
-        r1 = r1 > 0.f ? r1 : e1;
-        r2 = r2 > 0.f ? r2 : e2;
-        r3 = r3 > 0.f ? r3 : e3;
+        elu4(r0, r1, r2, r3);
     }
     h01 = pack_h2(r0, r1);
     h23 = pack_h2(r2, r3);

@@ -35,7 +35,9 @@ cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, in
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256, 1)
+// Two CTAs per SM (2 x 84 KB of shared memory, <= 128 registers): the kernel alternates between loading a codebook
+// tile and scoring it with a barrier on either side, so a second resident CTA fills the load phases of the first.
+__global__ void __launch_bounds__(256, 2)
 rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee,
                   int size, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum) {
     extern __shared__ __align__(16) float smem[];
