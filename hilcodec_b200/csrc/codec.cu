@@ -872,12 +872,14 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
         // a1 holds the halo columns (8 per tile: always smaller than an activation buffer)
         return run_resblock(u[0].pw, u[1].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, u[1].dw_w, u[1].dw_b,
                             cin[0], cout[0], cin[1], cout[1], a1, st);
-    // the ELU between the two blocks is applied when the first one stores (once per element) rather than in the
-    // second one's GEMM transform (once per element and 128-row output tile)
-    HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, PRE_ELU,
-                    1.f, a1, a2, st));
-    HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, PRE_NONE, 1.f, u[1].dw_w, u[1].dw_b, cin[1], cout[1], h, PRE_NONE, 1.f, a1,
-                    h, st));
+    // For C >= 256 the ELU between the two blocks is applied when the first one stores (once per element) rather than
+    // in the second one's GEMM transform (once per element and 128-row output tile); below that the first block's
+    // epilogue is the longer stage and the extra work there costs more than it saves (measured at C = 192).
+    const int mid = C >= 256 ? PRE_ELU : PRE_NONE;
+    HIL_TRY(run_dws(u[0].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, cin[0], cout[0], nullptr, mid, 1.f, a1,
+                    a2, st));
+    HIL_TRY(run_dws(u[1].pw, a2, bs, Tp, B, Ts, mid == PRE_ELU ? PRE_NONE : PRE_ELU, 1.f, u[1].dw_w, u[1].dw_b, cin[1],
+                    cout[1], h, PRE_NONE, 1.f, a1, h, st));
     return HIL_OK;
 }
 

@@ -64,6 +64,7 @@ struct Params {
     float c_big, c_small;   // 2^-s and 2^-s * 2^-11
     const float* bias;
     int reduce_add;         // 1: Y += tile (TMA reduce), 0: Y = tile
+    int xform_sleep;        // ns of back-off in the transform warps' barrier polls (0 = spin)
     int post_elu;           // fused DWS only: store ELU(y) (the consumer then needs no activation prologue)
     int t_step, t_halo;     // tile tt covers columns [tt * t_step - t_halo, ... + BN)
     const float* dw_w;      // [M][5]
@@ -331,8 +332,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             [[maybe_unused]] const int tt = (int)(rest % p.tiles_t);
             [[maybe_unused]] const int b = (int)(rest / p.tiles_t);
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(raw_full(r), rph);
-                mbar_wait(op_empty(s), sph ^ 1);
+                mbar_wait_ns(raw_full(r), rph, p.xform_sleep);
+                mbar_wait_ns(op_empty(s), sph ^ 1, p.xform_sleep);
                 const uint32_t bhi = op_base + s * OP_BYTES + 2 * A_TILE + panel * B_PANEL;
                 if constexpr (kUp > 0) {
                     const float* raw = reinterpret_cast<const float*>(gen_base + (raw_base - base) + r * RAW_BYTES);
@@ -619,6 +620,7 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
@@ -679,6 +681,7 @@ static cudaError_t launch_up(const PackedMat& W, const float* x, long long x_bs,
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = 0;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = 0;
     p.t_in = T_in; p.up_w = up_w; p.up_ci = ci; p.up_co = co;
     const int num_sms = tc::device_sm_count();
@@ -732,6 +735,7 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.reduce_add = skip ? 1 : 0;
     p.post_elu = post_elu;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);

@@ -23,6 +23,7 @@
 // Warp roles (512 threads, 1 CTA/SM): 0 X producer (TMA), 1 MMA issuer, 2 TMEM allocator, 3 weight producer
 // (TMA, W0 then W1 pieces through one ring), 8-15 workers: transform (ELU + split of the input tile) and E1, two warps
 // per TMEM lane quarter; 4-7 epilogue E2.  E2 of tile i overlaps the transform / G1 / E1 of tile i+1.
+// (Tried and measured slower: issuing G1(i+1) ahead of G2(i); per-warp 32-row staging + TMA stores in E2.)
 // Arithmetic is the one of gemm_h.cu, instruction for instruction, so the result is bit-identical to the two
 // fused-DWS launches it replaces (tests/test_gpu_ops.py::test_resblock_fused).
 #include <cstdlib>
@@ -69,6 +70,7 @@ struct Params {
     int nkb, num_m, tiles_t;
     long long total_tiles;
     int pre;
+    int xform_sleep;               // ns of back-off in the worker warps' barrier polls (0 = spin)
     float pre_scale;
     float c_big0, c_big1;          // 2^-s of W0 / W1 (fp16 weight scaling, see gemm_h.cu)
     const float* dw0_w;            // [C][5]
@@ -299,8 +301,8 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(raw_full(r), rph);
-                mbar_wait(b_empty(s), sph ^ 1);
+                mbar_wait_ns(raw_full(r), rph, p.xform_sleep);
+                mbar_wait_ns(b_empty(s), sph ^ 1, p.xform_sleep);
                 const uint8_t* raw = gen_base + (raw_base - base) + r * G::RAW_BYTES;
                 const uint32_t bdst = b_base + s * G::B_STAGE;
                 if (p.pre == PRE_ELU) xform_tile_rows<PRE_ELU, BN>(raw, bdst, xw, lane, 1.0f);
@@ -323,9 +325,9 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
             const bool has_tail = tcol0 + BN > p.T - 4;      // the tile holds some of the last 4 time steps
             const int c_begin = half * CH, c_end = min(c_begin + CH, n_chunks);
-            mbar_wait(d1_full, it & 1);
+            mbar_wait_ns(d2_full, (it & 1) ^ 1, p.xform_sleep);   // G2 of the previous tile has finished reading B2
+            mbar_wait_ns(d1_full, it & 1, p.xform_sleep);
             tc_fence_after();
-            bool b2_free = false;                            // G2 of the previous tile must have read B2 before it is rewritten
 #pragma unroll 1
             for (int mb = 0; mb < NUM_M; ++mb) {
                 const int mrow0 = mb * BM + q * 32;
@@ -390,10 +392,6 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                         }
                         uint32_t hi[4], lo[4];
                         elu_split8(o, hi, lo);
-                        if (!b2_free) {
-                            mbar_wait(d2_full, (it & 1) ^ 1);
-                            b2_free = true;
-                        }
                         const uint32_t g8 = (uint32_t)(c * 4 + j8);   // 8-column group inside the tile
                         const uint32_t dst = b2row + (g8 >> 3) * B_PANEL + (((g8 & 7u) ^ (uint32_t)(lane & 7)) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
@@ -415,6 +413,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
         // ===================================================================== epilogue E2: D2 -> dw1 -> h += (TMA reduce-add)
         const int q = warp - 4;
         const int row = q * 32 + lane;                      // row inside an m-block = TMEM lane
+        const bool issuer = (q == 0 && lane == 0);
         const uint32_t sw = (uint32_t)(row & 7);
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE);
         const float c_big1 = p.c_big1, c_inv1 = 1.0f / p.c_big1;
@@ -455,8 +454,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                 const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + mb * 2 * BN;
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c, ++g) {
-                    // every warp stages and stores its own 32-row slab (no barrier between the epilogue warps)
-                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES + q * (OUT_BYTES / 4);
+                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
                     float v[36];
                     if (warp_ok) {
                         uint32_t rb[32], rs[32];
@@ -486,10 +484,9 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                         tc_fence_before();
                         mbar_arrive(d2_empty);
                     }
-                    if (!warp_ok) continue;           // nothing to store for weight-padding rows (g advances for all warps)
-                    if (lane == 0) tma_wait_read<1>();   // this warp's store from two chunks ago has drained the buffer
-                    __syncwarp();
-                    {
+                    if (issuer) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
+                    epi_bar_sync();
+                    if (warp_ok) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
                             if (c == 0 && j4 < 2) continue;   // tile columns 0..7 are halo: they belong to the left neighbour
@@ -502,7 +499,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                                 for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[i + k], a);
                                 o[e] = a;
                             }
-                            const uint32_t dst = c == 0 ? obuf + lane * 96 + (j4 - 2) * 16 : obuf + lane * 128 + (((uint32_t)j4 ^ sw) << 4);
+                            const uint32_t dst = c == 0 ? obuf + row * 96 + (j4 - 2) * 16 : obuf + row * 128 + (((uint32_t)j4 ^ sw) << 4);
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]),
                                          "f"(o[3])
                                          : "memory");
@@ -510,16 +507,16 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                         carry[0] = v[32]; carry[1] = v[33]; carry[2] = v[34]; carry[3] = v[35];
                     }
                     fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (c == 0) tma_reduce_add_3d(&map_y24, obuf, tcol0 + HALO, mrow0, b);
-                        else tma_reduce_add_3d(&map_y, obuf, tcol0 + c * 32, mrow0, b);
+                    epi_bar_sync();
+                    if (issuer) {
+                        if (c == 0) tma_reduce_add_3d(&map_y24, obuf, tcol0 + HALO, mb * BM, b);
+                        else tma_reduce_add_3d(&map_y, obuf, tcol0 + c * 32, mb * BM, b);
                         tma_commit();
                     }
                 }
             }
         }
-        if (lane == 0) tma_wait_all();
+        if (issuer) tma_wait_all();
     }
 
     tc_fence_before();
@@ -603,8 +600,8 @@ static cudaError_t launch_rb(const PackedMat& W0, const PackedMat& W1, float* h,
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)rs * 4, (cuuint64_t)bs * 4};
         const cuuint32_t box_x[3] = {(cuuint32_t)G::VAL, BK, 1};
-        const cuuint32_t box_y[3] = {32, 32, 1};      // one epilogue warp's slab: 32 rows x 32 (24) columns
-        const cuuint32_t box_y24[3] = {24, 32, 1};
+        const cuuint32_t box_y[3] = {32, BM, 1};
+        const cuuint32_t box_y24[3] = {24, BM, 1};
         if (!tc::make_map(&mx, h, 3, dims, strides, box_x, CU_TENSOR_MAP_SWIZZLE_NONE) ||
             !tc::make_map(&my, h, 3, dims, strides, box_y, CU_TENSOR_MAP_SWIZZLE_128B) ||
             !tc::make_map(&my24, h, 3, dims, strides, box_y24, CU_TENSOR_MAP_SWIZZLE_NONE))
@@ -624,6 +621,7 @@ static cudaError_t launch_rb(const PackedMat& W0, const PackedMat& W1, float* h,
     p.total_tiles = (long long)tiles_t * B;
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f;
     p.c_big0 = W0.h_inv_scale; p.c_big1 = W1.h_inv_scale;
+    p.xform_sleep = tc::xform_sleep_env();
     p.dw0_w = dw0_w; p.dw0_b = dw0_b; p.dw1_w = dw1_w; p.dw1_b = dw1_b;
     p.c0_in = c0_in; p.c0_out = c0_out; p.c1_in = c1_in; p.c1_out = c1_out;
     const int num_sms = tc::device_sm_count();

@@ -1,6 +1,8 @@
 // PTX helpers shared by the tcgen05 kernels (gemm_tc.cu, stft_tc.cu): mbarrier, TMA, UMMA
 // descriptors, TMEM loads.  sm_100a only.
 #pragma once
+#include <cstdlib>
+
 #include <cuda.h>
 
 #include "common.cuh"
@@ -41,6 +43,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (kSleepNs > 0) __nanosleep(kSleepNs);
         if (++spins > (1u << 22)) __trap();
     }
+}
+// same with a run-time back-off (A/B knob for the transform / worker warps: HILCODEC_XFORM_SLEEP=<ns>)
+__device__ __forceinline__ void mbar_wait_ns(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (ns) __nanosleep(ns);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+inline int xform_sleep_env() {
+    static const int v = []() { const char* e = std::getenv("HILCODEC_XFORM_SLEEP"); return e ? std::atoi(e) : 0; }();
+    return v;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
