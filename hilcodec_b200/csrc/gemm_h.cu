@@ -49,6 +49,11 @@ constexpr int OP_BYTES = 2 * A_TILE + 2 * B_TILE; // 32 KB: A_hi, A_lo, B_hi, B_
 constexpr int B_PANEL = 8 * 128 * (BK / 8);       // 4 KB: 64 columns x 32 k (4 swizzle atoms of 8 k-rows x 128 B)
 constexpr int NUM_THREADS = 512;
 constexpr int NUM_XFORM_WARPS = 8;
+#ifndef HIL_XFORM_GROUPS
+#define HIL_XFORM_GROUPS 2
+#endif
+constexpr int XG = HIL_XFORM_GROUPS;              // k-blocks the transform warps convert concurrently
+constexpr int XW_PER_G = NUM_XFORM_WARPS / XG;    // warps per k-block
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
 constexpr int TMEM_COLS = 512;
@@ -215,11 +220,11 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int r = 0; r < RAW_STAGES; ++r) {
             mbar_init(raw_full(r), 1);
-            mbar_init(raw_empty(r), NUM_XFORM_WARPS);
+            mbar_init(raw_empty(r), XW_PER_G);
         }
         for (int s = 0; s < OP_STAGES; ++s) {
             mbar_init(a_full(s), 1);
-            mbar_init(b_ready(s), NUM_XFORM_WARPS);
+            mbar_init(b_ready(s), XW_PER_G);
             mbar_init(op_empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -318,44 +323,60 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
     } else if (warp >= 8) {
         // ===================================================================== transform: raw fp32 -> B_hi / B_lo fp16
-        // Warp w converts k-rows 4w .. 4w+3 of the box; a lane owns 4 consecutive columns of a row: one
-        // conflict-free LDS.128, two STS.64 into the 128B-swizzled MN-major atoms.
+        // The 8 warps work as XG groups, each group converting every XG-th k-block (a warp owns 4 * XG k-rows of the
+        // box; a lane owns 4 consecutive columns of a row: conflict-free LDS.128, STS.64 into the 128B-swizzled MN-major
+        // atoms).  With one group the conversion of a k-block is one serial latency chain (wait -> LDS -> math -> STS
+        // -> fence -> arrive, ~1000 cycles measured) that paces the whole mainloop; XG chains overlap.
         const int xw = warp - 8;
+        const int xg = xw / XW_PER_G, xl = xw % XW_PER_G;
         const uint32_t panel = (uint32_t)(lane >> 4);     // 64-column panel
         const uint32_t chunk = (uint32_t)((lane >> 1) & 7);  // 16-byte chunk (8 columns) inside the 128-byte row
         const uint32_t half8 = (uint32_t)(lane & 1) * 8u;
-        int r = 0, s = 0;
-        uint32_t rph = 0, sph = 0;
+        uint32_t n = 0;                                    // k-blocks seen by this CTA (all tiles)
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             [[maybe_unused]] const int m_blk = (int)(tile % p.num_m);
             [[maybe_unused]] const long long rest = tile / p.num_m;
             [[maybe_unused]] const int tt = (int)(rest % p.tiles_t);
             [[maybe_unused]] const int b = (int)(rest / p.tiles_t);
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb, ++n) {
+                if ((int)(n % XG) != xg) continue;
+                const int r = (int)(n % RAW_STAGES), s = (int)(n % OP_STAGES);
+                const uint32_t rph = (n / RAW_STAGES) & 1u, sph = (n / OP_STAGES) & 1u;
                 mbar_wait_ns(raw_full(r), rph, p.xform_sleep);
                 mbar_wait_ns(op_empty(s), sph ^ 1, p.xform_sleep);
                 const uint32_t bhi = op_base + s * OP_BYTES + 2 * A_TILE + panel * B_PANEL;
                 if constexpr (kUp > 0) {
                     const float* raw = reinterpret_cast<const float*>(gen_base + (raw_base - base) + r * RAW_BYTES);
-                    float wreg[4][8];
-                    load_up_taps<kUp>(raw + BK * up_ni(kUp), xw, tt * BN + 4 * lane, wreg);
                     const float* ci = p.up_ci + (size_t)b * p.K;
                     float* co = m_blk == 0 ? p.up_co + (size_t)b * p.K : nullptr;
-                    if (p.pre == PRE_NONE)
-                        xform_rows_up<kUp, PRE_NONE>(raw, wreg, xw, lane, bhi, chunk, half8, 1.0f, tt * BN + 4 * lane,
-                                                     up_box_start<kUp>(tt), kb * BK, p.K, ci, co, p.t_in);
-                    else
-                        xform_rows_up<kUp, PRE_SCALE_ELU>(raw, wreg, xw, lane, bhi, chunk, half8, p.pre_scale, tt * BN + 4 * lane,
-                                                          up_box_start<kUp>(tt), kb * BK, p.K, ci, co, p.t_in);
+#pragma unroll
+                    for (int h = 0; h < XG; ++h) {
+                        const int xq = xl * XG + h;            // 4-row slice of the box
+                        float wreg[4][8];
+                        load_up_taps<kUp>(raw + BK * up_ni(kUp), xq, tt * BN + 4 * lane, wreg);
+                        if (p.pre == PRE_NONE)
+                            xform_rows_up<kUp, PRE_NONE>(raw, wreg, xq, lane, bhi, chunk, half8, 1.0f, tt * BN + 4 * lane,
+                                                         up_box_start<kUp>(tt), kb * BK, p.K, ci, co, p.t_in);
+                        else
+                            xform_rows_up<kUp, PRE_SCALE_ELU>(raw, wreg, xq, lane, bhi, chunk, half8, p.pre_scale,
+                                                              tt * BN + 4 * lane, up_box_start<kUp>(tt), kb * BK, p.K, ci, co,
+                                                              p.t_in);
+                    }
                 } else {
                     const float4* src = reinterpret_cast<const float4*>(gen_base + (raw_base - base) + r * RAW_BYTES);
-                    float4 v[4];
+                    float4 v[XG][4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = src[(xw * 4 + q) * (BN / 4) + lane];
-                    if (p.pre == PRE_NONE) xform_rows<PRE_NONE>(v, 1.0f, xw, bhi, chunk, half8);
-                    else if (p.elu_poly) xform_rows<PRE_SCALE_ELU, true>(v, p.pre_scale, xw, bhi, chunk, half8);
-                    else if (p.pre == PRE_ELU) xform_rows<PRE_ELU>(v, 1.0f, xw, bhi, chunk, half8);
-                    else xform_rows<PRE_SCALE_ELU>(v, p.pre_scale, xw, bhi, chunk, half8);
+                    for (int h = 0; h < XG; ++h)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[h][q] = src[((xl * XG + h) * 4 + q) * (BN / 4) + lane];
+#pragma unroll
+                    for (int h = 0; h < XG; ++h) {
+                        const int xq = xl * XG + h;
+                        if (p.pre == PRE_NONE) xform_rows<PRE_NONE>(v[h], 1.0f, xq, bhi, chunk, half8);
+                        else if (p.elu_poly) xform_rows<PRE_SCALE_ELU, true>(v[h], p.pre_scale, xq, bhi, chunk, half8);
+                        else if (p.pre == PRE_ELU) xform_rows<PRE_ELU>(v[h], 1.0f, xq, bhi, chunk, half8);
+                        else xform_rows<PRE_SCALE_ELU>(v[h], p.pre_scale, xq, bhi, chunk, half8);
+                    }
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -363,8 +384,6 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     mbar_arrive(b_ready(s));
                     mbar_arrive(raw_empty(r));
                 }
-                if (++r == RAW_STAGES) { r = 0; rph ^= 1; }
-                if (++s == OP_STAGES) { s = 0; sph ^= 1; }
             }
         }
     } else if (warp >= 4 && warp < 8) {
