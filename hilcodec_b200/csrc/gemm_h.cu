@@ -53,7 +53,6 @@ constexpr int NUM_XFORM_WARPS = 8;
 #define HIL_XFORM_GROUPS 2
 #endif
 constexpr int XG = HIL_XFORM_GROUPS;              // k-blocks the transform warps convert concurrently
-constexpr int XW_PER_G = NUM_XFORM_WARPS / XG;    // warps per k-block
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
 constexpr int TMEM_COLS = 512;
@@ -187,17 +186,28 @@ __device__ __forceinline__ void load_up_taps(const float* wsm, int xw, int n_abs
 }
 
 // ------------------------------------------------------------------------------- kernel
-template <bool kDw, int kUp = 0>
+// kEpi = 1: warps 4-7 epilogue, 8-15 transform (layers with long K loops: the transform is the busy stage).
+// kEpi = 2: warps 4-7 and 8-11 are TWO epilogue groups, one per TMEM accumulator stage, draining alternate tiles
+//           concurrently; warps 12-15 transform.  For K <= 256 the serial TMEM -> registers -> SMEM -> TMA chain of
+//           one group (about 2000 cycles per 32-column chunk) is longer than the tile's mainloop.  Shared memory is
+//           re-cut: 4 raw stages instead of 6, 4 staging buffers instead of 2.
+template <bool kDw, int kUp = 0, int kEpi = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
               const __grid_constant__ CUtensorMap map_y28, const Params p) {
+    static_assert(kEpi == 1 || kEpi == 2, "one or two epilogue groups");
+    constexpr int RAW_STAGES = kEpi == 2 ? th::RAW_STAGES - 2 : th::RAW_STAGES;
+    constexpr int NUM_XW = kEpi == 2 ? NUM_XFORM_WARPS / 2 : NUM_XFORM_WARPS;   // transform warps
+    constexpr int XW0 = 16 - NUM_XW;                    // first transform warp
+    constexpr int XW_PER_G = NUM_XW / XG;               // warps per transform group (one k-block)
+    constexpr int SPW = BK / 4 / XW_PER_G;              // 4-row slices of the box per transform warp
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t raw_base = base;
     const uint32_t op_base = raw_base + RAW_STAGES * RAW_BYTES;
     const uint32_t out_base = op_base + OP_STAGES * OP_BYTES;
-    const uint32_t bars = out_base + 2 * OUT_BYTES;
+    const uint32_t bars = out_base + 2 * kEpi * OUT_BYTES;
     auto raw_full = [&](int r) { return bars + 8u * r; };
     auto raw_empty = [&](int r) { return bars + 8u * (RAW_STAGES + r); };
     auto a_full = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };
@@ -321,13 +331,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 if (++s == OP_STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= XW0) {
         // ===================================================================== transform: raw fp32 -> B_hi / B_lo fp16
-        // The 8 warps work as XG groups, each group converting every XG-th k-block (a warp owns 4 * XG k-rows of the
-        // box; a lane owns 4 consecutive columns of a row: conflict-free LDS.128, STS.64 into the 128B-swizzled MN-major
+        // The transform warps work as XG groups, each group converting every XG-th k-block (a warp owns SPW 4-row
+        // slices of the box; a lane owns 4 consecutive columns of a row: conflict-free LDS.128, STS.64 into the 128B-swizzled MN-major
         // atoms).  With one group the conversion of a k-block is one serial latency chain (wait -> LDS -> math -> STS
         // -> fence -> arrive, ~1000 cycles measured) that paces the whole mainloop; XG chains overlap.
-        const int xw = warp - 8;
+        const int xw = warp - XW0;
         const int xg = xw / XW_PER_G, xl = xw % XW_PER_G;
         const uint32_t panel = (uint32_t)(lane >> 4);     // 64-column panel
         const uint32_t chunk = (uint32_t)((lane >> 1) & 7);  // 16-byte chunk (8 columns) inside the 128-byte row
@@ -350,8 +360,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     const float* ci = p.up_ci + (size_t)b * p.K;
                     float* co = m_blk == 0 ? p.up_co + (size_t)b * p.K : nullptr;
 #pragma unroll
-                    for (int h = 0; h < XG; ++h) {
-                        const int xq = xl * XG + h;            // 4-row slice of the box
+                    for (int h = 0; h < SPW; ++h) {
+                        const int xq = xl * SPW + h;           // 4-row slice of the box
                         float wreg[4][8];
                         load_up_taps<kUp>(raw + BK * up_ni(kUp), xq, tt * BN + 4 * lane, wreg);
                         if (p.pre == PRE_NONE)
@@ -364,14 +374,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     }
                 } else {
                     const float4* src = reinterpret_cast<const float4*>(gen_base + (raw_base - base) + r * RAW_BYTES);
-                    float4 v[XG][4];
+                    float4 v[SPW][4];
 #pragma unroll
-                    for (int h = 0; h < XG; ++h)
+                    for (int h = 0; h < SPW; ++h)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) v[h][q] = src[((xl * XG + h) * 4 + q) * (BN / 4) + lane];
+                        for (int q = 0; q < 4; ++q) v[h][q] = src[((xl * SPW + h) * 4 + q) * (BN / 4) + lane];
 #pragma unroll
-                    for (int h = 0; h < XG; ++h) {
-                        const int xq = xl * XG + h;
+                    for (int h = 0; h < SPW; ++h) {
+                        const int xq = xl * SPW + h;
                         if (p.pre == PRE_NONE) xform_rows<PRE_NONE>(v[h], 1.0f, xq, bhi, chunk, half8);
                         else if (p.elu_poly) xform_rows<PRE_SCALE_ELU, true>(v[h], p.pre_scale, xq, bhi, chunk, half8);
                         else if (p.pre == PRE_ELU) xform_rows<PRE_ELU>(v[h], 1.0f, xq, bhi, chunk, half8);
@@ -386,11 +396,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================================================================== epilogue
-        const int q = warp - 4;
+    } else if (warp >= 4 && warp < 4 + 4 * kEpi) {
+        // ===================================================================== epilogue (group eg drains tiles it % kEpi == eg)
+        const int eg = (warp - 4) >> 2;
+        const int q = warp & 3;                             // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
         const bool issuer = (q == 0 && lane == 0);
+        const uint32_t my_out = out_base + eg * 2 * OUT_BYTES;   // this group's two staging buffers
+        auto epi_bar_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory"); };
         const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
         const float c_big = p.c_big;                        // 2^-s; c_small = c_big * 2^-11
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE), cb2 = pk2(c_big, c_big);
@@ -398,6 +411,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
         if constexpr (!kDw) {
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                if (kEpi == 2 && (int)(it & 1) != eg) continue;
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
                 const int tt = (int)(rest % p.tiles_t);
@@ -414,7 +428,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c, ++g) {
-                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                    const uint32_t obuf = my_out + (g & 1) * OUT_BYTES;
                     if (issuer) tma_wait_read<1>();          // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
                     uint32_t rb[32], rs[32];
@@ -453,6 +467,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             // ---- fused DWS epilogue (see gemm_tc.cu): the tile holds 128 pointwise columns for times
             // [t0-4, t0+124); each thread owns one channel row and slides the 5-tap window along it in registers.
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                if (kEpi == 2 && (int)(it & 1) != eg) continue;
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
                 const int tt = (int)(rest % p.tiles_t);
@@ -481,7 +496,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c, ++g) {
-                    const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
+                    const uint32_t obuf = my_out + (g & 1) * OUT_BYTES;
                     uint32_t rb[32], rs[32];
                     tmem_ld32(t_big + c * 32, rb);
                     tmem_ld32(t_big + BN + c * 32, rs);
@@ -575,6 +590,13 @@ static int elu_poly_env() {
     return v;
 }
 
+// Short K loops (K <= HILCODEC_EPI2_MAXK, default 256) leave the epilogue as the longest stage of a tile: use the
+// configuration with two epilogue groups and four transform warps.  HILCODEC_EPI2_MAXK=0 disables it.
+static bool two_epilogue_groups(int K) {
+    static const int maxk = []() { const char* e = std::getenv("HILCODEC_EPI2_MAXK"); return e ? std::atoi(e) : 256; }();
+    return K <= maxk;
+}
+
 static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, CUtensorMap* map_hi,
                              CUtensorMap* map_lo, CUtensorMap* map_x, int* num_sms_out) {
     using namespace th;
@@ -583,6 +605,10 @@ static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs,
         cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(gemm_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(gemm_h_kernel<false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(gemm_h_kernel<true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -642,7 +668,10 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    if (two_epilogue_groups(W.K))
+        gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    else
+        gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     return cudaGetLastError();
 }
 
@@ -757,7 +786,10 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
+    if (two_epilogue_groups(W.K))
+        gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
+    else
+        gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
     return cudaGetLastError();
 }
 

@@ -39,6 +39,8 @@ constexpr int BM = 128, BK = 32, HALO = 8;
 constexpr int NUM_THREADS = 512;
 constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
+constexpr int XG = 2;                             // k-blocks the worker warps convert concurrently
+constexpr int XW_PER_G = NUM_XFORM_WARPS / XG;
 constexpr int RAW_STAGES = 3, B_STAGES = 2, A_STAGES = 3;
 constexpr int A_TILE = BM * BK * 2;       // 8 KB: one fp16 plane of a 128 x 32 weight piece
 constexpr int A_PIECE = 2 * A_TILE;       // A_hi | A_lo
@@ -156,10 +158,10 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int r = 0; r < RAW_STAGES; ++r) {
             mbar_init(raw_full(r), 1);
-            mbar_init(raw_empty(r), NUM_XFORM_WARPS);
+            mbar_init(raw_empty(r), XW_PER_G);
         }
         for (int s = 0; s < B_STAGES; ++s) {
-            mbar_init(b_ready(s), NUM_XFORM_WARPS);
+            mbar_init(b_ready(s), XW_PER_G);
             mbar_init(b_empty(s), 1);
         }
         for (int s = 0; s < A_STAGES; ++s) {
@@ -296,26 +298,33 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             bv = (ok && p.dw0_b) ? __ldg(p.dw0_b + m) : 0.f;
         };
         if constexpr (NUM_M == 1 && RB_HOIST) load_taps(0, wk0h, bv0h);
-        int r = 0, s = 0;
-        uint32_t rph = 0, sph = 0;
+        // the transform runs as two groups of 4 warps converting alternate k-blocks (8 k-rows per warp), so two
+        // wait -> LDS -> math -> STS -> fence -> arrive chains are in flight (see gemm_h.cu)
+        const int xg = xw / XW_PER_G, xl = xw % XW_PER_G;
+        uint32_t n = 0;                                      // k-blocks seen by this CTA (all tiles)
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb, ++n) {
+                if ((int)(n % XG) != xg) continue;
+                const int r = (int)(n % RAW_STAGES), s = (int)(n % B_STAGES);
+                const uint32_t rph = (n / RAW_STAGES) & 1u, sph = (n / B_STAGES) & 1u;
                 mbar_wait_ns(raw_full(r), rph, p.xform_sleep);
                 mbar_wait_ns(b_empty(s), sph ^ 1, p.xform_sleep);
                 const uint8_t* raw = gen_base + (raw_base - base) + r * G::RAW_BYTES;
                 const uint32_t bdst = b_base + s * G::B_STAGE;
-                if (p.pre == PRE_ELU) xform_tile_rows<PRE_ELU, BN>(raw, bdst, xw, lane, 1.0f);
-                else if (p.pre == PRE_SCALE_ELU) xform_tile_rows<PRE_SCALE_ELU, BN>(raw, bdst, xw, lane, p.pre_scale);
-                else xform_tile_rows<PRE_NONE, BN>(raw, bdst, xw, lane, 1.0f);
+#pragma unroll
+                for (int h = 0; h < XG; ++h) {
+                    const int xq = xl * XG + h;              // 4-row slice of the box
+                    if (p.pre == PRE_ELU) xform_tile_rows<PRE_ELU, BN>(raw, bdst, xq, lane, 1.0f);
+                    else if (p.pre == PRE_SCALE_ELU) xform_tile_rows<PRE_SCALE_ELU, BN>(raw, bdst, xq, lane, p.pre_scale);
+                    else xform_tile_rows<PRE_NONE, BN>(raw, bdst, xq, lane, 1.0f);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(b_ready(s));
                     mbar_arrive(raw_empty(r));
                 }
-                if (++r == RAW_STAGES) { r = 0; rph ^= 1; }
-                if (++s == B_STAGES) { s = 0; sph ^= 1; }
             }
 
             // ---------------------------------------------------------------- E1: D1 -> dw0 -> ELU -> split -> B2
