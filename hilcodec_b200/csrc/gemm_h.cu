@@ -590,10 +590,11 @@ static int elu_poly_env() {
     return v;
 }
 
-// Short K loops (K <= HILCODEC_EPI2_MAXK, default 256) leave the epilogue as the longest stage of a tile: use the
-// configuration with two epilogue groups and four transform warps.  HILCODEC_EPI2_MAXK=0 disables it.
+// Experiment, off by default: for K <= HILCODEC_EPI2_MAXK use the configuration with two epilogue groups and four
+// transform warps.  Measured on the music256 step: 63.7 / 64.5 ms with MAXK = 256 against 62.9 / 63.5 ms without --
+// halving the transform warps costs more than the second epilogue group gains, even for the short-K layers.
 static bool two_epilogue_groups(int K) {
-    static const int maxk = []() { const char* e = std::getenv("HILCODEC_EPI2_MAXK"); return e ? std::atoi(e) : 256; }();
+    static const int maxk = []() { const char* e = std::getenv("HILCODEC_EPI2_MAXK"); return e ? std::atoi(e) : 0; }();
     return K <= maxk;
 }
 
