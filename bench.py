@@ -308,15 +308,18 @@ def main_ours(args):
     except Exception:
         pass
     bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-    traffic = None
+    traffic, traffic_step = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch_avg")
+            tj = json.load(f)
+        traffic, traffic_step = tj.get("dram_bytes_per_launch_avg"), tj.get("dram_bytes_per_step")
     except Exception:
         pass
     pw = cats.get("pointwise_gemm", {"tflops": 0.0, "gbs": 0.0, "ms_per_step": 0.0, "launches_per_step": 0})
-    if traffic is not None:
-        traffic = traffic * pw["launches_per_step"]   # ncu DRAM bytes of the category's launches in one step
+    if traffic_step is not None and model_name == "hil_music" and B == 256:
+        traffic = traffic_step                        # ncu DRAM bytes of the category's launches in one music256 step
+    elif traffic is not None:
+        traffic = traffic * pw["launches_per_step"]   # other workloads: per-launch average x launches (rough)
     dominant = max(cats, key=lambda k: cats[k]["ms_per_step"]) if cats else None
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # The dominant kernels are the tensor-core GEMMs (plain 1x1, fused DWS block, fused ResBlock, fused upsampling

@@ -40,8 +40,16 @@ namespace th {
 using namespace tc;
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int RAW_STAGES = 6;
-constexpr int OP_STAGES = 3;
+#ifndef HIL_XFORM_GROUPS
+#define HIL_XFORM_GROUPS 2
+#endif
+constexpr int XG = HIL_XFORM_GROUPS;              // k-blocks the transform warps convert concurrently
+// A transform group waits for "the previous use of my operand stage has been consumed" by mbarrier parity, which is
+// only unambiguous while a group cannot run two uses ahead: either XG <= 2 (its own waits on the stages in between
+// imply it) or one operand stage per group (XG == OP_STAGES).  XG = 4 therefore takes 4 + 4 stages instead of 6 + 3.
+constexpr int RAW_STAGES = XG == 4 ? 4 : 6;
+constexpr int OP_STAGES = XG == 4 ? 4 : 3;
+static_assert(XG == 1 || XG == 2 || XG == OP_STAGES, "see the parity note above");
 constexpr int RAW_BYTES = BK * BN * 4;            // 16 KB fp32 activation box
 constexpr int A_TILE = BM * BK * 2;               // 8 KB
 constexpr int B_TILE = BK * BN * 2;               // 8 KB
@@ -49,10 +57,6 @@ constexpr int OP_BYTES = 2 * A_TILE + 2 * B_TILE; // 32 KB: A_hi, A_lo, B_hi, B_
 constexpr int B_PANEL = 8 * 128 * (BK / 8);       // 4 KB: 64 columns x 32 k (4 swizzle atoms of 8 k-rows x 128 B)
 constexpr int NUM_THREADS = 512;
 constexpr int NUM_XFORM_WARPS = 8;
-#ifndef HIL_XFORM_GROUPS
-#define HIL_XFORM_GROUPS 2
-#endif
-constexpr int XG = HIL_XFORM_GROUPS;              // k-blocks the transform warps convert concurrently
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
 constexpr int TMEM_COLS = 512;
@@ -593,9 +597,10 @@ static int elu_poly_env() {
 // Experiment, off by default: for K <= HILCODEC_EPI2_MAXK use the configuration with two epilogue groups and four
 // transform warps.  Measured on the music256 step: 63.7 / 64.5 ms with MAXK = 256 against 62.9 / 63.5 ms without --
 // halving the transform warps costs more than the second epilogue group gains, even for the short-K layers.
-static bool two_epilogue_groups(int K) {
+static bool two_epilogue_groups(int K, bool dw) {
     static const int maxk = []() { const char* e = std::getenv("HILCODEC_EPI2_MAXK"); return e ? std::atoi(e) : 0; }();
-    return K <= maxk;
+    static const bool dw_only = std::getenv("HILCODEC_EPI2_DW_ONLY") != nullptr;
+    return K <= maxk && (dw || !dw_only);
 }
 
 static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, CUtensorMap* map_hi,
@@ -669,7 +674,7 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    if (two_epilogue_groups(W.K))
+    if (two_epilogue_groups(W.K, false))
         gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     else
         gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
@@ -787,7 +792,7 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    if (two_epilogue_groups(W.K))
+    if (two_epilogue_groups(W.K, true))
         gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
     else
         gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);

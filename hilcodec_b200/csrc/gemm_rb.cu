@@ -41,7 +41,12 @@ constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
 constexpr int XG = 2;                             // k-blocks the worker warps convert concurrently
 constexpr int XW_PER_G = NUM_XFORM_WARPS / XG;
-constexpr int RAW_STAGES = 3, B_STAGES = 2, A_STAGES = 3;
+// Stage counts are multiples of XG so that a ring stage is always filled for, and released by, the same transform
+// group: the groups wait by mbarrier parity, which is ambiguous if a group could run two uses of a stage ahead of the
+// other group (e.g. 3 raw stages shared by 2 groups: a late TMA completion for k-block n-3 would let the other group
+// pass the wait for k-block n).  4 raw + 2 weight stages cost the same shared memory as 3 + 3.
+constexpr int RAW_STAGES = 4, B_STAGES = 2, A_STAGES = 2;
+static_assert(RAW_STAGES % XG == 0 && B_STAGES % XG == 0, "see above");
 constexpr int A_TILE = BM * BK * 2;       // 8 KB: one fp16 plane of a 128 x 32 weight piece
 constexpr int A_PIECE = 2 * A_TILE;       // A_hi | A_lo
 constexpr int B_PANEL = 8 * 128 * (BK / 8);  // 4 KB: 64 columns x 32 k (4 swizzle atoms of 8 k-rows x 128 B)
