@@ -47,7 +47,11 @@ constexpr int XG = HIL_XFORM_GROUPS;              // k-blocks the transform warp
 // A transform group waits for "the previous use of my operand stage has been consumed" by mbarrier parity, which is
 // only unambiguous while a group cannot run two uses ahead: either XG <= 2 (its own waits on the stages in between
 // imply it) or one operand stage per group (XG == OP_STAGES).  XG = 4 therefore takes 4 + 4 stages instead of 6 + 3.
-constexpr int RAW_STAGES = XG == 4 ? 4 : 6;
+#ifndef HIL_OUT_BUFS
+#define HIL_OUT_BUFS 2
+#endif
+constexpr int OUT_BUFS = HIL_OUT_BUFS;            // epilogue staging buffers (kEpi = 1); 4 trades two raw stages for them
+constexpr int RAW_STAGES = (XG == 4 || OUT_BUFS == 4) ? 4 : 6;
 constexpr int OP_STAGES = XG == 4 ? 4 : 3;
 static_assert(XG == 1 || XG == 2 || XG == OP_STAGES, "see the parity note above");
 constexpr int RAW_BYTES = BK * BN * 4;            // 16 KB fp32 activation box
@@ -60,7 +64,7 @@ constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)RAW_STAGES * RAW_BYTES + (size_t)OP_STAGES * OP_BYTES + 2 * OUT_BYTES + 256;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)6 * RAW_BYTES + (size_t)3 * OP_BYTES + 2 * OUT_BYTES + 256;   // 224 KB + slack in every configuration
 
 struct Params {
     int M, K, T, B;
@@ -201,7 +205,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
               const __grid_constant__ CUtensorMap map_y28, const Params p) {
     static_assert(kEpi == 1 || kEpi == 2, "one or two epilogue groups");
-    constexpr int RAW_STAGES = kEpi == 2 ? th::RAW_STAGES - 2 : th::RAW_STAGES;
+    constexpr int RAW_STAGES = kEpi == 2 ? 4 : th::RAW_STAGES;
+    constexpr int NOUT = kEpi == 2 ? 2 : OUT_BUFS;     // staging buffers per epilogue group
     constexpr int NUM_XW = kEpi == 2 ? NUM_XFORM_WARPS / 2 : NUM_XFORM_WARPS;   // transform warps
     constexpr int XW0 = 16 - NUM_XW;                    // first transform warp
     constexpr int XW_PER_G = NUM_XW / XG;               // warps per transform group (one k-block)
@@ -211,7 +216,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const uint32_t raw_base = base;
     const uint32_t op_base = raw_base + RAW_STAGES * RAW_BYTES;
     const uint32_t out_base = op_base + OP_STAGES * OP_BYTES;
-    const uint32_t bars = out_base + 2 * kEpi * OUT_BYTES;
+    const uint32_t bars = out_base + NOUT * kEpi * OUT_BYTES;
     auto raw_full = [&](int r) { return bars + 8u * r; };
     auto raw_empty = [&](int r) { return bars + 8u * (RAW_STAGES + r); };
     auto a_full = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };
@@ -406,7 +411,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const int q = warp & 3;                             // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
         const bool issuer = (q == 0 && lane == 0);
-        const uint32_t my_out = out_base + eg * 2 * OUT_BYTES;   // this group's two staging buffers
+        const uint32_t my_out = out_base + eg * NOUT * OUT_BYTES;   // this group's staging buffers
         auto epi_bar_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory"); };
         const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
         const float c_big = p.c_big;                        // 2^-s; c_small = c_big * 2^-11
@@ -432,8 +437,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c, ++g) {
-                    const uint32_t obuf = my_out + (g & 1) * OUT_BYTES;
-                    if (issuer) tma_wait_read<1>();          // the store that used this buffer two chunks ago has drained it
+                    const uint32_t obuf = my_out + (g % NOUT) * OUT_BYTES;
+                    if (issuer) tma_wait_read<NOUT - 1>();          // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
                     uint32_t rb[32], rs[32];
                     tmem_ld32(t_big + c * 32, rb);
@@ -500,7 +505,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c, ++g) {
-                    const uint32_t obuf = my_out + (g & 1) * OUT_BYTES;
+                    const uint32_t obuf = my_out + (g % NOUT) * OUT_BYTES;
                     uint32_t rb[32], rs[32];
                     tmem_ld32(t_big + c * 32, rb);
                     tmem_ld32(t_big + BN + c * 32, rs);
@@ -526,7 +531,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                                 p.cache_out[((size_t)b * p.M + m) * 4 + (t - (p.T - 4))] = v[4 + j] * c_big;
                         }
                     }
-                    if (issuer) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
+                    if (issuer) tma_wait_read<NOUT - 1>();   // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
