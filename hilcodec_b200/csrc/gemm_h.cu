@@ -60,6 +60,10 @@ constexpr int B_TILE = BK * BN * 2;               // 8 KB
 constexpr int OP_BYTES = 2 * A_TILE + 2 * B_TILE; // 32 KB: A_hi, A_lo, B_hi, B_lo
 constexpr int B_PANEL = 8 * 128 * (BK / 8);       // 4 KB: 64 columns x 32 k (4 swizzle atoms of 8 k-rows x 128 B)
 constexpr int NUM_THREADS = 512;
+#ifndef HIL_EPI2_EXTRA_THREADS
+#define HIL_EPI2_EXTRA_THREADS 0
+#endif
+constexpr int EPI2_EXTRA_THREADS = HIL_EPI2_EXTRA_THREADS;   // 128: the kEpi = 2 configuration keeps all 8 transform warps (640 threads)
 constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
@@ -200,15 +204,15 @@ __device__ __forceinline__ void load_up_taps(const float* wsm, int xw, int n_abs
 //           one group (about 2000 cycles per 32-column chunk) is longer than the tile's mainloop.  Shared memory is
 //           re-cut: 4 raw stages instead of 6, 4 staging buffers instead of 2.
 template <bool kDw, int kUp = 0, int kEpi = 1>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS + (kEpi - 1) * EPI2_EXTRA_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
               const __grid_constant__ CUtensorMap map_y28, const Params p) {
     static_assert(kEpi == 1 || kEpi == 2, "one or two epilogue groups");
     constexpr int RAW_STAGES = kEpi == 2 ? 4 : th::RAW_STAGES;
     constexpr int NOUT = kEpi == 2 ? 2 : OUT_BUFS;     // staging buffers per epilogue group
-    constexpr int NUM_XW = kEpi == 2 ? NUM_XFORM_WARPS / 2 : NUM_XFORM_WARPS;   // transform warps
-    constexpr int XW0 = 16 - NUM_XW;                    // first transform warp
+    constexpr int NUM_XW = (kEpi == 2 && EPI2_EXTRA_THREADS == 0) ? NUM_XFORM_WARPS / 2 : NUM_XFORM_WARPS;   // transform warps
+    constexpr int XW0 = (NUM_THREADS + (kEpi - 1) * EPI2_EXTRA_THREADS) / 32 - NUM_XW;   // first transform warp
     constexpr int XW_PER_G = NUM_XW / XG;               // warps per transform group (one k-block)
     constexpr int SPW = BK / 4 / XW_PER_G;              // 4-row slices of the box per transform warp
     extern __shared__ uint8_t smem_raw[];
@@ -599,9 +603,10 @@ static int elu_poly_env() {
     return v;
 }
 
-// Experiment, off by default: for K <= HILCODEC_EPI2_MAXK use the configuration with two epilogue groups and four
-// transform warps.  Measured on the music256 step: 63.7 / 64.5 ms with MAXK = 256 against 62.9 / 63.5 ms without --
-// halving the transform warps costs more than the second epilogue group gains, even for the short-K layers.
+// Experiment, off by default: for K <= HILCODEC_EPI2_MAXK use the configuration with two epilogue groups.  Measured on
+// the music256 step (A/B in one box): with four transform warps 63.7 / 64.5 ms (MAXK = 256) against 62.9 / 63.5 ms
+// without; with all eight transform warps kept (-DHIL_EPI2_EXTRA_THREADS=128: 640 threads, 96 registers, no spills)
+// 60.3 / 60.6 ms (MAXK = 192, DWS only) against 61.7 / 60.4 ms without -- inside the box-to-box noise.
 static bool two_epilogue_groups(int K, bool dw) {
     static const int maxk = []() { const char* e = std::getenv("HILCODEC_EPI2_MAXK"); return e ? std::atoi(e) : 0; }();
     static const bool dw_only = std::getenv("HILCODEC_EPI2_DW_ONLY") != nullptr;
@@ -680,7 +685,7 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     if (two_epilogue_groups(W.K, false))
-        gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+        gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     else
         gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     return cudaGetLastError();
@@ -798,7 +803,7 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     if (two_epilogue_groups(W.K, true))
-        gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
+        gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
     else
         gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
     return cudaGetLastError();
