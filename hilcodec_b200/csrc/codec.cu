@@ -216,7 +216,7 @@ static int32_t run_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
 static int32_t run_upsample(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T_in, int S, int pre,
                             float pre_scale, const float* up_w, const float* ci, float* co, const float* bias, float* tmp,
                             float* Y, long long y_bs, int y_rs, bool allow_fused, cudaStream_t st,
-                            bool allow_fused_wide = false) {
+                            bool allow_fused_wide = false, bool allow_planes = false) {
     const int K = W.K, T = S * T_in;
     if (allow_fused && g_use_tc && g_use_h && g_fuse_up && (W.M <= 256 || g_fuse_up_wide || allow_fused_wide) &&
         gemm_h_up_usable(W, x, x_bs, x_rs, T_in, S, pre, Y, y_bs, y_rs)) {
@@ -226,6 +226,26 @@ static int32_t run_upsample(const PackedMat& W, const float* x, long long x_bs, 
         return HIL_OK;
     }
     const int Tp2 = pitch4(T);
+    // Wide layers, off by default (HILCODEC_PLANES=1): the transposed conv writes fp16 hi/lo planes into `tmp` (same
+    // bytes as the fp32 tensor) and the 1x1 conv consumes them by TMA with no conversion pass.  Measured: the GEMM is
+    // not faster without its transform (1577 vs 1544 us at decoder stage 1: ~900 cycles per k-block either way, the
+    // 32 KB of operands per k-block and SM coming from L2 are the limit) and the planes-writing conv is slower.
+    static const bool use_planes = []() { const char* e = std::getenv("HILCODEC_PLANES"); return e && e[0] == '1'; }();
+    const int p_rs = (T + 7) & ~7;
+    const long long p_bs = (long long)K * p_rs;
+    uint16_t* hi = reinterpret_cast<uint16_t*>(tmp);
+    uint16_t* lo = hi + (long long)B * p_bs;
+    if (((allow_fused && use_planes) || allow_planes) && g_use_tc && g_use_h && p_rs <= Tp2 && (pre == PRE_NONE || pre == PRE_SCALE_ELU) &&
+        dwconv_transpose_planes_usable(x, x_bs, x_rs, T_in, S, p_bs, p_rs) &&
+        gemm_h_planes_usable(W, hi, lo, p_bs, p_rs, T, Y, y_bs, y_rs)) {
+        const double nin = (double)B * K * T_in, n = (double)B * T;
+        HIL_LAUNCH(CAT_DWT, 4.0 * nin * S, 4.0 * (nin + nin * S), st,
+                   launch_dwconv_transpose_planes(x, x_bs, x_rs, ci, co, up_w, hi, lo, p_bs, p_rs, B, K, T_in, S, pre, pre_scale,
+                                                  st));
+        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * K * n, 4.0 * n * (K + W.M) + 4.0 * W.M * K, st,
+                   launch_gemm_h_planes(W, hi, lo, p_bs, p_rs, B, T, bias, Y, y_bs, y_rs, st));
+        return HIL_OK;
+    }
     HIL_TRY(run_dwconv_transpose(x, x_bs, x_rs, ci, co, up_w, tmp, (long long)K * Tp2, Tp2, B, K, T_in, S, pre, pre_scale, st));
     return run_gemm_linear(W, tmp, (long long)K * Tp2, Tp2, B, T, PRE_NONE, 1.f, bias, nullptr, Y, y_bs, y_rs, st);
 }
@@ -1345,13 +1365,18 @@ int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out,
     cudaStream_t st = (cudaStream_t)stream;
     const int T = S * T_in;
     int32_t rc;
-    if (fused && !(g_use_tc && g_use_h && gemm_h_up_usable(pm, x, (long long)K * T_in, T_in, T_in, S, pre, y, (long long)M * T, T)))
+    if (fused == 1 && !(g_use_tc && g_use_h && gemm_h_up_usable(pm, x, (long long)K * T_in, T_in, T_in, S, pre, y, (long long)M * T, T)))
         rc = fail(HIL_ERR_INVALID, "fused upsampling kernel not usable for this shape / mode");
     else {
         const bool keep = g_fuse_up;
         g_fuse_up = true;
-        rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp, y,
-                          (long long)M * T, T, fused != 0, st, true);
+        // fused: 1 = one kernel, 2 = transposed conv -> fp16 planes -> planes-input GEMM, 0 = fp32 intermediate
+        if (fused == 2)
+            rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp,
+                              y, (long long)M * T, T, false, st, false, true);
+        else
+            rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp,
+                              y, (long long)M * T, T, fused != 0, st, true, false);
         g_fuse_up = keep;
     }
     cudaError_t e2 = cudaStreamSynchronize(st);

@@ -109,6 +109,16 @@ cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs,
                              float pre_scale, const float* up_w, const float* cache_in, float* cache_out, const float* bias,
                              float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
+// 1x1 conv + bias on fp16 hi/lo planes [B][K][pitch] (no transform pass), and the transposed conv that writes them
+bool gemm_h_planes_usable(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int T,
+                          const float* Y, long long y_bs, int y_rs);
+cudaError_t launch_gemm_h_planes(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int B,
+                                 int T, const float* bias, float* Y, long long y_bs, int y_rs, cudaStream_t st);
+bool dwconv_transpose_planes_usable(const float* x, long long x_bs, int x_rs, int T, int S, long long p_bs, int p_rs);
+cudaError_t launch_dwconv_transpose_planes(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                                           const float* w, uint16_t* hi, uint16_t* lo, long long p_bs, int p_rs, int B, int C,
+                                           int T, int S, int pre, float pre_scale, cudaStream_t st);
+
 // ---- gemm_rb.cu: whole ResBlock (two DWSBlocks + residual add) in one kernel, h updated in place (C <= 256)
 bool resblock_h_usable(const PackedMat& W0, const PackedMat& W1, const float* h, long long bs, int rs, int T);
 size_t resblock_h_halo_floats(int C, int T, int B);

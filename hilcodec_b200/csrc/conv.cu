@@ -5,7 +5,7 @@
 // Every cached conv follows causal_layers.py:160-165 / :183-188:
 //     xin = cat(cache, x);  cache' = xin[..., -len(cache):];  y = conv(xin)   (no padding)
 // cache_in and cache_out are distinct buffers (ping-pong), so tiles never race on them.
-#include "common.cuh"
+#include "h_split.cuh"
 
 namespace hil {
 
@@ -367,6 +367,72 @@ cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
     }
     HIL_DWT(2) HIL_DWT(3) HIL_DWT(4) HIL_DWT(5) HIL_DWT(6) HIL_DWT(8)
 #undef HIL_DWT
+    return cudaErrorInvalidValue;
+}
+
+// Same transposed conv, output written as the fp16 hi / lo planes the tensor-core GEMM consumes directly
+// (x = hi + lo * 2^-11, gemm_h.cu): the 1x1 conv behind it then needs no conversion pass.  planes: [B][C][pitch] halfs.
+template <int S>
+__global__ void dwconvT_planes_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
+                                      float* __restrict__ cache_out, const float* __restrict__ w, uint16_t* __restrict__ hi,
+                                      uint16_t* __restrict__ lo, long long p_bs, int p_rs, int C, int T, int pre,
+                                      float pre_scale) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float* xr = x + b * x_bs + (long long)c * x_rs;
+    const float cprev = cache_in[(size_t)b * C + c];
+    float wc[2 * S];
+#pragma unroll
+    for (int k = 0; k < 2 * S; ++k) wc[k] = w[(size_t)c * 2 * S + k];
+    uint16_t* hr = hi + b * p_bs + (long long)c * p_rs;
+    uint16_t* lr = lo + b * p_bs + (long long)c * p_rs;
+    const int Tq = T >> 2;   // T % 4 == 0 (checked by the launcher)
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Tq; q += gridDim.x * blockDim.x) {
+        const int i0 = q * 4;
+        float e[5];
+        e[0] = i0 == 0 ? cprev : apply_act_ex2(xr[i0 - 1], pre, pre_scale);
+        const float4 v = *reinterpret_cast<const float4*>(xr + i0);
+        e[1] = apply_act_ex2(v.x, pre, pre_scale); e[2] = apply_act_ex2(v.y, pre, pre_scale);
+        e[3] = apply_act_ex2(v.z, pre, pre_scale); e[4] = apply_act_ex2(v.w, pre, pre_scale);
+        float o[4 * S];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < S; ++r) o[j * S + r] = __fadd_rn(__fmul_rn(e[1 + j], wc[r]), __fmul_rn(e[j], wc[r + S]));
+#pragma unroll
+        for (int k = 0; k < S; ++k) {   // 4 outputs -> 4 + 4 halfs: one 8-byte store per plane
+            uint32_t h01, h23, l01, l23;
+            th::split4<PRE_NONE>(make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]), 1.0f, h01, h23, l01, l23);
+            *reinterpret_cast<uint2*>(hr + (long long)i0 * S + 4 * k) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2*>(lr + (long long)i0 * S + 4 * k) = make_uint2(l01, l23);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        cache_out[(size_t)b * C + c] = T > 0 ? apply_act_ex2(xr[T - 1], pre, pre_scale) : cprev;
+}
+
+bool dwconv_transpose_planes_usable(const float* x, long long x_bs, int x_rs, int T, int S, long long p_bs, int p_rs) {
+    if (S != 2 && S != 4 && S != 5 && S != 8) return false;
+    if ((T & 3) || (x_rs & 3) || (x_bs & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) return false;
+    if ((p_rs & 7) || (p_bs & 7)) return false;
+    return true;
+}
+
+cudaError_t launch_dwconv_transpose_planes(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
+                                           const float* w, uint16_t* hi, uint16_t* lo, long long p_bs, int p_rs, int B, int C,
+                                           int T, int S, int pre, float pre_scale, cudaStream_t st) {
+    if (B == 0 || C == 0) return cudaSuccess;
+    if (C > 65535 || B > 65535) return cudaErrorInvalidValue;
+    const int Tq = T / 4;
+    const int threads = Tq >= 128 ? 128 : 32;
+    dim3 grid(max(1, min((Tq + threads - 1) / threads, 512)), C, B);
+#define HIL_DWTP(SS)                                                                                                      \
+    if (S == SS) {                                                                                                        \
+        dwconvT_planes_kernel<SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, hi, lo, p_bs, p_rs, C, \
+                                                            T, pre, pre_scale);                                           \
+        return cudaGetLastError();                                                                                        \
+    }
+    HIL_DWTP(2) HIL_DWTP(4) HIL_DWTP(5) HIL_DWTP(8)
+#undef HIL_DWTP
     return cudaErrorInvalidValue;
 }
 

@@ -203,11 +203,15 @@ __device__ __forceinline__ void load_up_taps(const float* wsm, int xw, int n_abs
 //           concurrently; warps 12-15 transform.  For K <= 256 the serial TMEM -> registers -> SMEM -> TMA chain of
 //           one group (about 2000 cycles per 32-column chunk) is longer than the tile's mainloop.  Shared memory is
 //           re-cut: 4 raw stages instead of 6, 4 staging buffers instead of 2.
-template <bool kDw, int kUp = 0, int kEpi = 1>
+// kPl = 1: the activations arrive already split, as two fp16 planes (hi, lo * 2^11) written by the producer kernel;
+//          map_x / map_xl are [B][K][T] fp16 tensor maps with 64 x 32 SWIZZLE_128B boxes and the B operand goes
+//          TMA -> operand ring -> MMA with no transform pass (no raw ring traffic, half the shared-memory bytes per k-block).
+template <bool kDw, int kUp = 0, int kEpi = 1, int kPl = 0>
 __global__ void __launch_bounds__(NUM_THREADS + (kEpi - 1) * EPI2_EXTRA_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-              const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
-              const __grid_constant__ CUtensorMap map_y28, const Params p) {
+              const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xl,
+              const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y28, const Params p) {
+    static_assert(kPl == 0 || (kUp == 0 && kEpi == 1), "planes input: plain / fused-DWS kernels only");
     static_assert(kEpi == 1 || kEpi == 2, "one or two epilogue groups");
     constexpr int RAW_STAGES = kEpi == 2 ? 4 : th::RAW_STAGES;
     constexpr int NOUT = kEpi == 2 ? 2 : OUT_BUFS;     // staging buffers per epilogue group
@@ -247,7 +251,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
         for (int s = 0; s < OP_STAGES; ++s) {
             mbar_init(a_full(s), 1);
-            mbar_init(b_ready(s), XW_PER_G);
+            mbar_init(b_ready(s), kPl ? 1 : XW_PER_G);
             mbar_init(op_empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -268,7 +272,26 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     if (warp == 0) {
         // ===================================================================== X producer (raw ring)
-        if (lane == 0) {
+        if (kPl && lane == 0) {   // planes: four 4 KB panels (hi / lo x two 64-column panels) straight into the operand stage
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                const int tc0 = tt * p.t_step - p.t_halo;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait<32>(op_empty(s), ph ^ 1);
+                    const uint32_t bst = op_base + s * OP_BYTES + 2 * A_TILE;
+                    mbar_arrive_expect_tx(b_ready(s), 2 * B_TILE);
+                    tma_load_3d(&map_x, bst, b_ready(s), tc0, kb * BK, b);
+                    tma_load_3d(&map_x, bst + B_PANEL, b_ready(s), tc0 + 64, kb * BK, b);
+                    tma_load_3d(&map_xl, bst + B_TILE, b_ready(s), tc0, kb * BK, b);
+                    tma_load_3d(&map_xl, bst + B_TILE + B_PANEL, b_ready(s), tc0 + 64, kb * BK, b);
+                    if (++s == OP_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        } else if (lane == 0) {
             int r = 0;
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -356,7 +379,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const uint32_t chunk = (uint32_t)((lane >> 1) & 7);  // 16-byte chunk (8 columns) inside the 128-byte row
         const uint32_t half8 = (uint32_t)(lane & 1) * 8u;
         uint32_t n = 0;                                    // k-blocks seen by this CTA (all tiles)
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (long long tile = blockIdx.x; !kPl && tile < p.total_tiles; tile += gridDim.x) {
             [[maybe_unused]] const int m_blk = (int)(tile % p.num_m);
             [[maybe_unused]] const long long rest = tile / p.num_m;
             [[maybe_unused]] const int tt = (int)(rest % p.tiles_t);
@@ -685,9 +708,9 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     if (two_epilogue_groups(W.K, false))
-        gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+        gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
     else
-        gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+        gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
     return cudaGetLastError();
 }
 
@@ -750,7 +773,7 @@ static cudaError_t launch_up(const PackedMat& W, const float* x, long long x_bs,
     p.t_in = T_in; p.up_w = up_w; p.up_ci = ci; p.up_co = co;
     const int num_sms = tc::device_sm_count();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_h_kernel<false, S><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    gemm_h_kernel<false, S><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
     return cudaGetLastError();
 }
 
@@ -763,6 +786,67 @@ cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs,
     HIL_UP(2) HIL_UP(4) HIL_UP(5) HIL_UP(8)
 #undef HIL_UP
     return cudaErrorInvalidValue;
+}
+
+// Plain 1x1 conv + bias whose input is a pair of fp16 planes [B][K][pitch] (x = hi + lo * 2^-11), e.g. written by
+// launch_dwconv_transpose_planes: no activation prologue, no transform pass.
+bool gemm_h_planes_usable(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int T,
+                          const float* Y, long long y_bs, int y_rs) {
+    if (!W.H_hi || !W.H_lo) return false;
+    if (T < 64 || (W.K & 31)) return false;
+    if ((p_rs & 7) || (p_bs & 7) || (y_rs & 3) || (y_bs & 3)) return false;   // 16-byte multiples
+    if ((reinterpret_cast<uintptr_t>(hi) & 15) || (reinterpret_cast<uintptr_t>(lo) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15))
+        return false;
+    return true;
+}
+
+cudaError_t launch_gemm_h_planes(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int B,
+                                 int T, const float* bias, float* Y, long long y_bs, int y_rs, cudaStream_t st) {
+    using namespace th;
+    if (B == 0 || T == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<false, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    CUtensorMap map_hi, map_lo, map_xh, map_xl, map_y;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)W.Kp32, (cuuint64_t)W.Mp128};
+        const cuuint64_t strides[1] = {(cuuint64_t)W.Kp32 * 2};
+        const cuuint32_t box[2] = {BK, BM};
+        if (!tc::make_map_dt(&map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !tc::make_map_dt(&map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)p_rs * 2, (cuuint64_t)p_bs * 2};
+        const cuuint32_t box[3] = {64, BK, 1};   // one 64-column panel: 128-byte rows, the MMA's SWIZZLE_128B atom layout
+        if (!tc::make_map_dt(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !tc::make_map_dt(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {32, BM, 1};
+        if (!tc::make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidValue;
+    }
+    Params p{};
+    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
+    p.num_m = (W.M + BM - 1) / BM;
+    p.t_step = BN; p.t_halo = 0;
+    p.tiles_t = (T + BN - 1) / BN;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.pre = PRE_NONE; p.pre_scale = 1.0f; p.bias = bias; p.reduce_add = 0;
+    p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.xform_sleep = 0;
+    const int num_sms = tc::device_sm_count();
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    gemm_h_kernel<false, 0, 1, 1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_xh, map_xl, map_y, map_y, p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
@@ -803,9 +887,9 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     if (two_epilogue_groups(W.K, true))
-        gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
+        gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y28, p);
     else
-        gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
+        gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y28, p);
     return cudaGetLastError();
 }
 

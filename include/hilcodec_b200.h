@@ -178,8 +178,10 @@ int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, co
                         int32_t fused, void* stream);
 /* Decoder upsampling layer, streaming.py:633-637: pre(x) -> CausalConvTranspose1d (causal_layers.py:183-188,
  * depthwise, kernel 2S, stride S, cache [B,K,1]) -> nn.Conv1d(k=1) + bias.  x [B,K,T_in] -> y [B,M,S*T_in].
- * fused = 1: one tensor-core kernel (S in {2,4,5,8}, K % 32 == 0, S*T_in >= 128, pre 0 or 2), fused = 0:
- * hil_op_dwconv_transpose + hil_op_pointwise through tmp [B,K,S*T_in].  w_pw_host is a HOST [M,K,1] weight. */
+ * fused = 1: one tensor-core kernel (S in {2,4,5,8}, K % 32 == 0, S*T_in >= 128, pre 0 or 2), fused = 2: the
+ * transposed conv writes fp16 hi/lo planes into tmp and the 1x1 conv reads them by TMA (no conversion pass; the
+ * wide decoder stages), fused = 0: hil_op_dwconv_transpose + hil_op_pointwise through tmp [B,K,S*T_in] (fp32).
+ * w_pw_host is a HOST [M,K,1] weight. */
 int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out, const float* w_up, const float* w_pw_host,
                         const float* bias, float* tmp, float* y, int32_t B, int32_t K, int32_t M, int32_t T_in, int32_t S,
                         int32_t pre, float pre_scale, int32_t fused, void* stream);
