@@ -206,9 +206,15 @@ inline bool make_map_dt(CUtensorMap* map, CUtensorMapDataType dtype, const void*
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint32_t estr[3] = {1, 1, 1};
+    // HILCODEC_L2PROMO=0..3 (none / 64 B / 128 B / 256 B, default 256 B): A/B knob
+    static const CUtensorMapL2promotion promo = []() {
+        const char* e = std::getenv("HILCODEC_L2PROMO");
+        const int v = e ? std::atoi(e) : 3;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+             : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }();
     return fn(map, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 inline bool make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                      const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
