@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libhilcodec_b200.so")
 
 HIL_MAX_STRIDES = 8
 HIL_ENCODER, HIL_DECODER = 0, 1
+HIL_GRAPH_DEPLOY, HIL_GRAPH_TRAIN = 0, 1
 PRE_NONE, PRE_ELU, PRE_SCALE_ELU = 0, 1, 2
 
 
@@ -46,6 +47,8 @@ SIGNATURES = {
     "hil_config_default": (None, [C.POINTER(HilConfig), _I]),
     "hil_model_create": (_I, [C.POINTER(HilConfig), C.POINTER(_P)]),
     "hil_model_set_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "hil_model_set_graph": (_I, [_P, _I]),
+    "hil_model_graph": (_I, [_P]),
     "hil_model_finalize": (_I, [_P]),
     "hil_model_destroy": (None, [_P]),
     "hil_model_hop": (_I, [_P]),
@@ -59,6 +62,7 @@ SIGNATURES = {
     "hil_state_workspace_bytes": (C.c_size_t, [_P]),
     "hil_encode": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "hil_encode_caches": (_I, [_P, _P, _P, _I, _I, _P, C.POINTER(_P), C.POINTER(_P), _P]),
+    "hil_encode_ragged": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "hil_rvq_encode": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "hil_rvq_decode": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "hil_decode": (_I, [_P, _P, _P, _I, _I, _P, _P]),

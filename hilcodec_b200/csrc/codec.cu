@@ -263,10 +263,10 @@ static int32_t run_l2norm_chlast(const float* x, long long x_bs, int x_rs, float
     return HIL_OK;
 }
 static int32_t run_rvq_encode(const float* z, const float* cb, const float* ee, int size, int dim, long long frames, int n,
-                              int64_t* idx, float* qsum, cudaStream_t st) {
+                              int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
     HIL_LAUNCH(CAT_RVQ, 2.0 * frames * (double)n * size * dim,
                4.0 * frames * dim * (qsum ? 2 : 1) + 8.0 * frames * n + 4.0 * (double)n * size * dim, st,
-               launch_rvq_encode(z, cb, ee, size, dim, frames, n, idx, qsum, st));
+               launch_rvq_encode(z, cb, ee, size, dim, frames, n, idx, qsum, drop_xx, st));
     return HIL_OK;
 }
 static int32_t run_rvq_decode(const int64_t* idx, const float* cb, int size, int dim, long long frames, int n, float* q,
@@ -342,6 +342,7 @@ struct hil_model {
     std::vector<std::vector<int64_t>> enc_cache_shape, dec_cache_shape;  // [C, len]
     int hop = 1;
     float enc_post_scale = 1.f, dec_post_scale = 1.f;
+    int graph = HIL_GRAPH_DEPLOY;  // hil_model_set_graph
 };
 
 struct hil_state {
@@ -690,6 +691,16 @@ void hil_model_destroy(hil_model* m) {
 
 int32_t hil_model_hop(const hil_model* m) { return m ? m->hop : 0; }
 
+int32_t hil_model_set_graph(hil_model* m, int32_t graph) {
+    if (!m) return fail(HIL_ERR_INVALID, "null model");
+    if (m->finalized) return fail(HIL_ERR_STATE, "model already finalized (immutable)");
+    if (graph != HIL_GRAPH_DEPLOY && graph != HIL_GRAPH_TRAIN) return fail(HIL_ERR_INVALID, "unknown graph");
+    m->graph = graph;
+    return HIL_OK;
+}
+
+int32_t hil_model_graph(const hil_model* m) { return m ? m->graph : -1; }
+
 int32_t hil_model_num_caches(const hil_model* m, int32_t which) {
     if (!m || !m->finalized) return 0;
     return (int32_t)(which == HIL_ENCODER ? m->enc_cache_shape.size() : m->dec_cache_shape.size());
@@ -903,12 +914,21 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     return HIL_OK;
 }
 
+// T_valid < T (hil_encode_ragged): `wav` holds T_valid samples per clip and T = hop * ceil(T_valid / hop).  The
+// training graph's convs pad themselves on the right with zeros up to a full last window (modules/conv.py:61-68,
+// :222-236), i.e. each strided depthwise conv sees ITS input -- not the waveform -- zero-extended.  Every layer here
+// is causal, so columns at or past ceil(T_valid / stride) never reach a valid column except through the strided
+// convs' last window: the chunk is run at length T and those columns are zeroed in front of each strided conv.
 int32_t encode_impl(hil_model* m, const Buffers& w, const float* wav, int B, int T, float* z, const float* const* cin,
-                    float* const* cout, cudaStream_t st) {
+                    float* const* cout, cudaStream_t st, int T_valid = -1) {
     const hil_config& c = m->cfg;
     const int Tw = m->n_fft_post - 1;
     const int Wp = w.Wp;
-    HIL_TRY(run_wavcat(wav, cin[0], cout[0], w.wav_ext, Wp, B, T, Tw, st));
+    if (T_valid < 0) T_valid = T;
+    HIL_TRY(run_wavcat(wav, cin[0], cout[0], w.wav_ext, Wp, B, T_valid, Tw, st));
+    if (T_valid < T)  // keep the never-used tail finite
+        HIL_CUDA(cudaMemset2DAsync(w.wav_ext + Tw + T_valid, (size_t)Wp * sizeof(float), 0,
+                                   (size_t)(T - T_valid) * sizeof(float), (size_t)B, st));
     int C = c.channels_enc, Ts = T, stride = 1, ci = 1;
     float *h = w.h, *a1 = w.a1, *a2 = w.a2;
     {
@@ -935,6 +955,10 @@ int32_t encode_impl(hil_model* m, const Buffers& w, const float* wav, int B, int
         HIL_TRY(run_gemm_linear(sg.down_pw, h, bs, Tp, B, Ts, PRE_SCALE_ELU, m->enc_post_scale, nullptr, nullptr, a1,
                                 2 * bs, Tp, st));
         const int Ts2 = Ts / sg.ratio, Tp2 = pitch4(Ts2);
+        const int Lv = (T_valid + stride - 1) / stride;  // valid columns at this rate
+        if (Lv < Ts)
+            HIL_CUDA(cudaMemset2DAsync(a1 + Lv, (size_t)Tp * sizeof(float), 0, (size_t)(Ts - Lv) * sizeof(float),
+                                       (size_t)B * 2 * C, st));
         HIL_TRY(run_dwconv(a1, 2 * bs, Tp, cin[ci], cout[ci], sg.down_w, sg.down_b, nullptr, h,
                                (long long)2 * C * Tp2, Tp2, B, 2 * C, Ts, 2 * sg.ratio, sg.ratio, PRE_NONE, 1.f, st));
         ci += 1;
@@ -963,6 +987,7 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
     const hil_config& c = m->cfg;
     int C = c.channels_dec << c.n_strides, Ts = F, ci = 0;
     float *h = w.h, *a1 = w.a1, *a2 = w.a2;
+    const double rs2 = (double)c.res_scale_dec * (double)c.res_scale_dec;
     {
         const int Tp = pitch4(Ts);
         const long long bs = (long long)C * Tp;
@@ -988,8 +1013,10 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
         C /= 2;
         Ts = Ts2;
         for (int j = 0; j < c.n_residual_dec; ++j) {
-            // deploy-path quirk: pre_scale is 1.0 for every decoder ResBlock (streaming.py:576-583)
-            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, 1.0f, cin + ci, cout + ci, st));
+            // deploy-path quirk: pre_scale is 1.0 for every decoder ResBlock (streaming.py:576-583); the training
+            // graph passes idx = j (modules/seanet.py:443-451)
+            const float pre = m->graph == HIL_GRAPH_TRAIN ? (float)std::pow(1.0 + j * rs2, -0.5) : 1.0f;
+            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, pre, cin + ci, cout + ci, st));
             ci += 2;
         }
     }
@@ -1035,6 +1062,20 @@ int32_t hil_encode(hil_model* m, hil_state* s, const float* wav, int32_t B, int3
     return HIL_OK;
 }
 
+int32_t hil_encode_ragged(hil_model* m, hil_state* s, const float* wav, int32_t B, int32_t T, float* z, void* stream) {
+    if (!m) return fail(HIL_ERR_INVALID, "null model/state");
+    const long long Tpad = ((long long)T + m->hop - 1) / m->hop * m->hop;
+    HIL_TRY(check_call(m, s, B, T <= 0 ? T : Tpad, true));
+    if (!wav || !z) return fail(HIL_ERR_INVALID, "null pointer");
+    if (!m->has_enc) return fail(HIL_ERR_STATE, "model has no encoder weights");
+    Buffers w;
+    HIL_TRY(ensure_workspace(s, B, (int)Tpad, &w));
+    HIL_TRY(hil_state_reset(s, stream));  // one-shot: zero history
+    const int g = s->enc_gen;
+    HIL_TRY(encode_impl(m, w, wav, B, (int)Tpad, z, s->enc_c[g].data(), s->enc_c[g ^ 1].data(), (cudaStream_t)stream, T));
+    return HIL_OK;  // enc_gen not advanced: the zeroed generation stays current
+}
+
 int32_t hil_decode_caches(hil_model* m, hil_state* s, const float* q, int32_t B, int32_t F, float* wav,
                           const float* const* cin, float* const* cout, void* stream) {
     HIL_TRY(check_call(m, s, B, (long long)F * (m ? m->hop : 1), false));
@@ -1061,7 +1102,7 @@ int32_t hil_rvq_encode(hil_model* m, const float* z, int32_t B, int32_t F, int32
     // assert 1 <= n <= len(self.layers)  (models/hilcodec/vector_quantize.py:213)
     if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
     HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, qsum,
-                               (cudaStream_t)stream));
+                               m->graph == HIL_GRAPH_TRAIN, (cudaStream_t)stream));
     return HIL_OK;
 }
 
@@ -1089,7 +1130,8 @@ int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav, int32_t 
     const int ge = s->enc_gen, gd = s->dec_gen;
     HIL_TRY(encode_impl(m, w, wav, B, T, z, s->enc_c[ge].data(), s->enc_c[ge ^ 1].data(), st));
     s->enc_gen = ge ^ 1;
-    HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, w.q, st));
+    HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, w.q,
+                           m->graph == HIL_GRAPH_TRAIN, st));
     HIL_TRY(decode_impl(m, w, w.q, B, F, wav_out, s->dec_c[gd].data(), s->dec_c[gd ^ 1].data(), st));
     s->dec_gen = gd ^ 1;
     return HIL_OK;

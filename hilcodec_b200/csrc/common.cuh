@@ -173,7 +173,7 @@ cudaError_t launch_l2norm_chlast(const float* x, long long x_bs, int x_rs, float
 // codebooks [n_q][size][dim], ee [n_q][size] = sum_k e^2
 cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, int size, int dim, cudaStream_t st);
 cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
-                              int n, int64_t* idx, float* qsum, cudaStream_t st);
+                              int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st);
 cudaError_t launch_rvq_decode(const int64_t* idx, const float* codebooks, int size, int dim, long long frames, int n,
                               float* q, cudaStream_t st);
 

@@ -6,6 +6,9 @@
 //
 //   dist[c] = -((sum_k r_k^2 - 2 * sum_k r_k e_ck) + sum_k e_ck^2);  idx = argmax (first wins)
 //   r <- r - E[idx];   qsum <- qsum + E[idx]   (stage order, fp32)
+// drop_xx = the training graph's search (models/hilcodec/vector_quantize.py:146-152):
+//   distance[c] = (-2 r) . e_c + sum_k e_ck^2;  idx = argmin (first wins)
+// which is the same expression with sum_k r_k^2 replaced by 0 (0 - a = -a and the outer negation are exact).
 //
 // Layout: a CTA owns FT = 32 frames; warp w owns frames 4w..4w+3 (so the per-frame argmax
 // reduction and the residual update are warp-local shuffles); lane l scores codes
@@ -39,7 +42,7 @@ cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, in
 // tile and scoring it with a barrier on either side, so a second resident CTA fills the load phases of the first.
 __global__ void __launch_bounds__(256, 2)
 rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee,
-                  int size, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum) {
+                  int size, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum, int drop_xx) {
     extern __shared__ __align__(16) float smem[];
     float* R = smem;                              // [RVQ_FT][RVQ_PITCH]
     float* E = smem + RVQ_FT * RVQ_PITCH;         // [RVQ_CT][RVQ_PITCH]
@@ -72,7 +75,7 @@ rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codeboo
             p = fmaf(v.y, v.y, p); p = fmaf(v.z, v.z, p); p = fmaf(v.w, v.w, p);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-            xx[f] = p;
+            xx[f] = drop_xx ? 0.f : p;
         }
 
         float best[4];
@@ -166,7 +169,7 @@ rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codeboo
 }
 
 cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
-                              int n, int64_t* idx, float* qsum, cudaStream_t st) {
+                              int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
     if (dim != RVQ_DIM) return cudaErrorInvalidValue;
     if (frames == 0 || n == 0) return cudaSuccess;
     static bool attr_set = false;
@@ -177,7 +180,7 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
         attr_set = true;
     }
     const unsigned grid = (unsigned)((frames + RVQ_FT - 1) / RVQ_FT);
-    rvq_encode_kernel<<<grid, 256, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum);
+    rvq_encode_kernel<<<grid, 256, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,11 @@ Restates `HILCodec.remove_weight_reparameterizations` (streaming.py:740-747):
     res_scale * res_scale_param,
   * `Decoder.merge_scaling`  (streaming.py:609-617): conv_post.weight *= wav_std (bias untouched).
 A dict that is already folded (no reparametrisation keys) passes through unchanged.
+
+`graph="train"` folds for the TRAINING graph instead (models/hilcodec/modules/seanet.py): identical except
+that the decoder ends with `Scale(wav_std)` AFTER conv + bias (seanet.py:464-466), so `conv_post.bias` is
+scaled by wav_std as well.  `to_train_graph()` applies that one difference to weights
+that are already folded for deployment.
 """
 from __future__ import annotations
 
@@ -18,6 +23,7 @@ import re
 import typing as tp
 from collections import OrderedDict
 
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -48,9 +54,21 @@ def _remove_weight_norm(sd: "OrderedDict[str, Tensor]") -> "OrderedDict[str, Ten
     return out
 
 
-def fold_state_dict(sd: "OrderedDict[str, Tensor]", cfg: CodecConfig, part: str = "") -> "OrderedDict[str, Tensor]":
+def to_train_graph(weights: tp.Mapping[str, tp.Any], part: str = "") -> "OrderedDict[str, tp.Any]":
+    """Deployment-folded weights -> training-graph weights: conv_post.bias *= wav_std (seanet.py:464-466)."""
+    out = OrderedDict(weights)
+    key = ("decoder." if part == "" else "") + "conv_post.bias"
+    if key in out:
+        out[key] = out[key] * float(WAV_STD) if isinstance(out[key], Tensor) else (out[key] * np.float32(WAV_STD))
+    return out
+
+
+def fold_state_dict(sd: "OrderedDict[str, Tensor]", cfg: CodecConfig, part: str = "",
+                    graph: str = "deploy") -> "OrderedDict[str, Tensor]":
     """`part` is "" for a HILCodec-level dict (keys start with encoder./decoder./...),
     or "encoder" / "decoder" / "quantizer" for a sub-module dict."""
+    if graph not in ("deploy", "train"):
+        raise ValueError(f"Unknown graph: {graph}")
     sd = OrderedDict((k, torch.as_tensor(v).detach().cpu()) for k, v in sd.items())
     if not _needs_fold(sd):
         return sd
@@ -87,4 +105,6 @@ def fold_state_dict(sd: "OrderedDict[str, Tensor]", cfg: CodecConfig, part: str 
             sd[sp + "layer.bias"] = b * scale
     if dec is not None and dec + "conv_post.weight" in sd:
         sd[dec + "conv_post.weight"] = sd[dec + "conv_post.weight"].float() * WAV_STD
+        if graph == "train" and dec + "conv_post.bias" in sd:
+            sd[dec + "conv_post.bias"] = sd[dec + "conv_post.bias"].float() * WAV_STD
     return sd

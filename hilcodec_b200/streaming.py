@@ -44,8 +44,9 @@ def _stream_ptr(device: torch.device) -> int:
 class _NativeCodec:
     """Owns one `hil_model` (+ per-batch `hil_state`s) per CUDA device for a weight set."""
 
-    def __init__(self, cfg: CodecConfig):
+    def __init__(self, cfg: CodecConfig, graph: int = _lib.HIL_GRAPH_DEPLOY):
         self.cfg = cfg
+        self.graph = graph  # HIL_GRAPH_DEPLOY (streaming.py) or HIL_GRAPH_TRAIN (models.py / seanet.py)
         self.weights: "OrderedDict[str, Tensor]" = OrderedDict()  # folded fp32 CPU tensors
         self._models: tp.Dict[int, int] = {}
         self._states: tp.Dict[tp.Tuple[int, int], int] = {}
@@ -63,6 +64,13 @@ class _NativeCodec:
             t = torch.as_tensor(np.asarray(v) if not isinstance(v, Tensor) else v).detach()
             self.weights[k] = t.to(device="cpu", dtype=torch.float32).contiguous().clone()
         self.invalidate()
+
+    def set_graph(self, graph: int) -> None:
+        if graph not in (_lib.HIL_GRAPH_DEPLOY, _lib.HIL_GRAPH_TRAIN):
+            raise ValueError(f"Unknown graph: {graph}")
+        if graph != self.graph:
+            self.graph = graph
+            self.invalidate()
 
     def invalidate(self) -> None:
         lib = self._lib_handle
@@ -115,6 +123,7 @@ class _NativeCodec:
                         continue
                     dims = (C.c_int64 * t.dim())(*t.shape)
                     _lib.check(lib.hil_model_set_tensor(handle, name.encode(), C.c_void_p(t.data_ptr()), dims, t.dim()))
+                _lib.check(lib.hil_model_set_graph(handle, self.graph))
                 _lib.check(lib.hil_model_finalize(handle))
             except Exception:
                 lib.hil_model_destroy(handle)
@@ -181,6 +190,22 @@ class _NativeCodec:
             _lib.check(self._lib.hil_encode_caches(
                 self.model(dev), self.state(dev, B), x.data_ptr(), B, T, z.data_ptr(), pin, pout, _stream_ptr(dev)))
         return z, outs
+
+    def encode_ragged(self, x: Tensor) -> Tensor:
+        """One-shot training-graph encoder call for any T >= 1 (`hil_encode_ragged`): [B,1,T] -> [B,ceil(T/hop),dim]."""
+        _require_cuda(x, "x")
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"expected x of shape [B, 1, T], got {tuple(x.shape)}")
+        B, _, T = x.shape
+        if T == 0:
+            raise ValueError("empty input")
+        dev = x.device
+        with torch.cuda.device(dev):
+            x = x.contiguous()
+            z = torch.empty(B, -(-T // self.cfg.hop), self.cfg.dim, dtype=torch.float32, device=dev)
+            _lib.check(self._lib.hil_encode_ragged(
+                self.model(dev), self.state(dev, B), x.data_ptr(), B, T, z.data_ptr(), _stream_ptr(dev)))
+        return z
 
     def decode(self, q: Tensor, caches: tp.Sequence[Tensor]) -> tp.Tuple[Tensor, tp.List[Tensor]]:
         _require_cuda(q, "x")

@@ -61,6 +61,15 @@ typedef struct hil_model hil_model;
 typedef struct hil_state hil_state;
 
 enum { HIL_ENCODER = 0, HIL_DECODER = 1 };
+/* Which of the reference's two graphs the model computes (they share all weights but differ in three places,
+ * SURVEY.md section 8 quirks 1, 2, 4):
+ *   HIL_GRAPH_DEPLOY  models/hilcodec/streaming.py (the ONNX export; default; what the golden vectors pin)
+ *   HIL_GRAPH_TRAIN   models/hilcodec/models.py:111-118 (SEANetEncoder/Decoder, modules/seanet.py; what the
+ *                     validation / PESQ loops of wrapper.py:347,373,391 call): decoder ResBlock j uses
+ *                     pre_scale (1 + j*res_scale^2)^-0.5 (seanet.py:443-451), the codebook search is
+ *                     argmin(-2 x.e + |e|^2) without the |x|^2 term (vector_quantize.py:132-153), and the weights
+ *                     are expected with conv_post.bias * wav_std (seanet.py:464-466; fold.py graph="train"). */
+enum { HIL_GRAPH_DEPLOY = 0, HIL_GRAPH_TRAIN = 1 };
 
 int32_t hil_abi_version(void);
 const char* hil_last_error(void);
@@ -70,6 +79,9 @@ void hil_config_default(hil_config* cfg, int32_t num_quantizers);
 int32_t hil_model_create(const hil_config* cfg, hil_model** out);
 /* host fp32 data; dims as in the reference state_dict (e.g. [C,C,1], [C,1,5], [1024,128]) */
 int32_t hil_model_set_tensor(hil_model* m, const char* name, const float* host, const int64_t* dims, int32_t ndim);
+/* selects the graph variant; only before hil_model_finalize (HIL_ERR_STATE afterwards) */
+int32_t hil_model_set_graph(hil_model* m, int32_t graph);
+int32_t hil_model_graph(const hil_model* m);
 /* uploads + repacks weights for the kernels; after this the model is immutable */
 int32_t hil_model_finalize(hil_model* m);
 void hil_model_destroy(hil_model* m);
@@ -94,6 +106,11 @@ int32_t hil_encode(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, 
  * (must not alias); `s` only lends its workspace. */
 int32_t hil_encode_caches(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, int32_t T, float* z_dev,
                           const float* const* caches_in, float* const* caches_out, void* stream);
+/* SEANetEncoder.forward modules/seanet.py:368-378 for ANY length T >= 1 (one-shot, zero history): every causal
+ * conv of the training graph pads itself on the right so that its last window is full (SConv1d.forward
+ * modules/conv.py:222-236, get_extra_padding_for_conv1d :61-68).  wav [B,1,T] -> z [B,ceil(T/hop),dim].
+ * Resets the caches in `s` first (hil_state_reset) and leaves them reset. */
+int32_t hil_encode_ragged(hil_model* m, hil_state* s, const float* wav_dev, int32_t B, int32_t T, float* z_dev, void* stream);
 /* ResidualVQ.forward streaming.py:89-100 (+ per-stage EuclideanCodebook.forward :51-68):
  * z [B,F,dim] -> idx [n,B,F] int64; qsum (optional) [B,F,dim] = Dequantizer(idx). */
 int32_t hil_rvq_encode(hil_model* m, const float* z_dev, int32_t B, int32_t F, int32_t n, int64_t* idx_dev,

@@ -249,11 +249,15 @@ def rvq_margins(cfg: CodecConfig, p: Params, z: Tensor, n: int) -> Tuple[Tensor,
 # --------------------------------------------------------------------------- decoder
 
 def decoder_forward(cfg: CodecConfig, p: Params, q: Tensor,
-                    caches: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, List[Tensor]]:
+                    caches: Optional[Sequence[Tensor]] = None, train_graph: bool = False) -> Tuple[Tensor, List[Tensor]]:
     """Decoder.forward streaming.py:619-648.  q [B,F,dim] -> wav [B,1,hop*F], 30 caches.
 
     Deploy-path quirks kept on purpose: ResBlock pre_scale is 1.0 (streaming.py:576-583
-    never passes idx) and conv_post.bias is not scaled by wav_std (:609-617)."""
+    never passes idx) and conv_post.bias is not scaled by wav_std (:609-617).
+
+    `train_graph=True` restates SEANetDecoder (modules/seanet.py:381-479) instead: ResBlock j of every
+    stage uses pre_scale (1 + j * res_scale^2)^-0.5 (seanet.py:443-451 passes idx=j), and `p` must be
+    folded for the training graph (conv_post.bias * wav_std, hilcodec_b200/fold.py graph="train")."""
     if caches is None:
         caches = zero_caches(decoder_cache_shapes(cfg, q.shape[0]), q.dtype)
     d = "decoder."
@@ -270,7 +274,8 @@ def decoder_forward(cfg: CodecConfig, p: Params, q: Tensor,
         out.append(c)
         idx += 1
         for j in range(cfg.n_residual_dec):
-            h, cs = res_block(h, caches[idx:idx + 2], p, f"{d}blocks.{i}.{j}.", 1.0)
+            pre = (1 + j * cfg.res_scale_dec ** 2) ** -0.5 if train_graph else 1.0
+            h, cs = res_block(h, caches[idx:idx + 2], p, f"{d}blocks.{i}.{j}.", pre)
             out.extend(cs)
             idx += 2
         h = h * post_scale
@@ -290,6 +295,107 @@ def codec_forward(cfg: CodecConfig, p: Params, x: Tensor, n: int,
     q = rvq_decode(cfg, p, idx, n)
     y, cd = decoder_forward(cfg, p, q, dec_caches)
     return {"z": z, "indices": idx, "q": q, "wav": y, "enc_caches": ce, "dec_caches": cd}
+
+
+# --------------------------------------------------------------------------- training graph
+# models/hilcodec/models.py:111-118 = SEANetEncoder -> ResidualVQ(channel_last=False) -> SEANetDecoder, eval mode,
+# restated on FOLDED weights (training-graph fold).  Differences from the deployment graph above:
+#   * every causal conv pads itself: left (k-1) - (s-1) zeros, right "extra padding" so that the last window is full
+#     (modules/conv.py:61-68, :222-236) => any T >= 1 is accepted and T_out = ceil(T_in / stride) per layer;
+#   * the STFT pads n_fft-1 zeros on the left (modules/conv.py:348-358) and clamps the power at 1e-12 before the sqrt
+#     (invisible behind the log's clamp at 1e-5);
+#   * codebook search drops the sum(x^2) term and takes argmin (vector_quantize.py:132-153);
+#   * decoder pre_scale / conv_post bias as described in decoder_forward(train_graph=True).
+
+def _extra_padding(length: int, kernel: int, stride: int, padding_total: int) -> int:
+    """get_extra_padding_for_conv1d, modules/conv.py:61-68."""
+    n_frames = (length - kernel + padding_total) / stride + 1
+    ideal = (math.ceil(n_frames) - 1) * stride + (kernel - padding_total)
+    return ideal - length
+
+
+def sconv1d_causal(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int, groups: int) -> Tensor:
+    """SConv1d.forward modules/conv.py:222-236 (causal, pad_mode constant, dilation 1)."""
+    k = w.shape[2]
+    padding_total = (k - 1) - (stride - 1)
+    extra = _extra_padding(x.shape[2], k, stride, padding_total)
+    return F.conv1d(F.pad(x, (padding_total, extra)), w, b, stride=stride, groups=groups)
+
+
+def stft_logmag_train(wav: Tensor, w_dft: Tensor, hop: int) -> Tensor:
+    """CausalSTFT.forward modules/conv.py:348-358 + SpecBlock compression seanet.py:231-232."""
+    s = F.conv1d(F.pad(wav, (w_dft.shape[2] - 1, 0)), w_dft, None, stride=hop)
+    b, c, t = s.shape
+    mag = s.view(b, 2, c // 2, t).square().sum(dim=1).clamp_min(1e-12).sqrt()
+    return mag.clamp_min(1e-5).log()
+
+
+def encoder_forward_train(cfg: CodecConfig, p: Params, x: Tensor) -> Tensor:
+    """SEANetEncoder.forward seanet.py:368-378.  x [B,1,T] (any T >= 1) -> z [B,dim,ceil(T/hop)] (channel-first)."""
+    e = "encoder."
+    wav = x
+    h = sconv1d_causal(x, p[e + "conv_pre.weight"], p[e + "conv_pre.bias"], 1, 1)
+    stride = 1
+    post_scale = (1 + cfg.n_residual_enc * cfg.res_scale_enc ** 2) ** -0.5
+
+    def dws(u: Tensor, prefix: str) -> Tensor:
+        w_dw = p[prefix + "depthwise.weight"]
+        u = F.conv1d(elu(u), p[prefix + "pointwise.1.weight"])
+        return sconv1d_causal(u, w_dw, p.get(prefix + "depthwise.bias"), 1, w_dw.shape[0])
+
+    for s, r in enumerate(cfg.enc_ratios):
+        y = stft_logmag_train(wav, p[f"{e}spec_blocks.{s}.spec.weight"], stride)
+        h = h + F.conv1d(y, p[f"{e}spec_blocks.{s}.layer.weight"], p[f"{e}spec_blocks.{s}.layer.bias"])
+        for j in range(cfg.n_residual_enc):
+            pre = (1 + (j + 1) * cfg.res_scale_enc ** 2) ** -0.5  # seanet.py:295-296, idx=j (1-based) with a spec branch
+            u = h * pre
+            for i in range(2):
+                u = dws(u, f"{e}blocks.{s}.{j}.block.{i}.")
+            h = u + h
+        h = F.conv1d(elu(h * post_scale), p[f"{e}downsample_pointwise.{s}.1.weight"])
+        h = sconv1d_causal(h, p[f"{e}downsample_depthwise.{s}.weight"], p[f"{e}downsample_depthwise.{s}.bias"],
+                           r, h.shape[1])
+        stride *= r
+    y = stft_logmag_train(wav, p[e + "spec_post.spec.weight"], stride)
+    h = h + F.conv1d(y, p[e + "spec_post.layer.weight"], p[e + "spec_post.layer.bias"])
+    w_dw = p[e + "conv_post_depthwise.weight"]
+    h = sconv1d_causal(elu(h), w_dw, None, 1, w_dw.shape[0])
+    h = F.conv1d(h, p[e + "conv_post_pointwise.weight"], p[e + "conv_post_pointwise.bias"])
+    return F.normalize(h, p=2.0, dim=1, eps=1e-12) * (cfg.dim ** 0.5)  # L2Norm seanet.py:152-163
+
+
+def codebook_search_train(x: Tensor, embed: Tensor) -> Tuple[Tensor, Tensor]:
+    """EuclideanCodebook.forward (eval) models/hilcodec/vector_quantize.py:132-153: no sum(x^2), argmin."""
+    b, t, c = x.shape
+    flat = x.reshape(b * t, c)
+    et = embed.t()
+    distance = - 2 * flat @ et + et.pow(2).sum(0, keepdim=True)
+    ind = distance.min(dim=-1).indices.view(b, t)
+    return F.embedding(ind, embed), ind
+
+
+def rvq_forward_train(cfg: CodecConfig, p: Params, x: Tensor, n: Optional[int] = None):
+    """ResidualVQ.forward (eval) vector_quantize.py:199-243.  x [B,dim,F] -> (quantized [B,dim,F], loss, indices [B,n,F])."""
+    high = cfg.num_quantizers if n is None else n
+    assert 1 <= high <= cfg.num_quantizers
+    residual = x.transpose(1, 2)
+    indices = []
+    out = None
+    for i in range(high):
+        q, ind = codebook_search_train(residual, p[f"quantizer.layers.{i}.embed"])
+        indices.append(ind)
+        residual = residual - q
+        out = q if out is None else out + q
+    out = out.transpose(1, 2)
+    return out, F.mse_loss(x, out), torch.stack(indices, dim=1)
+
+
+def codec_forward_train(cfg: CodecConfig, p: Params, x: Tensor, n: Optional[int] = None):
+    """HILCodec.forward models/hilcodec/models.py:111-118 (eval).  `p`: weights folded with graph="train"."""
+    z = encoder_forward_train(cfg, p, x)
+    q, loss, idx = rvq_forward_train(cfg, p, z, n)
+    y, _ = decoder_forward(cfg, p, q.transpose(1, 2), None, train_graph=True)
+    return {"z": z, "q": q, "indices": idx, "loss_vq": loss, "wav": y}
 
 
 def to_dtype(p: Params, dtype) -> Params:

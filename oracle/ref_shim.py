@@ -97,3 +97,101 @@ def reference_forward(model, x, n, enc_caches=None, dec_caches=None):
         q = model.dequantizer(idx, n)
         y, cd = model.decoder(q, *dec_caches)
     return {"z": z, "indices": idx, "q": q, "wav": y, "enc_caches": list(ce), "dec_caches": list(cd)}
+
+
+# ------------------------------------------------------------------ training graph
+def _model_kwargs(num_quantizers: int) -> dict:
+    import yaml
+
+    with open(os.path.join(REF, "configs", "hilcodec_music.yaml")) as f:
+        kw = yaml.safe_load(f)["model_kwargs"]
+    kw["vq_kwargs"]["num_quantizers"] = num_quantizers
+    return kw
+
+
+def build_reference_training_model(state_dict, num_quantizers: int):
+    """Reference TRAINING-graph `models.hilcodec.models.HILCodec` (eval) loaded with a training-format state
+    dict (`hilcodec_b200.checkpoint.random_training_state_dict`).  The EMA statistics and `_extra_state` of the
+    codebooks keep their constructor values (they do not enter the eval forward)."""
+    import torch
+
+    import_streaming()  # registers the package stubs
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from models.hilcodec.models import HILCodec  # type: ignore
+        model = HILCodec(24000, **_model_kwargs(num_quantizers)).eval()
+    r = model.load_state_dict({k: torch.as_tensor(v) for k, v in state_dict.items()}, strict=False)
+    assert not r.unexpected_keys, r.unexpected_keys
+    assert all(k.endswith(("ema_embed", "ema_num", "_extra_state", "spec.weight")) for k in r.missing_keys), r.missing_keys
+    for layer in model.quantizer.layers:
+        layer.initted = True  # skip the k-means initialisation branch (vector_quantize.py:138-139)
+    return model
+
+
+def streaming_model_from_training(train_model, num_quantizers: int):
+    """`scripts/HILCodec Onnx.ipynb` cells 0-1, restated: build the reference `streaming.HILCodec`, copy every
+    conv of the training model into it, fold.  Returns the folded streaming model (the deployment weights the
+    reference itself would export)."""
+    streaming = import_streaming()
+    kw = _model_kwargs(num_quantizers)
+    for k in ("spec_learnable", "causal", "pad_mode"):
+        kw.pop(k)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = streaming.HILCodec(24000, **kw).eval()
+    me, enc = model.encoder, train_model.encoder
+    me.conv_pre.load_state_dict(enc.conv_pre[1].conv.conv.state_dict())
+    for mine, theirs in zip(me.blocks, enc.blocks):
+        for a, b in zip(mine, theirs):
+            a.block[0].pointwise[1].load_state_dict(b.block[1].conv.conv.state_dict())
+            a.block[0].depthwise.load_state_dict(b.block[2].conv.conv.state_dict())
+            a.block[1].pointwise[1].load_state_dict(b.block[4].conv.conv.state_dict())
+            a.block[1].depthwise.load_state_dict(b.block[5].conv.conv.state_dict())
+            a.res_scale_param.data.copy_(b.res_scale_param.data)
+    for a, b in zip(me.spec_blocks, enc.spec_blocks):
+        a.layer.load_state_dict(b.layer.conv.conv.state_dict())
+        a.scale_param.data.copy_(b.scale_param.data)
+    for p, d, b in zip(me.downsample_pointwise, me.downsample_depthwise, enc.downsample):
+        p[1].load_state_dict(b[2].conv.conv.state_dict())
+        d.load_state_dict(b[3].conv.conv.state_dict())
+    me.spec_post.layer.load_state_dict(enc.spec_post.layer.conv.conv.state_dict())
+    me.spec_post.scale_param.data.copy_(enc.spec_post.scale_param.data)
+    me.conv_post_depthwise.load_state_dict(enc.conv_post[1].conv.conv.state_dict())
+    me.conv_post_pointwise.load_state_dict(enc.conv_post[2].conv.conv.state_dict())
+    md, dec = model.decoder, train_model.decoder.model
+    md.conv_pre_pointwise.load_state_dict(dec[0].conv.conv.state_dict())
+    md.conv_pre_depthwise.load_state_dict(dec[1].conv.conv.state_dict())
+    idx = 2
+    for ud, up, blocks in zip(md.upsample_depthwise, md.upsample_pointwise, md.blocks):
+        idx += 2
+        ud.load_state_dict(dec[idx].convtr.convtr.state_dict()); idx += 1
+        up.load_state_dict(dec[idx].conv.conv.state_dict()); idx += 1
+        for blk in blocks:
+            blk.block[0].pointwise[1].load_state_dict(dec[idx].block[1].conv.conv.state_dict())
+            blk.block[0].depthwise.load_state_dict(dec[idx].block[2].conv.conv.state_dict())
+            blk.block[1].pointwise[1].load_state_dict(dec[idx].block[4].conv.conv.state_dict())
+            blk.block[1].depthwise.load_state_dict(dec[idx].block[5].conv.conv.state_dict())
+            blk.res_scale_param.data.copy_(dec[idx].res_scale_param.data)
+            idx += 1
+    idx += 2
+    md.conv_post.load_state_dict(dec[idx].conv.conv.state_dict())
+    for a, b, c in zip(model.quantizer.layers, model.dequantizer.layers, train_model.quantizer.layers):
+        a.embed.data.copy_(c.embed.data)
+        b.embed.data.copy_(c.embed.data)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.remove_weight_reparameterizations()
+    return model
+
+
+def reference_training_forward(train_model, x, n):
+    """`models.HILCodec.forward` (models.py:111-118), spelled out to also return the latents and indices."""
+    import torch
+
+    with torch.no_grad():
+        z = train_model.encoder(x)
+        q, num_replaces, loss_vq, idx = train_model.quantizer(z, n, return_indices=True)
+        y = train_model.decoder(q).float()
+        y2, nr2, loss2 = train_model(x, n)
+    assert torch.equal(y, y2) and torch.equal(loss_vq, loss2)
+    return {"z": z, "q": q, "indices": idx, "loss_vq": loss_vq, "wav": y, "num_replaces": num_replaces}

@@ -12,6 +12,12 @@
   (`hilcodec_b200.weights.random_weights(cfg, seed)`, reproducible anywhere), one-shot
   and frame-by-frame, so the CUDA path can be checked on the GPU box where the reference
   itself cannot be imported.
+* `ref_train_random.npz` -- outputs of the reference's TRAINING graph (`models/hilcodec/models.py`
+  `HILCodec.forward`, eval) on a seeded training-format checkpoint
+  (`hilcodec_b200.checkpoint.random_training_state_dict(cfg, seed)`: weight-norm pairs, un-merged
+  scales), for input lengths that are and are not multiples of the hop.
+
+    python tests/golden/make_golden.py train     # only (re)generate the training-graph fixture
 """
 import os
 import sys
@@ -79,10 +85,33 @@ def ref_random(name, n_q, seed, batch, frames, stream_hops):
           "wav", float(np.abs(out["stream_wav"] - out["wav"]).max()))
 
 
+def ref_train(name, n_q, seed, n, batch, lengths):
+    from hilcodec_b200 import checkpoint
+
+    cfg = W.CodecConfig(num_quantizers=n_q)
+    model = ref_shim.build_reference_training_model(checkpoint.random_training_state_dict(cfg, seed), n_q)
+    out = {"seed": np.int64(seed), "n_q": np.int64(n_q), "n": np.int64(n), "lengths": np.asarray(lengths, np.int64)}
+    for T in lengths:
+        x = synth_wav(batch, T, 4321 + T)
+        r = ref_shim.reference_training_forward(model, x, n)
+        out[f"x_{T}"] = x.numpy()
+        out[f"z_{T}"] = r["z"].numpy()
+        out[f"q_{T}"] = r["q"].numpy()
+        out[f"indices_{T}"] = r["indices"].numpy().astype(np.int16)
+        out[f"wav_{T}"] = r["wav"].numpy()
+        out[f"loss_{T}"] = np.float32(r["loss_vq"].item())
+        print(name, T, tuple(r["z"].shape), tuple(r["wav"].shape), float(r["loss_vq"]))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["train"]:
+        ref_train("ref_train_random.npz", 6, 3, 5, batch=2, lengths=[320 * 8, 320 * 12 + 77, 333, 1])
+        sys.exit(0)
     speech_kat()
     ref_random("ref_random_speech.npz", 8, 1, batch=2, frames=12, stream_hops=1)
     ref_random("ref_random_music.npz", 12, 2, batch=3, frames=10, stream_hops=3)
+    ref_train("ref_train_random.npz", 6, 3, 5, batch=2, lengths=[320 * 8, 320 * 12 + 77, 333, 1])
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
