@@ -1,20 +1,40 @@
-"""Config 4: frame-by-frame streaming latency, eager launches vs CUDA-graph replay."""
-import sys, os, time
+"""BASELINE config 4: hil_music frame-by-frame streaming (hop 320, GPU-resident caches), 30 s clip = 2250
+sequential frames, B = 1 stream and B = 64 streams; eager launches vs CUDA-graph replay (`StreamState.step`).
+Wall-clock around the whole sequential loop (the latency a caller sees), one JSON line per case."""
+import json
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
+
 from hilcodec_b200 import streaming as S, weights as W
+
 cfg = W.HIL_MUSIC
-w = W.load_pretrained("hil_music") if W.have_pretrained("hil_music") else W.random_weights(cfg, 0)
+pre = W.have_pretrained("hil_music")
+w = W.load_pretrained("hil_music") if pre else W.random_weights(cfg, 0)
 m = S.HILCodec.from_weights(w, 12).cuda()
+FRAMES, WARM = 2250, 20
 for B in (1, 64):
-    x = (0.1 * torch.randn(B, 1, 320 * 300, device="cuda")).clamp(-1, 1)
+    x = (0.1 * torch.randn(B, 1, 320 * (FRAMES + WARM), device="cuda")).clamp(-1, 1)
     for mode in ("eager", "graph"):
+        n = FRAMES if mode == "graph" else 300
         st = m.new_stream_state(B)
+
         def run(f):
             chunk = x[:, :, f * 320:(f + 1) * 320]
             return m.codec_forward(chunk, 12, state=st) if mode == "eager" else st.step(chunk, 12)
-        for f in range(20): run(f)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        for f in range(20, 300): run(f)
-        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 280
-        print(f"B={B} {mode}: {dt*1e3:.3f} ms/frame -> {B/dt:.0f} frames/s, {B*(1/75)/dt:.1f}x real time", flush=True)
+
+        for f in range(WARM):
+            run(f)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for f in range(WARM, WARM + n):
+            run(f)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n
+        print(json.dumps({"workload": "configs[3]: hil_music streaming, hop 320, per-frame causal cache", "streams": B,
+                          "mode": mode, "frames_timed": n, "ms_per_frame": dt * 1e3, "frames_per_s": B / dt,
+                          "x_realtime_per_stream": (1 / 75) / dt, "weights": "published" if pre else "random-init"}),
+              flush=True)
