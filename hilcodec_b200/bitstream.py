@@ -1,8 +1,8 @@
 """Bitstream packing of RVQ indices: 10 bits per codebook per frame.
 
 The reference stores indices as int16 `.npy` (`test_onnx.py:99`); on a wire HILCodec's nominal
-rate is 0.75 kbps per codebook.  Packing runs on the GPU (`csrc/bitpack.cu`); `pack_numpy` /
-`unpack_numpy` state the format for host-side consumers and tests.
+rate is 0.75 kbps per codebook.  Packing runs on the GPU (`csrc/bitpack.cu`) and only there; the host-side
+restatement of the format used by the tests is `oracle/bitstream_oracle.py`.
 
 Format: frame-major, `bytes_per_frame = ceil(n * bits / 8)`; inside a frame the n indices are
 concatenated LSB first, `bits = log2(codebook_size)` each.
@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import ctypes as C
 
-import numpy as np
 import torch
 
 from . import _lib
@@ -54,28 +53,3 @@ def unpack(model, packed: torch.Tensor, n: int) -> torch.Tensor:
         _lib.check(lib.hil_unpack_indices(h, packed.contiguous().data_ptr(), B, F, n, idx.data_ptr(),
                                           torch.cuda.current_stream(dev).cuda_stream))
     return idx
-
-
-def pack_numpy(indices: np.ndarray, bits: int = 10) -> np.ndarray:
-    """Host statement of the format: indices [n,B,F] -> uint8 [B,F,bytes_per_frame]."""
-    n, B, F = indices.shape
-    bpf = bytes_per_frame(n, bits)
-    out = np.zeros((B, F, bpf), dtype=np.uint8)
-    for b in range(B):
-        for f in range(F):
-            acc = 0
-            for s in range(n):
-                acc |= (int(indices[s, b, f]) & ((1 << bits) - 1)) << (s * bits)
-            out[b, f] = np.frombuffer(acc.to_bytes(bpf, "little"), dtype=np.uint8)
-    return out
-
-
-def unpack_numpy(packed: np.ndarray, n: int, bits: int = 10) -> np.ndarray:
-    B, F, bpf = packed.shape
-    out = np.zeros((n, B, F), dtype=np.int64)
-    for b in range(B):
-        for f in range(F):
-            acc = int.from_bytes(packed[b, f].tobytes(), "little")
-            for s in range(n):
-                out[s, b, f] = (acc >> (s * bits)) & ((1 << bits) - 1)
-    return out
