@@ -119,11 +119,14 @@ static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_b
     const bool tmajor = g_use_tc && g_use_tm && gemm_tm_usable(W, X, x_bs, x_rs, T, Y, y_bs, y_rs);
     const bool tcore = g_use_tc && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
     const bool hcore = g_use_tc && g_use_h && gemm_h_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
+    // short chunks (streaming) that no tensor-core kernel takes: skinny-N kernel when enabled (HILCODEC_SKINNY=1)
+    const bool skinny = !tmajor && !tcore && !hcore && gemm_skinny_usable(W, B, T);
     HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
                tmajor  ? launch_gemm_tm(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
                : hcore ? launch_gemm_h(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
                : tcore ? launch_gemm_tc(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
-                       : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
+               : skinny ? launch_gemm_skinny_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
+                        : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
     return HIL_OK;
 }
 // DWSBlock (ELU/none -> 1x1 -> depthwise k5 + bias [+ skip] [+ activation]): one fused tensor-core kernel
@@ -137,7 +140,8 @@ static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
                                   long long y_bs, int y_rs, cudaStream_t st) {
     const double n = (double)B * T;
     HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M) + 4.0 * W.M * W.K, st,
-               launch_gemm_chlast_in(W, Q, B, T, bias, Y, y_bs, y_rs, st));
+               gemm_skinny_usable(W, B, T) ? launch_gemm_skinny_chlast_in(W, Q, B, T, bias, Y, y_bs, y_rs, st)
+                                           : launch_gemm_chlast_in(W, Q, B, T, bias, Y, y_bs, y_rs, st));
     return HIL_OK;
 }
 static int32_t run_gemm_stft_logmag(const PackedMat& Wd, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
@@ -146,7 +150,8 @@ static int32_t run_gemm_stft_logmag(const PackedMat& Wd, const float* wav, long 
     const bool tcore = g_use_tc && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs);
     HIL_LAUNCH(CAT_GEMM_STFT, 2.0 * Wd.M * Wd.K * n, 4.0 * (n * hop + n * (Wd.M / 2)) + 4.0 * Wd.M * Wd.K, st,
                tcore ? launch_stft_tc(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
-                     : launch_gemm_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st));
+               : gemm_skinny_usable(Wd, B, T) ? launch_gemm_skinny_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
+                                              : launch_gemm_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st));
     return HIL_OK;
 }
 static int32_t run_wavcat(const float* x, const float* ci, float* co, float* wav_ext, long long w_bs, int B, int T, int P,
@@ -357,6 +362,7 @@ struct hil_state {
     size_t ws_floats = 0;
     int64_t* idx_dev = nullptr;
     size_t idx_elems = 0;
+    void* rvq_scratch = nullptr;  // inside cache_arena
     float* io_dev = nullptr;  // staging for the *_host call
     size_t io_floats = 0;
     // streaming executor: instantiated CUDA graphs of one fused step, keyed by everything a replay bakes in
@@ -727,7 +733,8 @@ int32_t hil_state_create(hil_model* m, int32_t batch, hil_state** out) {
     };
     count(m->enc_cache_shape);
     count(m->dec_cache_shape);
-    cudaError_t e = cudaMalloc(&s->cache_arena, 2 * total * sizeof(float));
+    // + the candidate scratch of the few-frame RVQ variant (rvq.cu, 128 KB), carved from the same allocation
+    cudaError_t e = cudaMalloc(&s->cache_arena, 2 * total * sizeof(float) + rvq_split_scratch_bytes());
     if (e != cudaSuccess) {
         delete s;
         return fail(HIL_ERR_NOMEM, std::string("cudaMalloc caches: ") + cudaGetErrorString(e));
@@ -743,6 +750,7 @@ int32_t hil_state_create(hil_model* m, int32_t batch, hil_state** out) {
             off += ((size_t)batch * sh[0] * sh[1] + 63) & ~size_t(63);
         }
     }
+    s->rvq_scratch = s->cache_arena + 2 * total;
     e = cudaMemset(s->cache_arena, 0, 2 * total * sizeof(float));
     if (e != cudaSuccess) {
         cudaFree(s->cache_arena);
@@ -1130,8 +1138,18 @@ int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav, int32_t 
     const int ge = s->enc_gen, gd = s->dec_gen;
     HIL_TRY(encode_impl(m, w, wav, B, T, z, s->enc_c[ge].data(), s->enc_c[ge ^ 1].data(), st));
     s->enc_gen = ge ^ 1;
-    HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, w.q,
-                           m->graph == HIL_GRAPH_TRAIN, st));
+    if (rvq_split_usable(m->cfg.codebook_size, m->cfg.dim, (long long)B * F)) {
+        // streaming: n + 1 short launches instead of one CTA walking every stage (HILCODEC_RVQ_SPLIT=1)
+        const long long fr = (long long)B * F;
+        g_prof.launches += n;  // HIL_LAUNCH below counts one
+        HIL_LAUNCH(CAT_RVQ, 2.0 * fr * (double)n * m->cfg.codebook_size * m->cfg.dim,
+                   8.0 * fr * m->cfg.dim + 8.0 * fr * n + 4.0 * (double)n * m->cfg.codebook_size * m->cfg.dim, st,
+                   launch_rvq_encode_split(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, fr, n, idx, w.q,
+                                           m->graph == HIL_GRAPH_TRAIN, s->rvq_scratch, st));
+    } else {
+        HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, w.q,
+                               m->graph == HIL_GRAPH_TRAIN, st));
+    }
     HIL_TRY(decode_impl(m, w, w.q, B, F, wav_out, s->dec_c[gd].data(), s->dec_c[gd ^ 1].data(), st));
     s->dec_gen = gd ^ 1;
     return HIL_OK;

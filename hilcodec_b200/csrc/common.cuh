@@ -84,6 +84,16 @@ cudaError_t launch_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
 cudaError_t launch_gemm_stft_logmag(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T,
                                     float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
+// ---- gemm_skinny.cu: the three contracts above for short chunks (streaming), off unless HILCODEC_SKINNY=1
+bool gemm_skinny_usable(const PackedMat& W, int B, int T);
+cudaError_t launch_gemm_skinny_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                                      float pre_scale, const float* bias, const float* R, float* Y, long long y_bs,
+                                      int y_rs, cudaStream_t st);
+cudaError_t launch_gemm_skinny_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,
+                                         long long y_bs, int y_rs, cudaStream_t st);
+cudaError_t launch_gemm_skinny_stft_logmag(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T,
+                                           float* Y, long long y_bs, int y_rs, cudaStream_t st);
+
 // ---- gemm_tc.cu: same contract as launch_gemm_linear, on the tensor pipe (tcgen05, 3xTF32)
 bool gemm_tc_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
                     long long y_bs, int y_rs);
@@ -174,6 +184,12 @@ cudaError_t launch_l2norm_chlast(const float* x, long long x_bs, int x_rs, float
 cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, int size, int dim, cudaStream_t st);
 cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
                               int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st);
+// few-frame (streaming) variant: one launch per stage over (code tiles) x (frame blocks); off unless HILCODEC_RVQ_SPLIT=1
+bool rvq_split_usable(int size, int dim, long long frames);
+size_t rvq_split_scratch_bytes();
+cudaError_t launch_rvq_encode_split(const float* z, const float* codebooks, const float* ee, int size, int dim,
+                                    long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, void* scratch,
+                                    cudaStream_t st);
 cudaError_t launch_rvq_decode(const int64_t* idx, const float* codebooks, int size, int dim, long long frames, int n,
                               float* q, cudaStream_t st);
 

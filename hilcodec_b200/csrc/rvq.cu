@@ -13,10 +13,14 @@
 // Layout: a CTA owns FT = 32 frames; warp w owns frames 4w..4w+3 (so the per-frame argmax
 // reduction and the residual update are warp-local shuffles); lane l scores codes
 // l, l+32, l+64, l+96 of each 128-code tile staged in shared memory.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hil {
 
+constexpr int RVQ_SPLIT_MAX_FRAMES = 1024;
+constexpr int RVQ_SPLIT_MAX_TILES = 8;
 constexpr int RVQ_FT = 32;      // frames per CTA
 constexpr int RVQ_CT = 128;     // codes per smem tile
 constexpr int RVQ_DIM = 128;    // vector dimension (fixed by the kernel's lane mapping)
@@ -182,6 +186,181 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
     const unsigned grid = (unsigned)((frames + RVQ_FT - 1) / RVQ_FT);
     rvq_encode_kernel<<<grid, 256, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx ? 1 : 0);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Split variant for FEW frames (streaming: one frame per stream and hop).  The kernel above gives 32 frames to one
+// CTA, which then walks all n stages x 8 code tiles alone (~3.5 us per tile => ~340 us for n = 12 however few frames
+// there are).  Here stage s is ONE launch of (code tiles) x (frame blocks) CTAs: every CTA first finishes stage s-1
+// (picks the best of the per-tile candidates the previous launch left in `part_in`, lowest code index on ties, and
+// rebuilds the residual r = ((z - E_0[i_0]) - E_1[i_1]) ... in stage order, i.e. the same fp32 operations as above),
+// then scores ITS 128 codes of stage s with the same FMA order as above and leaves (best distance, index) per frame
+// in `part_out`.  A last launch (s == n) writes the final index and the dequantised sum.  n + 1 launches of ~4 us
+// instead of one of ~340 us; results are bit-identical to rvq_encode_kernel.
+// OFF by default (HILCODEC_RVQ_SPLIT=1): written after this round's GPU budget was spent -- compiled, not yet run.
+struct RvqCand { float d; int i; };
+
+__global__ void __launch_bounds__(256, 2)
+rvq_stage_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee, int size,
+                 int tiles, long long frames, int s, int n, int64_t* __restrict__ idx, float* __restrict__ qsum,
+                 const RvqCand* __restrict__ part_in, RvqCand* __restrict__ part_out, int drop_xx) {
+    extern __shared__ __align__(16) float smem[];
+    float* R = smem;                              // [RVQ_FT][RVQ_PITCH]
+    float* E = smem + RVQ_FT * RVQ_PITCH;         // [RVQ_CT][RVQ_PITCH]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long f0 = (long long)blockIdx.y * RVQ_FT;
+    const int tile = blockIdx.x;
+    const bool last = s == n;
+
+    // ---- finish stage s-1 and rebuild the residual of this warp's 4 frames (lane owns dims 4*lane .. 4*lane+3)
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const long long fr = f0 + warp * 4 + f;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fr < frames) {
+            r = *reinterpret_cast<const float4*>(z + fr * RVQ_DIM + lane * 4);
+            for (int j = 0; j < s; ++j) {
+                int bi;
+                if (j < s - 1) {
+                    bi = (int)idx[(size_t)j * frames + fr];
+                } else {
+                    float bd = -INFINITY;
+                    bi = 0x7fffffff;
+                    for (int t = 0; t < tiles; ++t) {       // ascending code ranges: strict > keeps the first maximum
+                        const RvqCand c = part_in[(size_t)fr * tiles + t];
+                        if (c.d > bd || (c.d == bd && c.i < bi)) { bd = c.d; bi = c.i; }
+                    }
+                    if (bi < 0 || bi >= size) bi = 0;       // all-NaN row, as above
+                    if (tile == 0 && lane == 0) idx[(size_t)j * frames + fr] = bi;
+                }
+                const float4 e = *reinterpret_cast<const float4*>(codebooks + ((size_t)j * size + bi) * RVQ_DIM + lane * 4);
+                r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y); r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
+                q.x = __fadd_rn(q.x, e.x); q.y = __fadd_rn(q.y, e.y); q.z = __fadd_rn(q.z, e.z); q.w = __fadd_rn(q.w, e.w);
+            }
+            if (last && tile == 0 && qsum) *reinterpret_cast<float4*>(qsum + fr * RVQ_DIM + lane * 4) = q;
+        }
+        *reinterpret_cast<float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]) = r;
+    }
+    if (last) return;
+
+    const float* cb = codebooks + (size_t)s * size * RVQ_DIM;
+    const float* ees = ee + (size_t)s * size;
+    const int c0 = tile * RVQ_CT;
+
+    // this CTA's code tile
+    for (int i = tid; i < RVQ_CT * (RVQ_DIM / 4); i += 256) {
+        const int cr = i / (RVQ_DIM / 4), k4 = i - cr * (RVQ_DIM / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + cr < size) v = *reinterpret_cast<const float4*>(cb + (size_t)(c0 + cr) * RVQ_DIM + k4 * 4);
+        *reinterpret_cast<float4*>(&E[cr * RVQ_PITCH + k4 * 4]) = v;
+    }
+    __syncthreads();  // R rows of this warp and the E tile are complete
+
+    // xx[f], identical to rvq_encode_kernel
+    float xx[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const float4 v = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]);
+        float p = __fmul_rn(v.x, v.x);
+        p = fmaf(v.y, v.y, p); p = fmaf(v.z, v.z, p); p = fmaf(v.w, v.w, p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        xx[f] = drop_xx ? 0.f : p;
+    }
+
+    float dot[4][4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dot[f][j] = 0.f;
+#pragma unroll 4
+    for (int k4 = 0; k4 < RVQ_DIM / 4; ++k4) {
+        float4 r4[4], e4[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) r4[f] = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + k4 * 4]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e4[j] = *reinterpret_cast<const float4*>(&E[(lane + 32 * j) * RVQ_PITCH + k4 * 4]);
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float d = dot[f][j];
+                d = fmaf(r4[f].x, e4[j].x, d);
+                d = fmaf(r4[f].y, e4[j].y, d);
+                d = fmaf(r4[f].z, e4[j].z, d);
+                d = fmaf(r4[f].w, e4[j].w, d);
+                dot[f][j] = d;
+            }
+    }
+    float best[4];
+    int besti[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { best[f] = -INFINITY; besti[f] = 0x7fffffff; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int code = c0 + lane + 32 * j;
+        if (code < size) {
+            const float e2 = ees[code];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const float d = -__fadd_rn(__fsub_rn(xx[f], __fmul_rn(2.f, dot[f][j])), e2);
+                if (d > best[f]) { best[f] = d; besti[f] = code; }
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        float bd = best[f];
+        int bi = besti[f];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        const long long fr = f0 + warp * 4 + f;
+        if (lane == 0 && fr < frames) {
+            RvqCand c;
+            c.d = bd; c.i = bi;
+            part_out[(size_t)fr * tiles + tile] = c;
+        }
+    }
+}
+
+bool rvq_split_usable(int size, int dim, long long frames) {
+    static const bool on = [] { const char* e = std::getenv("HILCODEC_RVQ_SPLIT"); return e && e[0] == '1'; }();
+    return on && dim == RVQ_DIM && frames > 0 && frames <= RVQ_SPLIT_MAX_FRAMES && (size + RVQ_CT - 1) / RVQ_CT <= RVQ_SPLIT_MAX_TILES;
+}
+
+// scratch: 2 * RVQ_SPLIT_MAX_FRAMES * RVQ_SPLIT_MAX_TILES candidates (rvq_split_scratch_bytes())
+size_t rvq_split_scratch_bytes() { return (size_t)2 * RVQ_SPLIT_MAX_FRAMES * RVQ_SPLIT_MAX_TILES * sizeof(RvqCand); }
+
+cudaError_t launch_rvq_encode_split(const float* z, const float* codebooks, const float* ee, int size, int dim,
+                                    long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, void* scratch,
+                                    cudaStream_t st) {
+    if (dim != RVQ_DIM || !scratch) return cudaErrorInvalidValue;
+    if (frames == 0 || n == 0) return cudaSuccess;
+    static bool attr_set = false;
+    const size_t smem = (size_t)(RVQ_FT + RVQ_CT) * RVQ_PITCH * sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rvq_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = (size + RVQ_CT - 1) / RVQ_CT;
+    RvqCand* part[2] = {reinterpret_cast<RvqCand*>(scratch),
+                        reinterpret_cast<RvqCand*>(scratch) + (size_t)RVQ_SPLIT_MAX_FRAMES * RVQ_SPLIT_MAX_TILES};
+    const unsigned fblocks = (unsigned)((frames + RVQ_FT - 1) / RVQ_FT);
+    for (int s = 0; s <= n; ++s) {
+        const dim3 grid(s == n ? 1 : tiles, fblocks);
+        rvq_stage_kernel<<<grid, 256, smem, st>>>(z, codebooks, ee, size, tiles, frames, s, n, idx, qsum, part[(s + 1) & 1],
+                                                  part[s & 1], drop_xx ? 1 : 0);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // Dequantizer: q[f][:] = ((0 + E_0[i_0]) + E_1[i_1]) + ...   one thread per 4 dims.

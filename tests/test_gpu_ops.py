@@ -104,6 +104,11 @@ def test_dwconv_transpose(B, Cc, T, S, pre):
     (1, 128, 1024, 5, 0, True, False),
     (4, 192, 192, 1, 1, False, False),     # one column per stream
     (1, 256, 257, 129, 2, True, True),
+    # one stream, one hop (the streaming shapes; with HILCODEC_SKINNY=1 these run on gemm_skinny.cu)
+    (1, 768, 1536, 8, 2, True, True),
+    (1, 1536, 128, 1, 0, False, False),
+    (3, 384, 768, 40, 1, False, True),
+    (64, 96, 96, 5, 1, True, False),
 ])
 def test_pointwise(B, M, K, T, pre, bias, res):
     lib = _lib.load()
