@@ -1,0 +1,48 @@
+// Runs rvq.cu's one-kernel search (rvq_encode_kernel) and its per-stage variant (rvq_stage_kernel) -- source text
+// extracted into rvq_extracted.inc -- on the CPU emulation layer.
+// argv: size frames n drop_xx in.bin out.bin;  in.bin = z[frames*128] codebooks[n*size*128] (float32);
+// out.bin = idx_mono[n*frames] idx_split[n*frames] (int64) qsum_mono[frames*128] qsum_split[frames*128] (float32)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cuda_emu.h"
+namespace hil {
+#include "rvq_extracted.inc"
+}
+using namespace hil;
+
+int main(int argc, char** argv) {
+    if (argc != 7) return 2;
+    const int size = atoi(argv[1]);
+    const long long frames = atoll(argv[2]);
+    const int n = atoi(argv[3]), drop_xx = atoi(argv[4]);
+    std::vector<float> z((size_t)frames * RVQ_DIM), cb((size_t)n * size * RVQ_DIM), ee((size_t)n * size);
+    FILE* f = std::fopen(argv[5], "rb");
+    if (std::fread(z.data(), 4, z.size(), f) != z.size() || std::fread(cb.data(), 4, cb.size(), f) != cb.size()) return 3;
+    std::fclose(f);
+    for (size_t r = 0; r < ee.size(); ++r) {  // codebook_norm_kernel
+        float s = 0.f;
+        for (int k = 0; k < RVQ_DIM; ++k) s = __fadd_rn(s, __fmul_rn(cb[r * RVQ_DIM + k], cb[r * RVQ_DIM + k]));
+        ee[r] = s;
+    }
+    std::vector<int64_t> idx_a((size_t)n * frames, -1), idx_b((size_t)n * frames, -1);
+    std::vector<float> q_a(z.size(), -1.f), q_b(z.size(), -1.f);
+    const unsigned fblocks = (unsigned)((frames + RVQ_FT - 1) / RVQ_FT);
+    emu_launch(fblocks, 1, 256, [&] { rvq_encode_kernel(z.data(), cb.data(), ee.data(), size, frames, n, idx_a.data(), q_a.data(), drop_xx); });
+    const int tiles = (size + RVQ_CT - 1) / RVQ_CT;
+    std::vector<RvqCand> part[2];
+    part[0].resize((size_t)frames * tiles); part[1].resize((size_t)frames * tiles);
+    for (int s = 0; s <= n; ++s)   // launch_rvq_encode_split
+        emu_launch(s == n ? 1 : tiles, fblocks, 256, [&] {
+            rvq_stage_kernel(z.data(), cb.data(), ee.data(), size, tiles, frames, s, n, idx_b.data(), q_b.data(),
+                             part[(s + 1) & 1].data(), part[s & 1].data(), drop_xx);
+        });
+    f = std::fopen(argv[6], "wb");
+    std::fwrite(idx_a.data(), 8, idx_a.size(), f);
+    std::fwrite(idx_b.data(), 8, idx_b.size(), f);
+    std::fwrite(q_a.data(), 4, q_a.size(), f);
+    std::fwrite(q_b.data(), 4, q_b.size(), f);
+    std::fclose(f);
+    return 0;
+}

@@ -1,0 +1,197 @@
+"""The SOURCE of the small FP32 CUDA kernels, compiled for the CPU against a thread-per-CUDA-thread emulation
+layer (tests/emu/cuda_emu.h) and checked against numpy / the oracle.
+
+These kernels (`gemm_skinny.cu`, the per-stage RVQ kernel in `rvq.cu`) were written when no GPU time was left, so
+this is the only execution their logic has had: it verifies indexing, the fixed-order reductions and the arithmetic
+of the very text nvcc compiles, not performance and not GPU memory-model behaviour.  The tcgen05 kernels cannot be
+emulated this way and are covered by the `-m gpu` tests only."""
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "hilcodec_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+
+
+def _function(src: str, start: int) -> str:
+    """Text from `start` to the closing brace of the first top-level block after it."""
+    i = src.index("{", start)
+    depth = 0
+    for j in range(i, len(src)):
+        depth += src[j] == "{"
+        depth -= src[j] == "}"
+        if depth == 0:
+            return src[start:j + 1]
+    raise ValueError("unbalanced braces")
+
+
+def _common_bits() -> str:
+    src = open(os.path.join(CSRC, "common.cuh")).read()
+    out = [re.search(r"enum Pre \{[^}]*\};", src).group(0)]
+    for name in ("elu1", "apply_pre"):
+        m = re.search(rf"__device__ __forceinline__ float {name}\(", src)
+        out.append(_function(src, m.start()))
+    return "\n".join(out)
+
+
+def _build(tmp, name, inc_name, inc_text, harness):
+    with open(os.path.join(tmp, inc_name), "w") as f:
+        f.write(inc_text)
+    exe = os.path.join(tmp, name)
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-I", EMU, "-I", tmp,
+           os.path.join(EMU, harness), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+@pytest.fixture(scope="module")
+def skinny_exe(tmp_path_factory):
+    src = open(os.path.join(CSRC, "gemm_skinny.cu")).read()
+    a = src.index("enum { SK_PLAIN")
+    k = src.index("template <int NT, int KC, int LD, int EPI>\n__global__")
+    text = src[a:k] + _function(src, k)
+    text = text.replace("extern __shared__ __align__(16) float sk_smem[];", "float* sk_smem = g_dyn_smem;")
+    assert "g_dyn_smem" in text
+    return _build(str(tmp_path_factory.mktemp("emu_skinny")), "skinny", "skinny_extracted.inc",
+                  _common_bits() + "\n" + text, "harness_skinny.cpp")
+
+
+def _pack_kmajor(w, Mp):
+    """[M][K] -> k-major [Kp16][Mp], zero padded (the layout hil_model_finalize gives gemm.cu / gemm_skinny.cu)."""
+    M, K = w.shape
+    Kp = (K + 15) // 16 * 16
+    a = np.zeros((Kp, Mp), np.float32)
+    a[:K, :M] = w.T
+    return a
+
+
+def _run(exe, tmp, LD, EPI, A, Mp, M, K, B, T, pre, pre_scale, X, bias, R, hop, x_bs, x_ks, y_bs, y_rs, M_out):
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    parts = [A.ravel(), X.ravel()] + ([bias.ravel()] if bias is not None else []) + ([R.ravel()] if R is not None else [])
+    np.concatenate(parts).astype(np.float32).tofile(fin)
+    args = [LD, EPI, Mp, M, K, B, T, pre, pre_scale, int(bias is not None), int(R is not None), hop, x_bs, x_ks, y_bs, y_rs,
+            M_out, fin, fout]
+    r = subprocess.run([exe] + [str(v) for v in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    return np.fromfile(fout, np.float32)
+
+
+@pytest.mark.parametrize("B,M,K,T,pre,bias,res", [
+    (1, 96, 192, 8, 2, True, True),      # NT = 8, K split over the warps, pre-scale + ELU, bias, residual
+    (1, 64, 33, 1, 0, True, True),       # one column, odd K (SpecBlock 1x1), two of the eight warps busy
+    (3, 128, 100, 5, 1, False, False),   # N = 15 -> NT = 16, columns of three streams
+    (2, 64, 64, 13, 0, True, False),     # N = 26 -> NT = 32, KC = 16
+    (1, 96, 40, 40, 1, False, True),     # N = 40 -> NT = 64
+    (2, 32, 300, 40, 2, True, True),     # N = 80 -> two column tiles, second one ragged
+    (1, 64, 1536, 8, 1, True, False),    # the widest layer: all eight warps, six chunks of 32 k each
+    (1, 32, 256, 4, 0, False, False),    # K = 8 warps x one chunk
+])
+def test_skinny_linear_source_on_cpu(skinny_exe, tmp_path, B, M, K, T, pre, bias, res):
+    g = torch.Generator().manual_seed(M + K + T)
+    x = torch.randn(B, K, T, generator=g)
+    w = torch.randn(M, K, generator=g) / K ** 0.5
+    b = torch.randn(M, generator=g) if bias else None
+    r = torch.randn(B, M, T, generator=g) if res else None
+    xin = x if pre == 0 else F.elu(x * 0.8660254 if pre == 2 else x)
+    ref = F.conv1d(xin.double(), w.double()[:, :, None], b.double() if bias else None)
+    if res:
+        ref = ref + r.double()
+    Mp = (M + 31) // 32 * 32
+    y = _run(skinny_exe, str(tmp_path), 0, 0, _pack_kmajor(w.numpy(), Mp), Mp, M, K, B, T, pre, 0.8660254, x.numpy(),
+             b.numpy() if bias else None, r.numpy() if res else None, 0, K * T, T, M * T, T, M)
+    assert np.abs(y.reshape(B, M, T) - ref.numpy()).max() < 2e-5
+
+
+def test_skinny_channel_last_source_on_cpu(skinny_exe, tmp_path):
+    """Decoder input: q [B, F, 128] channel-last -> [B, M, F]."""
+    g = torch.Generator().manual_seed(7)
+    B, Fr, K, M = 2, 3, 128, 96
+    q = torch.randn(B, Fr, K, generator=g)
+    w = torch.randn(M, K, generator=g) / K ** 0.5
+    ref = F.conv1d(q.transpose(1, 2).double(), w.double()[:, :, None])
+    y = _run(skinny_exe, str(tmp_path), 1, 0, _pack_kmajor(w.numpy(), M), M, M, K, B, Fr, 0, 1.0, q.numpy(), None, None,
+             0, 0, 1, M * Fr, Fr, M)
+    assert np.abs(y.reshape(B, M, Fr) - ref.numpy()).max() < 2e-5
+
+
+@pytest.mark.parametrize("B,n_fft,hop,T", [(2, 64, 40, 3), (1, 128, 320, 1)])
+def test_skinny_stft_source_on_cpu(skinny_exe, tmp_path, B, n_fft, hop, T):
+    """DFT-as-conv + magnitude + clamp + log; rows interleaved (cos_f, sin_f) as hil_model_finalize packs them."""
+    from hilcodec_b200.weights import dft_basis
+    g = torch.Generator().manual_seed(n_fft)
+    L = (T - 1) * hop + n_fft
+    wav = 0.1 * torch.randn(B, 1, L, generator=g)
+    wav[0, 0, : L // 2] = 0.0
+    basis = torch.from_numpy(dft_basis(n_fft))  # [2F,1,N] = [cos; sin]
+    Fr = n_fft // 2 + 1
+    s = F.conv1d(wav.double(), basis.double(), None, stride=hop).view(B, 2, Fr, T)
+    ref = s.square().sum(1).sqrt().clamp_min(1e-5).log()
+    inter = torch.stack((basis[:Fr, 0], basis[Fr:, 0]), 1).reshape(2 * Fr, n_fft)  # rows (cos_f, sin_f)
+    Mp = (2 * Fr + 95) // 96 * 96
+    y = _run(skinny_exe, str(tmp_path), 2, 1, _pack_kmajor(inter.numpy(), Mp), Mp, 2 * Fr, n_fft, B, T, 0, 1.0, wav.numpy(),
+             None, None, hop, L, 1, Fr * T, T, Fr)
+    err = np.abs(y.reshape(B, Fr, T) - ref.numpy())
+    assert np.median(err) < 1e-5 and err.max() < 1e-2  # the log amplifies fp32 noise where the magnitude cancels
+
+
+@pytest.fixture(scope="module")
+def rvq_exe(tmp_path_factory):
+    src = open(os.path.join(CSRC, "rvq.cu")).read()
+    a = src.index("constexpr int RVQ_SPLIT_MAX_FRAMES")
+    b = src.index("constexpr int RVQ_PITCH")
+    consts = src[a:src.index("\n", b) + 1]
+    mono = _function(src, src.index("__global__ void __launch_bounds__(256, 2)\nrvq_encode_kernel("))
+    stage = _function(src, src.index("__global__ void __launch_bounds__(256, 2)\nrvq_stage_kernel("))
+    text = consts + mono + "\nstruct RvqCand { float d; int i; };\n" + stage
+    assert text.count("extern __shared__ __align__(16) float smem[];") == 2
+    text = text.replace("extern __shared__ __align__(16) float smem[];", "float* smem = g_dyn_smem;")
+    return _build(str(tmp_path_factory.mktemp("emu_rvq")), "rvq", "rvq_extracted.inc", text, "harness_rvq.cpp")
+
+
+@pytest.mark.parametrize("size,frames,n,drop_xx", [(1024, 5, 3, 0), (256, 40, 4, 1), (200, 33, 2, 0)])
+def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx):
+    """The one-kernel search against the oracle, and the per-stage variant bit-identical to it."""
+    from oracle import hilcodec_oracle as O
+
+    g = torch.Generator().manual_seed(size + frames)
+    z = F.normalize(torch.randn(1, frames, 128, generator=g), dim=2) * 128 ** 0.5
+    cbs = [torch.randn(size, 128, generator=g) * 0.7 ** i for i in range(n)]
+    cbs[0][7] = cbs[0][3]  # an exact tie: the first index must win
+    fin, fout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
+    np.concatenate([z.numpy().ravel()] + [c.numpy().ravel() for c in cbs]).astype(np.float32).tofile(fin)
+    r = subprocess.run([rvq_exe, str(size), str(frames), str(n), str(drop_xx), fin, fout], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = np.fromfile(fout, np.uint8)
+    ni = n * frames * 8
+    idx_a = raw[:ni].view(np.int64).reshape(n, frames)
+    idx_b = raw[ni:2 * ni].view(np.int64).reshape(n, frames)
+    q = raw[2 * ni:].view(np.float32).reshape(2, frames, 128)
+    assert np.array_equal(idx_a, idx_b) and np.array_equal(q[0], q[1])  # split == one-kernel, bit for bit
+    assert not (idx_a[0] == 7).any()
+    p = {f"quantizer.layers.{i}.embed": c for i, c in enumerate(cbs)}
+    cfg = O.CodecConfig(num_quantizers=n, codebook_size=size)
+    if drop_xx:
+        q_ref, _, idx_ref = O.rvq_forward_train(cfg, p, z.transpose(1, 2), n)
+        idx_ref, q_ref = idx_ref.permute(1, 0, 2), q_ref.transpose(1, 2)
+    else:
+        idx_ref = O.rvq_encode(cfg, p, z, n)
+        q_ref = O.rvq_decode(cfg, p, idx_ref, n)
+    same = idx_a == idx_ref[:, 0].numpy()
+    if not same.all():  # near-tie policy of the GPU tests
+        _, gaps = O.rvq_margins(cfg, p, z, n)
+        first = np.argmax(~same, axis=0)
+        bad = np.nonzero((~same).any(axis=0))[0]
+        assert all(float(gaps[first[f], 0, f]) < 1e-5 for f in bad)
+    else:
+        assert np.array_equal(q[0], q_ref[0].numpy())
