@@ -190,6 +190,15 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
                          : launch_gemm_tc_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st));
         return HIL_OK;
     }
+    if (gemm_skinny_dws_usable(W, B, T) && X != Y) {
+        // streaming chunk: the depthwise conv rides in the skinny GEMM's epilogue (HILCODEC_SKINNY=1)
+        const double n = (double)B * T;
+        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
+                   4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
+                   launch_gemm_skinny_dws(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, post, post_scale, Y,
+                                          bs, rs, st));
+        return HIL_OK;
+    }
     HIL_TRY(run_gemm_linear(W, X, bs, rs, B, T, pre, pre_scale, nullptr, nullptr, tmp, bs, rs, st));
     return run_dwconv(tmp, bs, rs, ci, co, dw_w, dw_b, skip, Y, bs, rs, B, W.M, T, 5, 1, PRE_NONE, 1.f, st, post,
                       post_scale);

@@ -89,6 +89,11 @@ bool gemm_skinny_usable(const PackedMat& W, int B, int T);
 cudaError_t launch_gemm_skinny_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                       float pre_scale, const float* bias, const float* R, float* Y, long long y_bs,
                                       int y_rs, cudaStream_t st);
+bool gemm_skinny_dws_usable(const PackedMat& W, int B, int T);
+cudaError_t launch_gemm_skinny_dws(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                                   float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
+                                   float* cache_out, const float* skip, int post, float post_scale, float* Y,
+                                   long long y_bs, int y_rs, cudaStream_t st);
 cudaError_t launch_gemm_skinny_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,
                                          long long y_bs, int y_rs, cudaStream_t st);
 cudaError_t launch_gemm_skinny_stft_logmag(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T,

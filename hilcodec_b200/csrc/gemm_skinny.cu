@@ -25,7 +25,7 @@ namespace hil {
 namespace {
 
 enum { SK_PLAIN = 0, SK_CHLAST = 1, SK_IM2COL = 2 };
-enum { SK_LINEAR = 0, SK_LOGMAG = 1 };
+enum { SK_LINEAR = 0, SK_LOGMAG = 1, SK_DW5 = 2 };
 
 constexpr int SK_ROWS = 32;
 constexpr int SK_WARPS = 8;
@@ -47,6 +47,16 @@ struct SkinnyParams {
     long long y_bs;
     int y_rs;
     int M_out;        // rows of Y (M, or M/2 for LOGMAG)
+    int cols_per_tile;  // NT, or (whole streams per tile) * T for SK_DW5
+    // SK_DW5: DWSBlock tail (streaming.py:189-192 + the ResBlock add :268-274) -- causal depthwise k5 over the GEMM
+    // result with its 4-sample cache, + bias, + skip, activation on the stored value (as dwconv5_kernel in conv.cu)
+    const float* dw_w;      // [M][5]
+    const float* dw_b;      // [M] | null
+    const float* cache_in;  // [B][M][4]
+    float* cache_out;       // [B][M][4]
+    const float* skip;      // laid out like Y | null
+    int post;
+    float post_scale;
 };
 
 template <int NT, int KC, int LD, int EPI>
@@ -57,9 +67,9 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_kernel(const SkinnyParam
     __shared__ long long coloff[NT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned n0 = blockIdx.x * (unsigned)NT;
+    const unsigned n0 = blockIdx.x * (unsigned)p.cols_per_tile;
     const int m0 = blockIdx.y * SK_ROWS;
-    const int ncol = (int)min((unsigned)NT, p.N - n0);         // valid columns of this tile
+    const int ncol = (int)min((unsigned)p.cols_per_tile, p.N - n0);  // valid columns of this tile
 
     if (tid < NT) {
         long long off = 0;
@@ -151,6 +161,49 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_kernel(const SkinnyParam
             if (p.R) s += p.R[yo];
             p.Y[yo] = s;
         }
+    } else if (EPI == SK_DW5) {
+        // the tile holds whole streams (cols_per_tile is a multiple of T): reduce into shared memory, then slide the
+        // 5-tap window along each stream's row; samples before the chunk come from the cache
+        float* v = xs_all;  // [SK_ROWS][NT]; the X staging area is free after the barrier above
+        for (int o = tid; o < SK_ROWS * ncol; o += SK_WARPS * 32) {
+            const int row = o / ncol, j = o - row * ncol;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < SK_WARPS; ++w) s += red[(w * NT + j) * (SK_ROWS + 1) + row];
+            v[row * NT + j] = s;
+        }
+        __syncthreads();
+        const int T = p.T;
+        const unsigned b0 = n0 / (unsigned)T;
+        for (int o = tid; o < SK_ROWS * ncol; o += SK_WARPS * 32) {
+            const int row = o / ncol, j = o - row * ncol;
+            const int m = m0 + row;
+            if (m >= p.M) continue;
+            const int bl = j / T, t = j - bl * T;
+            const unsigned b = b0 + bl;
+            const float* ci = p.cache_in + ((size_t)b * p.M + m) * 4;
+            const float* vr = v + row * NT + bl * T;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int tau = t - 4 + k;
+                a = fmaf(p.dw_w[m * 5 + k], tau >= 0 ? vr[tau] : ci[4 + tau], a);
+            }
+            a += p.dw_b ? p.dw_b[m] : 0.f;
+            const long long yo = (long long)b * p.y_bs + (long long)m * p.y_rs + t;
+            if (p.skip) a += p.skip[yo];
+            p.Y[yo] = apply_act_fast(a, p.post, p.post_scale);
+        }
+        const int nstream = ncol / T;
+        for (int o = tid; o < SK_ROWS * nstream * 4; o += SK_WARPS * 32) {
+            const int i = o & 3, bl = (o >> 2) % nstream, row = (o >> 2) / nstream;
+            const int m = m0 + row;
+            if (m >= p.M) continue;
+            const unsigned b = b0 + bl;
+            const int tau = T - 4 + i;  // cache_out = last 4 of cat(cache_in, v)
+            p.cache_out[((size_t)b * p.M + m) * 4 + i] =
+                tau >= 0 ? v[row * NT + bl * T + tau] : p.cache_in[((size_t)b * p.M + m) * 4 + 4 + tau];
+        }
     } else {  // rows (2f, 2f+1) = (re_f, im_f); m0 is even
         for (int o = tid; o < (SK_ROWS / 2) * ncol; o += SK_WARPS * 32) {
             const int pr = o / ncol, j = o - pr * ncol;
@@ -181,8 +234,11 @@ cudaError_t launch_one(const SkinnyParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const dim3 grid((p.N + NT - 1) / NT, p.Mp / SK_ROWS);
-    skinny_kernel<NT, KC, LD, EPI><<<grid, SK_WARPS * 32, smem, st>>>(p);
+    SkinnyParams q = p;
+    if (EPI == SK_DW5) q.cols_per_tile = NT / p.T * p.T;  // whole streams per tile (T <= NT checked by the caller)
+    else q.cols_per_tile = NT;
+    const dim3 grid((q.N + q.cols_per_tile - 1) / q.cols_per_tile, q.Mp / SK_ROWS);
+    skinny_kernel<NT, KC, LD, EPI><<<grid, SK_WARPS * 32, smem, st>>>(q);
     return cudaGetLastError();
 }
 
@@ -190,6 +246,7 @@ template <int LD, int EPI>
 cudaError_t dispatch(const SkinnyParams& p, cudaStream_t st) {
     if (p.N == 0) return cudaSuccess;
     if (p.Mp % SK_ROWS) return cudaErrorInvalidValue;
+    // SK_DW5 needs T <= NT; N >= T, so the choice by N guarantees it whenever T <= 64
     if (p.N <= 8) return launch_one<8, 32, LD, EPI>(p, st);
     if (p.N <= 16) return launch_one<16, 32, LD, EPI>(p, st);
     if (p.N <= 32) return launch_one<32, 16, LD, EPI>(p, st);
@@ -224,6 +281,22 @@ cudaError_t launch_gemm_skinny_linear(const PackedMat& W, const float* X, long l
     p.X = X; p.x_bs = x_bs; p.x_ks = x_rs; p.pre = pre; p.pre_scale = pre_scale;
     p.bias = bias; p.R = R; p.Y = Y; p.y_bs = y_bs; p.y_rs = y_rs;
     return dispatch<SK_PLAIN, SK_LINEAR>(p, st);
+}
+
+// DWSBlock for short chunks in ONE launch: y = post(dw5(W * pre(x); cache) + b_dw + skip), T <= 64
+bool gemm_skinny_dws_usable(const PackedMat& W, int B, int T) { return T <= 64 && gemm_skinny_usable(W, B, T); }
+
+cudaError_t launch_gemm_skinny_dws(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                                   float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
+                                   float* cache_out, const float* skip, int post, float post_scale, float* Y,
+                                   long long y_bs, int y_rs, cudaStream_t st) {
+    if (T > 64 || !dw_w || !cache_in || !cache_out) return cudaErrorInvalidValue;
+    SkinnyParams p = base(W, B, T);
+    p.X = X; p.x_bs = x_bs; p.x_ks = x_rs; p.pre = pre; p.pre_scale = pre_scale;
+    p.Y = Y; p.y_bs = y_bs; p.y_rs = y_rs;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out; p.skip = skip;
+    p.post = post; p.post_scale = post_scale;
+    return dispatch<SK_PLAIN, SK_DW5>(p, st);
 }
 
 cudaError_t launch_gemm_skinny_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,

@@ -15,7 +15,9 @@ template <int LD, int EPI> void run(const SkinnyParams& p) {
     const unsigned gy = p.Mp / SK_ROWS;
     auto go = [&](auto nt, auto kc) {
         constexpr int NT = decltype(nt)::value, KC = decltype(kc)::value;
-        emu_launch((p.N + NT - 1) / NT, gy, SK_WARPS * 32, [&] { skinny_kernel<NT, KC, LD, EPI>(p); });
+        SkinnyParams q = p;  // launch_one() in gemm_skinny.cu
+        q.cols_per_tile = EPI == SK_DW5 ? NT / p.T * p.T : NT;
+        emu_launch((q.N + q.cols_per_tile - 1) / q.cols_per_tile, gy, SK_WARPS * 32, [&] { skinny_kernel<NT, KC, LD, EPI>(q); });
     };
     // same choice as dispatch() in gemm_skinny.cu
     if (p.N <= 8) go(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
@@ -25,7 +27,7 @@ template <int LD, int EPI> void run(const SkinnyParams& p) {
 }
 
 int main(int argc, char** argv) {
-    if (argc != 20) { std::fprintf(stderr, "bad args %d\n", argc); return 2; }
+    if (argc != 20 && argc != 24) { std::fprintf(stderr, "bad args %d\n", argc); return 2; }
     int a = 1;
     const int LD = atoi(argv[a++]), EPI = atoi(argv[a++]);
     SkinnyParams p{};
@@ -44,6 +46,25 @@ int main(int argc, char** argv) {
     if (std::fread(in.data(), 4, in.size(), f) != in.size()) return 3;
     std::fclose(f);
     const size_t nA = (size_t)Kp * p.Mp, ny = (size_t)B * p.y_bs;
+    if (EPI == 2) {
+        const int has_dwb = atoi(argv[a++]), has_skip = atoi(argv[a++]);
+        p.post = atoi(argv[a++]); p.post_scale = (float)atof(argv[a++]);
+        const size_t nc = (size_t)B * p.M * 4;
+        const size_t nx = in.size() - nA - (size_t)p.M * 5 - (has_dwb ? p.M : 0) - nc - (has_skip ? ny : 0);
+        const float* q = in.data();
+        p.A = q; q += nA; p.X = q; q += nx; p.dw_w = q; q += (size_t)p.M * 5;
+        p.dw_b = has_dwb ? q : nullptr; q += has_dwb ? p.M : 0;
+        p.cache_in = q; q += nc; p.skip = has_skip ? q : nullptr;
+        std::vector<float> y(ny, -12345.f), co(nc, -12345.f);
+        p.Y = y.data(); p.cache_out = co.data();
+        if (LD != 0) return 4;
+        run<SK_PLAIN, SK_DW5>(p);
+        f = std::fopen(fout, "wb");
+        std::fwrite(y.data(), 4, y.size(), f);
+        std::fwrite(co.data(), 4, co.size(), f);
+        std::fclose(f);
+        return 0;
+    }
     const size_t nx = in.size() - nA - (has_bias ? p.M : 0) - (has_res ? ny : 0);
     p.A = in.data(); p.X = in.data() + nA;
     p.bias = has_bias ? in.data() + nA + nx : nullptr;

@@ -62,8 +62,12 @@ def skinny_exe(tmp_path_factory):
     text = src[a:k] + _function(src, k)
     text = text.replace("extern __shared__ __align__(16) float sk_smem[];", "float* sk_smem = g_dyn_smem;")
     assert "g_dyn_smem" in text
+    # apply_act_fast uses ex2.approx through inline PTX: stand-in with the same meaning (differs by <= 2.4e-7)
+    act = ("inline float apply_act_fast(float x, int mode, float s) {\n"
+           "    if (mode == PRE_NONE) return x;\n    if (mode == PRE_SCALE_ELU) x = x * s;\n"
+           "    return x > 0.f ? x : expm1f(x);\n}\n")
     return _build(str(tmp_path_factory.mktemp("emu_skinny")), "skinny", "skinny_extracted.inc",
-                  _common_bits() + "\n" + text, "harness_skinny.cpp")
+                  _common_bits() + "\n" + act + text, "harness_skinny.cpp")
 
 
 def _pack_kmajor(w, Mp):
@@ -110,6 +114,44 @@ def test_skinny_linear_source_on_cpu(skinny_exe, tmp_path, B, M, K, T, pre, bias
     y = _run(skinny_exe, str(tmp_path), 0, 0, _pack_kmajor(w.numpy(), Mp), Mp, M, K, B, T, pre, 0.8660254, x.numpy(),
              b.numpy() if bias else None, r.numpy() if res else None, 0, K * T, T, M * T, T, M)
     assert np.abs(y.reshape(B, M, T) - ref.numpy()).max() < 2e-5
+
+
+@pytest.mark.parametrize("B,C,K,T,pre,dwb,skip,post", [
+    (1, 96, 96, 8, 1, True, True, 0),     # one stream, one hop at 75*8 Hz: ResBlock tail (skip), NT = 8
+    (1, 64, 128, 1, 2, True, False, 1),   # one frame per call: the window is cache + 1 sample; store-side ELU
+    (5, 32, 64, 3, 1, False, False, 0),   # five streams of 3 columns -> NT = 16 holds 5 whole streams
+    (3, 32, 48, 40, 0, True, True, 2),    # NT = 64 holds one 40-column stream per tile -> 3 column tiles
+    (9, 64, 32, 8, 1, True, True, 0),     # NT = 64: 8 streams per tile, second tile has one
+])
+def test_skinny_fused_dws_source_on_cpu(skinny_exe, tmp_path, B, C, K, T, pre, dwb, skip, post):
+    """DWSBlock for a short chunk in one launch: act -> 1x1 -> causal depthwise k5 (+cache) + bias + skip -> act."""
+    g = torch.Generator().manual_seed(C + K + T)
+    x = torch.randn(B, K, T, generator=g)
+    w = torch.randn(C, K, generator=g) / K ** 0.5
+    dw_w = torch.randn(C, 1, 5, generator=g) / 5 ** 0.5
+    dw_b = torch.randn(C, generator=g) if dwb else None
+    cache = torch.randn(B, C, 4, generator=g)
+    sk = torch.randn(B, C, T, generator=g) if skip else None
+    xin = x if pre == 0 else F.elu(x * 0.8660254 if pre == 2 else x)
+    v = F.conv1d(xin.double(), w.double()[:, :, None])
+    cat = torch.cat((cache.double(), v), 2)
+    ref = F.conv1d(cat, dw_w.double(), dw_b.double() if dwb else None, groups=C)
+    if skip:
+        ref = ref + sk.double()
+    if post:
+        ref = F.elu(ref * 0.7 if post == 2 else ref)
+    fin, fout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
+    Mp = (C + 31) // 32 * 32
+    parts = [_pack_kmajor(w.numpy(), Mp).ravel(), x.numpy().ravel(), dw_w.numpy().ravel()]
+    parts += ([dw_b.numpy()] if dwb else []) + [cache.numpy().ravel()] + ([sk.numpy().ravel()] if skip else [])
+    np.concatenate(parts).astype(np.float32).tofile(fin)
+    args = [0, 2, Mp, C, K, B, T, pre, 0.8660254, 0, 0, 0, K * T, T, C * T, T, C, fin, fout, int(dwb), int(skip), post, 0.7]
+    r = subprocess.run([skinny_exe] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    out = np.fromfile(fout, np.float32)
+    y, co = out[:B * C * T].reshape(B, C, T), out[B * C * T:].reshape(B, C, 4)
+    assert np.abs(y - ref.numpy()).max() < 3e-5
+    assert np.abs(co - cat[:, :, -4:].numpy()).max() < 3e-5
 
 
 def test_skinny_channel_last_source_on_cpu(skinny_exe, tmp_path):
