@@ -97,38 +97,47 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_kernel(const SkinnyParam
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[j] = 0.f;
 
-    for (int k0 = kbeg; k0 < kend; k0 += KC) {
-        // weights of the chunk: KC independent coalesced loads per lane, in flight together with the X loads
-        float a[KC];
+    // Software pipeline over chunks of KC k-rows: the weights (KC coalesced loads per lane) and the raw activations
+    // (XR loads per lane) of chunk c+1 are requested before chunk c is staged and multiplied, so that a warp always
+    // has one chunk of global loads in flight.
+    constexpr int XR = KC * NT / 32;
+    float a_cur[KC], a_nxt[KC], x_cur[XR], x_nxt[XR];
+    auto load_chunk = [&](int k0, float (&a)[KC], float (&x)[XR]) {
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
             const int k = k0 + kk;
             a[kk] = k < kend ? __ldg(p.A + (size_t)k * p.Mp + m0 + lane) : 0.f;
         }
-        // stage pre(X[k0 .. k0+KC) x columns) for this warp
-        if (LD == SK_PLAIN) {
-            // consecutive lanes -> consecutive columns (t contiguous in memory)
-            for (int i = lane; i < KC * NT; i += 32) {
-                const int kk = i / NT, j = i - kk * NT;
-                const int k = k0 + kk;
-                float v = 0.f;
-                if (k < kend && j < ncol) v = apply_pre(__ldg(p.X + coloff[j] + (long long)k * p.x_ks), p.pre, p.pre_scale);
-                xs[kk * NT + j] = v;
-            }
-        } else {
-            // consecutive lanes -> consecutive k (k contiguous in memory for channel-last / im2col inputs)
-            for (int i = lane; i < KC * NT; i += 32) {
-                const int j = i / KC, kk = i - j * KC;
-                const int k = k0 + kk;
-                float v = 0.f;
-                if (k < kend && j < ncol) v = __ldg(p.X + coloff[j] + k);
-                xs[kk * NT + j] = v;
-            }
+#pragma unroll
+        for (int r = 0; r < XR; ++r) {
+            const int i = lane + 32 * r;
+            // PLAIN: consecutive lanes -> consecutive columns (t contiguous in memory); CHLAST / IM2COL: consecutive
+            // lanes -> consecutive k (k contiguous in memory)
+            const int kk = LD == SK_PLAIN ? i / NT : i % KC;
+            const int j = LD == SK_PLAIN ? i % NT : i / KC;
+            const int k = k0 + kk;
+            float v = 0.f;
+            if (k < kend && j < ncol) v = __ldg(p.X + coloff[j] + (LD == SK_PLAIN ? (long long)k * p.x_ks : (long long)k));
+            x[r] = v;
+        }
+    };
+    if (kbeg < kend) load_chunk(kbeg, a_cur, x_cur);
+    for (int k0 = kbeg; k0 < kend; k0 += KC) {
+        if (k0 + KC < kend) load_chunk(k0 + KC, a_nxt, x_nxt);
+        // stage pre(X) of this chunk for the warp (pre() of a padded 0 may be non-zero, so padding is re-zeroed)
+#pragma unroll
+        for (int r = 0; r < XR; ++r) {
+            const int i = lane + 32 * r;
+            const int kk = LD == SK_PLAIN ? i / NT : i % KC;
+            const int j = LD == SK_PLAIN ? i % NT : i / KC;
+            float v = x_cur[r];
+            if (LD == SK_PLAIN && p.pre != PRE_NONE) v = (k0 + kk < kend && j < ncol) ? apply_pre(v, p.pre, p.pre_scale) : 0.f;
+            xs[kk * NT + j] = v;
         }
         __syncwarp();
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
-            const float av = a[kk];
+            const float av = a_cur[kk];
 #pragma unroll
             for (int q = 0; q < NT / 4; ++q) {
                 const float4 x4 = *reinterpret_cast<const float4*>(&xs[kk * NT + q * 4]);
@@ -139,6 +148,10 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_kernel(const SkinnyParam
             }
         }
         __syncwarp();
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) a_cur[kk] = a_nxt[kk];
+#pragma unroll
+        for (int r = 0; r < XR; ++r) x_cur[r] = x_nxt[r];
     }
 
     // partial sums -> shared memory, fixed-order reduction over the warps
