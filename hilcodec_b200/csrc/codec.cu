@@ -116,9 +116,10 @@ static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_b
                                float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                                cudaStream_t st) {
     const double n = (double)B * T;
-    const bool tmajor = g_use_tc && g_use_tm && gemm_tm_usable(W, X, x_bs, x_rs, T, Y, y_bs, y_rs);
-    const bool tcore = g_use_tc && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
-    const bool hcore = g_use_tc && g_use_h && gemm_h_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
+    const bool use_tc = g_use_tc && !gemm_skinny_preferred(W, B, T);
+    const bool tmajor = use_tc && g_use_tm && gemm_tm_usable(W, X, x_bs, x_rs, T, Y, y_bs, y_rs);
+    const bool tcore = use_tc && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
+    const bool hcore = use_tc && g_use_h && gemm_h_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
     // short chunks (streaming) that no tensor-core kernel takes: skinny-N kernel when enabled (HILCODEC_SKINNY=1)
     const bool skinny = !tmajor && !tcore && !hcore && gemm_skinny_usable(W, B, T);
     HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
@@ -147,7 +148,7 @@ static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
 static int32_t run_gemm_stft_logmag(const PackedMat& Wd, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
                                     long long y_bs, int y_rs, cudaStream_t st) {
     const double n = (double)B * T;
-    const bool tcore = g_use_tc && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs);
+    const bool tcore = g_use_tc && !gemm_skinny_preferred(Wd, B, T) && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs);
     HIL_LAUNCH(CAT_GEMM_STFT, 2.0 * Wd.M * Wd.K * n, 4.0 * (n * hop + n * (Wd.M / 2)) + 4.0 * Wd.M * Wd.K, st,
                tcore ? launch_stft_tc(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
                : gemm_skinny_usable(Wd, B, T) ? launch_gemm_skinny_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
@@ -181,7 +182,7 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
     const bool hcore = g_use_h && gemm_h_usable(W, X, bs, rs, T, skip, Y, bs, rs);
     // store-side ELU (post == PRE_ELU, no skip) exists in the fp16-split kernel only
     const bool post_ok = post == PRE_NONE || (post == PRE_ELU && !skip && hcore);
-    if (g_use_tc && g_fuse_dw && post_ok && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
+    if (g_use_tc && g_fuse_dw && post_ok && !gemm_skinny_preferred(W, B, T) && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
         const double n = (double)B * T;
         HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
                    4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
@@ -232,6 +233,7 @@ static int32_t run_upsample(const PackedMat& W, const float* x, long long x_bs, 
                             float* Y, long long y_bs, int y_rs, bool allow_fused, cudaStream_t st,
                             bool allow_fused_wide = false, bool allow_planes = false) {
     const int K = W.K, T = S * T_in;
+    if (gemm_skinny_preferred(W, B, T)) allow_fused = allow_fused_wide = allow_planes = false;
     if (allow_fused && g_use_tc && g_use_h && g_fuse_up && (W.M <= 256 || g_fuse_up_wide || allow_fused_wide) &&
         gemm_h_up_usable(W, x, x_bs, x_rs, T_in, S, pre, Y, y_bs, y_rs)) {
         const double n = (double)B * T;
@@ -915,7 +917,7 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     // matrices from L2 for every 56 outputs, which measured slower than two fused-DWS launches (HILCODEC_RB_WIDE=1
     // enables it for 128 < C <= 256)
     static const bool rb_wide = std::getenv("HILCODEC_RB_WIDE") != nullptr;
-    if (g_use_tc && g_use_h && g_fuse_dw && g_fuse_rb && (C <= 128 || rb_wide) &&
+    if (g_use_tc && g_use_h && g_fuse_dw && g_fuse_rb && (C <= 128 || rb_wide) && !gemm_skinny_preferred(u[0].pw, B, Ts) &&
         resblock_h_usable(u[0].pw, u[1].pw, h, bs, Tp, Ts))
         // a1 holds the halo columns (8 per tile: always smaller than an activation buffer)
         return run_resblock(u[0].pw, u[1].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, u[1].dw_w, u[1].dw_b,

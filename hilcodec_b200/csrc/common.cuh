@@ -89,6 +89,7 @@ bool gemm_skinny_usable(const PackedMat& W, int B, int T);
 cudaError_t launch_gemm_skinny_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                       float pre_scale, const float* bias, const float* R, float* Y, long long y_bs,
                                       int y_rs, cudaStream_t st);
+bool gemm_skinny_preferred(const PackedMat& W, int B, int T);  // over the tensor-core kernels (HILCODEC_SKINNY_PREFER=1)
 bool gemm_skinny_dws_usable(const PackedMat& W, int B, int T);
 cudaError_t launch_gemm_skinny_dws(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                    float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,

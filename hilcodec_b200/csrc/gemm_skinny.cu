@@ -287,6 +287,14 @@ bool gemm_skinny_usable(const PackedMat& W, int B, int T) {
     return on && W.A != nullptr && (W.Mp % SK_ROWS) == 0 && N > 0 && N <= max_n;
 }
 
+// HILCODEC_SKINNY_PREFER=1: also take the chunks a tensor-core kernel would accept (T >= 64) when the WHOLE launch is
+// small (N <= HILCODEC_SKINNY_MAXN): for one stream the 160- and 320-column layers are 2-3 tiles of a persistent
+// tcgen05 kernel whose fixed costs (TMEM allocation, barrier set-up, pipeline fill) outweigh the work.
+bool gemm_skinny_preferred(const PackedMat& W, int B, int T) {
+    static const bool on = [] { const char* e = std::getenv("HILCODEC_SKINNY_PREFER"); return e && e[0] == '1'; }();
+    return on && gemm_skinny_usable(W, B, T);
+}
+
 cudaError_t launch_gemm_skinny_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                       float pre_scale, const float* bias, const float* R, float* Y, long long y_bs,
                                       int y_rs, cudaStream_t st) {
