@@ -172,8 +172,174 @@ rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codeboo
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// v2 of the one-kernel search for LARGE batches (HILCODEC_RVQ_V2=1; off by default: emulation-verified bit-identical
+// to rvq_encode_kernel, not yet measured on a GPU).  Two changes, same arithmetic per frame:
+//  * FPW = 8 frames per warp instead of 4: per k4 step a warp issues 8 broadcast LDS.128 (residuals) + 4 four-wavefront
+//    LDS.128 (codes) = 24 shared-memory wavefronts for 128 FFMA instead of 20 for 64, which moves the inner loop from
+//    the LDS pipe (1 wavefront / clk / SM) to the FMA pipes (4 warp-FFMA / clk / SM);
+//  * the number of warps per CTA is chosen by the launcher so that ONE wave of 2 CTAs per SM covers all frames
+//    (config 3: 19 200 frames = 2400 warp units over 296 CTA slots -> 9 warps per CTA, 267 CTAs) instead of 600
+//    32-frame CTAs running as 2.03 -> 3 rounds.
+template <int FPW>
+__global__ void __launch_bounds__(288, 2)
+rvq_encode_v2_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee,
+                     int size, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum, int drop_xx) {
+    extern __shared__ __align__(16) float smem[];
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int FT = nwarps * FPW;                   // frames per CTA
+    float* R = smem;                               // [FT][RVQ_PITCH]
+    float* E = smem + (size_t)FT * RVQ_PITCH;      // [RVQ_CT][RVQ_PITCH]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long f0 = (long long)blockIdx.x * FT;
+
+    for (int i = tid; i < FT * (RVQ_DIM / 4); i += nthreads) {
+        const int fr = i / (RVQ_DIM / 4), k4 = i - fr * (RVQ_DIM / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f0 + fr < frames) v = *reinterpret_cast<const float4*>(z + (f0 + fr) * RVQ_DIM + k4 * 4);
+        *reinterpret_cast<float4*>(&R[fr * RVQ_PITCH + k4 * 4]) = v;
+    }
+    __syncthreads();
+
+    for (int s = 0; s < n; ++s) {
+        const float* cb = codebooks + (size_t)s * size * RVQ_DIM;
+        const float* ees = ee + (size_t)s * size;
+
+        float xx[FPW];
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const float4 v = *reinterpret_cast<const float4*>(&R[(warp * FPW + f) * RVQ_PITCH + lane * 4]);
+            float p = __fmul_rn(v.x, v.x);
+            p = fmaf(v.y, v.y, p); p = fmaf(v.z, v.z, p); p = fmaf(v.w, v.w, p);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            xx[f] = drop_xx ? 0.f : p;
+        }
+
+        float best[FPW];
+        int besti[FPW];
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) { best[f] = -INFINITY; besti[f] = 0x7fffffff; }
+
+        for (int c0 = 0; c0 < size; c0 += RVQ_CT) {
+            __syncthreads();  // previous tile fully consumed
+            for (int i = tid; i < RVQ_CT * (RVQ_DIM / 4); i += nthreads) {
+                const int cr = i / (RVQ_DIM / 4), k4 = i - cr * (RVQ_DIM / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + cr < size) v = *reinterpret_cast<const float4*>(cb + (size_t)(c0 + cr) * RVQ_DIM + k4 * 4);
+                *reinterpret_cast<float4*>(&E[cr * RVQ_PITCH + k4 * 4]) = v;
+            }
+            __syncthreads();
+
+            float dot[FPW][4];
+#pragma unroll
+            for (int f = 0; f < FPW; ++f)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dot[f][j] = 0.f;
+#pragma unroll 2
+            for (int k4 = 0; k4 < RVQ_DIM / 4; ++k4) {
+                float4 e4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    e4[j] = *reinterpret_cast<const float4*>(&E[(lane + 32 * j) * RVQ_PITCH + k4 * 4]);
+#pragma unroll
+                for (int f = 0; f < FPW; ++f) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(&R[(warp * FPW + f) * RVQ_PITCH + k4 * 4]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float d = dot[f][j];   // the same sequential-k FMA chain as rvq_encode_kernel
+                        d = fmaf(r4.x, e4[j].x, d);
+                        d = fmaf(r4.y, e4[j].y, d);
+                        d = fmaf(r4.z, e4[j].z, d);
+                        d = fmaf(r4.w, e4[j].w, d);
+                        dot[f][j] = d;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int code = c0 + lane + 32 * j;
+                if (code < size) {
+                    const float e2 = ees[code];
+#pragma unroll
+                    for (int f = 0; f < FPW; ++f) {
+                        const float d = -__fadd_rn(__fsub_rn(xx[f], __fmul_rn(2.f, dot[f][j])), e2);
+                        if (d > best[f]) { best[f] = d; besti[f] = code; }
+                    }
+                }
+            }
+        }
+
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            float bd = best[f];
+            int bi = besti[f];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bi < 0 || bi >= size) bi = 0;
+            const long long fr = f0 + warp * FPW + f;
+            const float4 e = *reinterpret_cast<const float4*>(cb + (size_t)bi * RVQ_DIM + lane * 4);
+            float4* rp = reinterpret_cast<float4*>(&R[(warp * FPW + f) * RVQ_PITCH + lane * 4]);
+            float4 r = *rp;
+            r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y); r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
+            *rp = r;
+            if (qsum && fr < frames) {
+                // the dequantised sum lives in its output row between stages (this lane's 16 bytes, L2-resident) instead
+                // of in 32 registers: q = ((0 + e_0) + e_1) + ... in stage order, as the one-kernel search
+                float4* qp = reinterpret_cast<float4*>(qsum + fr * RVQ_DIM + lane * 4);
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s > 0) q = *qp;
+                q.x = __fadd_rn(q.x, e.x); q.y = __fadd_rn(q.y, e.y); q.z = __fadd_rn(q.z, e.z); q.w = __fadd_rn(q.w, e.w);
+                *qp = q;
+            }
+            if (lane == 0 && fr < frames) idx[(size_t)s * frames + fr] = bi;
+        }
+        __syncwarp();
+    }
+
+}
+
+// warps per CTA such that one wave of `slots` CTAs covers all warp units when possible (<= 9 warps = 288 threads keeps
+// two CTAs per SM within the register and shared-memory budgets), otherwise 8
+int rvq_v2_warps(long long frames, int fpw, int slots) {
+    const long long units = (frames + fpw - 1) / fpw;
+    const long long w = (units + slots - 1) / slots;
+    if (w <= 9) return (int)(w < 1 ? 1 : w);
+    return 8;
+}
+
+static cudaError_t launch_rvq_encode_v2(const float* z, const float* codebooks, const float* ee, int size, long long frames,
+                                        int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
+    constexpr int FPW = 8;
+    static int slots = 0;
+    if (!slots) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 2 * (sms > 0 ? sms : 148);
+        const size_t max_smem = (size_t)(9 * FPW + RVQ_CT) * RVQ_PITCH * sizeof(float);
+        const cudaError_t e = cudaFuncSetAttribute(rvq_encode_v2_kernel<FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)max_smem);
+        if (e != cudaSuccess) { slots = 0; return e; }
+    }
+    const int warps = rvq_v2_warps(frames, FPW, slots);
+    const int ft = warps * FPW;
+    const size_t smem = (size_t)(ft + RVQ_CT) * RVQ_PITCH * sizeof(float);
+    const unsigned grid = (unsigned)((frames + ft - 1) / ft);
+    rvq_encode_v2_kernel<FPW><<<grid, warps * 32, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx ? 1 : 0);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
                               int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
+    static const bool v2 = [] { const char* e = std::getenv("HILCODEC_RVQ_V2"); return e && e[0] == '1'; }();
+    if (v2 && dim == RVQ_DIM && frames > 0 && n > 0)
+        return launch_rvq_encode_v2(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx, st);
     if (dim != RVQ_DIM) return cudaErrorInvalidValue;
     if (frames == 0 || n == 0) return cudaSuccess;
     static bool attr_set = false;

@@ -194,15 +194,19 @@ def rvq_exe(tmp_path_factory):
     consts = src[a:src.index("\n", b) + 1]
     mono = _function(src, src.index("__global__ void __launch_bounds__(256, 2)\nrvq_encode_kernel("))
     stage = _function(src, src.index("__global__ void __launch_bounds__(256, 2)\nrvq_stage_kernel("))
-    text = consts + mono + "\nstruct RvqCand { float d; int i; };\n" + stage
-    assert text.count("extern __shared__ __align__(16) float smem[];") == 2
+    v2 = _function(src, src.index("template <int FPW>\n__global__ void __launch_bounds__(288, 2)\nrvq_encode_v2_kernel("))
+    warps = _function(src, src.index("int rvq_v2_warps("))
+    text = consts + mono + "\nstruct RvqCand { float d; int i; };\n" + stage + "\n" + v2 + "\n" + warps
+    assert text.count("extern __shared__ __align__(16) float smem[];") == 3
     text = text.replace("extern __shared__ __align__(16) float smem[];", "float* smem = g_dyn_smem;")
     return _build(str(tmp_path_factory.mktemp("emu_rvq")), "rvq", "rvq_extracted.inc", text, "harness_rvq.cpp")
 
 
-@pytest.mark.parametrize("size,frames,n,drop_xx", [(1024, 5, 3, 0), (256, 40, 4, 1), (200, 33, 2, 0)])
-def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx):
-    """The one-kernel search against the oracle, and the per-stage variant bit-identical to it."""
+@pytest.mark.parametrize("size,frames,n,drop_xx,slots", [(1024, 5, 3, 0, 296), (256, 40, 4, 1, 2), (200, 33, 2, 0, 1),
+                                                          (128, 100, 2, 0, 1)])
+def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx, slots):
+    """The one-kernel search against the oracle; the per-stage variant and the large-batch v2 kernel (1, 3, 5 and 8
+    warps per CTA in these cases) bit-identical to it."""
     from oracle import hilcodec_oracle as O
 
     g = torch.Generator().manual_seed(size + frames)
@@ -211,15 +215,17 @@ def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx):
     cbs[0][7] = cbs[0][3]  # an exact tie: the first index must win
     fin, fout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
     np.concatenate([z.numpy().ravel()] + [c.numpy().ravel() for c in cbs]).astype(np.float32).tofile(fin)
-    r = subprocess.run([rvq_exe, str(size), str(frames), str(n), str(drop_xx), fin, fout], capture_output=True, text=True,
-                       timeout=900)
+    r = subprocess.run([rvq_exe, str(size), str(frames), str(n), str(drop_xx), fin, fout, str(slots)], capture_output=True,
+                       text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     raw = np.fromfile(fout, np.uint8)
     ni = n * frames * 8
     idx_a = raw[:ni].view(np.int64).reshape(n, frames)
     idx_b = raw[ni:2 * ni].view(np.int64).reshape(n, frames)
-    q = raw[2 * ni:].view(np.float32).reshape(2, frames, 128)
+    idx_c = raw[2 * ni:3 * ni].view(np.int64).reshape(n, frames)
+    q = raw[3 * ni:].view(np.float32).reshape(3, frames, 128)
     assert np.array_equal(idx_a, idx_b) and np.array_equal(q[0], q[1])  # split == one-kernel, bit for bit
+    assert np.array_equal(idx_a, idx_c) and np.array_equal(q[0], q[2])  # v2 == one-kernel, bit for bit
     assert not (idx_a[0] == 7).any()
     p = {f"quantizer.layers.{i}.embed": c for i, c in enumerate(cbs)}
     cfg = O.CodecConfig(num_quantizers=n, codebook_size=size)

@@ -11,3 +11,11 @@ for cfg in "HILCODEC_NONE=1" "HILCODEC_SKINNY=1" "HILCODEC_SKINNY=1 HILCODEC_RVQ
   env $cfg timeout 200 python tools/gpu/stream_time.py > gpurun_out/ab_stream_$tag.jsonl 2>&1
   echo "stream [$cfg] rc=$?"; grep -o '"streams": [0-9]*, "mode": "[a-z]*", "frames_timed": [0-9]*, "ms_per_frame": [0-9.]*' gpurun_out/ab_stream_$tag.jsonl
 done
+# large-batch RVQ v2 (8 frames per warp, one balanced wave): parity, then the headline step with and without it
+HILCODEC_RVQ_V2=1 timeout 300 python -m pytest tests -m gpu -x -q --tb=short -p no:cacheprovider > gpurun_out/ab_pytest_rvq_v2.log 2>&1
+echo "pytest [HILCODEC_RVQ_V2=1] rc=$?"; tail -3 gpurun_out/ab_pytest_rvq_v2.log | cut -c1-300
+for v in 0 1; do
+  HILCODEC_RVQ_V2=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_rvq_v2_$v.json 2> gpurun_out/ab_bench_rvq_v2_$v.err
+  echo "bench [HILCODEC_RVQ_V2=$v] rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/ab_bench_rvq_v2_$v.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('kernel_ms', d.get('profile', '')))" | cut -c1-600
+done
