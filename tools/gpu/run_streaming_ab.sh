@@ -17,5 +17,5 @@ echo "pytest [HILCODEC_RVQ_V2=1] rc=$?"; tail -3 gpurun_out/ab_pytest_rvq_v2.log
 for v in 0 1; do
   HILCODEC_RVQ_V2=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_rvq_v2_$v.json 2> gpurun_out/ab_bench_rvq_v2_$v.err
   echo "bench [HILCODEC_RVQ_V2=$v] rc=$?"; python -c "
-import json; d=json.loads(open('gpurun_out/ab_bench_rvq_v2_$v.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('kernel_ms', d.get('profile', '')))" | cut -c1-600
+import json; d=json.loads(open('gpurun_out/ab_bench_rvq_v2_$v.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('kernel_categories'))" | cut -c1-600
 done
