@@ -230,6 +230,36 @@ def test_full_size_properties_config2():
     assert bad == 0 or worst < 1e-5, (bad, worst)
 
 
+def test_full_size_properties_config3():
+    """BASELINE config 3 size (hil_music, 256 x 24000, n_q = 12: the bench workload, 19 200 frames per step): batch
+    rows are independent of the batch they ride in, outputs are finite and bounded by tanh, ||z_t|| = sqrt(128),
+    and dequantising the indices reproduces the decoder input."""
+    cfg = W.HIL_MUSIC
+    w = W.load_pretrained("hil_music") if W.have_pretrained("hil_music") else W.random_weights(cfg, 4)
+    m = _model(w, 12)
+    x = synth_wav(256, 24000, seed=4321).cuda()
+    idx, y = m.codec_forward(x, 12)
+    assert idx.shape == (12, 256, 75) and y.shape == (256, 1, 24000)
+    assert torch.isfinite(y).all() and y.abs().max().item() <= 1.0
+    assert int(idx.min()) >= 0 and int(idx.max()) < 1024
+    p = params(w)
+    for b in (0, 101, 255):
+        xb = x[b:b + 1].contiguous()
+        i1, y1 = m.codec_forward(xb, 12)
+        ce, _ = m.initialize_cache(xb)
+        zb, _ = m.encoder(xb, *ce)
+        bad, worst = index_report(oracle_cfg(12), p, zb, i1, idx[:, b:b + 1].cpu(), 12)
+        assert bad == 0 or worst < 1e-5, (b, bad, worst)
+        if bad == 0:
+            assert (y1[0] - y[b]).abs().max().item() < 1e-4
+    ce, cd = m.initialize_cache(x)
+    z, _ = m.encoder(x, *ce)
+    assert (z.norm(dim=2) - 128 ** 0.5).abs().max().item() < 1e-3
+    y2, _ = m.decoder(m.dequantizer(idx, 12), *cd)   # the four-call flow's second half on the fused path's indices
+    assert (y2 - y).abs().max().item() < 1e-4
+    del x, y, y2, z
+
+
 def test_config4_streaming_30s_clip():
     """BASELINE config 4: hil_music, one 30 s stream fed hop by hop (hop = 320: 2250 sequential frames; the
     config's "hop=300" is AudioDec's hop and cannot be fed to HILCodec) with the per-layer
