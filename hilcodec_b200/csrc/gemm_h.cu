@@ -82,6 +82,7 @@ struct Params {
     int reduce_add;         // 1: Y += tile (TMA reduce), 0: Y = tile
     int xform_sleep;        // ns of back-off in the transform warps' barrier polls (0 = spin)
     int post_elu;           // fused DWS only: store ELU(y) (the consumer then needs no activation prologue)
+    int cx;                 // 1: launched as 2-CTA clusters that share the activation boxes (see the X producer)
     int t_step, t_halo;     // tile tt covers columns [tt * t_step - t_halo, ... + BN)
     const float* dw_w;      // [M][5]
     const float* dw_b;      // [M] or null
@@ -237,6 +238,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + BK - 1) / BK;
+    // Activation-box sharing (HILCODEC_CLUSTER_X=1, plain and fused-DWS kernels, num_m even): the grid is launched as
+    // 2-CTA clusters; tiles are m-block-fastest, so with an even grid the two CTAs of a cluster always work on tiles 2j and
+    // 2j+1 = the same (b, t) columns and two different weight blocks.  Each X producer loads HALF of the [32 k][128 t] box
+    // (16 k-rows, map_xl = the half-height tensor map) and multicasts it into both CTAs' raw stage; each CTA's raw_full
+    // still expects the whole box.  A raw stage is therefore written by both producers and must be released to both:
+    // the transform warps arrive on their own raw_empty and on the peer's.
+    const bool cx = (kUp == 0 && kPl == 0) ? p.cx != 0 : false;
+    const uint32_t crank = cx ? cluster_ctarank() : 0u;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi);
@@ -247,7 +256,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int r = 0; r < RAW_STAGES; ++r) {
             mbar_init(raw_full(r), 1);
-            mbar_init(raw_empty(r), XW_PER_G);
+            mbar_init(raw_empty(r), cx ? 2 * XW_PER_G : XW_PER_G);   // cx: the peer CTA's transform warps release it too
         }
         for (int s = 0; s < OP_STAGES; ++s) {
             mbar_init(a_full(s), 1);
@@ -268,6 +277,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (cx) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to / arrives on them
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
 
     if (warp == 0) {
@@ -305,6 +315,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                         mbar_arrive_expect_tx(raw_full(r), XB + WB);
                         tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), up_box_start<kUp>(tt), kb * BK, b);
                         bulk_load(raw_base + r * RAW_BYTES + XB, p.up_w + (size_t)kb * BK * 2 * kUp, WB, raw_full(r));
+                    } else if (cx) {
+                        mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);   // my half + the peer's half
+                        tma_load_3d_mc(&map_xl, raw_base + r * RAW_BYTES + crank * (RAW_BYTES / 2), raw_full(r),
+                                       tt * p.t_step - p.t_halo, kb * BK + (int)crank * (BK / 2), b, (uint16_t)3);
                     } else {
                         mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
                         tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
@@ -429,6 +443,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 if (lane == 0) {
                     mbar_arrive(b_ready(s));
                     mbar_arrive(raw_empty(r));
+                    if (cx) mbar_arrive_remote(raw_empty(r), crank ^ 1u);
                 }
             }
         }
@@ -601,6 +616,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
+    if (cx) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         const uint32_t ncols = TMEM_COLS;
@@ -669,6 +685,49 @@ static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs,
     return cudaSuccess;
 }
 
+// HILCODEC_CLUSTER_X=1 (off by default: written at the end of round 1 without GPU time, compiled only): 2-CTA clusters
+// that share the activation boxes by TMA multicast, for layers with an even number of 128-row weight blocks and at
+// least HILCODEC_CLUSTER_X_MINM (default 384) output channels.  Returns the grid (0 = not applicable).
+template <class Kernel>
+static unsigned cluster_x_grid(Kernel kernel, const PackedMat& W, const th::Params& p, const float* X, long long x_bs, int x_rs,
+                               int B, int T, CUtensorMap* map_xh) {
+    using namespace th;
+    static const bool on = []() { const char* e = std::getenv("HILCODEC_CLUSTER_X"); return e && e[0] == '1'; }();
+    static const int min_m = []() { const char* e = std::getenv("HILCODEC_CLUSTER_X_MINM"); return e ? std::atoi(e) : 384; }();
+    if (!on || W.M < min_m || (p.num_m & 1) || (W.K % BK) != 0 || p.total_tiles < 2) return 0;
+    const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)x_rs * 4, (cuuint64_t)x_bs * 4};
+    const cuuint32_t box[3] = {BN, BK / 2, 1};
+    if (!tc::make_map(map_xh, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 0;
+    static int max_clusters = -1;   // the same for every instantiation: one 512-thread, ~225 KB CTA per SM
+    if (max_clusters < 0) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.gridDim = dim3(2 * (unsigned)tc::device_sm_count()); cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES; cfg.attrs = &attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 0; }
+        max_clusters = n;
+    }
+    if (max_clusters < 1) return 0;
+    const long long g = 2LL * max_clusters;
+    return (unsigned)(p.total_tiles < g ? p.total_tiles : g);   // total_tiles is even (num_m is)
+}
+
+template <class Kernel, class... Args>
+static cudaError_t launch_clustered(Kernel kernel, unsigned grid, cudaStream_t st, Args... args) {
+    using namespace th;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static cudaError_t seed_residual(const float* R, float* Y, long long y_bs, int y_rs, int B, int M, int T, cudaStream_t st) {
     for (int b = 0; b < B; ++b) {   // out-of-place residual: seed Y with R, then accumulate in place
         cudaError_t e = cudaMemcpy2DAsync(Y + (long long)b * y_bs, (size_t)y_rs * 4, R + (long long)b * y_bs, (size_t)y_rs * 4,
@@ -707,10 +766,16 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    if (two_epilogue_groups(W.K, false))
+    if (two_epilogue_groups(W.K, false)) {
         gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
-    else
+    } else {
+        CUtensorMap map_xh;
+        if (const unsigned cgrid = cluster_x_grid(gemm_h_kernel<false>, W, p, X, x_bs, x_rs, B, T, &map_xh)) {
+            p.cx = 1;
+            return launch_clustered(gemm_h_kernel<false>, cgrid, st, map_hi, map_lo, map_x, map_xh, map_y, map_y, p);
+        }
         gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
+    }
     return cudaGetLastError();
 }
 
@@ -886,10 +951,16 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    if (two_epilogue_groups(W.K, true))
+    if (two_epilogue_groups(W.K, true)) {
         gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y28, p);
-    else
+    } else {
+        CUtensorMap map_xh;
+        if (const unsigned cgrid = cluster_x_grid(gemm_h_kernel<true>, W, p, X, x_bs, x_rs, B, T, &map_xh)) {
+            p.cx = 1;
+            return launch_clustered(gemm_h_kernel<true>, cgrid, st, map_hi, map_lo, map_x, map_xh, map_y, map_y28, p);
+        }
         gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y28, p);
+    }
     return cudaGetLastError();
 }
 

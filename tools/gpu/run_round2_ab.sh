@@ -19,3 +19,12 @@ for v in 0 1; do
   echo "bench [HILCODEC_RVQ_V2=$v] rc=$?"; python -c "
 import json; d=json.loads(open('gpurun_out/ab_bench_rvq_v2_$v.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('kernel_categories'))" | cut -c1-600
 done
+# activation-box multicast across 2-CTA clusters in the wide layers (gemm_h.cu, HILCODEC_CLUSTER_X=1): parity first (a
+# protocol error traps -> launch failure, not a hang; the outer timeout bounds it anyway), then the headline step
+HILCODEC_CLUSTER_X=1 timeout 300 python -m pytest tests/test_gpu_codec.py tests/test_gpu_ops.py -x -q --tb=short -p no:cacheprovider > gpurun_out/ab_pytest_cluster_x.log 2>&1
+echo "pytest [HILCODEC_CLUSTER_X=1] rc=$?"; tail -3 gpurun_out/ab_pytest_cluster_x.log | cut -c1-300
+for v in 0 1; do
+  HILCODEC_CLUSTER_X=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_cluster_x_$v.json 2> gpurun_out/ab_bench_cluster_x_$v.err
+  echo "bench [HILCODEC_CLUSTER_X=$v] rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/ab_bench_cluster_x_$v.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('kernel_categories'))" | cut -c1-600
+done
