@@ -27,6 +27,7 @@ struct alignas(16) float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
 inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 // compiled with -ffp-contract=off: these stay separately rounded operations
@@ -56,9 +57,10 @@ template <class T> inline T __shfl_xor_sync(unsigned, T v, int o) {
 }
 
 // run `kernel()` for every CTA of the grid (CTAs one after the other, the threads of a CTA concurrently)
-template <class F> void emu_launch(unsigned gx, unsigned gy, unsigned threads, F kernel) {
-    gridDim = {gx, gy, 1};
+template <class F> void emu_launch(unsigned gx, unsigned gy, unsigned threads, F kernel, unsigned gz = 1) {
+    gridDim = {gx, gy, gz};
     blockDim = {threads, 1, 1};
+    for (unsigned bz = 0; bz < gz; ++bz)
     for (unsigned by = 0; by < gy; ++by)
         for (unsigned bx = 0; bx < gx; ++bx) {
             std::barrier<> cta((std::ptrdiff_t)threads);
@@ -69,7 +71,7 @@ template <class F> void emu_launch(unsigned gx, unsigned gy, unsigned threads, F
             for (unsigned t = 0; t < threads; ++t)
                 ts.emplace_back([=, &kernel] {
                     threadIdx = {t, 0, 0};
-                    blockIdx = {bx, by, 0};
+                    blockIdx = {bx, by, bz};
                     kernel();
                     emu::cta_bar->arrive_and_drop();               // a thread that returned no longer takes part
                     emu::warp_bar[t >> 5]->arrive_and_drop();

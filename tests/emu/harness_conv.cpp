@@ -1,0 +1,71 @@
+// Runs conv.cu's causal depthwise kernels (source text extracted into conv_extracted.inc) on the CPU emulation layer
+// with the launch geometry of launch_dwconv / launch_dwconv_transpose.
+// argv: mode K S B C T pre pre_scale has_bias has_skip post post_scale in.bin out.bin
+//   mode 0 dwconv_kernel<K,S>   1 dwconv5_kernel   2 dwconv_strided4_kernel<K,S>   3 dwconvT_kernel<S> (K = 2S)
+// rows are pitched to a multiple of 4 floats.  in.bin = x[B*C*Tp] cache[B*C*P] w[C*K] bias[C]? skip[B*C*Top]?
+// out.bin = y[B*C*Top] cache_out[B*C*P]        (mode 3: P = 1, no bias / skip / post, T_out = S*T)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cuda_emu.h"
+namespace hil {
+#include "conv_extracted.inc"
+}
+using namespace hil;
+
+int main(int argc, char** argv) {
+    if (argc != 15) return 2;
+    int a = 1;
+    const int mode = atoi(argv[a++]), K = atoi(argv[a++]), S = atoi(argv[a++]), B = atoi(argv[a++]), C = atoi(argv[a++]);
+    const int T = atoi(argv[a++]), pre = atoi(argv[a++]);
+    const float pre_scale = (float)atof(argv[a++]);
+    const int has_bias = atoi(argv[a++]), has_skip = atoi(argv[a++]), post = atoi(argv[a++]);
+    const float post_scale = (float)atof(argv[a++]);
+    const char* fin = argv[a++]; const char* fout = argv[a++];
+    const int P = mode == 3 ? 1 : K - S;
+    const int T_out = mode == 3 ? S * T : (P + T - K) / S + 1;
+    const int Tp = (T + 3) & ~3, Top = (T_out + 3) & ~3;
+    const size_t nx = (size_t)B * C * Tp, nc = (size_t)B * C * P, nw = (size_t)C * K, ny = (size_t)B * C * Top;
+    std::vector<float> in(nx + nc + nw + (has_bias ? C : 0) + (has_skip ? ny : 0));
+    FILE* f = std::fopen(fin, "rb");
+    if (std::fread(in.data(), 4, in.size(), f) != in.size()) return 3;
+    std::fclose(f);
+    const float* x = in.data(); const float* ci = x + nx; const float* w = ci + nc;
+    const float* bias = has_bias ? w + nw : nullptr;
+    const float* skip = has_skip ? w + nw + (has_bias ? C : 0) : nullptr;
+    std::vector<float> y(ny, -12345.f), co(nc, -12345.f);
+    const long long x_bs = (long long)C * Tp, y_bs = (long long)C * Top;
+    auto grid_x = [](int n, int threads) { return (unsigned)max(1, min((n + threads - 1) / threads, 512)); };
+#define ARGS x, x_bs, Tp, ci, co.data(), w, bias, skip, y.data(), y_bs, Top, C, T
+    if (mode == 1) {
+        const int Tq = (T + 3) / 4, th = Tq >= 128 ? 128 : 32;
+        emu_launch(grid_x(Tq, th), C, th, [&] { dwconv5_kernel(ARGS, pre, pre_scale, post, post_scale); }, B);
+    } else if (mode == 0 || mode == 2) {
+        const int n = mode == 2 ? (T_out + 3) / 4 : T_out, th = n >= 128 ? 128 : 32;
+        const unsigned gx = grid_x(n, th);
+#define RUN(KK, SS)                                                                                                      \
+    if (K == KK && S == SS) {                                                                                            \
+        if (mode == 2) emu_launch(gx, C, th, [&] { dwconv_strided4_kernel<KK, SS>(ARGS, T_out, pre, pre_scale, post, post_scale); }, B); \
+        else emu_launch(gx, C, th, [&] { dwconv_kernel<KK, SS>(ARGS, T_out, pre, pre_scale, post, post_scale); }, B);   \
+    }
+        RUN(4, 2) RUN(8, 4) RUN(10, 5) RUN(16, 8)
+        if (K == 5 && S == 1 && mode == 0)
+            emu_launch(gx, C, th, [&] { dwconv_kernel<5, 1>(ARGS, T_out, pre, pre_scale, post, post_scale); }, B);
+#undef RUN
+    } else if (mode == 3) {
+        const int Tq = (T + 3) / 4, th = Tq >= 128 ? 128 : 32;
+        const unsigned gx = grid_x(Tq, th);
+#define RUNT(SS) \
+    if (S == SS) emu_launch(gx, C, th, [&] { dwconvT_kernel<SS>(x, x_bs, Tp, ci, co.data(), w, y.data(), y_bs, Top, C, T, pre, pre_scale, 1); }, B);
+        RUNT(2) RUNT(4) RUNT(5) RUNT(8)
+#undef RUNT
+    } else {
+        return 4;
+    }
+    f = std::fopen(fout, "wb");
+    std::fwrite(y.data(), 4, y.size(), f);
+    std::fwrite(co.data(), 4, co.size(), f);
+    std::fclose(f);
+    return 0;
+}

@@ -243,3 +243,94 @@ def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx, 
         assert all(float(gaps[first[f], 0, f]) < 1e-5 for f in bad)
     else:
         assert np.array_equal(q[0], q_ref[0].numpy())
+
+
+# ------------------------------------------------------------------------------------------ conv.cu
+@pytest.fixture(scope="module")
+def conv_exe(tmp_path_factory):
+    src = open(os.path.join(CSRC, "conv.cu")).read()
+    parts = []
+    for sig in ("template <int K, int S>\n__global__ void dwconv_kernel(", "__global__ void dwconv5_kernel(",
+                "template <int K, int S>\n__global__ void dwconv_strided4_kernel(",
+                "template <int S>\n__global__ void dwconvT_kernel("):
+        parts.append(_function(src, src.index(sig)))
+    act = ("inline float apply_act_fast(float x, int mode, float s) {\n"
+           "    if (mode == PRE_NONE) return x;\n    if (mode == PRE_SCALE_ELU) x = x * s;\n"
+           "    return x > 0.f ? x : expm1f(x);\n}\n")
+    return _build(str(tmp_path_factory.mktemp("emu_conv")), "conv", "conv_extracted.inc",
+                  _common_bits() + "\n" + act + "\n".join(parts), "harness_conv.cpp")
+
+
+def _pitched(t):
+    """[B,C,T] -> rows padded to a multiple of 4 floats (the library's activation layout)."""
+    B, C, T = t.shape
+    Tp = (T + 3) // 4 * 4
+    out = np.zeros((B, C, Tp), np.float32)
+    out[:, :, :T] = t.numpy()
+    return out
+
+
+@pytest.mark.parametrize("mode,K,S,B,C,T,pre,bias,skip,post", [
+    (1, 5, 1, 2, 3, 37, 1, True, True, 0),     # dwconv5: 4 outputs per thread, ragged last group, ELU prologue, skip
+    (1, 5, 1, 1, 2, 1, 0, True, False, 1),     # one frame per call: the window is the cache + 1 sample; store-side ELU
+    (1, 5, 1, 1, 2, 600, 2, False, False, 2),  # 150 groups -> 128-thread CTAs, two of them
+    (0, 5, 1, 2, 2, 3, 0, True, False, 0),     # generic kernel, chunk shorter than the cache
+    (0, 16, 8, 1, 3, 8, 0, True, False, 0),    # encoder downsampling, one frame per call (k = 2r, s = r)
+    (0, 10, 5, 2, 2, 40, 1, True, True, 0),
+    (2, 4, 2, 2, 3, 320, 0, True, False, 0),   # vectorised strided kernel
+    (2, 8, 4, 1, 2, 72, 0, True, False, 0),    # 18 outputs: ragged last group of 4
+    (2, 10, 5, 1, 2, 600, 0, True, True, 1),   # stride 5: unaligned history
+    (2, 16, 8, 1, 2, 600, 0, False, False, 0),
+])
+def test_depthwise_kernels_source_on_cpu(conv_exe, tmp_path, mode, K, S, B, C, T, pre, bias, skip, post):
+    """CausalConv1d.forward causal_layers.py:160-165 (depthwise) through the three kernels of conv.cu."""
+    g = torch.Generator().manual_seed(K * 100 + T)
+    P = K - S
+    x = torch.randn(B, C, T, generator=g)
+    cache = torch.randn(B, C, P, generator=g)
+    w = torch.randn(C, 1, K, generator=g) / K ** 0.5
+    b = torch.randn(C, generator=g) if bias else None
+    xin = torch.cat((cache, x if pre == 0 else F.elu(x * 0.77 if pre == 2 else x)), 2)
+    ref = F.conv1d(xin.double(), w.double(), b.double() if bias else None, stride=S, groups=C)
+    T_out = ref.shape[2]
+    sk = torch.randn(B, C, T_out, generator=g) if skip else None
+    if skip:
+        ref = ref + sk.double()
+    if post:
+        ref = F.elu(ref * 0.6 if post == 2 else ref)
+    fin, fout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
+    parts = [_pitched(x).ravel(), cache.numpy().ravel(), w.numpy().ravel()] + ([b.numpy()] if bias else []) + \
+            ([_pitched(sk).ravel()] if skip else [])
+    np.concatenate(parts).astype(np.float32).tofile(fin)
+    args = [mode, K, S, B, C, T, pre, 0.77, int(bias), int(skip), post, 0.6, fin, fout]
+    r = subprocess.run([conv_exe] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    out = np.fromfile(fout, np.float32)
+    Top = (T_out + 3) // 4 * 4
+    y = out[:B * C * Top].reshape(B, C, Top)[:, :, :T_out]
+    co = out[B * C * Top:].reshape(B, C, P)
+    assert np.abs(y - ref.numpy()).max() < 1e-5
+    assert np.abs(co - xin[:, :, -P:].numpy()).max() < 1e-6
+
+
+@pytest.mark.parametrize("S,B,C,T,pre", [(2, 2, 3, 40, 2), (4, 1, 2, 1, 0), (5, 1, 2, 37, 1), (8, 2, 2, 600, 2)])
+def test_transposed_depthwise_kernel_source_on_cpu(conv_exe, tmp_path, S, B, C, T, pre):
+    """CausalConvTranspose1d.forward causal_layers.py:183-188 (depthwise, k = 2s) with its one-sample cache."""
+    g = torch.Generator().manual_seed(S * 10 + T)
+    x = torch.randn(B, C, T, generator=g)
+    cache = torch.randn(B, C, 1, generator=g)
+    w = torch.randn(C, 1, 2 * S, generator=g)
+    xin = torch.cat((cache, x if pre == 0 else F.elu(x * 0.77 if pre == 2 else x)), 2)
+    ref = F.conv_transpose1d(xin.double(), w.double(), None, stride=S, padding=S, output_padding=0, groups=C)
+    assert ref.shape[2] == S * T
+    fin, fout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
+    np.concatenate([_pitched(x).ravel(), cache.numpy().ravel(), w.numpy().ravel()]).astype(np.float32).tofile(fin)
+    args = [3, 2 * S, S, B, C, T, pre, 0.77, 0, 0, 0, 1.0, fin, fout]
+    r = subprocess.run([conv_exe] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    out = np.fromfile(fout, np.float32)
+    Top = (S * T + 3) // 4 * 4
+    y = out[:B * C * Top].reshape(B, C, Top)[:, :, :S * T]
+    co = out[B * C * Top:].reshape(B, C, 1)
+    assert np.abs(y - ref.numpy()).max() < 1e-5
+    assert np.abs(co - xin[:, :, -1:].numpy()).max() < 1e-6
