@@ -17,12 +17,15 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
+#include <cstddef>
+using std::size_t;
 
 struct uint3e { unsigned x = 0, y = 0, z = 0; };
 inline thread_local uint3e threadIdx, blockIdx;
 inline uint3e blockDim, gridDim;
 
+struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 

@@ -334,3 +334,85 @@ def test_transposed_depthwise_kernel_source_on_cpu(conv_exe, tmp_path, S, B, C, 
     co = out[B * C * Top:].reshape(B, C, 1)
     assert np.abs(y - ref.numpy()).max() < 1e-5
     assert np.abs(co - xin[:, :, -1:].numpy()).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ gemm.cu
+@pytest.fixture(scope="module")
+def gemm_exe(tmp_path_factory):
+    src = open(os.path.join(CSRC, "gemm.cu")).read()
+    a = src.index("enum { LD_PLAIN")
+    k = src.index("template <int TM, int LD, int EPI>\n__global__")
+    return _build(str(tmp_path_factory.mktemp("emu_gemm")), "gemm", "gemm_extracted.inc",
+                  _common_bits() + "\n" + src[a:k] + _function(src, k), "harness_gemm.cpp")
+
+
+def _tm(M):
+    """choose_tm() of gemm.cu."""
+    if M % 128 == 0:
+        return 8
+    if M % 96 == 0:
+        return 6
+    if M % 64 == 0:
+        return 4
+    if M > 256:
+        return 8
+    return 8 if M > 96 else (6 if M > 64 else 4)
+
+
+def _run_gemm(exe, tmp, LD, EPI, TM, A, Mp, M, K, B, T, pre, X, bias, R, hop, x_bs, x_rs, y_bs, y_rs, M_out):
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    parts = [A.ravel(), X.ravel()] + ([bias.ravel()] if bias is not None else []) + ([R.ravel()] if R is not None else [])
+    np.concatenate(parts).astype(np.float32).tofile(fin)
+    args = [LD, EPI, TM, Mp, M, K, B, T, pre, 0.8660254, int(bias is not None), int(R is not None), hop, x_bs, x_rs, y_bs,
+            y_rs, M_out, fin, fout]
+    r = subprocess.run([exe] + [str(v) for v in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    return np.fromfile(fout, np.float32)
+
+
+@pytest.mark.parametrize("B,M,K,T,pre,bias,res", [
+    (2, 64, 33, 75, 0, True, True),      # TM = 4, odd K, ragged T (scalar loads), bias + residual
+    (1, 96, 192, 8, 2, True, False),     # TM = 6, one hop of one stream: 8 of 128 columns used
+    (3, 128, 100, 44, 1, False, False),  # TM = 8, N = 132 -> two column tiles over three streams (vector loads)
+    (1, 100, 70, 5, 1, True, True),      # M not a multiple of the row tile
+])
+def test_ffma_gemm_source_on_cpu(gemm_exe, tmp_path, B, M, K, T, pre, bias, res):
+    g = torch.Generator().manual_seed(M + K + T)
+    x = torch.randn(B, K, T, generator=g)
+    w = torch.randn(M, K, generator=g) / K ** 0.5
+    b = torch.randn(M, generator=g) if bias else None
+    r = torch.randn(B, M, T, generator=g) if res else None
+    xin = x if pre == 0 else F.elu(x * 0.8660254 if pre == 2 else x)
+    ref = F.conv1d(xin.double(), w.double()[:, :, None], b.double() if bias else None)
+    if res:
+        ref = ref + r.double()
+    TM = _tm(M)
+    Mp = (M + 16 * TM - 1) // (16 * TM) * (16 * TM)
+    y = _run_gemm(gemm_exe, str(tmp_path), 0, 0, TM, _pack_kmajor(w.numpy(), Mp), Mp, M, K, B, T, pre, x.numpy(),
+                  b.numpy() if bias else None, r.numpy() if res else None, 0, K * T, T, M * T, T, M)
+    assert np.abs(y.reshape(B, M, T) - ref.numpy()).max() < 2e-5
+
+
+def test_ffma_gemm_channel_last_and_stft_source_on_cpu(gemm_exe, tmp_path):
+    from hilcodec_b200.weights import dft_basis
+    g = torch.Generator().manual_seed(11)
+    B, Fr, K, M = 2, 3, 128, 192
+    q = torch.randn(B, Fr, K, generator=g)
+    w = torch.randn(M, K, generator=g) / K ** 0.5
+    ref = F.conv1d(q.transpose(1, 2).double(), w.double()[:, :, None])
+    y = _run_gemm(gemm_exe, str(tmp_path), 1, 0, 6, _pack_kmajor(w.numpy(), M), M, M, K, B, Fr, 0, q.numpy(), None, None,
+                  0, 0, 0, M * Fr, Fr, M)
+    assert np.abs(y.reshape(B, M, Fr) - ref.numpy()).max() < 2e-5
+    n_fft, hop, T = 64, 8, 5
+    L = (T - 1) * hop + n_fft
+    wav = 0.1 * torch.randn(B, 1, L, generator=g)
+    basis = torch.from_numpy(dft_basis(n_fft))
+    F2 = n_fft // 2 + 1
+    s = F.conv1d(wav.double(), basis.double(), None, stride=hop).view(B, 2, F2, T)
+    ref = s.square().sum(1).sqrt().clamp_min(1e-5).log()
+    inter = torch.stack((basis[:F2, 0], basis[F2:, 0]), 1).reshape(2 * F2, n_fft)
+    Mp = (2 * F2 + 95) // 96 * 96
+    y = _run_gemm(gemm_exe, str(tmp_path), 2, 1, 6, _pack_kmajor(inter.numpy(), Mp), Mp, 2 * F2, n_fft, B, T, 0, wav.numpy(),
+                  None, None, hop, L, 0, F2 * T, T, F2)
+    err = np.abs(y.reshape(B, F2, T) - ref.numpy())
+    assert np.median(err) < 1e-5 and err.max() < 1e-2
