@@ -37,6 +37,7 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
 
 alignas(16) inline float g_dyn_smem[64 * 1024];  // 256 KB: "dynamic shared memory" of the one CTA that is running
 

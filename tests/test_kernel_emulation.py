@@ -416,3 +416,92 @@ def test_ffma_gemm_channel_last_and_stft_source_on_cpu(gemm_exe, tmp_path):
                   None, None, hop, L, 0, F2 * T, T, F2)
     err = np.abs(y.reshape(B, F2, T) - ref.numpy())
     assert np.median(err) < 1e-5 and err.max() < 1e-2
+
+
+# ------------------------------------------------------------------------------------------ glue kernels
+@pytest.fixture(scope="module")
+def misc_exe(tmp_path_factory):
+    conv = open(os.path.join(CSRC, "conv.cu")).read()
+    bitp = open(os.path.join(CSRC, "bitpack.cu")).read()
+    parts = [_function(conv, conv.index(sig)) for sig in (
+        "__global__ void wavcat_kernel(", "template <int K>\n__global__ void conv_pre_kernel(",
+        "template <int K>\n__global__ void conv_post_tanh_kernel(", "__global__ void l2norm_chlast_kernel(")]
+    parts += [_function(bitp, bitp.index(sig)) for sig in ("__global__ void pack_indices_kernel(",
+                                                           "__global__ void unpack_indices_kernel(")]
+    text = "\n".join(parts)
+    assert text.count("extern __shared__ float sw[];") == 2
+    text = text.replace("extern __shared__ float sw[];", "float* sw = g_dyn_smem;")
+    act = ("inline float apply_act_ex2(float x, int mode, float s) {\n"   # ex2.approx stand-in, differs by <= 2.4e-7
+           "    if (mode == PRE_NONE) return x;\n    if (mode == PRE_SCALE_ELU) x = x * s;\n"
+           "    return x > 0.f ? x : expm1f(x);\n}\n")
+    return _build(str(tmp_path_factory.mktemp("emu_misc")), "misc", "misc_extracted.inc", _common_bits() + "\n" + act + text,
+                  "harness_misc.cpp")
+
+
+def _misc(exe, tmp, args, arrays):
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    with open(fin, "wb") as f:
+        for a in arrays:
+            f.write(np.ascontiguousarray(a).tobytes())
+    r = subprocess.run([exe] + [str(a) for a in args] + [fin, fout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    return np.fromfile(fout, np.uint8)
+
+
+@pytest.mark.parametrize("n,frames", [(8, 300), (12, 129), (1, 5), (3, 77)])
+def test_bitpack_kernels_source_on_cpu(misc_exe, tmp_path, n, frames):
+    """Byte-exact against the numpy statement of the format, and unpack(pack(x)) == x."""
+    from oracle import bitstream_oracle
+    rng = np.random.default_rng(n)
+    idx = rng.integers(0, 1024, size=(n, 1, frames)).astype(np.int64)
+    idx[:, 0, 0] = 1023
+    raw = _misc(misc_exe, str(tmp_path), ["pack", frames, n, 10], [idx])
+    bpf = bitstream_oracle.bytes_per_frame(n)
+    packed = raw[:frames * bpf].reshape(1, frames, bpf)
+    back = raw[frames * bpf:].view(np.int64).reshape(n, 1, frames)
+    assert np.array_equal(packed, bitstream_oracle.pack_numpy(idx))
+    assert np.array_equal(back, idx)
+
+
+def test_encoder_head_and_tail_kernels_source_on_cpu(misc_exe, tmp_path):
+    g = torch.Generator().manual_seed(5)
+    # wav history concat (Encoder.forward streaming.py:485-488)
+    B, T, P = 2, 37, 15
+    x, cache = torch.randn(B, T, generator=g), torch.randn(B, P, generator=g)
+    raw = _misc(misc_exe, str(tmp_path), ["wavcat", B, T, P], [x.numpy(), cache.numpy()]).view(np.float32)
+    Wp = (P + T + 3) // 4 * 4
+    cat = torch.cat((cache, x), 1).numpy()
+    assert np.array_equal(raw[:B * Wp].reshape(B, Wp)[:, :P + T], cat)
+    assert np.array_equal(raw[B * Wp:].reshape(B, P), cat[:, -P:])
+    # conv_pre (streaming.py:490): 1 -> C channels, 5 taps, on [4 history samples | chunk]
+    B, C, T = 2, 6, 1030
+    win = torch.randn(B, 1, T + 4, generator=g)
+    w, b = torch.randn(C, 1, 5, generator=g), torch.randn(C, generator=g)
+    ref = F.conv1d(win.double(), w.double(), b.double())
+    raw = _misc(misc_exe, str(tmp_path), ["convpre", B, C, T], [win.numpy(), w.numpy(), b.numpy()]).view(np.float32)
+    Tp = (T + 3) // 4 * 4
+    assert np.abs(raw.reshape(B, C, Tp)[:, :, :T] - ref.numpy()).max() < 1e-5
+    # L2Norm + transpose (streaming.py:284-285, :517)
+    B, C, Fr = 3, 128, 7
+    h = torch.randn(B, C, Fr, generator=g)
+    h[1, :, 2] = 0.0   # zero vector: the 1e-12 clamp
+    ref = (F.normalize(h.double(), p=2.0, dim=1, eps=1e-12) * 128 ** 0.5).transpose(1, 2)
+    raw = _misc(misc_exe, str(tmp_path), ["l2norm", B, C, Fr, 128 ** 0.5], [_pitched(h)]).view(np.float32)
+    assert np.abs(raw.reshape(B, Fr, C) - ref.numpy()).max() < 1e-5
+
+
+@pytest.mark.parametrize("B,C,T,pre", [(2, 96, 45, 2), (1, 8, 1, 1), (1, 16, 2100, 0)])
+def test_decoder_tail_kernel_source_on_cpu(misc_exe, tmp_path, B, C, T, pre):
+    """Decoder.forward streaming.py:644-647: (scale ->) ELU -> CausalConv1d(C -> 1, k5) -> Tanh, with its cache."""
+    g = torch.Generator().manual_seed(C + T)
+    x = torch.randn(B, C, T, generator=g)
+    cache = torch.randn(B, C, 4, generator=g)
+    w = torch.randn(1, C, 5, generator=g) / (5 * C) ** 0.5
+    b = torch.randn(1, generator=g)
+    act = x if pre == 0 else F.elu(x * 0.70710677 if pre == 2 else x)
+    xin = torch.cat((cache, act), 2)
+    ref = torch.tanh(F.conv1d(xin.double(), w.double(), b.double()))
+    raw = _misc(misc_exe, str(tmp_path), ["convpost", B, C, T, pre, 0.70710677],
+                [_pitched(x), cache.numpy(), w.numpy(), b.numpy()]).view(np.float32)
+    assert np.abs(raw[:B * T].reshape(B, 1, T) - ref.numpy()).max() < 1e-5
+    assert np.abs(raw[B * T:].reshape(B, C, 4) - xin[:, :, -4:].numpy()).max() < 1e-6
