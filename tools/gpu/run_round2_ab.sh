@@ -6,7 +6,7 @@ for cfg in "HILCODEC_SKINNY=1" "HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1" "HILCODE
   env $cfg timeout 300 python -m pytest tests -m gpu -x -q --tb=short -p no:cacheprovider > gpurun_out/ab_pytest_$tag.log 2>&1
   echo "pytest [$cfg] rc=$?"; tail -3 gpurun_out/ab_pytest_$tag.log | cut -c1-300
 done
-for cfg in "HILCODEC_NONE=1" "HILCODEC_SKINNY=1" "HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1" "HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1 HILCODEC_SKINNY_PREFER=1"; do
+for cfg in "HILCODEC_NONE=1" "HILCODEC_SKINNY=1" "HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1" "HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1 HILCODEC_SKINNY_PREFER=1" "HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1 HILCODEC_SKINNY_MAXN=4096"; do
   tag=$(echo "$cfg" | tr ' =' '__')
   env $cfg timeout 200 python tools/gpu/stream_time.py > gpurun_out/ab_stream_$tag.jsonl 2>&1
   echo "stream [$cfg] rc=$?"; grep -o '"streams": [0-9]*, "mode": "[a-z]*", "frames_timed": [0-9]*, "ms_per_frame": [0-9.]*' gpurun_out/ab_stream_$tag.jsonl
