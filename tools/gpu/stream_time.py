@@ -38,3 +38,28 @@ for B in (1, 64):
                           "mode": mode, "frames_timed": n, "ms_per_frame": dt * 1e3, "frames_per_s": B / dt,
                           "x_realtime_per_stream": (1 / 75) / dt, "weights": "published" if pre else "random-init"}),
               flush=True)
+
+# Where a frame goes: the library's own event-bracketed launch profile (hil_profile_begin / hil_profile_end, the
+# categories bench.py reports) over 50 eager frames of one stream.  Per-launch event pairs add ~2 us each, so the SHARES
+# matter, not the sum.
+import ctypes as C
+
+from hilcodec_b200 import _lib
+
+lib = _lib.load()
+CATS = ["pointwise_gemm", "stft_gemm", "depthwise", "depthwise_transposed", "conv_pre", "conv_post_tanh", "rvq", "misc"]
+for B in (1, 64):
+    x = (0.1 * torch.randn(B, 1, 320 * 80, device="cuda")).clamp(-1, 1)
+    st = m.new_stream_state(B)
+    for f in range(20):
+        m.codec_forward(x[:, :, f * 320:(f + 1) * 320], 12, state=st)
+    torch.cuda.synchronize()
+    n_cat = len(CATS)
+    ms, fl, by, cnt = (C.c_double * n_cat)(), (C.c_double * n_cat)(), (C.c_double * n_cat)(), (C.c_int64 * n_cat)()
+    _lib.check(lib.hil_profile_begin())
+    for f in range(20, 70):
+        m.codec_forward(x[:, :, f * 320:(f + 1) * 320], 12, state=st)
+    _lib.check(lib.hil_profile_end(ms, fl, by, cnt, n_cat))
+    print(json.dumps({"streams": B, "profile_frames": 50,
+                      "per_frame": {c: {"ms": ms[i] / 50, "launches": cnt[i] // 50} for i, c in enumerate(CATS) if cnt[i]}}),
+          flush=True)
