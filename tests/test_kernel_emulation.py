@@ -213,6 +213,9 @@ def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx, 
     z = F.normalize(torch.randn(1, frames, 128, generator=g), dim=2) * 128 ** 0.5
     cbs = [torch.randn(size, 128, generator=g) * 0.7 ** i for i in range(n)]
     cbs[0][7] = cbs[0][3]  # an exact tie: the first index must win
+    if size > 130:
+        cbs[0][130] = cbs[0][3]  # ... also across code tiles (codes 0-127 | 128-255)
+    z[0, 0] = cbs[0][3]
     fin, fout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
     np.concatenate([z.numpy().ravel()] + [c.numpy().ravel() for c in cbs]).astype(np.float32).tofile(fin)
     r = subprocess.run([rvq_exe, str(size), str(frames), str(n), str(drop_xx), fin, fout, str(slots)], capture_output=True,
@@ -226,7 +229,8 @@ def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx, 
     q = raw[3 * ni:].view(np.float32).reshape(3, frames, 128)
     assert np.array_equal(idx_a, idx_b) and np.array_equal(q[0], q[1])  # split == one-kernel, bit for bit
     assert np.array_equal(idx_a, idx_c) and np.array_equal(q[0], q[2])  # v2 == one-kernel, bit for bit
-    assert not (idx_a[0] == 7).any()
+    assert not (idx_a[0] == 7).any() and not (idx_a[0] == 130).any()
+    assert idx_a[0, 0] == 3  # frame 0 IS code 3 of stage 0 (set below): its two exact copies must lose
     p = {f"quantizer.layers.{i}.embed": c for i, c in enumerate(cbs)}
     cfg = O.CodecConfig(num_quantizers=n, codebook_size=size)
     if drop_xx:
