@@ -28,3 +28,6 @@ for v in 0 1; do
   echo "bench [HILCODEC_CLUSTER_X=$v] rc=$?"; python -c "
 import json; d=json.loads(open('gpurun_out/ab_bench_cluster_x_$v.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('kernel_categories'))" | cut -c1-600
 done
+# config 4 in bench.py's JSON contract (default kernels, then the streaming kernels)
+timeout 200 python bench.py --workload stream1 --steps 5 --warmup 3 > gpurun_out/ab_bench_stream1_default.json 2> gpurun_out/ab_bench_stream1_default.err; echo "bench stream1 rc=$?"; cut -c1-400 gpurun_out/ab_bench_stream1_default.json
+HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1 timeout 200 python bench.py --workload stream1 --steps 5 --warmup 3 > gpurun_out/ab_bench_stream1_skinny.json 2> gpurun_out/ab_bench_stream1_skinny.err; echo "bench stream1 skinny rc=$?"; cut -c1-400 gpurun_out/ab_bench_stream1_skinny.json
