@@ -79,3 +79,40 @@ def test_dropin_surface_and_errors():
         S.HILCodec(24000, norm="layer_norm")
     with pytest.raises(RuntimeError, match="missing"):
         S.HILCodec(24000, vq_kwargs=dict(dim=128, num_quantizers=8)).load_state_dict({})
+
+
+def test_graph_selection_without_gpu():
+    """hil_model_set_graph: deploy (default) / train before finalize, rejected values, NULL handles."""
+    lib = _lib.load()
+    c = _lib.HilConfig()
+    lib.hil_config_default(C.byref(c), 8)
+    h = C.c_void_p()
+    assert lib.hil_model_create(C.byref(c), C.byref(h)) == 0
+    assert lib.hil_model_graph(h) == _lib.HIL_GRAPH_DEPLOY
+    assert lib.hil_model_set_graph(h, _lib.HIL_GRAPH_TRAIN) == 0 and lib.hil_model_graph(h) == _lib.HIL_GRAPH_TRAIN
+    assert lib.hil_model_set_graph(h, 7) == -1 and b"unknown graph" in lib.hil_last_error()
+    assert lib.hil_model_graph(h) == _lib.HIL_GRAPH_TRAIN
+    assert lib.hil_model_set_graph(None, 0) == -1 and lib.hil_model_graph(None) == -1
+    # calls on a model that was never finalized fail before any CUDA call
+    assert lib.hil_encode_ragged(h, None, None, 1, 100, None, None) == -1
+    lib.hil_model_destroy(h)
+
+
+def test_training_graph_adapter_surface_without_gpu():
+    """hilcodec_b200/models.py: constructors, graph plumbing and the no-CPU-path rule."""
+    from hilcodec_b200 import checkpoint, models
+    cfg = W.CodecConfig(num_quantizers=3)
+    m = models.HILCodec.from_training_state_dict(checkpoint.random_training_state_dict(cfg, 0), 3)
+    assert m.graph == "train" and m.deploy._core.graph == _lib.HIL_GRAPH_TRAIN and m.quantizer.num_quantizers == 3
+    d = models.HILCodec.from_training_state_dict(checkpoint.random_training_state_dict(cfg, 0), 3, graph="deploy")
+    assert d.deploy._core.graph == _lib.HIL_GRAPH_DEPLOY
+    bias_t = m.deploy._core.weights["decoder.conv_post.bias"]
+    bias_d = d.deploy._core.weights["decoder.conv_post.bias"]
+    assert torch.allclose(bias_t, bias_d * W.WAV_STD)
+    t2 = models.HILCodec(d.deploy, graph="train")          # same weights, training-graph output scaling
+    assert t2.deploy is not d.deploy and t2.deploy._core.graph == _lib.HIL_GRAPH_TRAIN
+    assert torch.allclose(t2.deploy._core.weights["decoder.conv_post.bias"], bias_t)
+    with pytest.raises(ValueError, match="Unknown graph"):
+        models.HILCodec(d.deploy, graph="onnx")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 333))
