@@ -42,6 +42,8 @@ static int32_t fail(hil_status st, const std::string& msg) {
 // counter bench.py reports as `gpu_launches`, and, while a profile is open
 // (hil_profile_begin .. hil_profile_end), brackets the launch with CUDA events on the launch
 // stream and books its algorithmic FLOPs / bytes under a kernel category.
+constexpr int HIL_MAX_RES = 16;  // ResBlocks per stage (2 / 3 in the published configs)
+
 namespace {
 
 enum Cat { CAT_GEMM_PW = 0, CAT_GEMM_STFT, CAT_DW, CAT_DWT, CAT_CONV_PRE, CAT_CONV_POST, CAT_RVQ, CAT_MISC, CAT_COUNT };
@@ -537,6 +539,8 @@ int32_t hil_model_create(const hil_config* cfg, hil_model** out) {
     if (cfg->dim != 128) return fail(HIL_ERR_INVALID, "only dim=128 is built (both published configs)");
     if (cfg->num_quantizers < 1 || cfg->codebook_size < 1) return fail(HIL_ERR_INVALID, "bad quantizer config");
     if (cfg->channels_enc % 4 || cfg->channels_dec % 4) return fail(HIL_ERR_INVALID, "channels must be multiples of 4");
+    if (cfg->n_residual_enc < 0 || cfg->n_residual_enc > HIL_MAX_RES || cfg->n_residual_dec < 0 || cfg->n_residual_dec > HIL_MAX_RES)
+        return fail(HIL_ERR_INVALID, "n_residual out of range");
     for (int i = 0; i < cfg->n_strides; ++i) {
         const int r = cfg->strides[i];
         if (!(r == 2 || r == 4 || r == 5 || r == 8 || r == 3 || r == 6))
@@ -933,6 +937,43 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     return HIL_OK;
 }
 
+// The ResBlocks of one stage (streaming.py:503-505 / :638-642), optionally in sub-batches that fit the L2
+// (HILCODEC_STAGE_CHUNK_MB=<MB>, 0 / unset = off: written without GPU time, to be measured).  Unchunked, every DWSBlock
+// launch streams the whole [B][C][T] tensor from and to HBM (config 3, decoder stage 2: 2.4 GB per pass, 15 passes
+// per stage; the fused-DWS launches move 70 GB per step and run at half the HBM bandwidth).  Clips are independent, so
+// the same launches can run on `nb` clips at a time with nb chosen so that the chunk of h and the chunk-sized
+// intermediate (always the SAME buffer: its dirty lines are overwritten in the L2 before they are evicted) stay
+// resident across all ResBlocks of the stage: HBM then sees one read and one write of h per stage.  Results are
+// bit-identical (same tiles, same arithmetic); the price is ~2 x n_res launches per chunk.
+static int stage_chunk_clips(int B, int C, int Tp) {
+    static const long long budget = []() {
+        const char* e = std::getenv("HILCODEC_STAGE_CHUNK_MB");
+        return e ? std::atoll(e) * (1LL << 20) : 0LL;
+    }();
+    if (budget <= 0) return B;
+    const long long per_clip = 2LL * C * Tp * (long long)sizeof(float);   // h + the intermediate
+    const long long nb = budget / (per_clip > 0 ? per_clip : 1);
+    return (int)(nb < 1 ? 1 : (nb > B ? B : nb));
+}
+
+static int32_t res_blocks_of_stage(const Dws* units, int n_res, const float* pre_scales, float* h, float* a1, float* a2, int B,
+                                   int C, int Ts, const float* const* cin, float* const* cout, cudaStream_t st) {
+    const int Tp = pitch4(Ts);
+    const long long bs = (long long)C * Tp;
+    const int nb = stage_chunk_clips(B, C, Tp);
+    for (int b0 = 0; b0 < B; b0 += nb) {
+        const int nbb = B - b0 < nb ? B - b0 : nb;
+        for (int j = 0; j < n_res; ++j) {
+            // caches are [B][C][k-1]: the chunk's rows start b0 * C * (k-1) floats in (k = 5)
+            const size_t coff = (size_t)b0 * C * 4;
+            const float* ci2[2] = {cin[2 * j] + coff, cin[2 * j + 1] + coff};
+            float* co2[2] = {cout[2 * j] + coff, cout[2 * j + 1] + coff};
+            HIL_TRY(res_block(&units[2 * j], h + (long long)b0 * bs, a1, a2, nbb, C, Ts, pre_scales[j], ci2, co2, st));
+        }
+    }
+    return HIL_OK;
+}
+
 // T_valid < T (hil_encode_ragged): `wav` holds T_valid samples per clip and T = hop * ceil(T_valid / hop).  The
 // training graph's convs pad themselves on the right with zeros up to a full last window (modules/conv.py:61-68,
 // :222-236), i.e. each strided depthwise conv sees ITS input -- not the waveform -- zero-extended.  Every layer here
@@ -965,10 +1006,12 @@ int32_t encode_impl(hil_model* m, const Buffers& w, const float* wav, int B, int
                                          (long long)F * Tp, Tp, st));
         HIL_TRY(run_gemm_linear(sg.spec_pw, w.spec, (long long)F * Tp, Tp, B, Ts, PRE_NONE, 1.f, sg.spec_b, h, h, bs,
                                     Tp, st));
-        for (int j = 0; j < c.n_residual_enc; ++j) {
-            const float pre = (float)std::pow(1.0 + (j + 1) * rs2, -0.5);  // streaming.py:210 with idx=j+1
-            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, pre, cin + ci, cout + ci, st));
-            ci += 2;
+        {
+            float pre[HIL_MAX_RES];
+            for (int j = 0; j < c.n_residual_enc; ++j)
+                pre[j] = (float)std::pow(1.0 + (j + 1) * rs2, -0.5);  // streaming.py:210 with idx=j+1
+            HIL_TRY(res_blocks_of_stage(sg.units.data(), c.n_residual_enc, pre, h, a1, a2, B, C, Ts, cin + ci, cout + ci, st));
+            ci += 2 * c.n_residual_enc;
         }
         // Scale -> ELU -> 1x1 (C -> 2C) -> strided depthwise (streaming.py:506-510)
         HIL_TRY(run_gemm_linear(sg.down_pw, h, bs, Tp, B, Ts, PRE_SCALE_ELU, m->enc_post_scale, nullptr, nullptr, a1,
@@ -1031,12 +1074,14 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
         std::swap(h, a2);
         C /= 2;
         Ts = Ts2;
-        for (int j = 0; j < c.n_residual_dec; ++j) {
+        {
             // deploy-path quirk: pre_scale is 1.0 for every decoder ResBlock (streaming.py:576-583); the training
             // graph passes idx = j (modules/seanet.py:443-451)
-            const float pre = m->graph == HIL_GRAPH_TRAIN ? (float)std::pow(1.0 + j * rs2, -0.5) : 1.0f;
-            HIL_TRY(res_block(&sg.units[2 * j], h, a1, a2, B, C, Ts, pre, cin + ci, cout + ci, st));
-            ci += 2;
+            float pre[HIL_MAX_RES];
+            for (int j = 0; j < c.n_residual_dec; ++j)
+                pre[j] = m->graph == HIL_GRAPH_TRAIN ? (float)std::pow(1.0 + j * rs2, -0.5) : 1.0f;
+            HIL_TRY(res_blocks_of_stage(sg.units.data(), c.n_residual_dec, pre, h, a1, a2, B, C, Ts, cin + ci, cout + ci, st));
+            ci += 2 * c.n_residual_dec;
         }
     }
     {

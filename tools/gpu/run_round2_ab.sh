@@ -31,3 +31,11 @@ done
 # config 4 in bench.py's JSON contract (default kernels, then the streaming kernels)
 timeout 200 python bench.py --workload stream1 --steps 5 --warmup 3 > gpurun_out/ab_bench_stream1_default.json 2> gpurun_out/ab_bench_stream1_default.err; echo "bench stream1 rc=$?"; cut -c1-400 gpurun_out/ab_bench_stream1_default.json
 HILCODEC_SKINNY=1 HILCODEC_RVQ_SPLIT=1 timeout 200 python bench.py --workload stream1 --steps 5 --warmup 3 > gpurun_out/ab_bench_stream1_skinny.json 2> gpurun_out/ab_bench_stream1_skinny.err; echo "bench stream1 skinny rc=$?"; cut -c1-400 gpurun_out/ab_bench_stream1_skinny.json
+# stage-level sub-batching so that a stage's ResBlocks work out of the L2 (host-side only, bit-identical): parity, then A/B
+HILCODEC_STAGE_CHUNK_MB=64 timeout 300 python -m pytest tests/test_gpu_codec.py -x -q --tb=short -p no:cacheprovider > gpurun_out/ab_pytest_chunk.log 2>&1
+echo "pytest [HILCODEC_STAGE_CHUNK_MB=64] rc=$?"; tail -3 gpurun_out/ab_pytest_chunk.log | cut -c1-300
+for mb in 0 32 64 96; do
+  HILCODEC_STAGE_CHUNK_MB=$mb timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_chunk_$mb.json 2> gpurun_out/ab_bench_chunk_$mb.err
+  echo "bench [HILCODEC_STAGE_CHUNK_MB=$mb] rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/ab_bench_chunk_$mb.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['gpu_launches'], d.get('kernel_categories'))" | cut -c1-600
+done
