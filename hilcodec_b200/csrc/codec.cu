@@ -950,7 +950,10 @@ static int stage_chunk_clips(int B, int C, int Tp) {
         const char* e = std::getenv("HILCODEC_STAGE_CHUNK_MB");
         return e ? std::atoll(e) * (1LL << 20) : 0LL;
     }();
-    if (budget <= 0) return B;
+    // stages whose ResBlocks run as ONE kernel each (C <= 128, gemm_rb.cu) already read and write h once per block and are
+    // not HBM-bound: by default only the stages on fused-DWS launches are chunked (HILCODEC_STAGE_CHUNK_MINC=<C> to change)
+    static const int min_c = []() { const char* e = std::getenv("HILCODEC_STAGE_CHUNK_MINC"); return e ? std::atoi(e) : 129; }();
+    if (budget <= 0 || C < min_c) return B;
     const long long per_clip = 2LL * C * Tp * (long long)sizeof(float);   // h + the intermediate
     const long long nb = budget / (per_clip > 0 ? per_clip : 1);
     return (int)(nb < 1 ? 1 : (nb > B ? B : nb));
