@@ -264,8 +264,26 @@ static int32_t run_upsample(const PackedMat& W, const float* x, long long x_bs, 
                    launch_gemm_h_planes(W, hi, lo, p_bs, p_rs, B, T, bias, Y, y_bs, y_rs, st));
         return HIL_OK;
     }
-    HIL_TRY(run_dwconv_transpose(x, x_bs, x_rs, ci, co, up_w, tmp, (long long)K * Tp2, Tp2, B, K, T_in, S, pre, pre_scale, st));
-    return run_gemm_linear(W, tmp, (long long)K * Tp2, Tp2, B, T, PRE_NONE, 1.f, bias, nullptr, Y, y_bs, y_rs, st);
+    // HILCODEC_STAGE_CHUNK_MB (off by default, see res_blocks_of_stage): the [K][S * T_in] intermediate is the largest
+    // tensor of the decoder; in sub-batches that fit the L2 (always the same `tmp` rows) it never reaches HBM
+    static const long long budget = []() {
+        const char* e = std::getenv("HILCODEC_STAGE_CHUNK_MB");
+        return e ? std::atoll(e) * (1LL << 20) : 0LL;
+    }();
+    int nb = B;
+    if (budget > 0) {
+        const long long per_clip = (long long)K * Tp2 * (long long)sizeof(float);
+        const long long n = budget / (per_clip > 0 ? per_clip : 1);
+        nb = (int)(n < 1 ? 1 : (n > B ? B : n));
+    }
+    for (int b0 = 0; b0 < B; b0 += nb) {
+        const int nbb = B - b0 < nb ? B - b0 : nb;
+        HIL_TRY(run_dwconv_transpose(x + (long long)b0 * x_bs, x_bs, x_rs, ci + (size_t)b0 * K, co + (size_t)b0 * K, up_w, tmp,
+                                     (long long)K * Tp2, Tp2, nbb, K, T_in, S, pre, pre_scale, st));
+        HIL_TRY(run_gemm_linear(W, tmp, (long long)K * Tp2, Tp2, nbb, T, PRE_NONE, 1.f, bias, nullptr, Y + (long long)b0 * y_bs,
+                                y_bs, y_rs, st));
+    }
+    return HIL_OK;
 }
 
 static int32_t run_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
