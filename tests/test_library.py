@@ -50,6 +50,9 @@ def test_model_create_validates_config_without_gpu():
     assert lib.hil_model_create(C.byref(c), C.byref(h)) == -1
     assert b"kernel_size" in lib.hil_last_error()
     lib.hil_config_default(C.byref(c), 8)
+    c.n_residual_dec = 99
+    assert lib.hil_model_create(C.byref(c), C.byref(h)) == -1 and b"n_residual" in lib.hil_last_error()
+    lib.hil_config_default(C.byref(c), 8)
     assert lib.hil_model_create(C.byref(c), C.byref(h)) == 0
     # finalize with nothing set: HIL_ERR_MISSING, no CUDA call made
     assert lib.hil_model_finalize(h) == -2
