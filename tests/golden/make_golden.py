@@ -18,6 +18,10 @@
   scales), for input lengths that are and are not multiples of the hop.
 
     python tests/golden/make_golden.py train     # only (re)generate the training-graph fixture
+* `ref_music_published.npz` -- the reference's own streaming.py classes with the PUBLISHED hil_music weights on
+  60 frames of onnx/input_speech.wav (n_q = 12): hil_music has no golden output in the reference, this is its pin.
+
+    python tests/golden/make_golden.py music
 """
 import os
 import sys
@@ -85,6 +89,21 @@ def ref_random(name, n_q, seed, batch, frames, stream_hops):
           "wav", float(np.abs(out["stream_wav"] - out["wav"]).max()))
 
 
+def ref_music_published(name, frames=60):
+    """`hil_music` has no golden output in the reference: pin it with the reference's OWN classes run here on the
+    PUBLISHED weights (extracted from onnx/hil_music_*.onnx) and real speech (the head of onnx/input_speech.wav)."""
+    from scipy.io import wavfile
+
+    w = W.load_pretrained("hil_music")
+    model = ref_shim.build_reference_model(w, 12)
+    _, wav = wavfile.read(os.path.join(ref_shim.REF, "onnx", "input_speech.wav"))
+    x = torch.from_numpy(wav[24000:24000 + frames * 320].astype(np.float32) / 32768.0).view(1, 1, -1)
+    r = ref_shim.reference_forward(model, x, 12)
+    np.savez_compressed(os.path.join(HERE, name), x=x.numpy(), z=r["z"].numpy(),
+                        indices=r["indices"].numpy().astype(np.int16), wav=r["wav"].numpy())
+    print(name, tuple(r["indices"].shape), float(r["wav"].abs().max()))
+
+
 def ref_train(name, n_q, seed, n, batch, lengths):
     from hilcodec_b200 import checkpoint
 
@@ -106,6 +125,9 @@ def ref_train(name, n_q, seed, n, batch, lengths):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["music"]:
+        ref_music_published("ref_music_published.npz")
+        sys.exit(0)
     if sys.argv[1:] == ["train"]:
         ref_train("ref_train_random.npz", 6, 3, 5, batch=2, lengths=[320 * 8, 320 * 12 + 77, 333, 1])
         sys.exit(0)
@@ -113,5 +135,6 @@ if __name__ == "__main__":
     ref_random("ref_random_speech.npz", 8, 1, batch=2, frames=12, stream_hops=1)
     ref_random("ref_random_music.npz", 12, 2, batch=3, frames=10, stream_hops=3)
     ref_train("ref_train_random.npz", 6, 3, 5, batch=2, lengths=[320 * 8, 320 * 12 + 77, 333, 1])
+    ref_music_published("ref_music_published.npz")
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

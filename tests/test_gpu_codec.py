@@ -197,6 +197,26 @@ def test_pretrained_music_vs_oracle():
     assert (y2.cpu() - o["wav"]).abs().max().item() < TOL
 
 
+@pytest.mark.skipif(not W.have_pretrained("hil_music"), reason="published hil_music weights did not travel to this box")
+def test_pretrained_music_reference_fixture():
+    """The reference's own classes with the published hil_music weights on real speech (tests/golden/make_golden.py
+    music): the only reference-made pin `hil_music` has."""
+    g = np.load(os.path.join(GOLDEN, "ref_music_published.npz"))
+    w = W.load_pretrained("hil_music")
+    m = _model(w, 12)
+    x = torch.from_numpy(g["x"]).cuda()
+    ce, cd = m.initialize_cache(x)
+    z, _ = m.encoder(x, *ce)
+    idx = m.quantizer(z, 12)
+    y, _ = m.decoder(m.dequantizer(idx, 12), *cd)
+    assert np.abs(z.cpu().numpy() - g["z"]).max() < TOL
+    ref_idx = torch.from_numpy(g["indices"].astype(np.int64))
+    bad, worst = index_report(oracle_cfg(12), params(w), z, idx, ref_idx, 12)
+    assert bad == 0 or worst < 1e-5, (bad, worst)
+    if bad == 0:
+        assert np.abs(y.cpu().numpy() - g["wav"]).max() < TOL
+
+
 def test_full_size_properties_config2():
     """BASELINE config 2 size (64 x 24000): too big for the CPU oracle in a test, so check
     size-independent properties: batch rows are independent (row b of the batch == the same
