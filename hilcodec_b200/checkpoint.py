@@ -41,7 +41,7 @@ from torch import Tensor
 from . import fold
 from .weights import WAV_STD, CodecConfig, dft_basis, random_weights, tensor_shapes
 
-_PARAM = r"(bias|weight|weight_g|weight_v|parametrizations\.weight\.original[01])"
+_PARAM = r"(bias|weight|weight_g|weight_v|weight_scale|parametrizations\.weight\.original[01])"
 _BLOCK_SLOT = {1: "block.0.pointwise.1", 2: "block.0.depthwise", 4: "block.1.pointwise.1", 5: "block.1.depthwise"}
 
 
@@ -113,13 +113,17 @@ def training_to_streaming(sd: tp.Mapping[str, tp.Any], cfg: CodecConfig) -> "Ord
     return out
 
 
-def deployment_weights(sd: tp.Mapping[str, tp.Any], cfg: CodecConfig, graph: str = "deploy") -> "OrderedDict[str, np.ndarray]":
+def deployment_weights(sd: tp.Mapping[str, tp.Any], cfg: CodecConfig, graph: str = "deploy",
+                       norm: tp.Optional[str] = None,
+                       norm_kwargs: tp.Optional[tp.Mapping[str, tp.Any]] = None) -> "OrderedDict[str, np.ndarray]":
     """Training-graph OR streaming state dict (reparametrised or not) -> the folded fp32 tensors the kernels
     consume, in `weights.tensor_shapes(cfg)` naming.  `graph="train"` keeps the training graph's output scaling
-    (see fold.py); the decoder ResBlock `pre_scale` difference is a property of the graph, not of the weights."""
+    (see fold.py; applied to an already-folded deployment dict as well); the decoder ResBlock `pre_scale` difference
+    is a property of the graph, not of the weights.  `norm` / `norm_kwargs`: the training model's constructor
+    arguments ("weight_norm" default, or "weight_standardization" with its dim / eps), see `fold.fold_state_dict`."""
     if is_training_state_dict(sd):
         sd = training_to_streaming(sd, cfg)
-    folded = fold.fold_state_dict(OrderedDict(sd), cfg, part="", graph=graph)
+    folded = fold.fold_state_dict(OrderedDict(sd), cfg, part="", graph=graph, norm=norm, norm_kwargs=norm_kwargs)
     shapes = tensor_shapes(cfg)
     out: "OrderedDict[str, np.ndarray]" = OrderedDict()
     missing = []
@@ -139,12 +143,16 @@ def deployment_weights(sd: tp.Mapping[str, tp.Any], cfg: CodecConfig, graph: str
     return out
 
 
-def load_checkpoint(path: str, cfg: CodecConfig, graph: str = "deploy") -> "OrderedDict[str, np.ndarray]":
+def load_checkpoint(path: str, cfg: CodecConfig, graph: str = "deploy", norm: tp.Optional[str] = None,
+                    norm_kwargs: tp.Optional[tp.Mapping[str, tp.Any]] = None,
+                    allow_pickle: bool = False) -> "OrderedDict[str, np.ndarray]":
     """Read a training checkpoint (`wrapper.py:428-444`: {"model": state_dict, "disc": ..., "epoch": ...}) or a
-    bare state dict saved with torch.save, and convert it with `deployment_weights`."""
-    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    bare state dict saved with torch.save, and convert it with `deployment_weights`.  Only tensors are needed, so
+    the file is read with `weights_only=True` (no arbitrary pickle code from a third-party checkpoint runs);
+    `allow_pickle=True` is the explicit opt-in for legacy files that hold other Python objects."""
+    ckpt = torch.load(path, map_location="cpu", weights_only=not allow_pickle)
     sd = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt and isinstance(ckpt["model"], dict) else ckpt
-    return deployment_weights(sd, cfg, graph)
+    return deployment_weights(sd, cfg, graph, norm, norm_kwargs)
 
 
 # --------------------------------------------------------------------------------------- test support

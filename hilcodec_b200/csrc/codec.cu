@@ -3,6 +3,7 @@
 // Encoder.forward (streaming.py:482-517) and Decoder.forward (streaming.py:619-648) as a
 // sequence of kernel launches; see DESIGN.md for the kernel list and data layout.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -379,6 +380,10 @@ struct hil_model {
     int hop = 1;
     float enc_post_scale = 1.f, dec_post_scale = 1.f;
     int graph = HIL_GRAPH_DEPLOY;  // hil_model_set_graph
+    // states keep their model alive: hil_model_destroy with live states only marks the model and the last
+    // hil_state_destroy frees it (a state dereferences s->m in reset / export / import)
+    std::atomic<int> live_states{0};
+    bool destroy_requested = false;
 };
 
 struct hil_state {
@@ -400,6 +405,7 @@ struct hil_state {
     struct GraphEntry {
         const float* wav; int64_t* idx; float* out; int T, n, enc_gen, dec_gen;
         int seen = 0;                 // eager calls before capturing (warms lazy attributes / workspace)
+        bool no_capture = false;      // capture / instantiate failed once: this key stays eager
         cudaGraphExec_t exec = nullptr;
         unsigned long long launches = 0;
     };
@@ -722,10 +728,18 @@ int32_t hil_model_finalize(hil_model* m) {
     return HIL_OK;
 }
 
-void hil_model_destroy(hil_model* m) {
-    if (!m) return;
+static void free_model(hil_model* m) {
     if (m->arena) cudaFree(m->arena);
     delete m;
+}
+
+void hil_model_destroy(hil_model* m) {
+    if (!m) return;
+    if (m->live_states > 0) {  // deferred: the last state of this model frees it
+        m->destroy_requested = true;
+        return;
+    }
+    free_model(m);
 }
 
 int32_t hil_model_hop(const hil_model* m) { return m ? m->hop : 0; }
@@ -790,6 +804,7 @@ int32_t hil_state_create(hil_model* m, int32_t batch, hil_state** out) {
         delete s;
         return fail(HIL_ERR_CUDA, std::string("cudaMemset caches: ") + cudaGetErrorString(e));
     }
+    ++m->live_states;
     *out = s;
     return HIL_OK;
 }
@@ -844,7 +859,9 @@ void hil_state_destroy(hil_state* s) {
     if (s->ws) cudaFree(s->ws);
     if (s->idx_dev) cudaFree(s->idx_dev);
     if (s->io_dev) cudaFree(s->io_dev);
+    hil_model* m = s->m;
     delete s;
+    if (m && --m->live_states == 0 && m->destroy_requested) free_model(m);
 }
 
 size_t hil_state_workspace_bytes(const hil_state* s) {
@@ -907,6 +924,10 @@ int32_t ensure_workspace(hil_state* s, int B, int T, Buffers* out) {
         // grow-only; the old block may still be in use by queued kernels, so drain first
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return fail(HIL_ERR_CUDA, std::string("sync before workspace growth: ") + cudaGetErrorString(e));
+        // the captured streaming graphs have the old workspace pointers baked in: drop them (re-captured on demand)
+        for (auto& g : s->graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        s->graphs.clear();
         if (s->ws) cudaFree(s->ws);
         s->ws = nullptr;
         s->ws_floats = 0;
@@ -1117,6 +1138,7 @@ int32_t check_call(hil_model* m, hil_state* s, int B, long long T, bool need_hop
     if (!m || !s) return fail(HIL_ERR_INVALID, "null model/state");
     if (!m->finalized) return fail(HIL_ERR_STATE, "model not finalized");
     if (s->m != m) return fail(HIL_ERR_STATE, "state belongs to another model");
+    if (m->destroy_requested) return fail(HIL_ERR_STATE, "model was destroyed (weights replaced): create a new state");
     if (B != s->B) return fail(HIL_ERR_STATE, "batch size differs from the one the state was created with");
     if (T <= 0) return fail(HIL_ERR_INVALID, "empty input");
     if (need_hop_multiple && T % m->hop) return fail(HIL_ERR_INVALID, "T must be a multiple of the hop length");
@@ -1255,6 +1277,11 @@ int32_t hil_codec_forward_graph(hil_model* m, hil_state* s, const float* wav, in
         HIL_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
         return HIL_OK;
     };
+    {   // grow the workspace BEFORE looking the entry up: growth drops every captured graph (their workspace pointers
+        // are stale) and must not happen inside a capture
+        Buffers wtmp;
+        HIL_TRY(ensure_workspace(s, B, T, &wtmp));
+    }
     hil_state::GraphEntry* e = nullptr;
     for (auto& g : s->graphs)
         if (g.wav == wav && g.idx == idx && g.out == wav_out && g.T == T && g.n == n && g.enc_gen == s->enc_gen &&
@@ -1266,7 +1293,8 @@ int32_t hil_codec_forward_graph(hil_model* m, hil_state* s, const float* wav, in
         s->graphs.push_back(g);
         e = &s->graphs.back();
     }
-    if (!e || e->seen++ == 0) {  // unknown key (callers that keep changing buffers stay eager) or first sight: eager
+    // unknown key (callers that keep changing buffers stay eager), first sight, or a key whose capture failed: eager
+    if (!e || e->no_capture || e->seen++ == 0) {
         HIL_TRY(hil_codec_forward(m, s, wav, B, T, n, nullptr, idx, wav_out, st));
         return finish();
     }
@@ -1278,19 +1306,26 @@ int32_t hil_codec_forward_graph(hil_model* m, hil_state* s, const float* wav, in
         return finish();
     }
     const unsigned long long l0 = g_prof.launches;
+    const int ge0 = s->enc_gen, gd0 = s->dec_gen;   // the capture only RECORDS the step: restore these if it fails
     cudaGraph_t graph = nullptr;
-    HIL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int32_t rc = hil_codec_forward(m, s, wav, B, T, n, nullptr, idx, wav_out, st);
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc != HIL_OK) {
-        if (graph) cudaGraphDestroy(graph);
-        return rc;
-    }
-    HIL_CUDA(ce);
     cudaGraphExec_t exec = nullptr;
-    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    HIL_CUDA(ie);
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int32_t rc = HIL_OK;
+    if (ce == cudaSuccess) {
+        rc = hil_codec_forward(m, s, wav, B, T, n, nullptr, idx, wav_out, st);
+        ce = cudaStreamEndCapture(st, &graph);
+        if (rc == HIL_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+    }
+    if (rc != HIL_OK || ce != cudaSuccess || !exec) {
+        // nothing ran: put the cache generations back, mark the key non-capturable and do the step eagerly
+        (void)cudaGetLastError();
+        s->enc_gen = ge0; s->dec_gen = gd0;
+        g_prof.launches = l0;
+        e->no_capture = true;
+        HIL_TRY(hil_codec_forward(m, s, wav, B, T, n, nullptr, idx, wav_out, st));
+        return finish();
+    }
     e->exec = exec;
     e->launches = g_prof.launches - l0;
     HIL_CUDA(cudaGraphLaunch(exec, st));   // the capture recorded the step but did not run it

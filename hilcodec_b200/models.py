@@ -119,16 +119,22 @@ class HILCodec(nn.Module):
 
     @classmethod
     def from_training_state_dict(cls, state_dict: tp.Mapping[str, tp.Any], num_quantizers: int, graph: str = "train",
-                                 sample_rate: int = 24_000) -> "HILCodec":
-        """`models.HILCodec.state_dict()` (weight-norm parametrised, un-merged scales) -> a servable model."""
+                                 sample_rate: int = 24_000, norm: tp.Optional[str] = None,
+                                 norm_kwargs: tp.Optional[tp.Mapping[str, tp.Any]] = None) -> "HILCodec":
+        """`models.HILCodec.state_dict()` (weight-norm or weight-standardisation parametrised -- `norm`, `norm_kwargs`
+        as given to the reference constructor, `models.py:49-50` -- un-merged scales) -> a servable model."""
         cfg = CodecConfig(num_quantizers=num_quantizers)
-        return cls._from_weights(checkpoint.deployment_weights(state_dict, cfg, graph), cfg, graph, sample_rate)
+        return cls._from_weights(checkpoint.deployment_weights(state_dict, cfg, graph, norm, norm_kwargs), cfg, graph,
+                                 sample_rate)
 
     @classmethod
-    def from_checkpoint(cls, path: str, num_quantizers: int, graph: str = "train", sample_rate: int = 24_000) -> "HILCodec":
+    def from_checkpoint(cls, path: str, num_quantizers: int, graph: str = "train", sample_rate: int = 24_000,
+                        norm: tp.Optional[str] = None, norm_kwargs: tp.Optional[tp.Mapping[str, tp.Any]] = None,
+                        allow_pickle: bool = False) -> "HILCodec":
         """A `{epoch:05d}.pth` written by the training wrapper (`wrapper.py:428-444`)."""
         cfg = CodecConfig(num_quantizers=num_quantizers)
-        return cls._from_weights(checkpoint.load_checkpoint(path, cfg, graph), cfg, graph, sample_rate)
+        return cls._from_weights(checkpoint.load_checkpoint(path, cfg, graph, norm, norm_kwargs, allow_pickle), cfg, graph,
+                                 sample_rate)
 
     # -- calls -----------------------------------------------------------------------------------------------
     def encode(self, x: Tensor) -> Tensor:

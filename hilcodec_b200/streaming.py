@@ -28,13 +28,27 @@ from . import _lib
 from .weights import CodecConfig, check_weights, dft_basis, tensor_shapes
 
 
-def _require_cuda(t: Tensor, what: str) -> None:
+def _require_cuda(t: Tensor, what: str, dtype: torch.dtype = torch.float32) -> None:
+    """The kernels reinterpret `data_ptr()` as `dtype`: anything else is rejected here (float32 for waveforms,
+    latents and caches, int64 for indices only)."""
+    if not isinstance(t, Tensor):
+        raise TypeError(f"hilcodec_b200: {what} must be a torch.Tensor, got {type(t).__name__}")
     if not t.is_cuda:
         raise RuntimeError(
             f"hilcodec_b200: {what} must be a CUDA tensor (this package has no CPU path; "
             f"move the module and its inputs to a B200 with .cuda())")
-    if t.dtype != torch.float32 and t.dtype != torch.int64:
-        raise TypeError(f"hilcodec_b200: {what} must be float32 (int64 for indices), got {t.dtype}")
+    if t.dtype != dtype:
+        raise TypeError(f"hilcodec_b200: {what} must be {dtype}, got {t.dtype}")
+
+
+def _check_wav(x: Tensor, hop: int) -> tp.Tuple[int, int]:
+    _require_cuda(x, "x")
+    if x.dim() != 3 or x.shape[1] != 1:
+        raise ValueError(f"expected x of shape [B, 1, T], got {tuple(x.shape)}")
+    B, _, T = x.shape
+    if T % hop or T == 0:
+        raise ValueError(f"T={T} must be a positive multiple of the hop length {hop}")
+    return B, T
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -51,6 +65,9 @@ class _NativeCodec:
         self._models: tp.Dict[int, int] = {}
         self._states: tp.Dict[tp.Tuple[int, int], int] = {}
         self._lib_handle = None
+        # bumped by invalidate(): a StreamState remembers the generation it was created in and refuses to run
+        # against a later one (its hil_state belongs to a model that has been replaced)
+        self.generation = 0
 
     @property
     def _lib(self):
@@ -73,6 +90,10 @@ class _NativeCodec:
             self.invalidate()
 
     def invalidate(self) -> None:
+        """Drop the native models (weights or graph changed).  The C side defers freeing a model until the last
+        `hil_state` created from it is destroyed, so StreamStates that are still alive stay safe to reset /
+        export / destroy; they raise on `step` / `codec_forward(state=...)` (see StreamState._check)."""
+        self.generation += 1
         lib = self._lib_handle
         if lib is not None:
             for s in self._states.values():
@@ -240,8 +261,8 @@ class _NativeCodec:
         return (idx, qsum) if with_sum else idx
 
     def rvq_decode(self, idx: Tensor, n: int) -> Tensor:
-        _require_cuda(idx, "indices")
-        if idx.dtype != torch.int64 or idx.dim() != 3:
+        _require_cuda(idx, "indices", torch.int64)
+        if idx.dim() != 3:
             raise TypeError("indices must be an int64 tensor of shape [n, B, T]")
         assert 1 <= n <= self.cfg.num_quantizers, "n must satisfy 1 <= n <= num_quantizers"
         if idx.shape[0] < n:
@@ -575,11 +596,8 @@ class HILCodec(nn.Module):
         """Fused enc -> RVQ -> dec in one C-ABI call (`hil_codec_forward`).  Returns
         (indices[n,B,F], wav[B,1,T]).  With `state` the caches persist on the GPU between calls
         (streaming); without it the call is one-shot from zero caches."""
-        _require_cuda(x, "x")
+        B, T = _check_wav(x, self.cfg.hop)
         assert 1 <= n <= self.cfg.num_quantizers, "n must satisfy 1 <= n <= num_quantizers"
-        B, _, T = x.shape
-        if T % self.cfg.hop or T == 0:
-            raise ValueError(f"T={T} must be a positive multiple of the hop length {self.cfg.hop}")
         core, dev = self._core, x.device
         with torch.cuda.device(dev):
             x = x.contiguous()
@@ -589,6 +607,8 @@ class HILCodec(nn.Module):
                 st = core.state(dev, B)
                 _lib.check(lib.hil_state_reset(st, _stream_ptr(dev)))
             else:
+                if state._core is not core:
+                    raise ValueError("state belongs to another model")
                 st = state.handle(B)
             idx = torch.empty(n, B, T // self.cfg.hop, dtype=torch.int64, device=dev)
             y = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
@@ -616,13 +636,23 @@ class StreamState:
             _lib.check(lib.hil_state_create(self._core.model(self.device), batch, C.byref(h)))
         self._h = h.value
         self._lib = lib
+        self._generation = self._core.generation
+        self._io: tp.Dict[tp.Tuple[int, int], tp.Tuple[Tensor, Tensor, Tensor]] = {}
+
+    def _check(self) -> None:
+        if self._generation != self._core.generation:
+            raise RuntimeError(
+                "hilcodec_b200: the model's weights or graph changed after this StreamState was created "
+                "(set_weights / load_state_dict / set_graph); create a new one with model.new_stream_state()")
 
     def handle(self, batch: int) -> int:
+        self._check()
         if batch != self.batch:
             raise ValueError(f"state was created for batch {self.batch}, got {batch}")
         return self._h
 
     def reset(self) -> None:
+        self._check()
         _lib.check(self._lib.hil_state_reset(self._h, _stream_ptr(self.device)))
 
     @torch.no_grad()
@@ -630,19 +660,15 @@ class StreamState:
         """One streaming chunk through the CUDA-graph executor (`hil_codec_forward_graph`).  The chunk is copied
         into a buffer owned by this state and the results are returned as views of state-owned buffers that the
         next `step` overwrites (clone them to keep them): fixed pointers are what lets the graph be replayed."""
-        _require_cuda(x, "x")
-        B, _, T = x.shape
+        self._check()
+        hop = self._core.cfg.hop
+        B, T = _check_wav(x, hop)
         if B != self.batch:
             raise ValueError(f"state was created for batch {self.batch}, got {B}")
-        hop = self._core.cfg.hop
-        if T % hop or T == 0:
-            raise ValueError(f"T={T} must be a positive multiple of the hop length {hop}")
         assert 1 <= n <= self._core.cfg.num_quantizers, "n must satisfy 1 <= n <= num_quantizers"
         key = (T, n)
-        bufs = self._io.get(key) if hasattr(self, "_io") else None
+        bufs = self._io.get(key)
         if bufs is None:
-            if not hasattr(self, "_io"):
-                self._io = {}
             bufs = (torch.empty(B, 1, T, dtype=torch.float32, device=self.device),
                     torch.empty(n, B, T // hop, dtype=torch.int64, device=self.device),
                     torch.empty(B, 1, T, dtype=torch.float32, device=self.device))
@@ -655,6 +681,7 @@ class StreamState:
         return idx, y
 
     def export(self) -> tp.Tuple[tp.List[Tensor], tp.List[Tensor]]:
+        self._check()
         out = []
         for which in (_lib.HIL_ENCODER, _lib.HIL_DECODER):
             lst = []
@@ -666,6 +693,7 @@ class StreamState:
         return out[0], out[1]
 
     def load(self, cache_enc: tp.Sequence[Tensor], cache_dec: tp.Sequence[Tensor]) -> None:
+        self._check()
         for which, lst in ((_lib.HIL_ENCODER, cache_enc), (_lib.HIL_DECODER, cache_dec)):
             shapes = self._core.cache_shapes(which, self.batch, self.device)
             if len(lst) != len(shapes):

@@ -398,5 +398,29 @@ def codec_forward_train(cfg: CodecConfig, p: Params, x: Tensor, n: Optional[int]
     return {"z": z, "q": q, "indices": idx, "loss_vq": loss, "wav": y}
 
 
+# --------------------------------------------------------------------------- generic RVQ (modules/vector_quantize.py)
+
+def generic_rvq_forward(embeds: Sequence[Tensor], x: Tensor, n: Optional[int] = None, channel_last: bool = False):
+    """`ResidualVQ.forward` (eval) of the GENERIC quantizer, modules/vector_quantize.py:490-516, with
+    `VectorQuantize.forward` :400-419 and `EuclideanCodebook.forward` :141-160 inlined: per stage the residual is
+    (transposed to [B,T,C] unless channel_last and) searched with the same negated full distance as the deployment
+    codebook, `quantized_out = 0. + q_0 + q_1 + ...` in the INPUT layout.  Returns (quantized_out, loss, indices
+    [n,B,T]) -- the reference returns (quantized_out, num_replaces = zeros, loss); the indices are extra."""
+    high = len(embeds) if n is None else n
+    assert 1 <= high <= len(embeds)
+    quantized_out = 0.
+    residual = x
+    indices = []
+    for embed in embeds[:high]:
+        r = residual if channel_last else residual.transpose(1, 2)
+        q, ind = codebook_search(r, embed)          # :151-160, same expression as streaming.py:58-66
+        if not channel_last:
+            q = q.transpose(1, 2)
+        indices.append(ind)
+        residual = residual - q
+        quantized_out = quantized_out + q
+    return quantized_out, F.mse_loss(x, quantized_out), torch.stack(indices)
+
+
 def to_dtype(p: Params, dtype) -> Params:
     return {k: v.to(dtype) for k, v in p.items()}

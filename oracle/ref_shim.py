@@ -19,17 +19,44 @@ import types
 import warnings
 from typing import Dict
 
-REF = os.environ.get("HILCODEC_REFERENCE", "/root/reference")
+_FULL = os.environ.get("HILCODEC_REFERENCE", "/root/reference")
+_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF, "models", "hilcodec", "streaming.py"))
+    """The full reference tree (dev container): training graph, generic modules, ONNX files."""
+    return os.path.isfile(os.path.join(_FULL, "models", "hilcodec", "streaming.py")) and \
+        os.path.isdir(os.path.join(_FULL, "onnx"))
+
+
+def deploy_available() -> bool:
+    """The deployment classes are importable: full tree, or the unmodified copy in oracle/_ref (GPU box)."""
+    return available() or os.path.isfile(os.path.join(_COPY, "models", "hilcodec", "streaming.py"))
+
+
+REF = _FULL if available() or not deploy_available() else _COPY
+
+
+def _stub_unused_imports() -> None:
+    """streaming.py:18-19 imports `functional.STDCT` and `utils.verbose` at module scope; neither is used by the
+    deployment forward (verbose() only guards a constructor warning).  In the oracle/_ref copy those packages are
+    absent: register stand-ins so the unmodified file imports."""
+    if REF == _COPY:
+        if "functional" not in sys.modules:
+            f = types.ModuleType("functional")
+            f.STDCT = f.STFT = None
+            sys.modules["functional"] = f
+        if "utils" not in sys.modules:
+            u = types.ModuleType("utils")
+            u.verbose = lambda: False
+            sys.modules["utils"] = u
 
 
 def import_streaming():
     """Return the reference module `models.hilcodec.streaming`."""
-    if not available():
-        raise ImportError(f"reference tree not found at {REF}")
+    if not deploy_available():
+        raise ImportError(f"reference tree not found at {_FULL} (nor a copy at {_COPY})")
+    _stub_unused_imports()
     if "librosa" not in sys.modules:
         lib = types.ModuleType("librosa")
         filt = types.ModuleType("librosa.filters")
@@ -109,17 +136,23 @@ def _model_kwargs(num_quantizers: int) -> dict:
     return kw
 
 
-def build_reference_training_model(state_dict, num_quantizers: int):
+def build_reference_training_model(state_dict, num_quantizers: int, norm: str = "weight_norm", norm_kwargs=None):
     """Reference TRAINING-graph `models.hilcodec.models.HILCodec` (eval) loaded with a training-format state
     dict (`hilcodec_b200.checkpoint.random_training_state_dict`).  The EMA statistics and `_extra_state` of the
-    codebooks keep their constructor values (they do not enter the eval forward)."""
+    codebooks keep their constructor values (they do not enter the eval forward).  `state_dict=None` keeps the
+    constructor's random initialisation (used for the weight-standardisation parametrisation, whose keys the
+    reference writes itself)."""
     import torch
 
     import_streaming()  # registers the package stubs
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         from models.hilcodec.models import HILCodec  # type: ignore
-        model = HILCodec(24000, **_model_kwargs(num_quantizers)).eval()
+        model = HILCodec(24000, **{**_model_kwargs(num_quantizers), "norm": norm, "norm_kwargs": dict(norm_kwargs or {})}).eval()
+    if state_dict is None:
+        for layer in model.quantizer.layers:
+            layer.initted = True
+        return model
     r = model.load_state_dict({k: torch.as_tensor(v) for k, v in state_dict.items()}, strict=False)
     assert not r.unexpected_keys, r.unexpected_keys
     assert all(k.endswith(("ema_embed", "ema_num", "_extra_state", "spec.weight")) for k in r.missing_keys), r.missing_keys

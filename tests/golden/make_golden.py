@@ -22,6 +22,10 @@
   60 frames of onnx/input_speech.wav (n_q = 12): hil_music has no golden output in the reference, this is its pin.
 
     python tests/golden/make_golden.py music
+* `ref_generic_rvq.npz` -- the reference's GENERIC quantizer (`modules/vector_quantize.py:471 ResidualVQ`, the class
+  north_star names) in eval mode on seeded codebooks and latents, channel-first and channel-last, n = None / 3 / 1.
+
+    python tests/golden/make_golden.py generic_rvq
 """
 import os
 import sys
@@ -123,8 +127,45 @@ def ref_train(name, n_q, seed, n, batch, lengths):
     np.savez_compressed(os.path.join(HERE, name), **out)
 
 
+def generic_rvq_inputs(seed, n_q, size, batch, frames):
+    """Seeded codebooks and latents of the generic-RVQ fixture (numpy PCG64: reproducible on the GPU box)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    embeds = [(rng.standard_normal((size, 128)) * (0.8 ** i)).astype(np.float32) for i in range(n_q)]
+    x = rng.standard_normal((batch, 128, frames)).astype(np.float32)
+    x *= np.float32(11.3137) / np.sqrt((x ** 2).sum(1, keepdims=True))   # like the encoder's L2-normalised latents
+    return embeds, x
+
+
+def ref_generic_rvq(name, seed=11, n_q=5, size=1024, batch=3, frames=50):
+    ref_shim.import_streaming()
+    from modules.vector_quantize import ResidualVQ  # type: ignore
+
+    embeds, x = generic_rvq_inputs(seed, n_q, size, batch, frames)
+    out = {"seed": np.int64(seed), "n_q": np.int64(n_q), "size": np.int64(size), "batch": np.int64(batch),
+           "frames": np.int64(frames)}
+    for channel_last in (False, True):
+        vq = ResidualVQ(n_q, dim=128, codebook_size=size, channel_last=channel_last).eval()
+        assert [k for k in vq.state_dict()][:4] == ["layers.0._codebook.initted", "layers.0._codebook.embed",
+                                                    "layers.0._codebook.ema_embed", "layers.0._codebook.ema_num"]
+        for layer, e in zip(vq.layers, embeds):
+            layer._codebook.embed.copy_(torch.from_numpy(e))
+        xin = torch.from_numpy(x if not channel_last else np.ascontiguousarray(x.transpose(0, 2, 1)))
+        for n in (None, 3, 1):
+            with torch.no_grad():
+                q, num_replaces, loss = vq(xin, n)
+            assert num_replaces.dtype == np.int64 and num_replaces.shape == (n_q,) and not num_replaces.any()
+            tag = f"{'cl' if channel_last else 'cf'}_{n}"
+            out[f"q_{tag}"] = q.numpy()
+            out[f"loss_{tag}"] = np.float32(loss.item())
+            print(name, tag, tuple(q.shape), float(loss))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["generic_rvq"]:
+        ref_generic_rvq("ref_generic_rvq.npz")
+        sys.exit(0)
     if sys.argv[1:] == ["music"]:
         ref_music_published("ref_music_published.npz")
         sys.exit(0)
@@ -136,5 +177,6 @@ if __name__ == "__main__":
     ref_random("ref_random_music.npz", 12, 2, batch=3, frames=10, stream_hops=3)
     ref_train("ref_train_random.npz", 6, 3, 5, batch=2, lengths=[320 * 8, 320 * 12 + 77, 333, 1])
     ref_music_published("ref_music_published.npz")
+    ref_generic_rvq("ref_generic_rvq.npz")
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
