@@ -3,17 +3,25 @@
 audio frames/s, 1 frame = 320 samples of 24 kHz audio = 1/75 s).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
 
-One "step" = one one-shot pass (zero caches) of the fused path over one batch of synthetic
-clips.  Workload per GPU: BASELINE.json configs[2] = hil_music, 256 clips x 24000 samples,
-n_q = 12 (the configuration the north-star target is quoted on); at N GPUs each rank runs its
-own 256-clip shard (weak scaling; N = 8 is configs[4], 2048 clips) with no data-path
-collective -- clips are independent.
+Headline workload (one "step" = one one-shot pass, zero caches, of the fused path over one batch of synthetic clips):
+BASELINE.json configs[2] = hil_music, 256 clips x 24000 samples, n_q = 12 per GPU -- the configuration the north-star
+target is quoted on; at N GPUs each rank runs its own 256-clip shard (weak scaling; N = 8 is configs[4], 2048 clips)
+with no data-path collective -- clips are independent.
 
-Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the launch stream,
-inputs resident in HBM, max over ranks; `e2e` goes through the C-ABI host-buffer call
-(`hil_codec_forward_host`: pinned-host H2D, forward, D2H of indices + PCM, stream sync).
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the launch stream, inputs resident in HBM, max
+over ranks; `e2e` goes through the C-ABI host-buffer call (`hil_codec_forward_host`: pinned-host H2D, forward, D2H of
+indices + PCM, stream sync).  At N = 1 with no --workload the same line also carries `other_workloads`: configs[1]
+(speech64) and configs[3] (stream1 / stream64: hil_music fed hop by hop, GPU-resident caches), each with its own value /
+e2e / roofline / cpu_baseline.  `--workload X` runs only X.
+
+CPU legs (`cpu_baseline`, `--impl reference`): the reference's OWN classes (models/hilcodec/streaming.py, unmodified
+copy in oracle/_ref made by oracle/build_ref.py) with the published weights on the box's host cores, `kind:
+"reference"`; if that copy is absent, the oracle port (`kind: "port"`).  Streaming is timed with the reference's
+protocol (scripts/HILCodec Onnx.ipynb cell 3, test_onnx.py:75-135): one 320-sample hop per call of encoder, quantizer,
+dequantizer and decoder, caches handed back as tensors -- with 1 thread (the reference's published setting,
+HILCodec Onnx.ipynb:35, test_onnx.py:4-8) and with all host cores.
 """
 from __future__ import annotations
 
@@ -35,13 +43,21 @@ WORKLOADS = {
     # name: (model, clips per GPU, samples, n_q, BASELINE.json config it is)
     "music256": ("hil_music", 256, 24000, 12, "configs[2]: hil_music, batch=256x24000 @24 kHz, n_q=12"),
     "speech64": ("hil_speech", 64, 24000, 8, "configs[1]: hil_speech, batch=64x24000 @24 kHz, n_q=8"),
-    # streaming (not a default bench line): `clips` concurrent streams fed hop by hop, one step = 75 hops = 1 s of audio
+    # streaming: `clips` concurrent streams fed hop by hop, one step = 75 hops = 1 s of audio per stream
     "stream1": ("hil_music", 1, 24000, 12, "configs[3]: hil_music streaming, hop 320, per-frame causal cache, 1 stream"),
     "stream64": ("hil_music", 64, 24000, 12, "configs[3]: hil_music streaming, hop 320, per-frame causal cache, 64 streams"),
 }
 FLOP_PER_FRAME = {"hil_speech": 456.257e6, "hil_music": 457.306e6}
-CATEGORIES = ["pointwise_gemm", "stft_gemm", "depthwise", "depthwise_transposed", "conv_pre", "conv_post_tanh",
-              "rvq", "misc"]
+FUSED_UNIT_BYTES_PER_FRAME = 4.2e6     # only ResBlock / resample-block inputs + outputs touch HBM
+LAYER_BOUNDARY_BYTES_PER_FRAME = 15.77e6   # every conv output written once and read once
+CATEGORIES = ["pointwise_gemm_narrow", "stft_gemm", "depthwise", "depthwise_transposed", "conv_pre", "conv_post_tanh",
+              "rvq", "misc", "pointwise_gemm_wide", "resblock_fused"]
+GEMM_CLASSES = {   # layer classes of the tensor-core GEMM kernels and the roofline that binds each
+    "pointwise_gemm_narrow": ("hbm", "th::gemm_h_kernel on layers with Cin, Cout < 384 (1x1, fused DWSBlock, fused upsampling)"),
+    "resblock_fused": ("hbm", "rb::resblock_kernel<128> (whole ResBlock, C <= 128)"),
+    "pointwise_gemm_wide": ("tensor", "th::gemm_h_kernel on layers with Cin or Cout >= 384"),
+}
+MMA_PER_PRODUCT = 3.0   # fp32-accurate product = hi*hi + hi*lo + lo*hi on kind::f16
 
 
 def parse_args():
@@ -50,8 +66,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="music256", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
     return ap.parse_args()
 
 
@@ -69,6 +86,18 @@ def synth(batch, samples, seed):
 
     g = torch.Generator().manual_seed(seed)
     return (0.1 * torch.randn(batch, 1, samples, generator=g)).clamp(-1, 1)
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    except Exception:
+        return {}, "fallback (B200_PROFILING.md): 6650 GB/s, 1590 TFLOP/s bf16"
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -92,6 +121,7 @@ class ClockSampler:
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+        return self
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -122,26 +152,76 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------- CPU reference arm
+# ----------------------------------------------------------------------------- CPU legs
+class CpuCodec:
+    """The reference's CPU implementation of the path: its own streaming.py classes when oracle/_ref (or the full
+    reference tree) is present, else the oracle port.  Test / measurement infrastructure: never on the product path."""
+
+    def __init__(self, model_name):
+        import numpy as np
+        import torch
+
+        from oracle import ref_shim
+
+        self.cfg, w, self.wdesc = load_weights(model_name)
+        self.n_q = self.cfg.num_quantizers
+        self.kind = "reference" if ref_shim.deploy_available() else "port"
+        if self.kind == "reference":
+            self.model = ref_shim.build_reference_model(w, self.n_q)
+            self.what = ("the reference's own models/hilcodec/streaming.py classes (unmodified copy, oracle/_ref), "
+                         f"{self.wdesc}, torch {torch.__version__} CPU")
+        else:
+            from oracle import hilcodec_oracle as O
+
+            self.O = O
+            self.p = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in w.items()}
+            self.ocfg = O.CodecConfig(num_quantizers=self.n_q)
+            self.what = f"oracle port of the reference's deployment graph, {self.wdesc}, torch {torch.__version__} CPU"
+
+    def one_shot(self, x, n):
+        import torch
+
+        from oracle import ref_shim
+
+        with torch.no_grad():
+            if self.kind == "reference":
+                return ref_shim.reference_forward(self.model, x, n)
+            return self.O.codec_forward(self.ocfg, self.p, x, n)
+
+    def stream(self, x, n, hop, frames):
+        """Frame by frame, caches as lists of tensors: notebook cell 3 / test_onnx.py:75-135.  Returns seconds."""
+        import torch
+
+        from oracle import ref_shim
+
+        with torch.no_grad():
+            if self.kind == "reference":
+                ce, cd = self.model.initialize_cache(x[:, :, :hop])
+            else:
+                ce = self.O.zero_caches(self.O.encoder_cache_shapes(self.ocfg, x.shape[0]))
+                cd = self.O.zero_caches(self.O.decoder_cache_shapes(self.ocfg, x.shape[0]))
+            t0 = time.perf_counter()
+            for f in range(frames):
+                chunk = x[:, :, f * hop:(f + 1) * hop]
+                if self.kind == "reference":
+                    r = ref_shim.reference_forward(self.model, chunk, n, ce, cd)
+                else:
+                    r = self.O.codec_forward(self.ocfg, self.p, chunk, n, ce, cd)
+                ce, cd = r["enc_caches"], r["dec_caches"]
+            return time.perf_counter() - t0
+
+
 def cpu_reference_run(model_name, n_q, samples, steps, warmup, budget_s):
-    """Time the CPU oracle port (oracle/hilcodec_oracle.py: the reference's deployment graph as
-    torch CPU ops -- the reference itself is a Python package that cannot travel to the GPU
-    box) on all host threads, on a bounded sample of the workload."""
-    import numpy as np
+    """One-shot batches on all host threads, on a bounded sample of the workload."""
     import torch
 
-    from oracle import hilcodec_oracle as O
-
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = host_cores()
     torch.set_num_threads(cores)
-    cfg, w, _ = load_weights(model_name)
-    p = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in w.items()}
-    ocfg = O.CodecConfig(num_quantizers=cfg.num_quantizers)
+    codec = CpuCodec(model_name)
 
     def run(x):
         t0 = time.perf_counter()
-        with torch.no_grad():
-            O.codec_forward(ocfg, p, x, n_q)
+        codec.one_shot(x, n_q)
         return time.perf_counter() - t0
 
     run(synth(1, samples, 99))                      # page-in / thread pool start
@@ -163,64 +243,182 @@ def cpu_reference_run(model_name, n_q, samples, steps, warmup, budget_s):
     for _ in range(warmup):
         step()
     times = [step() for _ in range(max(1, steps))]
-    frames = batch * (samples // cfg.hop)
+    frames = batch * (samples // codec.cfg.hop)
     sec = sum(times) / len(times)
     return {
-        "value": frames / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+        "value": frames / sec, "unit": "frames/s", "cores": cores, "kind": codec.kind,
         "sample": f"{reps} x {best_b} clips x {samples} samples of the workload per step (sub-batch {best_b} = fastest "
-                  f"of 1/2/4/8), {len(times)} timed steps ({sec:.2f} s/step), torch {torch.__version__} CPU, "
-                  f"{cores} threads",
+                  f"of 1/2/4/8), {len(times)} timed steps ({sec:.2f} s/step), {cores} threads; {codec.what}",
         "ms_per_step": sec * 1e3, "batch": batch,
     }
+
+
+def cpu_stream_run(model_name, n_q, streams, hop, budget_s, threads_list=None):
+    """The reference's frame-by-frame protocol on the host: 1 thread (its published setting) and all cores."""
+    import torch
+
+    cores = host_cores()
+    codec = CpuCodec(model_name)
+    out = {}
+    for threads in (threads_list or [1, cores]):
+        torch.set_num_threads(threads)
+        x = synth(streams, hop * 12, 77)
+        t = codec.stream(x, n_q, hop, 2)                         # warm-up, and a first estimate of a frame's cost
+        per = max(t / 2, 1e-4)
+        frames = int(max(2, min(75, budget_s / 2 / per)))
+        x = synth(streams, hop * frames, 1234)
+        sec = codec.stream(x, n_q, hop, frames)
+        out[threads] = {"value": streams * frames / sec, "unit": "frames/s", "cores": threads, "kind": codec.kind,
+                        "ms_per_frame": sec / frames * 1e3, "x_realtime_per_stream": (hop / 24000.0) / (sec / frames),
+                        "sample": f"{frames} sequential hops of {streams} stream(s), one encoder / quantizer / dequantizer / "
+                                  f"decoder call per hop with the caches handed back as tensors, {threads} thread(s); "
+                                  f"{codec.what}"}
+    torch.set_num_threads(cores)
+    best = out[cores] if cores in out else out[max(out)]
+    r = dict(best)
+    if 1 in out and cores != 1:
+        r["one_thread"] = out[1]     # the reference's own published protocol (RTF 0.41 on the authors' server)
+    return r
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    model_name, clips, samples, n_q, desc = WORKLOADS[args.workload]
-    r = cpu_reference_run(model_name, n_q, samples, args.steps, args.warmup, budget_s=150.0)
+    wl = args.workload or "music256"
+    model_name, clips, samples, n_q, desc = WORKLOADS[wl]
+    if wl.startswith("stream"):
+        hop = 320
+        r = cpu_stream_run(model_name, n_q, clips, hop, budget_s=min(150.0, 12.0 * max(1, args.steps)))
+        ms_step = r["ms_per_frame"] * (samples // hop)
+        cfgd = {"workload": desc, "model": model_name, "streams": clips, "hop": hop, "n_q": n_q,
+                "note": "CPU: bounded number of sequential hops, scaled to a 75-hop step"}
+    else:
+        r = cpu_reference_run(model_name, n_q, samples, args.steps, args.warmup, budget_s=150.0)
+        ms_step = r["ms_per_step"]
+        cfgd = {"workload": desc, "model": model_name, "clips_per_step": r["batch"], "samples": samples, "n_q": n_q,
+                "note": "CPU: bounded sample of the workload per step"}
     line = {
         "impl": "reference", "metric": "audio frames/sec (24 kHz enc+RVQ+dec)", "value": r["value"], "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "model": model_name, "clips_per_step": r["batch"], "samples": samples, "n_q": n_q,
-                   "note": "CPU: bounded sample of the workload per step"},
+        "config": cfgd,
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if "one_thread" in r:
+        line["cpu_baseline"]["one_thread"] = {k: r["one_thread"][k] for k in ("value", "unit", "cores", "ms_per_frame",
+                                                                             "x_realtime_per_stream")}
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- CUDA arm: shared set-up
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device (there is no CPU path in hilcodec_b200)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from hilcodec_b200 import _lib
+
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.peaks, self.peak_src = read_peaks()
+        self.hbm_peak = float(self.peaks.get("hbm_gbs", 6650.0))
+        self.bf16_peak = float(self.peaks.get("bf16_tflops_sustained", self.peaks.get("bf16_tflops", 1590.0)))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def profile_categories(ctx, step, prof_steps):
+    """Per-category kernel timing: a separate pass with CUDA events around every launch (hil_profile_begin / end)."""
+    n_cat = len(CATEGORIES)
+    arr_ms, arr_fl, arr_by = (C.c_double * n_cat)(), (C.c_double * n_cat)(), (C.c_double * n_cat)()
+    arr_n = (C.c_int64 * n_cat)()
+    ctx.torch.cuda.synchronize()
+    ctx._lib.check(ctx.lib.hil_profile_begin())
+    for _ in range(prof_steps):
+        step()
+    ctx._lib.check(ctx.lib.hil_profile_end(arr_ms, arr_fl, arr_by, arr_n, n_cat))
+    cats = {}
+    for i, name in enumerate(CATEGORIES):
+        if arr_n[i]:
+            cats[name] = {"ms_per_step": arr_ms[i] / prof_steps, "launches_per_step": arr_n[i] // prof_steps,
+                          "tflops": arr_fl[i] / (arr_ms[i] * 1e-3) / 1e12 if arr_ms[i] > 0 else 0.0,
+                          "gbs": arr_by[i] / (arr_ms[i] * 1e-3) / 1e9 if arr_ms[i] > 0 else 0.0,
+                          "algorithmic_bytes_per_step": arr_by[i] / prof_steps}
+    dump = os.environ.get("HILCODEC_DUMP_LAUNCHES")
+    if dump and ctx.rank == 0:   # launch-by-launch manifest of the profiled steps, for tools/summarize_launches.py
+        cap = 1 << 16
+        cat, ms, fl, by = (C.c_int32 * cap)(), (C.c_double * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+        n = ctx.lib.hil_profile_launches(cat, ms, fl, by, cap)
+        per = n // prof_steps
+        with open(dump, "w") as f:
+            json.dump({"launches_per_step": per,
+                       "launches": [{"cat": CATEGORIES[cat[i]], "ms": ms[i], "flops": fl[i], "bytes": by[i]}
+                                    for i in range(n - per, n)]}, f)
+    return cats
+
+
+def traffic_by_class():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic_by_class.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def class_roofline(ctx, name, c, traffic, workload):
+    bound, kernel = GEMM_CLASSES[name]
+    frac_hbm = c["gbs"] / ctx.hbm_peak
+    frac_tensor = c["tflops"] / ctx.bf16_peak
+    t = traffic.get(workload, {}).get(name) if traffic else None
+    per_launch = c["algorithmic_bytes_per_step"] / max(c["launches_per_step"], 1)
+    r = {"bound": bound, "kernel": kernel, "launches_per_step": c["launches_per_step"], "ms_per_step": c["ms_per_step"],
+         "achieved": c["gbs"] if bound == "hbm" else c["tflops"], "peak": ctx.hbm_peak if bound == "hbm" else ctx.bf16_peak,
+         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": frac_hbm if bound == "hbm" else frac_tensor,
+         "algorithmic_bytes_per_launch": per_launch,
+         "traffic": t["dram_bytes_per_launch_avg"] if t else None,
+         "hbm_frac": frac_hbm, "tensor_frac_of_bf16_peak": frac_tensor,
+         "tensor_frac_of_reachable": frac_tensor * MMA_PER_PRODUCT}
+    if t:
+        r["traffic_source"] = t.get("source")
+        r["traffic_over_algorithmic"] = t["dram_bytes_per_launch_avg"] / per_launch if per_launch else None
+    return r
+
+
 # ----------------------------------------------------------------------------- CUDA arm, streaming workloads
-def main_stream(args):
+def run_stream(ctx, wl, steps, warmup, with_cpu, cpu_budget=None):
     """BASELINE configs[3]: frame-by-frame streaming with GPU-resident caches.  One step = 75 sequential hops (1 s of
-    audio) of every stream; a hop is one CUDA-graph replay (`hil_codec_forward_graph`).  Single GPU (streams of
-    different GPUs are independent; `--gpus N` runs the same thing per rank and adds the rates up)."""
-    import torch
-    import torch.distributed as dist
-
-    from hilcodec_b200 import _lib
-    from hilcodec_b200 import streaming as S
+    audio) of every stream; a hop is one CUDA-graph replay (`hil_codec_forward_graph`).  Streams of different GPUs are
+    independent: `--gpus N` runs the same thing per rank and adds the rates up."""
+    torch, lib, _lib = ctx.torch, ctx.lib, ctx._lib
     from hilcodec_b200 import sharding
+    from hilcodec_b200 import streaming as S
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (there is no CPU path in hilcodec_b200)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    model_name, B, samples, n_q, desc = WORKLOADS[args.workload]
+    dev = ctx.dev
+    model_name, B, samples, n_q, desc = WORKLOADS[wl]
     cfg, w, wdesc = load_weights(model_name)
     model = S.HILCodec.from_weights(w, cfg.num_quantizers).cuda()
-    lib = _lib.load()
     hop, hops = cfg.hop, samples // cfg.hop
-    warm = max(args.warmup, 3)
-    x_host = synth(B, samples * (args.steps + warm + 2), 1234 + rank).pin_memory()
+    warm = max(warmup, 3)
+    x_host = synth(B, samples * (steps + warm + 2), 1234 + ctx.rank).pin_memory()
     x = x_host.to(dev)
     core = model._core
     hmodel, hstate = core.model(dev), core.state(dev, B)
@@ -241,100 +439,95 @@ def main_stream(args):
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    if world > 1:
-        dist.barrier()
+    sampler = ClockSampler(ctx.local).start() if ctx.rank == 0 else None
+    ctx.barrier()
     torch.cuda.synchronize()
     l0 = lib.hil_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches = (lib.hil_launch_count() - l0) // max(args.steps, 1)
+    ctx.barrier()
+    launches = (lib.hil_launch_count() - l0) // max(steps * hops, 1)
     ms = e0.elapsed_time(e1)
 
-    # e2e: every hop comes from pinned host memory and its indices + PCM go back to the host (C-ABI host call)
+    # e2e: every hop comes from pinned host memory and its indices + PCM go back to the host (C-ABI host call: H2D,
+    # graph replay, D2H, stream sync -- the latency a caller sees per hop)
     idx_host = torch.empty(n_q, B, 1, dtype=torch.int64).pin_memory()
     y_host = torch.empty(B, 1, hop, dtype=torch.float32).pin_memory()
     chunk_host = torch.empty(B, 1, hop, dtype=torch.float32).pin_memory()
-    checksum = 0.0
-    hpos = 0
+    checksum, hpos = 0.0, 0
+    for _ in range(3):   # the host call's own staging buffers / graph key
+        chunk_host.copy_(x_host[:, :, hpos:hpos + hop])
+        _lib.check(lib.hil_codec_forward_host(hmodel, hstate, chunk_host.data_ptr(), B, hop, n_q, idx_host.data_ptr(),
+                                              y_host.data_ptr(), sp))
+        hpos += hop
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps * hops):
+    for _ in range(steps * hops):
         chunk_host.copy_(x_host[:, :, hpos:hpos + hop])
         _lib.check(lib.hil_codec_forward_host(hmodel, hstate, chunk_host.data_ptr(), B, hop, n_q, idx_host.data_ptr(),
                                               y_host.data_ptr(), sp))
         checksum += float(y_host[0, 0, 0])
         hpos += hop
     ms_e2e = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
+    # where a hop goes (eager launches, events around each: shares matter, the sum carries ~2 us per launch of overhead)
+    st2 = core.state(dev, B)
+
+    def eager_hop():
+        _lib.check(lib.hil_codec_forward(hmodel, st2, xin.data_ptr(), B, hop, n_q, None, idx.data_ptr(), y.data_ptr(), sp))
+
+    cats = profile_categories(ctx, eager_hop, 20)
     ms, ms_e2e = sharding.reduce_max([ms, ms_e2e], device=dev)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    frames = B * hops * world
+    if ctx.rank != 0:
+        return None
+    frames = B * hops * ctx.world
     weight_bytes = float(sum(v.size * 4 for v in w.values()))
-    ms_hop = ms / (args.steps * hops)
+    ms_hop = ms / (steps * hops)
     line = {
-        "metric": "audio frames/sec (24 kHz enc+RVQ+dec)", "value": frames * args.steps / (ms * 1e-3), "unit": "frames/s",
-        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "metric": "audio frames/sec (24 kHz enc+RVQ+dec)", "value": frames * steps / (ms * 1e-3), "unit": "frames/s",
+        "n_gpus": ctx.world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": f"synthetic 0.1*randn audio, {wdesc}",
         "config": {"workload": desc, "model": model_name, "streams_per_gpu": B, "hop": hop, "hops_per_step": hops,
                    "n_q": n_q, "executor": "hil_codec_forward_graph (one CUDA-graph replay per hop)",
-                   "l2": "no flush: a hop re-reads the ~50 MB of weights, which fit the 126 MB L2, by design"},
+                   "l2": "no flush: a hop re-reads the ~50 MB of weights, which fit the 126 MB L2, by design",
+                   "deviation": "hop 320, not BASELINE's 300: 300 is AudioDec's hop and cannot be fed to HILCodec (BASELINE.md 2)"},
         "ms_per_hop": ms_hop, "x_realtime_per_stream": (hop / 24000.0) / (ms_hop * 1e-3),
-        "e2e": {"value": frames * args.steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": B * hop * 4 * hops,
-                "d2h_bytes_per_step": (n_q * B * 8 + B * hop * 4) * hops, "ms_per_step": ms_e2e / args.steps,
-                "api": "hil_codec_forward_host per hop (pinned host buffers, eager launches)", "checksum": checksum},
-        "gpu_launches": int(launches),
+        "e2e": {"value": frames * steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": B * hop * 4 * hops,
+                "d2h_bytes_per_step": (n_q * B * 8 + B * hop * 4) * hops, "ms_per_step": ms_e2e / steps,
+                "ms_per_hop": ms_e2e / (steps * hops),
+                "api": "hil_codec_forward_host per hop (pinned host buffers, graph replay, stream sync)", "checksum": checksum},
+        "gpu_launches": int(launches) * hops, "gpu_launches_per_hop": int(launches),
         "clocks": clocks,
-        # what a hop cannot avoid is reading every weight once; everything above that is latency
-        "roofline": {"bound": "hbm", "kernel": "whole hop (latency-bound chain of ~115 dependent launches)",
-                     "achieved": weight_bytes / (ms_hop * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": weight_bytes / (ms_hop * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+        # what a hop cannot avoid is reading every weight once; everything above that is launch / dependency latency
+        "roofline": {"bound": "hbm", "kernel": f"whole hop: a chain of {int(launches)} dependent launches; weights (L2-resident) read once per hop",
+                     "achieved": weight_bytes / (ms_hop * 1e-3) / 1e9, "peak": ctx.hbm_peak, "unit": "GB/s",
+                     "frac": weight_bytes / (ms_hop * 1e-3) / 1e9 / ctx.hbm_peak, "traffic": None,
+                     "algorithmic_bytes_per_hop": weight_bytes},
+        "kernel_categories_per_hop": {k: {"ms": v["ms_per_step"], "launches": v["launches_per_step"]} for k, v in cats.items()},
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if with_cpu and ctx.world == 1:
+        r = cpu_stream_run(model_name, n_q, B, hop, budget_s=cpu_budget or (16.0 if B == 1 else 24.0))
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_per_frame")}
+        if "one_thread" in r:
+            line["cpu_baseline"]["one_thread"] = {k: r["one_thread"][k] for k in ("value", "unit", "cores", "ms_per_frame",
+                                                                                 "x_realtime_per_stream", "sample")}
+    return line
 
 
-# ----------------------------------------------------------------------------- CUDA arm
-def main_ours(args):
-    import torch
-    import torch.distributed as dist
-
-    from hilcodec_b200 import _lib
+# ----------------------------------------------------------------------------- CUDA arm, one-shot batches
+def run_batch(ctx, wl, steps, warmup, with_cpu, cpu_budget=None):
+    torch, lib, _lib = ctx.torch, ctx.lib, ctx._lib
+    from hilcodec_b200 import sharding
     from hilcodec_b200 import streaming as S
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (there is no CPU path in hilcodec_b200)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    model_name, clips, samples, n_q, desc = WORKLOADS[args.workload]
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    model_name, clips, samples, n_q, desc = WORKLOADS[wl]
     cfg, w, wdesc = load_weights(model_name)
     model = S.HILCodec.from_weights(w, cfg.num_quantizers).cuda()
-    lib = _lib.load()
     B, T = clips, samples
     F = T // cfg.hop
     x_host = synth(B, T, 1234 + rank).pin_memory()
@@ -346,34 +539,29 @@ def main_ours(args):
     sp = stream.cuda_stream
     idx = torch.empty(n_q, B, F, dtype=torch.int64, device=dev)
     y = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
+    warm = max(warmup, 3)
 
     def step():
         _lib.check(lib.hil_state_reset(hstate, sp))
         _lib.check(lib.hil_codec_forward(hmodel, hstate, x.data_ptr(), B, T, n_q, None, idx.data_ptr(), y.data_ptr(), sp))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         step()
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
+    sampler = ClockSampler(ctx.local).start() if rank == 0 else None
+    ctx.barrier()
     torch.cuda.synchronize()
     l0 = lib.hil_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
-    barrier()
-    launches = (lib.hil_launch_count() - l0) // max(args.steps, 1)
+    ctx.barrier()
+    launches = (lib.hil_launch_count() - l0) // max(steps, 1)
     ms = e0.elapsed_time(e1)
 
     # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
@@ -387,99 +575,68 @@ def main_ours(args):
 
     for _ in range(2):
         step_host()
-    barrier()
+    ctx.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_host()
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    ctx.barrier()
+    clocks = sampler.stop() if sampler else None
     e2e_checksum = float(y_host.abs().sum())  # the device->host result is really read on the host
-
-    from hilcodec_b200 import sharding
     ms, ms_e2e = sharding.reduce_max([ms, ms_e2e], device=dev)  # a multi-GPU step is as slow as its slowest rank
 
-    # ---- per-category kernel timing (separate pass, CUDA events around every launch)
-    n_cat = len(CATEGORIES)
-    arr_ms, arr_fl, arr_by = (C.c_double * n_cat)(), (C.c_double * n_cat)(), (C.c_double * n_cat)()
-    arr_n = (C.c_int64 * n_cat)()
-    prof_steps = 2
-    torch.cuda.synchronize()
-    _lib.check(lib.hil_profile_begin())
-    for _ in range(prof_steps):
-        step()
-    _lib.check(lib.hil_profile_end(arr_ms, arr_fl, arr_by, arr_n, n_cat))
-    cats = {}
-    for i, name in enumerate(CATEGORIES):
-        if arr_n[i]:
-            cats[name] = {"ms_per_step": arr_ms[i] / prof_steps, "launches_per_step": arr_n[i] // prof_steps,
-                          "tflops": arr_fl[i] / (arr_ms[i] * 1e-3) / 1e12 if arr_ms[i] > 0 else 0.0,
-                          "gbs": arr_by[i] / (arr_ms[i] * 1e-3) / 1e9 if arr_ms[i] > 0 else 0.0}
+    # ---- config 5 "via NCCL": all-gather of every rank's indices + PCM (outside the step: the path itself has no
+    # collective; this is what collecting the results of the batch split costs)
+    gather = None
+    if world > 1:
+        placeholder = torch.empty(world * B, 1, 0, device=dev)   # forward_sharded only needs the full batch size
 
+        def gather_once():
+            return sharding.forward_sharded(lambda xs: (idx, y), placeholder, gather=True)
+
+        gather_once()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        g0.record(stream)
+        for _ in range(5):
+            gi, gy = gather_once()
+        g1.record(stream)
+        torch.cuda.synchronize()
+        gms = sharding.reduce_max([g0.elapsed_time(g1) / 5], device=dev)[0]
+        by = world * (idx.numel() * 8 + y.numel() * 4)
+        gather = {"ms": gms, "bytes_received_per_rank": by, "gbs_per_rank": by / (gms * 1e-3) / 1e9,
+                  "what": "torch.distributed.all_gather (NCCL) of idx [n,B,F] int64 + wav [B,1,T] fp32 from every rank, "
+                          "after the step; not inside `value`", "shape_ok": bool(gi.shape[1] == world * B and gy.shape[0] == world * B)}
+
+    cats = profile_categories(ctx, step, 2)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    peaks, peak_src = {}, "fallback (B200_PROFILING.md): 6650 GB/s, 1590 TFLOP/s bf16"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-        peak_src = "MEASURED_PEAKS.json"
-    except Exception:
-        pass
-    bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-    traffic, traffic_step = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
-            tj = json.load(f)
-        traffic, traffic_step = tj.get("dram_bytes_per_launch_avg"), tj.get("dram_bytes_per_step")
-    except Exception:
-        pass
-    pw = cats.get("pointwise_gemm", {"tflops": 0.0, "gbs": 0.0, "ms_per_step": 0.0, "launches_per_step": 0})
-    if traffic_step is not None and model_name == "hil_music" and B == 256:
-        traffic = traffic_step                        # ncu DRAM bytes of the category's launches in one music256 step
-    elif traffic is not None:
-        traffic = traffic * pw["launches_per_step"]   # other workloads: per-launch average x launches (rough)
-    dominant = max(cats, key=lambda k: cats[k]["ms_per_step"]) if cats else None
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # The dominant kernels are the tensor-core GEMMs (plain 1x1, fused DWS block, fused ResBlock, fused upsampling
-    # layer).  Two rooflines apply to them; the binding one is the one with the higher time floor for the step's
-    # algorithmic work: HBM (bytes / measured copy bandwidth) or the tensor pipe (3 fp16 MMAs per fp32-accurate
-    # product -> FLOPs * 3 / measured bf16 throughput).  Both fractions are reported.
-    MMA_PER_PRODUCT = 3.0
-    frac_hbm = pw["gbs"] / hbm_peak if hbm_peak else 0.0
-    frac_tensor = pw["tflops"] * MMA_PER_PRODUCT / bf16_peak if bf16_peak else 0.0
-    bound = "hbm" if frac_hbm >= frac_tensor else "tensor"
-    roofline = {
-        "bound": bound,
-        "kernel": "th::gemm_h_kernel / rb::resblock_kernel (tcgen05 kind::f16 hi/lo-split GEMMs: 1x1 conv, fused DWS "
-                  "block, fused ResBlock, fused upsampling layer; all launches of the step)",
-        "achieved": pw["gbs"] if bound == "hbm" else pw["tflops"],
-        "peak": hbm_peak if bound == "hbm" else bf16_peak,
-        "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-        "frac": frac_hbm if bound == "hbm" else pw["tflops"] / bf16_peak,
-        "traffic": traffic,
-        "peak_source": f"{peak_src}: hbm_gbs / bf16_tflops_sustained (kernels timed inside a long step)",
-        "hbm": {"achieved_gbs": pw["gbs"], "peak_gbs": hbm_peak, "frac": frac_hbm,
-                "bytes": "algorithmic: every launch reads its inputs once and writes its outputs once (codec.cu HIL_LAUNCH)"},
-        "tensor": {"achieved_tflops": pw["tflops"], "peak_tflops": bf16_peak, "frac_of_bf16_peak": pw["tflops"] / bf16_peak,
-                   "mma_per_product": MMA_PER_PRODUCT, "frac_of_reachable": frac_tensor},
-        "share_of_step": pw["ms_per_step"] / (sum(c["ms_per_step"] for c in cats.values()) or 1.0),
-        "dominant_category": dominant,
-        "note": "fp32-accurate arithmetic is required for bit-exact VQ indices: every product is 3 fp16 MMAs "
-                "(hi*hi, hi*lo, lo*hi) into two fp32 TMEM accumulators, so the tensor ceiling is bf16 peak / 3; the "
-                "binding roofline is the one with the larger fraction",
-    }
-
+    traffic = traffic_by_class()
+    total_ms = sum(c["ms_per_step"] for c in cats.values()) or 1.0
+    by_class = {k: class_roofline(ctx, k, cats[k], traffic, wl) for k in GEMM_CLASSES if k in cats}
+    for k, r in by_class.items():
+        r["share_of_step"] = cats[k]["ms_per_step"] / total_ms
+    dominant = max(by_class, key=lambda k: by_class[k]["ms_per_step"]) if by_class else None
     frames_total = B * F * world
-    value = frames_total * args.steps / (ms * 1e-3)
-    e2e_value = frames_total * args.steps / (ms_e2e * 1e-3)
+    value = frames_total * steps / (ms * 1e-3)
+    e2e_value = frames_total * steps / (ms_e2e * 1e-3)
+    frames_rank = B * F
+    step_s = ms / steps * 1e-3
+    roofline = dict(by_class[dominant]) if dominant else {}
+    roofline.update({
+        "dominant_class": dominant,
+        "peak_source": f"{ctx.peak_src}: hbm_gbs / bf16_tflops_sustained (kernels timed inside a long step)",
+        "bytes": "algorithmic: every launch reads its inputs once and writes its outputs once (codec.cu HIL_LAUNCH)",
+        "note": "fp32-accurate arithmetic is required for bit-exact VQ indices: every product is 3 fp16 MMAs (hi*hi, "
+                "hi*lo, lo*hi) into two fp32 TMEM accumulators, so the reachable tensor ceiling is the bf16 peak / 3",
+    })
     line = {
         "metric": "audio frames/sec (24 kHz enc+RVQ+dec)", "value": value, "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": f"synthetic 0.1*randn audio, {wdesc}",
         "config": {"workload": desc, "model": model_name, "clips_per_gpu": B, "samples": T, "n_q": n_q,
                    "sharding": f"batch-sharded x{world}, no data-path collective",
@@ -487,26 +644,61 @@ def main_ours(args):
         "rtf_x_realtime": value / 75.0,
         "model_tflops": value * FLOP_PER_FRAME[model_name] / 1e12,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * 4,
-                "d2h_bytes_per_step": n_q * B * F * 8 + B * T * 4, "ms_per_step": ms_e2e / args.steps,
+                "d2h_bytes_per_step": n_q * B * F * 8 + B * T * 4, "ms_per_step": ms_e2e / steps,
                 "api": "hil_codec_forward_host (pinned host buffers)", "checksum": e2e_checksum},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "kernel_categories": cats,
+        "roofline_by_class": by_class,
+        # the whole step against both rooflines, with SURVEY 8(d)'s two byte models next to the per-launch bytes
+        "step_roofline": {
+            "tensor_frac_of_reachable": frames_rank * FLOP_PER_FRAME[model_name] / step_s / 1e12 * MMA_PER_PRODUCT / ctx.bf16_peak,
+            "hbm_frac_fused_unit_bytes": frames_rank * FUSED_UNIT_BYTES_PER_FRAME / step_s / 1e9 / ctx.hbm_peak,
+            "hbm_frac_layer_boundary_bytes": frames_rank * LAYER_BOUNDARY_BYTES_PER_FRAME / step_s / 1e9 / ctx.hbm_peak,
+            "hbm_frac_per_launch_bytes": sum(c["algorithmic_bytes_per_step"] for c in cats.values()) / step_s / 1e9 / ctx.hbm_peak,
+            "bytes_per_frame": {"fused_unit_model": FUSED_UNIT_BYTES_PER_FRAME, "layer_boundary_model": LAYER_BOUNDARY_BYTES_PER_FRAME,
+                                "per_launch_algorithmic": sum(c["algorithmic_bytes_per_step"] for c in cats.values()) / frames_rank},
+        },
+        "kernel_categories": {k: {kk: vv for kk, vv in v.items() if kk != "algorithmic_bytes_per_step"} for k, v in cats.items()},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(model_name, n_q, samples, steps=2, warmup=0, budget_s=40.0)
+    if gather:
+        line["gather"] = gather
+    if world == 1 and with_cpu:
+        r = cpu_reference_run(model_name, n_q, samples, steps=4, warmup=1, budget_s=cpu_budget or 40.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def condensed(line):
+    keep = ("value", "unit", "ms_per_step", "ms_per_hop", "x_realtime_per_stream", "rtf_x_realtime", "e2e", "roofline",
+            "cpu_baseline", "gpu_launches", "gpu_launches_per_hop", "config", "data", "steps", "warmup")
+    return {k: line[k] for k in keep if k in line}
+
+
+def main_ours(args):
+    ctx = Ctx()
+    wl = args.workload or "music256"
+    with_cpu = not args.no_cpu_baseline
+    run = run_stream if wl.startswith("stream") else run_batch
+    line = run(ctx, wl, args.steps, args.warmup, with_cpu)
+    if line is not None and args.workload is None and ctx.world == 1 and not args.no_other_workloads:
+        # the other BASELINE configs that fit one GPU, in the same contract (shorter runs: they are not the headline)
+        others = {}
+        for name, st in (("speech64", 10), ("stream1", 4), ("stream64", 4)):
+            try:
+                r = (run_stream if name.startswith("stream") else run_batch)(ctx, name, st, 3, with_cpu, cpu_budget=14.0)
+                others[name] = condensed(r)
+            except Exception as e:  # a secondary workload must not take the headline line down with it
+                others[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["other_workloads"] = others
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         main_reference(a)
-    elif a.workload.startswith("stream"):
-        main_stream(a)
     else:
         main_ours(a)

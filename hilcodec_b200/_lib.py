@@ -60,6 +60,9 @@ SIGNATURES = {
     "hil_state_import_cache": (_I, [_P, _I, _I, _P, _P]),
     "hil_state_destroy": (None, [_P]),
     "hil_state_workspace_bytes": (C.c_size_t, [_P]),
+    "hil_state_range_flag": (_I, [_P, _I, _P, C.POINTER(_I)]),
+    "hil_state_rollback": (_I, [_P, _I, _I]),
+    "hil_set_exact_fp32": (_I, [_I]),
     "hil_encode": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "hil_encode_caches": (_I, [_P, _P, _P, _I, _I, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "hil_encode_ragged": (_I, [_P, _P, _P, _I, _I, _P, _P]),
@@ -78,6 +81,7 @@ SIGNATURES = {
     "hil_profile_begin": (_I, []),
     "hil_profile_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                              C.POINTER(C.c_int64), _I]),
+    "hil_profile_launches": (_I, [C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _I]),
     "hil_op_dwconv": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "hil_op_dwconv_transpose": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "hil_op_pointwise": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhilcodec_b200.so")
-SOURCES = ["gemm.cu", "gemm_skinny.cu", "gemm_tc.cu", "gemm_h.cu", "gemm_rb.cu", "gemm_tm.cu", "stft_tc.cu", "conv.cu", "rvq.cu", "bitpack.cu", "codec.cu"]
+SOURCES = ["gemm.cu", "gemm_skinny.cu", "gemm_tc.cu", "gemm_h.cu", "gemm_rb.cu", "stft_tc.cu", "conv.cu", "rvq.cu", "bitpack.cu", "codec.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -47,7 +47,11 @@ constexpr int HIL_MAX_RES = 16;  // ResBlocks per stage (2 / 3 in the published 
 
 namespace {
 
-enum Cat { CAT_GEMM_PW = 0, CAT_GEMM_STFT, CAT_DW, CAT_DWT, CAT_CONV_PRE, CAT_CONV_POST, CAT_RVQ, CAT_MISC, CAT_COUNT };
+enum Cat { CAT_GEMM_PW = 0, CAT_GEMM_STFT, CAT_DW, CAT_DWT, CAT_CONV_PRE, CAT_CONV_POST, CAT_RVQ, CAT_MISC, CAT_GEMM_WIDE,
+           CAT_RESBLOCK, CAT_COUNT };
+// 1x1 / fused-DWS / fused-upsampling GEMMs by layer class: narrow layers (C < 384) are HBM-bound, wide ones are bound by
+// the tensor pipe and its operand stream out of L2
+static inline int gemm_cat(const hil::PackedMat& W) { return (W.M >= 384 || W.K >= 384) ? CAT_GEMM_WIDE : CAT_GEMM_PW; }
 
 struct ProfRec {
     int cat;
@@ -55,9 +59,15 @@ struct ProfRec {
     double flops, bytes;
 };
 
+struct ProfDone {
+    int cat;
+    double ms, flops, bytes;
+};
+
 struct Profiler {
     bool on = false;
     std::vector<ProfRec> recs;
+    std::vector<ProfDone> done;   // the last finished profile, launch by launch (hil_profile_launches)
     unsigned long long launches = 0;
 };
 Profiler g_prof;
@@ -94,11 +104,12 @@ struct LaunchScope {
 
 
 static bool g_use_tc = std::getenv("HILCODEC_DISABLE_TC") == nullptr;  // tensor-core GEMM on unless disabled
+// fp16-range guard (hil_set_exact_fp32): while set on this thread every GEMM / STFT runs on the FP32 FFMA kernels, whose
+// operands are never narrowed -- the path a call is repeated on when its tensor-core run produced non-finite output
+// (an activation beyond the fp16 range, |x| >= 65504, splits into Inf / NaN; the reference has no such limit)
+static thread_local bool tl_exact_fp32 = false;
+static inline bool tc_on() { return g_use_tc && !tl_exact_fp32; }
 static bool g_fuse_dw = std::getenv("HILCODEC_DISABLE_DWS_FUSION") == nullptr;
-// time-major kernel (gemm_tm.cu) for Cout <= 192: experimental, off by default -- correct (same bits as
-// gemm_tc.cu) but its register->global epilogue exposes the residual-load latency and it measured slower
-// (493 us vs 187 us on the stage-0 SpecBlock 1x1 at B = 64); enable with HILCODEC_ENABLE_TM=1 or mode bit 3.
-static bool g_use_tm = std::getenv("HILCODEC_ENABLE_TM") != nullptr;
 // fp16-split tensor-core kernel (gemm_h.cu, kind::f16 at twice the tf32 rate, decoupled load / operand rings):
 // mode bit 4 (16) of hil_set_tensor_cores, or HILCODEC_GEMM=tf32 to fall back to gemm_tc.cu.
 static bool g_use_h = []() { const char* e = std::getenv("HILCODEC_GEMM"); return !(e && std::strcmp(e, "tf32") == 0); }();
@@ -111,23 +122,20 @@ static bool g_fuse_rb = []() { const char* e = std::getenv("HILCODEC_FUSE_RESBLO
 // hil_set_tensor_cores or HILCODEC_FUSE_UPSAMPLE=0 keep the two launches.
 static bool g_fuse_up = []() { const char* e = std::getenv("HILCODEC_FUSE_UPSAMPLE"); return !(e && e[0] == '0'); }();
 // The fused kernel recomputes the transposed conv once per 128-row output tile; with more than two row tiles
-// (Cout > 256: decoder stages 0 and 1) that costs more than the HBM traffic it saves (measured), unless forced.
-static const bool g_fuse_up_wide = std::getenv("HILCODEC_FUSE_UPSAMPLE_WIDE") != nullptr;
+// (Cout > 256: decoder stages 0 and 1) that costs more than the HBM traffic it saves (measured in round 1), so
+// those layers keep the two launches.
 
 // ---- accounted launch wrappers (same arguments as the launch_* functions) ----------------
 static int32_t run_gemm_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                                cudaStream_t st) {
     const double n = (double)B * T;
-    const bool use_tc = g_use_tc && !gemm_skinny_preferred(W, B, T);
-    const bool tmajor = use_tc && g_use_tm && gemm_tm_usable(W, X, x_bs, x_rs, T, Y, y_bs, y_rs);
-    const bool tcore = use_tc && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
-    const bool hcore = use_tc && g_use_h && gemm_h_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs);
-    // short chunks (streaming) that no tensor-core kernel takes: skinny-N kernel when enabled (HILCODEC_SKINNY=1)
-    const bool skinny = !tmajor && !tcore && !hcore && gemm_skinny_usable(W, B, T);
-    HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
-               tmajor  ? launch_gemm_tm(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
-               : hcore ? launch_gemm_h(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
+    const bool tcore = tc_on() && gemm_tc_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs, B);
+    const bool hcore = tc_on() && g_use_h && gemm_h_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs, B);
+    // short chunks (streaming) that no tensor-core kernel takes: the skinny-N kernel (<= 512 columns), else gemm.cu
+    const bool skinny = !tcore && !hcore && gemm_skinny_usable(W, B, T);
+    HIL_LAUNCH(gemm_cat(W), 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M * (R ? 2 : 1)) + 4.0 * W.M * W.K, st,
+               hcore   ? launch_gemm_h(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
                : tcore ? launch_gemm_tc(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
                : skinny ? launch_gemm_skinny_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st)
                         : launch_gemm_linear(W, X, x_bs, x_rs, B, T, pre, pre_scale, bias, R, Y, y_bs, y_rs, st));
@@ -143,7 +151,7 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
 static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int T, const float* bias, float* Y,
                                   long long y_bs, int y_rs, cudaStream_t st) {
     const double n = (double)B * T;
-    HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M) + 4.0 * W.M * W.K, st,
+    HIL_LAUNCH(gemm_cat(W), 2.0 * W.M * W.K * n, 4.0 * n * (W.K + W.M) + 4.0 * W.M * W.K, st,
                gemm_skinny_usable(W, B, T) ? launch_gemm_skinny_chlast_in(W, Q, B, T, bias, Y, y_bs, y_rs, st)
                                            : launch_gemm_chlast_in(W, Q, B, T, bias, Y, y_bs, y_rs, st));
     return HIL_OK;
@@ -151,7 +159,7 @@ static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
 static int32_t run_gemm_stft_logmag(const PackedMat& Wd, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
                                     long long y_bs, int y_rs, cudaStream_t st) {
     const double n = (double)B * T;
-    const bool tcore = g_use_tc && !gemm_skinny_preferred(Wd, B, T) && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs);
+    const bool tcore = tc_on() && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs);
     HIL_LAUNCH(CAT_GEMM_STFT, 2.0 * Wd.M * Wd.K * n, 4.0 * (n * hop + n * (Wd.M / 2)) + 4.0 * Wd.M * Wd.K, st,
                tcore ? launch_stft_tc(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
                : gemm_skinny_usable(Wd, B, T) ? launch_gemm_skinny_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
@@ -182,12 +190,12 @@ static int32_t run_dwconv(const float* x, long long x_bs, int x_rs, const float*
 static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs, int B, int T, int pre, float pre_scale,
                        const float* dw_w, const float* dw_b, const float* ci, float* co, const float* skip, int post,
                        float post_scale, float* tmp, float* Y, cudaStream_t st) {
-    const bool hcore = g_use_h && gemm_h_usable(W, X, bs, rs, T, skip, Y, bs, rs);
+    const bool hcore = g_use_h && gemm_h_usable(W, X, bs, rs, T, skip, Y, bs, rs, B);
     // store-side ELU (post == PRE_ELU, no skip) exists in the fp16-split kernel only
     const bool post_ok = post == PRE_NONE || (post == PRE_ELU && !skip && hcore);
-    if (g_use_tc && g_fuse_dw && post_ok && !gemm_skinny_preferred(W, B, T) && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs)) {
+    if (tc_on() && g_fuse_dw && post_ok && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs, B)) {
         const double n = (double)B * T;
-        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
+        HIL_LAUNCH(gemm_cat(W), 2.0 * W.M * W.K * n + 10.0 * W.M * n,
                    4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
                    hcore ? launch_gemm_h_dw(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, Y, bs, rs, st,
                                             post == PRE_ELU)
@@ -195,9 +203,9 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
         return HIL_OK;
     }
     if (gemm_skinny_dws_usable(W, B, T) && X != Y) {
-        // streaming chunk: the depthwise conv rides in the skinny GEMM's epilogue (HILCODEC_SKINNY=1)
+        // streaming chunk: the depthwise conv rides in the skinny GEMM's epilogue
         const double n = (double)B * T;
-        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * W.K * n + 10.0 * W.M * n,
+        HIL_LAUNCH(gemm_cat(W), 2.0 * W.M * W.K * n + 10.0 * W.M * n,
                    4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,
                    launch_gemm_skinny_dws(W, X, bs, rs, B, T, pre, pre_scale, dw_w, dw_b, ci, co, skip, post, post_scale, Y,
                                           bs, rs, st));
@@ -211,11 +219,12 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
 // ResBlock.forward streaming.py:252-275 as ONE tensor-core kernel (+ the halo gather in front of it)
 static int32_t run_resblock(const PackedMat& W0, const PackedMat& W1, float* h, long long bs, int rs, int B, int T, int pre,
                             float pre_scale, const float* dw0_w, const float* dw0_b, const float* dw1_w, const float* dw1_b,
-                            const float* c0i, float* c0o, const float* c1i, float* c1o, float* halo, cudaStream_t st) {
+                            const float* c0i, float* c0o, const float* c1i, float* c1o, float* halo, cudaStream_t st,
+                            double flop_scale = 1.0) {   // 0.5 for the clip-pair form: half of diag(W, W) is zeros
     const double n = (double)B * T, C = W0.M;
     const double halo_bytes = 4.0 * (double)resblock_h_halo_floats(W0.M, T, B);
     HIL_LAUNCH(CAT_MISC, 0.0, 2.0 * halo_bytes, st, launch_resblock_halo(h, bs, rs, B, W0.M, T, halo, st));
-    HIL_LAUNCH(CAT_GEMM_PW, 2.0 * (2.0 * C * C * n + 10.0 * C * n), 8.0 * n * C + halo_bytes + 8.0 * C * C, st,
+    HIL_LAUNCH(CAT_RESBLOCK, 2.0 * (2.0 * C * C * n * flop_scale + 10.0 * C * n), 8.0 * n * C + halo_bytes + 8.0 * C * C * flop_scale, st,
                launch_resblock_h(W0, W1, h, bs, rs, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0i, c0o, c1i, c1o, halo,
                                  st));
     return HIL_OK;
@@ -234,69 +243,31 @@ static int32_t run_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
 static int32_t run_upsample(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T_in, int S, int pre,
                             float pre_scale, const float* up_w, const float* ci, float* co, const float* bias, float* tmp,
                             float* Y, long long y_bs, int y_rs, bool allow_fused, cudaStream_t st,
-                            bool allow_fused_wide = false, bool allow_planes = false) {
+                            bool allow_fused_wide = false) {
     const int K = W.K, T = S * T_in;
-    if (gemm_skinny_preferred(W, B, T)) allow_fused = allow_fused_wide = allow_planes = false;
-    if (allow_fused && g_use_tc && g_use_h && g_fuse_up && (W.M <= 256 || g_fuse_up_wide || allow_fused_wide) &&
+    if (allow_fused && tc_on() && g_use_h && g_fuse_up && (W.M <= 256 || allow_fused_wide) &&
         gemm_h_up_usable(W, x, x_bs, x_rs, T_in, S, pre, Y, y_bs, y_rs)) {
         const double n = (double)B * T;
-        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * K * n + 4.0 * K * n, 4.0 * ((double)B * K * T_in + n * W.M) + 4.0 * W.M * K, st,
+        HIL_LAUNCH(gemm_cat(W), 2.0 * W.M * K * n + 4.0 * K * n, 4.0 * ((double)B * K * T_in + n * W.M) + 4.0 * W.M * K, st,
                    launch_gemm_h_up(W, x, x_bs, x_rs, B, T_in, S, pre, pre_scale, up_w, ci, co, bias, Y, y_bs, y_rs, st));
         return HIL_OK;
     }
     const int Tp2 = pitch4(T);
-    // Wide layers, off by default (HILCODEC_PLANES=1): the transposed conv writes fp16 hi/lo planes into `tmp` (same
-    // bytes as the fp32 tensor) and the 1x1 conv consumes them by TMA with no conversion pass.  Measured: the GEMM is
-    // not faster without its transform (1577 vs 1544 us at decoder stage 1: ~900 cycles per k-block either way, the
-    // 32 KB of operands per k-block and SM coming from L2 are the limit) and the planes-writing conv is slower.
-    static const bool use_planes = []() { const char* e = std::getenv("HILCODEC_PLANES"); return e && e[0] == '1'; }();
-    const int p_rs = (T + 7) & ~7;
-    const long long p_bs = (long long)K * p_rs;
-    uint16_t* hi = reinterpret_cast<uint16_t*>(tmp);
-    uint16_t* lo = hi + (long long)B * p_bs;
-    if (((allow_fused && use_planes) || allow_planes) && g_use_tc && g_use_h && p_rs <= Tp2 && (pre == PRE_NONE || pre == PRE_SCALE_ELU) &&
-        dwconv_transpose_planes_usable(x, x_bs, x_rs, T_in, S, p_bs, p_rs) &&
-        gemm_h_planes_usable(W, hi, lo, p_bs, p_rs, T, Y, y_bs, y_rs)) {
-        const double nin = (double)B * K * T_in, n = (double)B * T;
-        HIL_LAUNCH(CAT_DWT, 4.0 * nin * S, 4.0 * (nin + nin * S), st,
-                   launch_dwconv_transpose_planes(x, x_bs, x_rs, ci, co, up_w, hi, lo, p_bs, p_rs, B, K, T_in, S, pre, pre_scale,
-                                                  st));
-        HIL_LAUNCH(CAT_GEMM_PW, 2.0 * W.M * K * n, 4.0 * n * (K + W.M) + 4.0 * W.M * K, st,
-                   launch_gemm_h_planes(W, hi, lo, p_bs, p_rs, B, T, bias, Y, y_bs, y_rs, st));
-        return HIL_OK;
-    }
-    // HILCODEC_STAGE_CHUNK_MB (off by default, see res_blocks_of_stage): the [K][S * T_in] intermediate is the largest
-    // tensor of the decoder; in sub-batches that fit the L2 (always the same `tmp` rows) it never reaches HBM
-    static const long long budget = []() {
-        const char* e = std::getenv("HILCODEC_STAGE_CHUNK_MB");
-        return e ? std::atoll(e) * (1LL << 20) : 0LL;
-    }();
-    int nb = B;
-    if (budget > 0) {
-        const long long per_clip = (long long)K * Tp2 * (long long)sizeof(float);
-        const long long n = budget / (per_clip > 0 ? per_clip : 1);
-        nb = (int)(n < 1 ? 1 : (n > B ? B : n));
-    }
-    for (int b0 = 0; b0 < B; b0 += nb) {
-        const int nbb = B - b0 < nb ? B - b0 : nb;
-        HIL_TRY(run_dwconv_transpose(x + (long long)b0 * x_bs, x_bs, x_rs, ci + (size_t)b0 * K, co + (size_t)b0 * K, up_w, tmp,
-                                     (long long)K * Tp2, Tp2, nbb, K, T_in, S, pre, pre_scale, st));
-        HIL_TRY(run_gemm_linear(W, tmp, (long long)K * Tp2, Tp2, nbb, T, PRE_NONE, 1.f, bias, nullptr, Y + (long long)b0 * y_bs,
-                                y_bs, y_rs, st));
-    }
-    return HIL_OK;
+    HIL_TRY(run_dwconv_transpose(x, x_bs, x_rs, ci, co, up_w, tmp, (long long)K * Tp2, Tp2, B, K, T_in, S, pre, pre_scale, st));
+    return run_gemm_linear(W, tmp, (long long)K * Tp2, Tp2, B, T, PRE_NONE, 1.f, bias, nullptr, Y, y_bs, y_rs, st);
 }
 
 static int32_t run_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* ci, float* co, const float* w,
                                   const float* bias, float* y, int B, int C, int T, int K, int pre, float pre_scale,
-                                  cudaStream_t st) {
+                                  int* nonfinite, cudaStream_t st) {
     HIL_LAUNCH(CAT_CONV_POST, 2.0 * B * C * (double)T * K, 4.0 * B * (double)T * (C + 1), st,
-               launch_conv_post_tanh(x, x_bs, x_rs, ci, co, w, bias, y, B, C, T, K, pre, pre_scale, st));
+               launch_conv_post_tanh(x, x_bs, x_rs, ci, co, w, bias, y, B, C, T, K, pre, pre_scale, nonfinite, st));
     return HIL_OK;
 }
 static int32_t run_l2norm_chlast(const float* x, long long x_bs, int x_rs, float* z, int B, int C, int F, float scale,
-                                 cudaStream_t st) {
-    HIL_LAUNCH(CAT_MISC, 0.0, 8.0 * B * C * (double)F, st, launch_l2norm_chlast(x, x_bs, x_rs, z, B, C, F, scale, st));
+                                 int* nonfinite, cudaStream_t st) {
+    HIL_LAUNCH(CAT_MISC, 0.0, 8.0 * B * C * (double)F, st,
+               launch_l2norm_chlast(x, x_bs, x_rs, z, B, C, F, scale, nonfinite, st));
     return HIL_OK;
 }
 static int32_t run_rvq_encode(const float* z, const float* cb, const float* ee, int size, int dim, long long frames, int n,
@@ -325,6 +296,13 @@ struct Dws {  // DWSBlock streaming.py:160-192
     PackedMat pw;
     const float* dw_w = nullptr;
     const float* dw_b = nullptr;
+    // Clip-pair form for C <= 64 (see res_block): [B][C][T] is the same memory as [B/2][2C][T], so two clips run as ONE
+    // 2C-channel problem with the block-diagonal weight diag(W, W) and the depthwise taps / biases repeated.  The fused
+    // ResBlock kernel maps channels to TMEM lanes; at C = 64 half of its epilogue lanes (and two of the four SM
+    // sub-partitions) would otherwise idle.  The extra products are exact zeros, so the result is bit-identical.
+    PackedMat pw2;
+    const float* dw_w2 = nullptr;
+    const float* dw_b2 = nullptr;
 };
 
 struct EncStage {
@@ -399,6 +377,7 @@ struct hil_state {
     int64_t* idx_dev = nullptr;
     size_t idx_elems = 0;
     void* rvq_scratch = nullptr;  // inside cache_arena
+    int* range_flag = nullptr;    // inside cache_arena: set by the tail kernels when z / wav come out non-finite
     float* io_dev = nullptr;  // staging for the *_host call
     size_t io_floats = 0;
     // streaming executor: instantiated CUDA graphs of one fused step, keyed by everything a replay bakes in
@@ -482,6 +461,28 @@ struct Builder {
         const HostTensor* t = get(name, {2 * F, 1, n_fft});
         if (!t) return;
         pack(t->data.data(), 2 * F, n_fft, 6, true, dst);
+    }
+    // diag(W, W) for the clip-pair form, and a per-channel array repeated for the second clip
+    void linear_pair(const std::string& name, int C, PackedMat* dst) {
+        const HostTensor* t = get(name, {C, C, 1});
+        if (!t) return;
+        std::vector<float> w2((size_t)4 * C * C, 0.f);
+        for (int r = 0; r < C; ++r)
+            for (int k = 0; k < C; ++k) {
+                const float v = t->data[(size_t)r * C + k];
+                w2[(size_t)r * 2 * C + k] = v;
+                w2[(size_t)(C + r) * 2 * C + C + k] = v;
+            }
+        pack(w2.data(), 2 * C, 2 * C, choose_tm(2 * C), false, dst);
+    }
+    void raw_pair(const std::string& name, std::vector<int64_t> dims, const float** dst) {
+        const HostTensor* t = get(name, dims);
+        if (!t) return;
+        const size_t n = t->data.size();
+        const size_t off = arena.alloc(2 * n);
+        std::memcpy(arena.buf.data() + off, t->data.data(), n * sizeof(float));
+        std::memcpy(arena.buf.data() + off + n, t->data.data(), n * sizeof(float));
+        ptrs.push_back({dst, off});
     }
     void pack(const float* w, int M, int K, int TM, bool interleave, PackedMat* dst) {
         const int BM = 16 * TM;
@@ -640,6 +641,11 @@ int32_t hil_model_finalize(hil_model* m) {
                 b.linear(N("encoder.blocks.%d.%d.block.%d.pointwise.1.weight", s, j, u), C, C, &d.pw);
                 b.raw(N("encoder.blocks.%d.%d.block.%d.depthwise.weight", s, j, u), {C, 1, k}, &d.dw_w);
                 b.raw(N("encoder.blocks.%d.%d.block.%d.depthwise.bias", s, j, u), {C}, &d.dw_b);
+                if (2 * C <= 128 && C % 16 == 0) {
+                    b.linear_pair(N("encoder.blocks.%d.%d.block.%d.pointwise.1.weight", s, j, u), C, &d.pw2);
+                    b.raw_pair(N("encoder.blocks.%d.%d.block.%d.depthwise.weight", s, j, u), {C, 1, k}, &d.dw_w2);
+                    b.raw_pair(N("encoder.blocks.%d.%d.block.%d.depthwise.bias", s, j, u), {C}, &d.dw_b2);
+                }
                 m->enc_cache_shape.push_back({C, k - 1});
             }
         b.linear(N("encoder.downsample_pointwise.%d.1.weight", s), 2 * C, C, &st.down_pw);
@@ -683,6 +689,11 @@ int32_t hil_model_finalize(hil_model* m) {
                 b.linear(N("decoder.blocks.%d.%d.block.%d.pointwise.1.weight", i, j, u), C / 2, C / 2, &d.pw);
                 b.raw(N("decoder.blocks.%d.%d.block.%d.depthwise.weight", i, j, u), {C / 2, 1, k}, &d.dw_w);
                 b.raw(N("decoder.blocks.%d.%d.block.%d.depthwise.bias", i, j, u), {C / 2}, &d.dw_b);
+                if (C <= 128 && (C / 2) % 16 == 0) {
+                    b.linear_pair(N("decoder.blocks.%d.%d.block.%d.pointwise.1.weight", i, j, u), C / 2, &d.pw2);
+                    b.raw_pair(N("decoder.blocks.%d.%d.block.%d.depthwise.weight", i, j, u), {C / 2, 1, k}, &d.dw_w2);
+                    b.raw_pair(N("decoder.blocks.%d.%d.block.%d.depthwise.bias", i, j, u), {C / 2}, &d.dw_b2);
+                }
                 m->dec_cache_shape.push_back({C / 2, k - 1});
             }
         C /= 2;
@@ -781,7 +792,7 @@ int32_t hil_state_create(hil_model* m, int32_t batch, hil_state** out) {
     count(m->enc_cache_shape);
     count(m->dec_cache_shape);
     // + the candidate scratch of the few-frame RVQ variant (rvq.cu, 128 KB), carved from the same allocation
-    cudaError_t e = cudaMalloc(&s->cache_arena, 2 * total * sizeof(float) + rvq_split_scratch_bytes());
+    cudaError_t e = cudaMalloc(&s->cache_arena, 2 * total * sizeof(float) + rvq_split_scratch_bytes() + 256);
     if (e != cudaSuccess) {
         delete s;
         return fail(HIL_ERR_NOMEM, std::string("cudaMalloc caches: ") + cudaGetErrorString(e));
@@ -798,7 +809,8 @@ int32_t hil_state_create(hil_model* m, int32_t batch, hil_state** out) {
         }
     }
     s->rvq_scratch = s->cache_arena + 2 * total;
-    e = cudaMemset(s->cache_arena, 0, 2 * total * sizeof(float));
+    s->range_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(s->rvq_scratch) + rvq_split_scratch_bytes());
+    e = cudaMemset(s->cache_arena, 0, 2 * total * sizeof(float) + rvq_split_scratch_bytes() + 256);
     if (e != cudaSuccess) {
         cudaFree(s->cache_arena);
         delete s;
@@ -868,6 +880,30 @@ size_t hil_state_workspace_bytes(const hil_state* s) {
     return s ? s->ws_floats * sizeof(float) + s->idx_elems * sizeof(int64_t) + s->io_floats * sizeof(float) : 0;
 }
 
+int32_t hil_state_range_flag(hil_state* s, int32_t clear, void* stream, int32_t* flag_out) {
+    if (!s || !flag_out) return fail(HIL_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int v = 0;
+    HIL_CUDA(cudaMemcpyAsync(&v, s->range_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HIL_CUDA(cudaStreamSynchronize(st));
+    if (v && clear) HIL_CUDA(cudaMemsetAsync(s->range_flag, 0, sizeof(int), st));
+    *flag_out = v;
+    return HIL_OK;
+}
+
+int32_t hil_state_rollback(hil_state* s, int32_t encoder, int32_t decoder) {
+    if (!s) return fail(HIL_ERR_INVALID, "null state");
+    if (encoder) s->enc_gen ^= 1;
+    if (decoder) s->dec_gen ^= 1;
+    return HIL_OK;
+}
+
+int32_t hil_set_exact_fp32(int32_t on) {
+    const int32_t prev = tl_exact_fp32 ? 1 : 0;
+    tl_exact_fp32 = on != 0;
+    return prev;
+}
+
 }  // extern "C"
 
 // ----------------------------------------------------------------------------- workspace plan
@@ -915,6 +951,7 @@ Plan make_plan(const hil_model* m, int B, int T) {
 struct Buffers {
     float *wav_ext, *spec, *h, *a1, *a2, *z, *q;
     int Wp;
+    int* range_flag;
 };
 
 int32_t ensure_workspace(hil_state* s, int B, int T, Buffers* out) {
@@ -944,6 +981,7 @@ int32_t ensure_workspace(hil_state* s, int B, int T, Buffers* out) {
     out->z = w; w += p.lat;
     out->q = w;
     out->Wp = p.Wp;
+    out->range_flag = s->range_flag;
     return HIL_OK;
 }
 
@@ -956,12 +994,15 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     const int Tp = pitch4(Ts);
     const long long bs = (long long)C * Tp;
     const int pre0 = pre_scale == 1.0f ? PRE_ELU : PRE_SCALE_ELU;
-    // C <= 128 only by default: with two m-blocks the kernel works on 64-column tiles and re-streams both weight
-    // matrices from L2 for every 56 outputs, which measured slower than two fused-DWS launches (HILCODEC_RB_WIDE=1
-    // enables it for 128 < C <= 256)
-    static const bool rb_wide = std::getenv("HILCODEC_RB_WIDE") != nullptr;
-    if (g_use_tc && g_use_h && g_fuse_dw && g_fuse_rb && (C <= 128 || rb_wide) && !gemm_skinny_preferred(u[0].pw, B, Ts) &&
-        resblock_h_usable(u[0].pw, u[1].pw, h, bs, Tp, Ts))
+    // one kernel per ResBlock for C <= 128 (the 64-column two-m-block variant for 128 < C <= 256 measured slower than
+    // two fused-DWS launches in round 1 and was removed)
+    static const bool pair_ok = []() { const char* e = std::getenv("HILCODEC_RB_PAIR"); return !(e && e[0] == '0'); }();
+    if (tc_on() && g_use_h && g_fuse_dw && g_fuse_rb && pair_ok && (B & 1) == 0 && u[0].pw2.H_hi && u[1].pw2.H_hi &&
+        resblock_h_usable(u[0].pw2, u[1].pw2, h, 2 * bs, Tp, Ts))
+        // clip pairs (C <= 64): B/2 problems of 2C channels on the same memory, block-diagonal weights (see struct Dws)
+        return run_resblock(u[0].pw2, u[1].pw2, h, 2 * bs, Tp, B / 2, Ts, pre0, pre_scale, u[0].dw_w2, u[0].dw_b2, u[1].dw_w2,
+                            u[1].dw_b2, cin[0], cout[0], cin[1], cout[1], a1, st, /*flop_scale=*/0.5);
+    if (tc_on() && g_use_h && g_fuse_dw && g_fuse_rb && resblock_h_usable(u[0].pw, u[1].pw, h, bs, Tp, Ts))
         // a1 holds the halo columns (8 per tile: always smaller than an activation buffer)
         return run_resblock(u[0].pw, u[1].pw, h, bs, Tp, B, Ts, pre0, pre_scale, u[0].dw_w, u[0].dw_b, u[1].dw_w, u[1].dw_b,
                             cin[0], cout[0], cin[1], cout[1], a1, st);
@@ -976,43 +1017,12 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     return HIL_OK;
 }
 
-// The ResBlocks of one stage (streaming.py:503-505 / :638-642), optionally in sub-batches that fit the L2
-// (HILCODEC_STAGE_CHUNK_MB=<MB>, 0 / unset = off: written without GPU time, to be measured).  Unchunked, every DWSBlock
-// launch streams the whole [B][C][T] tensor from and to HBM (config 3, decoder stage 2: 2.4 GB per pass, 15 passes
-// per stage; the fused-DWS launches move 70 GB per step and run at half the HBM bandwidth).  Clips are independent, so
-// the same launches can run on `nb` clips at a time with nb chosen so that the chunk of h and the chunk-sized
-// intermediate (always the SAME buffer: its dirty lines are overwritten in the L2 before they are evicted) stay
-// resident across all ResBlocks of the stage: HBM then sees one read and one write of h per stage.  Results are
-// bit-identical (same tiles, same arithmetic); the price is ~2 x n_res launches per chunk.
-static int stage_chunk_clips(int B, int C, int Tp) {
-    static const long long budget = []() {
-        const char* e = std::getenv("HILCODEC_STAGE_CHUNK_MB");
-        return e ? std::atoll(e) * (1LL << 20) : 0LL;
-    }();
-    // stages whose ResBlocks run as ONE kernel each (C <= 128, gemm_rb.cu) already read and write h once per block and are
-    // not HBM-bound: by default only the stages on fused-DWS launches are chunked (HILCODEC_STAGE_CHUNK_MINC=<C> to change)
-    static const int min_c = []() { const char* e = std::getenv("HILCODEC_STAGE_CHUNK_MINC"); return e ? std::atoi(e) : 129; }();
-    if (budget <= 0 || C < min_c) return B;
-    const long long per_clip = 2LL * C * Tp * (long long)sizeof(float);   // h + the intermediate
-    const long long nb = budget / (per_clip > 0 ? per_clip : 1);
-    return (int)(nb < 1 ? 1 : (nb > B ? B : nb));
-}
-
+// The ResBlocks of one stage (streaming.py:503-505 / :638-642).  (Sub-batching a stage so that it works out of the L2
+// was measured in round 2 -- 32 / 64 / 96 MB chunks: 87.7 / 68.7 / 67.4 ms per step against 63.6 -- and removed.)
 static int32_t res_blocks_of_stage(const Dws* units, int n_res, const float* pre_scales, float* h, float* a1, float* a2, int B,
                                    int C, int Ts, const float* const* cin, float* const* cout, cudaStream_t st) {
-    const int Tp = pitch4(Ts);
-    const long long bs = (long long)C * Tp;
-    const int nb = stage_chunk_clips(B, C, Tp);
-    for (int b0 = 0; b0 < B; b0 += nb) {
-        const int nbb = B - b0 < nb ? B - b0 : nb;
-        for (int j = 0; j < n_res; ++j) {
-            // caches are [B][C][k-1]: the chunk's rows start b0 * C * (k-1) floats in (k = 5)
-            const size_t coff = (size_t)b0 * C * 4;
-            const float* ci2[2] = {cin[2 * j] + coff, cin[2 * j + 1] + coff};
-            float* co2[2] = {cout[2 * j] + coff, cout[2 * j + 1] + coff};
-            HIL_TRY(res_block(&units[2 * j], h + (long long)b0 * bs, a1, a2, nbb, C, Ts, pre_scales[j], ci2, co2, st));
-        }
-    }
+    for (int j = 0; j < n_res; ++j)
+        HIL_TRY(res_block(&units[2 * j], h, a1, a2, B, C, Ts, pre_scales[j], cin + 2 * j, cout + 2 * j, st));
     return HIL_OK;
 }
 
@@ -1081,7 +1091,8 @@ int32_t encode_impl(hil_model* m, const Buffers& w, const float* wav, int B, int
                                PRE_ELU, 1.f, st));
         HIL_TRY(run_gemm_linear(m->post_pw, a1, bs, Tp, B, Ts, PRE_NONE, 1.f, m->post_pw_b, nullptr, a2,
                                     (long long)c.dim * Tp, Tp, st));
-        HIL_TRY(run_l2norm_chlast(a2, (long long)c.dim * Tp, Tp, z, B, c.dim, Ts, (float)std::sqrt((double)c.dim), st));
+        HIL_TRY(run_l2norm_chlast(a2, (long long)c.dim * Tp, Tp, z, B, c.dim, Ts, (float)std::sqrt((double)c.dim), w.range_flag,
+                                  st));
     }
     return HIL_OK;
 }
@@ -1129,7 +1140,7 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
     {
         const int Tp = pitch4(Ts);
         HIL_TRY(run_conv_post_tanh(h, (long long)C * Tp, Tp, cin[ci], cout[ci], m->dec_post_w, m->dec_post_b, wav, B, C,
-                                   Ts, c.kernel_size, PRE_SCALE_ELU, m->dec_post_scale, st));
+                                   Ts, c.kernel_size, PRE_SCALE_ELU, m->dec_post_scale, w.range_flag, st));
     }
     return HIL_OK;
 }
@@ -1356,11 +1367,32 @@ int32_t hil_codec_forward_host(hil_model* m, hil_state* s, const float* wav_host
     }
     float* wav_dev = s->io_dev;
     float* out_dev = s->io_dev + nwav;
+    // hop-sized chunks are launch-latency bound (~85 dependent launches): replay them as a CUDA graph (the staging
+    // buffers are stable, so the graph key is); one-shot batches launch eagerly
+    const bool small = (long long)B * T <= 64LL * 3200;
+    int flag = 0;
     HIL_CUDA(cudaMemcpyAsync(wav_dev, wav_host, nwav * sizeof(float), cudaMemcpyHostToDevice, st));
-    HIL_TRY(hil_codec_forward(m, s, wav_dev, B, T, n, nullptr, s->idx_dev, out_dev, stream));
+    if (small) HIL_TRY(hil_codec_forward_graph(m, s, wav_dev, B, T, n, s->idx_dev, out_dev, stream));
+    else HIL_TRY(hil_codec_forward(m, s, wav_dev, B, T, n, nullptr, s->idx_dev, out_dev, stream));
     HIL_CUDA(cudaMemcpyAsync(idx_host, s->idx_dev, nidx * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     HIL_CUDA(cudaMemcpyAsync(wav_out_host, out_dev, nwav * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HIL_CUDA(cudaMemcpyAsync(&flag, s->range_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     HIL_CUDA(cudaStreamSynchronize(st));
+    if (flag && !tl_exact_fp32) {
+        // fp16-range guard: something came out non-finite.  Repeat the step from the same cache generation on the FP32
+        // kernels (the reference's arithmetic range); if the input itself is non-finite the result is what it is.
+        HIL_CUDA(cudaMemsetAsync(s->range_flag, 0, sizeof(int), st));
+        s->enc_gen ^= 1;
+        s->dec_gen ^= 1;
+        tl_exact_fp32 = true;
+        const int32_t rc = hil_codec_forward(m, s, wav_dev, B, T, n, nullptr, s->idx_dev, out_dev, stream);
+        tl_exact_fp32 = false;
+        HIL_TRY(rc);
+        HIL_CUDA(cudaMemcpyAsync(idx_host, s->idx_dev, nidx * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        HIL_CUDA(cudaMemcpyAsync(wav_out_host, out_dev, nwav * sizeof(float), cudaMemcpyDeviceToHost, st));
+        HIL_CUDA(cudaMemsetAsync(s->range_flag, 0, sizeof(int), st));
+        HIL_CUDA(cudaStreamSynchronize(st));
+    }
     return HIL_OK;
 }
 
@@ -1394,9 +1426,8 @@ int32_t hil_unpack_indices(hil_model* m, const uint8_t* in, int32_t B, int32_t F
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 
 int32_t hil_set_tensor_cores(int32_t mode) {
-    const int32_t prev = (g_use_tc ? 1 : 0) | (g_use_tm ? 8 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32) | (g_fuse_up ? 0 : 64);
+    const int32_t prev = (g_use_tc ? 1 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32) | (g_fuse_up ? 0 : 64);
     g_use_tc = (mode & 1) != 0;
-    g_use_tm = (mode & 8) != 0;
     g_fuse_dw = (mode & 4) == 0;
     g_use_h = (mode & 16) != 0;
     g_fuse_rb = (mode & 32) == 0;
@@ -1416,15 +1447,28 @@ int32_t hil_profile_end(double* ms, double* flops, double* bytes, int64_t* launc
     if (!ms || !flops || !bytes || !launches || n_cat < CAT_COUNT) return fail(HIL_ERR_INVALID, "need HIL_PROFILE_CATEGORIES slots");
     HIL_CUDA(cudaDeviceSynchronize());
     for (int i = 0; i < n_cat; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    g_prof.done.clear();
     for (auto& r : g_prof.recs) {
         float t = 0.f;
         HIL_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
         ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat] += 1;
+        g_prof.done.push_back({r.cat, (double)t, r.flops, r.bytes});
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }
     g_prof.recs.clear();
     return HIL_OK;
+}
+
+int32_t hil_profile_launches(int32_t* cat, double* ms, double* flops, double* bytes, int32_t cap) {
+    const int32_t n = (int32_t)g_prof.done.size();
+    for (int32_t i = 0; i < n && i < cap; ++i) {
+        if (cat) cat[i] = g_prof.done[i].cat;
+        if (ms) ms[i] = g_prof.done[i].ms;
+        if (flops) flops[i] = g_prof.done[i].flops;
+        if (bytes) bytes[i] = g_prof.done[i].bytes;
+    }
+    return n;
 }
 
 // ----------------------------------------------------------------------------- operator level
@@ -1505,9 +1549,57 @@ int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, co
     int32_t rc = upload_packed(w1_host, C, C, choose_tm(C), false, &pm1, &dev1);
     cudaStream_t st = (cudaStream_t)stream;
     const long long bs = (long long)C * T;
+    if (rc == HIL_OK && fused && (B & 1) == 0 && 2 * C <= 128 && C % 16 == 0 && tc_on() && g_use_h) {
+        // the clip-pair form the model path uses for C <= 64 (struct Dws): diag(W, W), taps and biases repeated
+        hil_model dummy;
+        Builder b{&dummy};
+        HostTensor t0, t1;
+        t0.dims = {C, C, 1}; t0.data.assign(w0_host, w0_host + (size_t)C * C);
+        t1.dims = {C, C, 1}; t1.data.assign(w1_host, w1_host + (size_t)C * C);
+        dummy.host["w0"] = t0; dummy.host["w1"] = t1;
+        PackedMat p0, p1;
+        b.linear_pair("w0", C, &p0);
+        b.linear_pair("w1", C, &p1);
+        float *devw = nullptr, *taps = nullptr;
+        rc = HIL_OK;
+        if (cudaMalloc(&devw, b.arena.buf.size() * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&taps, (size_t)24 * C * sizeof(float)) != cudaSuccess)
+            rc = fail(HIL_ERR_NOMEM, "cudaMalloc (pair form)");
+        if (rc == HIL_OK) {
+            cudaMemcpy(devw, b.arena.buf.data(), b.arena.buf.size() * sizeof(float), cudaMemcpyHostToDevice);
+            for (size_t i = 0; i < 2; ++i) {
+                PackedMat* pm = i ? &p1 : &p0;
+                pm->A = devw + b.mats[i].off;
+                pm->A_hi = devw + b.mats[i].off_hi; pm->A_lo = devw + b.mats[i].off_lo;
+                pm->H_hi = reinterpret_cast<const uint16_t*>(devw + b.mats[i].off_hh);
+                pm->H_lo = reinterpret_cast<const uint16_t*>(devw + b.mats[i].off_hl);
+            }
+            // taps: [dw0_w x2 | dw1_w x2 | dw0_b x2 | dw1_b x2]
+            float* d0w2 = taps; float* d1w2 = taps + 10 * C; float* d0b2 = taps + 20 * C; float* d1b2 = taps + 22 * C;
+            for (int r = 0; r < 2; ++r) {
+                cudaMemcpyAsync(d0w2 + r * 5 * C, dw0_w, (size_t)5 * C * 4, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync(d1w2 + r * 5 * C, dw1_w, (size_t)5 * C * 4, cudaMemcpyDeviceToDevice, st);
+                if (dw0_b) cudaMemcpyAsync(d0b2 + r * C, dw0_b, (size_t)C * 4, cudaMemcpyDeviceToDevice, st);
+                if (dw1_b) cudaMemcpyAsync(d1b2 + r * C, dw1_b, (size_t)C * 4, cudaMemcpyDeviceToDevice, st);
+            }
+            if (!resblock_h_usable(p0, p1, h, 2 * bs, T, T))
+                rc = fail(HIL_ERR_INVALID, "fused ResBlock kernel not usable for this shape / mode");
+            else
+                rc = run_resblock(p0, p1, h, 2 * bs, T, B / 2, T, pre, pre_scale, d0w2, dw0_b ? d0b2 : nullptr, d1w2,
+                                  dw1_b ? d1b2 : nullptr, c0_in, c0_out, c1_in, c1_out, tmp1, st, 0.5);
+        }
+        cudaError_t e3 = cudaStreamSynchronize(st);
+        if (devw) cudaFree(devw);
+        if (taps) cudaFree(taps);
+        cudaFree(dev0);
+        if (dev1) cudaFree(dev1);
+        HIL_TRY(rc);
+        HIL_CUDA(e3);
+        return HIL_OK;
+    }
     if (rc == HIL_OK) {
         if (fused) {
-            if (!g_use_tc || !g_use_h || !resblock_h_usable(pm0, pm1, h, bs, T, T))
+            if (!tc_on() || !g_use_h || !resblock_h_usable(pm0, pm1, h, bs, T, T))
                 rc = fail(HIL_ERR_INVALID, "fused ResBlock kernel not usable for this shape / mode");
             else
                 rc = run_resblock(pm0, pm1, h, bs, T, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in,
@@ -1537,18 +1629,15 @@ int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out,
     cudaStream_t st = (cudaStream_t)stream;
     const int T = S * T_in;
     int32_t rc;
-    if (fused == 1 && !(g_use_tc && g_use_h && gemm_h_up_usable(pm, x, (long long)K * T_in, T_in, T_in, S, pre, y, (long long)M * T, T)))
+    if (fused != 0 && fused != 1) rc = fail(HIL_ERR_INVALID, "fused must be 0 or 1");
+    else if (fused == 1 && !(tc_on() && g_use_h && gemm_h_up_usable(pm, x, (long long)K * T_in, T_in, T_in, S, pre, y, (long long)M * T, T)))
         rc = fail(HIL_ERR_INVALID, "fused upsampling kernel not usable for this shape / mode");
     else {
         const bool keep = g_fuse_up;
         g_fuse_up = true;
-        // fused: 1 = one kernel, 2 = transposed conv -> fp16 planes -> planes-input GEMM, 0 = fp32 intermediate
-        if (fused == 2)
-            rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp,
-                              y, (long long)M * T, T, false, st, false, true);
-        else
-            rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp,
-                              y, (long long)M * T, T, fused != 0, st, true, false);
+        // fused: 1 = one kernel, 0 = transposed conv + 1x1 through the fp32 intermediate
+        rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp,
+                          y, (long long)M * T, T, fused != 0, st, true);
         g_fuse_up = keep;
     }
     cudaError_t e2 = cudaStreamSynchronize(st);

@@ -53,6 +53,10 @@ __device__ __forceinline__ float apply_act_fast(float x, int mode, float s) {
 }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// Chunk lengths the per-clip 128-column tensor-core tiles are used for: T >= 64, or -- many concurrent streams fed a
+// hop at a time -- T >= 32 once the launch has more columns than the skinny-N FP32 kernel takes (one partly filled tile
+// per clip still beats the FP32 pipes there; config 4 with 64 streams: the 40-column layers).
+static inline bool tc_chunk_ok(int B, int T) { return T >= 64 || (T >= 32 && (long long)B * T > 512); }
 static inline int pitch4(int t) { return (t + 3) & ~3; }
 
 // A weight matrix W[M][K] repacked k-major for the GEMM kernels: A[Kp][Mp], zero padded.
@@ -84,12 +88,11 @@ cudaError_t launch_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
 cudaError_t launch_gemm_stft_logmag(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T,
                                     float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
-// ---- gemm_skinny.cu: the three contracts above for short chunks (streaming), off unless HILCODEC_SKINNY=1
+// ---- gemm_skinny.cu: the three contracts above for short chunks (streaming: <= 512 columns); HILCODEC_SKINNY=0 disables
 bool gemm_skinny_usable(const PackedMat& W, int B, int T);
 cudaError_t launch_gemm_skinny_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                       float pre_scale, const float* bias, const float* R, float* Y, long long y_bs,
                                       int y_rs, cudaStream_t st);
-bool gemm_skinny_preferred(const PackedMat& W, int B, int T);  // over the tensor-core kernels (HILCODEC_SKINNY_PREFER=1)
 bool gemm_skinny_dws_usable(const PackedMat& W, int B, int T);
 cudaError_t launch_gemm_skinny_dws(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                                    float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
@@ -102,14 +105,14 @@ cudaError_t launch_gemm_skinny_stft_logmag(const PackedMat& Wdft, const float* w
 
 // ---- gemm_tc.cu: same contract as launch_gemm_linear, on the tensor pipe (tcgen05, 3xTF32)
 bool gemm_tc_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
-                    long long y_bs, int y_rs);
+                    long long y_bs, int y_rs, int B = 1);
 cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                            float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                            cudaStream_t st);
 
 // ---- gemm_h.cu: the same two contracts with fp16 hi/lo splits (tcgen05 kind::f16, 2x the tf32 rate)
 bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
-                   long long y_bs, int y_rs);
+                   long long y_bs, int y_rs, int B = 1);
 cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                           cudaStream_t st);
@@ -125,17 +128,7 @@ cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs,
                              float pre_scale, const float* up_w, const float* cache_in, float* cache_out, const float* bias,
                              float* Y, long long y_bs, int y_rs, cudaStream_t st);
 
-// 1x1 conv + bias on fp16 hi/lo planes [B][K][pitch] (no transform pass), and the transposed conv that writes them
-bool gemm_h_planes_usable(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int T,
-                          const float* Y, long long y_bs, int y_rs);
-cudaError_t launch_gemm_h_planes(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int B,
-                                 int T, const float* bias, float* Y, long long y_bs, int y_rs, cudaStream_t st);
-bool dwconv_transpose_planes_usable(const float* x, long long x_bs, int x_rs, int T, int S, long long p_bs, int p_rs);
-cudaError_t launch_dwconv_transpose_planes(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
-                                           const float* w, uint16_t* hi, uint16_t* lo, long long p_bs, int p_rs, int B, int C,
-                                           int T, int S, int pre, float pre_scale, cudaStream_t st);
-
-// ---- gemm_rb.cu: whole ResBlock (two DWSBlocks + residual add) in one kernel, h updated in place (C <= 256)
+// ---- gemm_rb.cu: whole ResBlock (two DWSBlocks + residual add) in one kernel, h updated in place (C <= 128)
 bool resblock_h_usable(const PackedMat& W0, const PackedMat& W1, const float* h, long long bs, int rs, int T);
 size_t resblock_h_halo_floats(int C, int T, int B);
 cudaError_t launch_resblock_halo(const float* h, long long bs, int rs, int B, int C, int T, float* halo, cudaStream_t st);
@@ -148,13 +141,6 @@ cudaError_t launch_resblock_h(const PackedMat& W0, const PackedMat& W1, float* h
 cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in,
                               float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st);
-
-// ---- gemm_tm.cu: time-major tensor-core kernel (activations via TMEM) for Cout <= 192
-bool gemm_tm_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* Y, long long y_bs,
-                    int y_rs);
-cudaError_t launch_gemm_tm(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
-                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
-                           cudaStream_t st);
 
 // ---- stft_tc.cu: launch_gemm_stft_logmag on the tensor pipe
 bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
@@ -180,17 +166,18 @@ cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
 // decoder conv_post: y[b][t] = tanh(bias + sum_c sum_k w[c][k] * xin[b][c][t+k]), xin = cat(cache, pre(x))
 cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                                   const float* w, const float* bias, float* y, int B, int C, int T, int K, int pre,
-                                  float pre_scale, cudaStream_t st);
+                                  float pre_scale, int* nonfinite, cudaStream_t st);
 // z[b][f][c] = x[b][c][f] / max(||x[b][:,f]||, 1e-12) * scale
+// nonfinite (may be null): set to 1 when a latent / PCM sample comes out NaN or Inf
 cudaError_t launch_l2norm_chlast(const float* x, long long x_bs, int x_rs, float* z, int B, int C, int F, float scale,
-                                 cudaStream_t st);
+                                 int* nonfinite, cudaStream_t st);
 
 // ---- rvq.cu ----------------------------------------------------------------------
 // codebooks [n_q][size][dim], ee [n_q][size] = sum_k e^2
 cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, int size, int dim, cudaStream_t st);
 cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
                               int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st);
-// few-frame (streaming) variant: one launch per stage over (code tiles) x (frame blocks); off unless HILCODEC_RVQ_SPLIT=1
+// few-frame (streaming) variant: one launch per stage over (code tiles) x (frame blocks); HILCODEC_RVQ_SPLIT=0 disables
 bool rvq_split_usable(int size, int dim, long long frames);
 size_t rvq_split_scratch_bytes();
 cudaError_t launch_rvq_encode_split(const float* z, const float* codebooks, const float* ee, int size, int dim,

@@ -370,79 +370,14 @@ cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
     return cudaErrorInvalidValue;
 }
 
-// Same transposed conv, output written as the fp16 hi / lo planes the tensor-core GEMM consumes directly
-// (x = hi + lo * 2^-11, gemm_h.cu): the 1x1 conv behind it then needs no conversion pass.  planes: [B][C][pitch] halfs.
-template <int S>
-__global__ void dwconvT_planes_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
-                                      float* __restrict__ cache_out, const float* __restrict__ w, uint16_t* __restrict__ hi,
-                                      uint16_t* __restrict__ lo, long long p_bs, int p_rs, int C, int T, int pre,
-                                      float pre_scale) {
-    const int c = blockIdx.y, b = blockIdx.z;
-    const float* xr = x + b * x_bs + (long long)c * x_rs;
-    const float cprev = cache_in[(size_t)b * C + c];
-    float wc[2 * S];
-#pragma unroll
-    for (int k = 0; k < 2 * S; ++k) wc[k] = w[(size_t)c * 2 * S + k];
-    uint16_t* hr = hi + b * p_bs + (long long)c * p_rs;
-    uint16_t* lr = lo + b * p_bs + (long long)c * p_rs;
-    const int Tq = T >> 2;   // T % 4 == 0 (checked by the launcher)
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Tq; q += gridDim.x * blockDim.x) {
-        const int i0 = q * 4;
-        float e[5];
-        e[0] = i0 == 0 ? cprev : apply_act_ex2(xr[i0 - 1], pre, pre_scale);
-        const float4 v = *reinterpret_cast<const float4*>(xr + i0);
-        e[1] = apply_act_ex2(v.x, pre, pre_scale); e[2] = apply_act_ex2(v.y, pre, pre_scale);
-        e[3] = apply_act_ex2(v.z, pre, pre_scale); e[4] = apply_act_ex2(v.w, pre, pre_scale);
-        float o[4 * S];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int r = 0; r < S; ++r) o[j * S + r] = __fadd_rn(__fmul_rn(e[1 + j], wc[r]), __fmul_rn(e[j], wc[r + S]));
-#pragma unroll
-        for (int k = 0; k < S; ++k) {   // 4 outputs -> 4 + 4 halfs: one 8-byte store per plane
-            uint32_t h01, h23, l01, l23;
-            th::split4<PRE_NONE>(make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]), 1.0f, h01, h23, l01, l23);
-            *reinterpret_cast<uint2*>(hr + (long long)i0 * S + 4 * k) = make_uint2(h01, h23);
-            *reinterpret_cast<uint2*>(lr + (long long)i0 * S + 4 * k) = make_uint2(l01, l23);
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        cache_out[(size_t)b * C + c] = T > 0 ? apply_act_ex2(xr[T - 1], pre, pre_scale) : cprev;
-}
-
-bool dwconv_transpose_planes_usable(const float* x, long long x_bs, int x_rs, int T, int S, long long p_bs, int p_rs) {
-    if (S != 2 && S != 4 && S != 5 && S != 8) return false;
-    if ((T & 3) || (x_rs & 3) || (x_bs & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) return false;
-    if ((p_rs & 7) || (p_bs & 7)) return false;
-    return true;
-}
-
-cudaError_t launch_dwconv_transpose_planes(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
-                                           const float* w, uint16_t* hi, uint16_t* lo, long long p_bs, int p_rs, int B, int C,
-                                           int T, int S, int pre, float pre_scale, cudaStream_t st) {
-    if (B == 0 || C == 0) return cudaSuccess;
-    if (C > 65535 || B > 65535) return cudaErrorInvalidValue;
-    const int Tq = T / 4;
-    const int threads = Tq >= 128 ? 128 : 32;
-    dim3 grid(max(1, min((Tq + threads - 1) / threads, 512)), C, B);
-#define HIL_DWTP(SS)                                                                                                      \
-    if (S == SS) {                                                                                                        \
-        dwconvT_planes_kernel<SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, hi, lo, p_bs, p_rs, C, \
-                                                            T, pre, pre_scale);                                           \
-        return cudaGetLastError();                                                                                        \
-    }
-    HIL_DWTP(2) HIL_DWTP(4) HIL_DWTP(5) HIL_DWTP(8)
-#undef HIL_DWTP
-    return cudaErrorInvalidValue;
-}
-
 // ------------------------------------------------------------------ decoder conv_post + tanh
 // Decoder.forward streaming.py:644-647: ELU -> CausalConv1d(C -> 1, k) -> Tanh
 template <int K>
 __global__ void conv_post_tanh_kernel(const float* __restrict__ x, long long x_bs, int x_rs,
                                       const float* __restrict__ cache_in, float* __restrict__ cache_out,
                                       const float* __restrict__ w, const float* __restrict__ bias,
-                                      float* __restrict__ y, int C, int T, int pre, float pre_scale, int vec) {
+                                      float* __restrict__ y, int C, int T, int pre, float pre_scale, int vec,
+                                      int* __restrict__ nonfinite) {
     constexpr int P = K - 1;
     constexpr int NO = 8;          // outputs per thread: P + NO activations feed NO * K MACs per channel
     static_assert(P == 4, "the vector path loads the 4 history samples as one float4");
@@ -489,7 +424,13 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, long long x_b
                 for (int k = 0; k < K; ++k) a[o] = fmaf(sw[c * K + k], xin[o + k], a[o]);
         }
         const float bv = bias ? bias[0] : 0.f;
-        for (int o = 0; o < NO && t0 + o < T; ++o) y[(size_t)b * T + t0 + o] = tanhf(a[o] + bv);
+        bool bad = false;
+        for (int o = 0; o < NO && t0 + o < T; ++o) {
+            const float v = tanhf(a[o] + bv);
+            bad |= !(fabsf(v) <= 1.0f);            // NaN: an activation left the fp16 range upstream (hil_state_range_flag)
+            y[(size_t)b * T + t0 + o] = v;
+        }
+        if (bad && nonfinite) *nonfinite = 1;
     }
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < C * P; i += blockDim.x) {
@@ -503,7 +444,7 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, long long x_b
 
 cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                                   const float* w, const float* bias, float* y, int B, int C, int T, int K, int pre,
-                                  float pre_scale, cudaStream_t st) {
+                                  float pre_scale, int* nonfinite, cudaStream_t st) {
     if (K != 5) return cudaErrorInvalidValue;
     if (B == 0) return cudaSuccess;
     const int Tq = (T + 7) / 8;
@@ -511,14 +452,14 @@ cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, cons
     const int vec = ((x_rs & 3) == 0) && ((x_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     dim3 grid(max(1, (Tq + threads - 1) / threads), B);
     conv_post_tanh_kernel<5><<<grid, threads, C * 5 * sizeof(float), st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias,
-                                                                           y, C, T, pre, pre_scale, vec);
+                                                                           y, C, T, pre, pre_scale, vec, nonfinite);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ L2 norm + channel-last
 // L2Norm.forward streaming.py:284-285 then x.transpose(1,2) (:517).  One warp per (b, f).
 __global__ void l2norm_chlast_kernel(const float* __restrict__ x, long long x_bs, int x_rs, float* __restrict__ z,
-                                     int C, int F, long long total, float scale) {
+                                     int C, int F, long long total, float scale, int* __restrict__ nonfinite) {
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= total) return;
@@ -531,17 +472,18 @@ __global__ void l2norm_chlast_kernel(const float* __restrict__ x, long long x_bs
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0 && nonfinite && !(ss <= 3.0e38f)) *nonfinite = 1;   // NaN / Inf latent (see hil_state_range_flag)
     const float denom = fmaxf(sqrtf(ss), 1e-12f);
     float* zr = z + (size_t)wid * C;
     for (int c = lane; c < C; c += 32) zr[c] = __fmul_rn(__fdiv_rn(xb[(long long)c * x_rs], denom), scale);
 }
 
 cudaError_t launch_l2norm_chlast(const float* x, long long x_bs, int x_rs, float* z, int B, int C, int F, float scale,
-                                 cudaStream_t st) {
+                                 int* nonfinite, cudaStream_t st) {
     const long long total = (long long)B * F;
     if (total == 0) return cudaSuccess;
     const long long threads = total * 32;
-    l2norm_chlast_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, x_bs, x_rs, z, C, F, total, scale);
+    l2norm_chlast_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, x_bs, x_rs, z, C, F, total, scale, nonfinite);
     return cudaGetLastError();
 }
 

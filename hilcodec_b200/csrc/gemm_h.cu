@@ -50,7 +50,7 @@ constexpr int XG = HIL_XFORM_GROUPS;              // k-blocks the transform warp
 #ifndef HIL_OUT_BUFS
 #define HIL_OUT_BUFS 2
 #endif
-constexpr int OUT_BUFS = HIL_OUT_BUFS;            // epilogue staging buffers (kEpi = 1); 4 trades two raw stages for them
+constexpr int OUT_BUFS = HIL_OUT_BUFS;            // epilogue staging buffers; 4 trades two raw stages for them
 constexpr int RAW_STAGES = (XG == 4 || OUT_BUFS == 4) ? 4 : 6;
 constexpr int OP_STAGES = XG == 4 ? 4 : 3;
 static_assert(XG == 1 || XG == 2 || XG == OP_STAGES, "see the parity note above");
@@ -60,10 +60,6 @@ constexpr int B_TILE = BK * BN * 2;               // 8 KB
 constexpr int OP_BYTES = 2 * A_TILE + 2 * B_TILE; // 32 KB: A_hi, A_lo, B_hi, B_lo
 constexpr int B_PANEL = 8 * 128 * (BK / 8);       // 4 KB: 64 columns x 32 k (4 swizzle atoms of 8 k-rows x 128 B)
 constexpr int NUM_THREADS = 512;
-#ifndef HIL_EPI2_EXTRA_THREADS
-#define HIL_EPI2_EXTRA_THREADS 0
-#endif
-constexpr int EPI2_EXTRA_THREADS = HIL_EPI2_EXTRA_THREADS;   // 128: the kEpi = 2 configuration keeps all 8 transform warps (640 threads)
 constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
@@ -82,7 +78,6 @@ struct Params {
     int reduce_add;         // 1: Y += tile (TMA reduce), 0: Y = tile
     int xform_sleep;        // ns of back-off in the transform warps' barrier polls (0 = spin)
     int post_elu;           // fused DWS only: store ELU(y) (the consumer then needs no activation prologue)
-    int cx;                 // 1: launched as 2-CTA clusters that share the activation boxes (see the X producer)
     int t_step, t_halo;     // tile tt covers columns [tt * t_step - t_halo, ... + BN)
     const float* dw_w;      // [M][5]
     const float* dw_b;      // [M] or null
@@ -199,25 +194,19 @@ __device__ __forceinline__ void load_up_taps(const float* wsm, int xw, int n_abs
 }
 
 // ------------------------------------------------------------------------------- kernel
-// kEpi = 1: warps 4-7 epilogue, 8-15 transform (layers with long K loops: the transform is the busy stage).
-// kEpi = 2: warps 4-7 and 8-11 are TWO epilogue groups, one per TMEM accumulator stage, draining alternate tiles
-//           concurrently; warps 12-15 transform.  For K <= 256 the serial TMEM -> registers -> SMEM -> TMA chain of
-//           one group (about 2000 cycles per 32-column chunk) is longer than the tile's mainloop.  Shared memory is
-//           re-cut: 4 raw stages instead of 6, 4 staging buffers instead of 2.
-// kPl = 1: the activations arrive already split, as two fp16 planes (hi, lo * 2^11) written by the producer kernel;
-//          map_x / map_xl are [B][K][T] fp16 tensor maps with 64 x 32 SWIZZLE_128B boxes and the B operand goes
-//          TMA -> operand ring -> MMA with no transform pass (no raw ring traffic, half the shared-memory bytes per k-block).
-template <bool kDw, int kUp = 0, int kEpi = 1, int kPl = 0>
-__global__ void __launch_bounds__(NUM_THREADS + (kEpi - 1) * EPI2_EXTRA_THREADS, 1)
+// Variants measured and removed in round 2 (profiles/r2_ab_results.md): two epilogue groups draining alternate tiles
+// (inside the box-to-box noise), fp16 hi/lo planes as the B operand with no transform pass (not faster: the operand
+// stream out of L2 paces the wide layers, not the transform), activation boxes shared by TMA multicast across 2-CTA
+// clusters (+5.7 % on the step: at cluster size 2 the multicast saves no L2 bandwidth and couples the two pipelines).
+template <bool kDw, int kUp = 0>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-              const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xl,
-              const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y28, const Params p) {
-    static_assert(kPl == 0 || (kUp == 0 && kEpi == 1), "planes input: plain / fused-DWS kernels only");
-    static_assert(kEpi == 1 || kEpi == 2, "one or two epilogue groups");
-    constexpr int RAW_STAGES = kEpi == 2 ? 4 : th::RAW_STAGES;
-    constexpr int NOUT = kEpi == 2 ? 2 : OUT_BUFS;     // staging buffers per epilogue group
-    constexpr int NUM_XW = (kEpi == 2 && EPI2_EXTRA_THREADS == 0) ? NUM_XFORM_WARPS / 2 : NUM_XFORM_WARPS;   // transform warps
-    constexpr int XW0 = (NUM_THREADS + (kEpi - 1) * EPI2_EXTRA_THREADS) / 32 - NUM_XW;   // first transform warp
+              const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+              const __grid_constant__ CUtensorMap map_y28, const Params p) {
+    constexpr int RAW_STAGES = th::RAW_STAGES;
+    constexpr int NOUT = OUT_BUFS;                      // epilogue staging buffers
+    constexpr int NUM_XW = NUM_XFORM_WARPS;             // transform warps
+    constexpr int XW0 = NUM_THREADS / 32 - NUM_XW;      // first transform warp
     constexpr int XW_PER_G = NUM_XW / XG;               // warps per transform group (one k-block)
     constexpr int SPW = BK / 4 / XW_PER_G;              // 4-row slices of the box per transform warp
     extern __shared__ uint8_t smem_raw[];
@@ -225,7 +214,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const uint32_t raw_base = base;
     const uint32_t op_base = raw_base + RAW_STAGES * RAW_BYTES;
     const uint32_t out_base = op_base + OP_STAGES * OP_BYTES;
-    const uint32_t bars = out_base + NOUT * kEpi * OUT_BYTES;
+    const uint32_t bars = out_base + NOUT * OUT_BYTES;
     auto raw_full = [&](int r) { return bars + 8u * r; };
     auto raw_empty = [&](int r) { return bars + 8u * (RAW_STAGES + r); };
     auto a_full = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };
@@ -238,15 +227,6 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + BK - 1) / BK;
-    // Activation-box sharing (HILCODEC_CLUSTER_X=1, plain and fused-DWS kernels, num_m even): the grid is launched as
-    // 2-CTA clusters; tiles are m-block-fastest, so with an even grid the two CTAs of a cluster always work on tiles 2j and
-    // 2j+1 = the same (b, t) columns and two different weight blocks.  Each X producer loads HALF of the [32 k][128 t] box
-    // (16 k-rows, map_xl = the half-height tensor map) and multicasts it into both CTAs' raw stage; each CTA's raw_full
-    // still expects the whole box.  A raw stage is therefore written by both producers and must be released to both:
-    // the transform warps arrive on their own raw_empty and on the peer's.
-    const bool cx = (kUp == 0 && kPl == 0) ? p.cx != 0 : false;
-    const uint32_t crank = cx ? cluster_ctarank() : 0u;
-
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi);
         prefetch_tmap(&map_a_lo);
@@ -256,11 +236,11 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int r = 0; r < RAW_STAGES; ++r) {
             mbar_init(raw_full(r), 1);
-            mbar_init(raw_empty(r), cx ? 2 * XW_PER_G : XW_PER_G);   // cx: the peer CTA's transform warps release it too
+            mbar_init(raw_empty(r), XW_PER_G);
         }
         for (int s = 0; s < OP_STAGES; ++s) {
             mbar_init(a_full(s), 1);
-            mbar_init(b_ready(s), kPl ? 1 : XW_PER_G);
+            mbar_init(b_ready(s), XW_PER_G);
             mbar_init(op_empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -277,31 +257,11 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (cx) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to / arrives on them
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
 
     if (warp == 0) {
         // ===================================================================== X producer (raw ring)
-        if (kPl && lane == 0) {   // planes: four 4 KB panels (hi / lo x two 64-column panels) straight into the operand stage
-            int s = 0;
-            uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const long long rest = tile / p.num_m;
-                const int tt = (int)(rest % p.tiles_t);
-                const int b = (int)(rest / p.tiles_t);
-                const int tc0 = tt * p.t_step - p.t_halo;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait<32>(op_empty(s), ph ^ 1);
-                    const uint32_t bst = op_base + s * OP_BYTES + 2 * A_TILE;
-                    mbar_arrive_expect_tx(b_ready(s), 2 * B_TILE);
-                    tma_load_3d(&map_x, bst, b_ready(s), tc0, kb * BK, b);
-                    tma_load_3d(&map_x, bst + B_PANEL, b_ready(s), tc0 + 64, kb * BK, b);
-                    tma_load_3d(&map_xl, bst + B_TILE, b_ready(s), tc0, kb * BK, b);
-                    tma_load_3d(&map_xl, bst + B_TILE + B_PANEL, b_ready(s), tc0 + 64, kb * BK, b);
-                    if (++s == OP_STAGES) { s = 0; ph ^= 1; }
-                }
-            }
-        } else if (lane == 0) {
+        if (lane == 0) {
             int r = 0;
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -315,10 +275,6 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                         mbar_arrive_expect_tx(raw_full(r), XB + WB);
                         tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), up_box_start<kUp>(tt), kb * BK, b);
                         bulk_load(raw_base + r * RAW_BYTES + XB, p.up_w + (size_t)kb * BK * 2 * kUp, WB, raw_full(r));
-                    } else if (cx) {
-                        mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);   // my half + the peer's half
-                        tma_load_3d_mc(&map_xl, raw_base + r * RAW_BYTES + crank * (RAW_BYTES / 2), raw_full(r),
-                                       tt * p.t_step - p.t_halo, kb * BK + (int)crank * (BK / 2), b, (uint16_t)3);
                     } else {
                         mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
                         tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
@@ -393,7 +349,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const uint32_t chunk = (uint32_t)((lane >> 1) & 7);  // 16-byte chunk (8 columns) inside the 128-byte row
         const uint32_t half8 = (uint32_t)(lane & 1) * 8u;
         uint32_t n = 0;                                    // k-blocks seen by this CTA (all tiles)
-        for (long long tile = blockIdx.x; !kPl && tile < p.total_tiles; tile += gridDim.x) {
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             [[maybe_unused]] const int m_blk = (int)(tile % p.num_m);
             [[maybe_unused]] const long long rest = tile / p.num_m;
             [[maybe_unused]] const int tt = (int)(rest % p.tiles_t);
@@ -443,18 +399,16 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 if (lane == 0) {
                     mbar_arrive(b_ready(s));
                     mbar_arrive(raw_empty(r));
-                    if (cx) mbar_arrive_remote(raw_empty(r), crank ^ 1u);
                 }
             }
         }
-    } else if (warp >= 4 && warp < 4 + 4 * kEpi) {
-        // ===================================================================== epilogue (group eg drains tiles it % kEpi == eg)
-        const int eg = (warp - 4) >> 2;
+    } else if (warp >= 4 && warp < 8) {
+        // ===================================================================== epilogue
         const int q = warp & 3;                             // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
         const bool issuer = (q == 0 && lane == 0);
-        const uint32_t my_out = out_base + eg * NOUT * OUT_BYTES;   // this group's staging buffers
-        auto epi_bar_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory"); };
+        const uint32_t my_out = out_base;
+        auto epi_bar_sync = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
         const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
         const float c_big = p.c_big;                        // 2^-s; c_small = c_big * 2^-11
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE), cb2 = pk2(c_big, c_big);
@@ -462,7 +416,6 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
         if constexpr (!kDw) {
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                if (kEpi == 2 && (int)(it & 1) != eg) continue;
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
                 const int tt = (int)(rest % p.tiles_t);
@@ -518,7 +471,6 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             // ---- fused DWS epilogue (see gemm_tc.cu): the tile holds 128 pointwise columns for times
             // [t0-4, t0+124); each thread owns one channel row and slides the 5-tap window along it in registers.
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                if (kEpi == 2 && (int)(it & 1) != eg) continue;
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
                 const int tt = (int)(rest % p.tiles_t);
@@ -616,7 +568,6 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
-    if (cx) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         const uint32_t ncols = TMEM_COLS;
@@ -628,9 +579,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
 // ------------------------------------------------------------------------------- host side
 bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
-                   long long y_bs, int y_rs) {
+                   long long y_bs, int y_rs, int B) {
     if (!W.H_hi || !W.H_lo) return false;
-    if (T < 64) return false;  // short chunks (streaming) go to the flattened-column FFMA kernel
+    if (!tc_chunk_ok(B, T)) return false;  // short chunks (streaming) go to the flattened-column FP32 kernels
     if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
     if (R && (reinterpret_cast<uintptr_t>(R) & 15)) return false;
@@ -642,16 +593,6 @@ static int elu_poly_env() {
     return v;
 }
 
-// Experiment, off by default: for K <= HILCODEC_EPI2_MAXK use the configuration with two epilogue groups.  Measured on
-// the music256 step (A/B in one box): with four transform warps 63.7 / 64.5 ms (MAXK = 256) against 62.9 / 63.5 ms
-// without; with all eight transform warps kept (-DHIL_EPI2_EXTRA_THREADS=128: 640 threads, 96 registers, no spills)
-// 60.3 / 60.6 ms (MAXK = 192, DWS only) against 61.7 / 60.4 ms without -- inside the box-to-box noise.
-static bool two_epilogue_groups(int K, bool dw) {
-    static const int maxk = []() { const char* e = std::getenv("HILCODEC_EPI2_MAXK"); return e ? std::atoi(e) : 0; }();
-    static const bool dw_only = std::getenv("HILCODEC_EPI2_DW_ONLY") != nullptr;
-    return K <= maxk && (dw || !dw_only);
-}
-
 static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, CUtensorMap* map_hi,
                              CUtensorMap* map_lo, CUtensorMap* map_x, int* num_sms_out) {
     using namespace th;
@@ -660,10 +601,6 @@ static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs,
         cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(gemm_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(gemm_h_kernel<false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(gemm_h_kernel<true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -683,49 +620,6 @@ static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs,
         if (!tc::make_map(map_x, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
     }
     return cudaSuccess;
-}
-
-// HILCODEC_CLUSTER_X=1 (off by default: written at the end of round 1 without GPU time, compiled only): 2-CTA clusters
-// that share the activation boxes by TMA multicast, for layers with an even number of 128-row weight blocks and at
-// least HILCODEC_CLUSTER_X_MINM (default 384) output channels.  Returns the grid (0 = not applicable).
-template <class Kernel>
-static unsigned cluster_x_grid(Kernel kernel, const PackedMat& W, const th::Params& p, const float* X, long long x_bs, int x_rs,
-                               int B, int T, CUtensorMap* map_xh) {
-    using namespace th;
-    static const bool on = []() { const char* e = std::getenv("HILCODEC_CLUSTER_X"); return e && e[0] == '1'; }();
-    static const int min_m = []() { const char* e = std::getenv("HILCODEC_CLUSTER_X_MINM"); return e ? std::atoi(e) : 384; }();
-    if (!on || W.M < min_m || (p.num_m & 1) || (W.K % BK) != 0 || p.total_tiles < 2) return 0;
-    const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)x_rs * 4, (cuuint64_t)x_bs * 4};
-    const cuuint32_t box[3] = {BN, BK / 2, 1};
-    if (!tc::make_map(map_xh, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 0;
-    static int max_clusters = -1;   // the same for every instantiation: one 512-thread, ~225 KB CTA per SM
-    if (max_clusters < 0) {
-        cudaLaunchConfig_t cfg{};
-        cudaLaunchAttribute attr{};
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.gridDim = dim3(2 * (unsigned)tc::device_sm_count()); cfg.blockDim = dim3(NUM_THREADS);
-        cfg.dynamicSmemBytes = SMEM_BYTES; cfg.attrs = &attr; cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 0; }
-        max_clusters = n;
-    }
-    if (max_clusters < 1) return 0;
-    const long long g = 2LL * max_clusters;
-    return (unsigned)(p.total_tiles < g ? p.total_tiles : g);   // total_tiles is even (num_m is)
-}
-
-template <class Kernel, class... Args>
-static cudaError_t launch_clustered(Kernel kernel, unsigned grid, cudaStream_t st, Args... args) {
-    using namespace th;
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 static cudaError_t seed_residual(const float* R, float* Y, long long y_bs, int y_rs, int B, int M, int T, cudaStream_t st) {
@@ -766,16 +660,7 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    if (two_epilogue_groups(W.K, false)) {
-        gemm_h_kernel<false, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
-    } else {
-        CUtensorMap map_xh;
-        if (const unsigned cgrid = cluster_x_grid(gemm_h_kernel<false>, W, p, X, x_bs, x_rs, B, T, &map_xh)) {
-            p.cx = 1;
-            return launch_clustered(gemm_h_kernel<false>, cgrid, st, map_hi, map_lo, map_x, map_xh, map_y, map_y, p);
-        }
-        gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
-    }
+    gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     return cudaGetLastError();
 }
 
@@ -838,7 +723,7 @@ static cudaError_t launch_up(const PackedMat& W, const float* x, long long x_bs,
     p.t_in = T_in; p.up_w = up_w; p.up_ci = ci; p.up_co = co;
     const int num_sms = tc::device_sm_count();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_h_kernel<false, S><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y, p);
+    gemm_h_kernel<false, S><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
     return cudaGetLastError();
 }
 
@@ -851,67 +736,6 @@ cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs,
     HIL_UP(2) HIL_UP(4) HIL_UP(5) HIL_UP(8)
 #undef HIL_UP
     return cudaErrorInvalidValue;
-}
-
-// Plain 1x1 conv + bias whose input is a pair of fp16 planes [B][K][pitch] (x = hi + lo * 2^-11), e.g. written by
-// launch_dwconv_transpose_planes: no activation prologue, no transform pass.
-bool gemm_h_planes_usable(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int T,
-                          const float* Y, long long y_bs, int y_rs) {
-    if (!W.H_hi || !W.H_lo) return false;
-    if (T < 64 || (W.K & 31)) return false;
-    if ((p_rs & 7) || (p_bs & 7) || (y_rs & 3) || (y_bs & 3)) return false;   // 16-byte multiples
-    if ((reinterpret_cast<uintptr_t>(hi) & 15) || (reinterpret_cast<uintptr_t>(lo) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15))
-        return false;
-    return true;
-}
-
-cudaError_t launch_gemm_h_planes(const PackedMat& W, const uint16_t* hi, const uint16_t* lo, long long p_bs, int p_rs, int B,
-                                 int T, const float* bias, float* Y, long long y_bs, int y_rs, cudaStream_t st) {
-    using namespace th;
-    if (B == 0 || T == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<false, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    CUtensorMap map_hi, map_lo, map_xh, map_xl, map_y;
-    {
-        const cuuint64_t dims[2] = {(cuuint64_t)W.Kp32, (cuuint64_t)W.Mp128};
-        const cuuint64_t strides[1] = {(cuuint64_t)W.Kp32 * 2};
-        const cuuint32_t box[2] = {BK, BM};
-        if (!tc::make_map_dt(&map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B) ||
-            !tc::make_map_dt(&map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
-            return cudaErrorInvalidValue;
-    }
-    {
-        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
-        const cuuint64_t strides[2] = {(cuuint64_t)p_rs * 2, (cuuint64_t)p_bs * 2};
-        const cuuint32_t box[3] = {64, BK, 1};   // one 64-column panel: 128-byte rows, the MMA's SWIZZLE_128B atom layout
-        if (!tc::make_map_dt(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
-            !tc::make_map_dt(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
-            return cudaErrorInvalidValue;
-    }
-    {
-        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
-        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
-        const cuuint32_t box[3] = {32, BM, 1};
-        if (!tc::make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return cudaErrorInvalidValue;
-    }
-    Params p{};
-    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
-    p.num_m = (W.M + BM - 1) / BM;
-    p.t_step = BN; p.t_halo = 0;
-    p.tiles_t = (T + BN - 1) / BN;
-    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
-    p.pre = PRE_NONE; p.pre_scale = 1.0f; p.bias = bias; p.reduce_add = 0;
-    p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
-    p.xform_sleep = 0;
-    const int num_sms = tc::device_sm_count();
-    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_h_kernel<false, 0, 1, 1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_xh, map_xl, map_y, map_y, p);
-    return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
@@ -951,16 +775,7 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    if (two_epilogue_groups(W.K, true)) {
-        gemm_h_kernel<true, 0, 2><<<grid, NUM_THREADS + EPI2_EXTRA_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y28, p);
-    } else {
-        CUtensorMap map_xh;
-        if (const unsigned cgrid = cluster_x_grid(gemm_h_kernel<true>, W, p, X, x_bs, x_rs, B, T, &map_xh)) {
-            p.cx = 1;
-            return launch_clustered(gemm_h_kernel<true>, cgrid, st, map_hi, map_lo, map_x, map_xh, map_y, map_y28, p);
-        }
-        gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_x, map_y, map_y28, p);
-    }
+    gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
     return cudaGetLastError();
 }
 

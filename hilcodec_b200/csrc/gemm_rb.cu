@@ -18,8 +18,10 @@
 // of one read) and the tile loads [halo | own columns] with two TMA boxes; its own columns are read before it
 // writes them and nobody else touches them.
 //
-// Geometry: C <= 128: one 128-row m-block, BN = 128;  128 < C <= 256: two m-blocks, BN = 64 -- either way an
-// accumulator (big | small) fills 256 TMEM columns, D1 and D2 fill the 512.
+// Geometry: C <= 128: one 128-row m-block, BN = 128: an accumulator (big | small) fills 256 TMEM columns, D1 and D2
+// fill the 512.  (The kernel stays templated on BN; the two-m-block BN = 64 instantiation for 128 < C <= 256
+// re-streamed both weight matrices from L2 for every 56 outputs, measured slower than two fused-DWS launches in
+// round 1 and is no longer built.)
 // Warp roles (512 threads, 1 CTA/SM): 0 X producer (TMA), 1 MMA issuer, 2 TMEM allocator, 3 weight producer
 // (TMA, W0 then W1 pieces through one ring), 8-15 workers: transform (ELU + split of the input tile) and E1, two warps
 // per TMEM lane quarter; 4-7 epilogue E2.  E2 of tile i overlaps the transform / G1 / E1 of tile i+1.
@@ -558,13 +560,13 @@ __global__ void halo_gather_kernel(const float* __restrict__ h, long long bs, in
 }  // namespace rb
 
 // ------------------------------------------------------------------------------- host side
-static int rb_bn(int C) { return C <= 128 ? 128 : 64; }
+static int rb_bn(int) { return 128; }
 
 bool resblock_h_usable(const PackedMat& W0, const PackedMat& W1, const float* h, long long bs, int rs, int T) {
     const int C = W0.M;
     if (W0.K != C || W1.M != C || W1.K != C) return false;
     if (!W0.H_hi || !W0.H_lo || !W1.H_hi || !W1.H_lo) return false;
-    if (C < 32 || C > 256 || (C & 31)) return false;
+    if (C < 32 || C > 128 || (C & 31)) return false;
     if (T < 128) return false;                    // short chunks (streaming) keep the two-kernel path
     if ((rs & 3) || (bs & 3) || (reinterpret_cast<uintptr_t>(h) & 15)) return false;
     return true;
@@ -651,11 +653,8 @@ cudaError_t launch_resblock_h(const PackedMat& W0, const PackedMat& W1, float* h
                               const float* c0_in, float* c0_out, const float* c1_in, float* c1_out, const float* halo,
                               cudaStream_t st) {
     if (B == 0 || T == 0) return cudaSuccess;
-    if (rb_bn(W0.M) == 128)
-        return launch_rb<128>(W0, W1, h, bs, rs, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in,
-                              c1_out, halo, st);
-    return launch_rb<64>(W0, W1, h, bs, rs, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in, c1_out,
-                         halo, st);
+    return launch_rb<128>(W0, W1, h, bs, rs, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in, c1_out,
+                          halo, st);
 }
 
 }  // namespace hil

@@ -14,8 +14,9 @@
 // clamp + log for the DFT.  Grid = (ceil(N / NT), Mp / 32): 24-48 CTAs for the wide layers instead of 6-12,
 // each with K/8 sequential k per warp instead of K.
 //
-// OFF by default (HILCODEC_SKINNY=1 enables it): written after this round's GPU budget was spent, so it has
-// been compiled for sm_100a but not yet run; tests/test_gpu_ops.py::test_skinny_gemm covers it when enabled.
+// Default since round 2 (measured on the B200 with the published hil_music weights, profiles/r2_ab_results.md: one
+// stream 3.36 -> 1.27 ms per hop with this kernel, 0.88 ms together with the per-stage RVQ launches; 64 streams
+// 4.35 -> 2.92 ms); the whole GPU parity suite runs through it wherever a chunk has <= 512 columns.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -276,23 +277,16 @@ SkinnyParams base(const PackedMat& W, int B, int T) {
 
 }  // namespace
 
-// HILCODEC_SKINNY=1 enables the kernel; HILCODEC_SKINNY_MAXN caps the column count it is used for.
+// On by default since round 2 (one hil_music stream: 3.36 -> 0.88 ms per hop together with the per-stage RVQ launches);
+// HILCODEC_SKINNY=0 falls back to gemm.cu for A/B runs, HILCODEC_SKINNY_MAXN caps the column count it is used for.
 bool gemm_skinny_usable(const PackedMat& W, int B, int T) {
-    static const bool on = [] { const char* e = std::getenv("HILCODEC_SKINNY"); return e && e[0] == '1'; }();
+    static const bool on = [] { const char* e = std::getenv("HILCODEC_SKINNY"); return !(e && e[0] == '0'); }();
     static const long long max_n = [] {
         const char* e = std::getenv("HILCODEC_SKINNY_MAXN");
         return e ? std::atoll(e) : 512LL;
     }();
     const long long N = (long long)B * T;
     return on && W.A != nullptr && (W.Mp % SK_ROWS) == 0 && N > 0 && N <= max_n;
-}
-
-// HILCODEC_SKINNY_PREFER=1: also take the chunks a tensor-core kernel would accept (T >= 64) when the WHOLE launch is
-// small (N <= HILCODEC_SKINNY_MAXN): for one stream the 160- and 320-column layers are 2-3 tiles of a persistent
-// tcgen05 kernel whose fixed costs (TMEM allocation, barrier set-up, pipeline fill) outweigh the work.
-bool gemm_skinny_preferred(const PackedMat& W, int B, int T) {
-    static const bool on = [] { const char* e = std::getenv("HILCODEC_SKINNY_PREFER"); return e && e[0] == '1'; }();
-    return on && gemm_skinny_usable(W, B, T);
 }
 
 cudaError_t launch_gemm_skinny_linear(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,

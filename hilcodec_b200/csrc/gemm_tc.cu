@@ -393,9 +393,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }  // namespace tc
 
 bool gemm_tc_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
-                    long long y_bs, int y_rs) {
+                    long long y_bs, int y_rs, int B) {
     if (!W.A_hi || !W.A_lo) return false;
-    if (T < 64) return false;  // short chunks (streaming) go to the flattened-column FFMA kernel
+    if (!tc_chunk_ok(B, T)) return false;  // short chunks (streaming) go to the flattened-column FP32 kernels
     if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
     if (R && (reinterpret_cast<uintptr_t>(R) & 15)) return false;

@@ -10,9 +10,9 @@
 //   distance[c] = (-2 r) . e_c + sum_k e_ck^2;  idx = argmin (first wins)
 // which is the same expression with sum_k r_k^2 replaced by 0 (0 - a = -a and the outer negation are exact).
 //
-// Layout: a CTA owns FT = 32 frames; warp w owns frames 4w..4w+3 (so the per-frame argmax
-// reduction and the residual update are warp-local shuffles); lane l scores codes
-// l, l+32, l+64, l+96 of each 128-code tile staged in shared memory.
+// Layout: warp w of a CTA owns FPW consecutive frames (so the per-frame argmax reduction and the
+// residual update are warp-local shuffles); lane l scores codes l, l+32, l+64, l+96 of each
+// 128-code tile staged in shared memory.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -42,140 +42,11 @@ cudaError_t launch_codebook_norms(const float* codebooks, float* ee, int n_q, in
     return cudaGetLastError();
 }
 
-// Two CTAs per SM (2 x 84 KB of shared memory, <= 128 registers): the kernel alternates between loading a codebook
-// tile and scoring it with a barrier on either side, so a second resident CTA fills the load phases of the first.
-__global__ void __launch_bounds__(256, 2)
-rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee,
-                  int size, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum, int drop_xx) {
-    extern __shared__ __align__(16) float smem[];
-    float* R = smem;                              // [RVQ_FT][RVQ_PITCH]
-    float* E = smem + RVQ_FT * RVQ_PITCH;         // [RVQ_CT][RVQ_PITCH]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long f0 = (long long)blockIdx.x * RVQ_FT;
-
-    // load residual tile (zero rows past the end)
-    for (int i = tid; i < RVQ_FT * (RVQ_DIM / 4); i += 256) {
-        const int fr = i / (RVQ_DIM / 4), k4 = i - fr * (RVQ_DIM / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f0 + fr < frames) v = *reinterpret_cast<const float4*>(z + (f0 + fr) * RVQ_DIM + k4 * 4);
-        *reinterpret_cast<float4*>(&R[fr * RVQ_PITCH + k4 * 4]) = v;
-    }
-    float4 qacc[4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f) qacc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-
-    for (int s = 0; s < n; ++s) {
-        const float* cb = codebooks + (size_t)s * size * RVQ_DIM;
-        const float* ees = ee + (size_t)s * size;
-
-        // xx[f] = sum_k r^2 for this warp's 4 frames (lane-strided partials + shuffle tree)
-        float xx[4];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            const float4 v = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]);
-            float p = __fmul_rn(v.x, v.x);
-            p = fmaf(v.y, v.y, p); p = fmaf(v.z, v.z, p); p = fmaf(v.w, v.w, p);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-            xx[f] = drop_xx ? 0.f : p;
-        }
-
-        float best[4];
-        int besti[4];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) { best[f] = -INFINITY; besti[f] = 0x7fffffff; }
-
-        for (int c0 = 0; c0 < size; c0 += RVQ_CT) {
-            __syncthreads();  // previous tile fully consumed
-            for (int i = tid; i < RVQ_CT * (RVQ_DIM / 4); i += 256) {
-                const int cr = i / (RVQ_DIM / 4), k4 = i - cr * (RVQ_DIM / 4);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c0 + cr < size) v = *reinterpret_cast<const float4*>(cb + (size_t)(c0 + cr) * RVQ_DIM + k4 * 4);
-                *reinterpret_cast<float4*>(&E[cr * RVQ_PITCH + k4 * 4]) = v;
-            }
-            __syncthreads();
-
-            float dot[4][4];
-#pragma unroll
-            for (int f = 0; f < 4; ++f)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dot[f][j] = 0.f;
-#pragma unroll 4
-            for (int k4 = 0; k4 < RVQ_DIM / 4; ++k4) {
-                float4 r4[4], e4[4];
-#pragma unroll
-                for (int f = 0; f < 4; ++f)
-                    r4[f] = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + k4 * 4]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    e4[j] = *reinterpret_cast<const float4*>(&E[(lane + 32 * j) * RVQ_PITCH + k4 * 4]);
-#pragma unroll
-                for (int f = 0; f < 4; ++f)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float d = dot[f][j];
-                        d = fmaf(r4[f].x, e4[j].x, d);
-                        d = fmaf(r4[f].y, e4[j].y, d);
-                        d = fmaf(r4[f].z, e4[j].z, d);
-                        d = fmaf(r4[f].w, e4[j].w, d);
-                        dot[f][j] = d;
-                    }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int code = c0 + lane + 32 * j;
-                if (code < size) {
-                    const float e2 = ees[code];
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        // -(xx - 2*dot + ee), evaluated left to right in fp32 like the reference
-                        const float d = -__fadd_rn(__fsub_rn(xx[f], __fmul_rn(2.f, dot[f][j])), e2);
-                        if (d > best[f]) { best[f] = d; besti[f] = code; }  // codes ascend per lane: first max wins
-                    }
-                }
-            }
-        }
-
-        // warp argmax with first-index tie break, then residual / dequant update
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            float bd = best[f];
-            int bi = besti[f];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-            }
-            if (bi < 0 || bi >= size) bi = 0;  // all-NaN row: torch's max returns the NaN position; keep in range
-            const long long fr = f0 + warp * 4 + f;
-            const float4 e = *reinterpret_cast<const float4*>(cb + (size_t)bi * RVQ_DIM + lane * 4);
-            float4* rp = reinterpret_cast<float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]);
-            float4 r = *rp;
-            r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y); r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
-            *rp = r;
-            qacc[f].x = __fadd_rn(qacc[f].x, e.x); qacc[f].y = __fadd_rn(qacc[f].y, e.y);
-            qacc[f].z = __fadd_rn(qacc[f].z, e.z); qacc[f].w = __fadd_rn(qacc[f].w, e.w);
-            if (lane == 0 && fr < frames) idx[(size_t)s * frames + fr] = bi;
-        }
-        __syncwarp();
-    }
-
-    if (qsum) {
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            const long long fr = f0 + warp * 4 + f;
-            if (fr < frames) *reinterpret_cast<float4*>(qsum + fr * RVQ_DIM + lane * 4) = qacc[f];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// v2 of the one-kernel search for LARGE batches (HILCODEC_RVQ_V2=1; off by default: emulation-verified bit-identical
-// to rvq_encode_kernel, not yet measured on a GPU).  Two changes, same arithmetic per frame:
-//  * FPW = 8 frames per warp instead of 4: per k4 step a warp issues 8 broadcast LDS.128 (residuals) + 4 four-wavefront
+// The one-kernel search (all n stages, residual in shared memory).  Round 1's kernel gave a warp 4 frames and a CTA 32;
+// this one (measured in round 2: 2.92 -> 2.22 ms at 19 200 frames x 12 stages, bit-identical indices and sums) differs
+// in two ways, same arithmetic per frame:
+//  * FPW = 8 frames per warp: per k4 step a warp issues 8 broadcast LDS.128 (residuals) + 4 four-wavefront
 //    LDS.128 (codes) = 24 shared-memory wavefronts for 128 FFMA instead of 20 for 64, which moves the inner loop from
 //    the LDS pipe (1 wavefront / clk / SM) to the FMA pipes (4 warp-FFMA / clk / SM);
 //  * the number of warps per CTA is chosen by the launcher so that ONE wave of 2 CTAs per SM covers all frames
@@ -183,7 +54,7 @@ rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codeboo
 //    32-frame CTAs running as 2.03 -> 3 rounds.
 template <int FPW>
 __global__ void __launch_bounds__(288, 2)
-rvq_encode_v2_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee,
+rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee,
                      int size, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum, int drop_xx) {
     extern __shared__ __align__(16) float smem[];
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -313,7 +184,7 @@ int rvq_v2_warps(long long frames, int fpw, int slots) {
     return 8;
 }
 
-static cudaError_t launch_rvq_encode_v2(const float* z, const float* codebooks, const float* ee, int size, long long frames,
+static cudaError_t launch_rvq_encode_big(const float* z, const float* codebooks, const float* ee, int size, long long frames,
                                         int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
     constexpr int FPW = 8;
     static int slots = 0;
@@ -323,7 +194,7 @@ static cudaError_t launch_rvq_encode_v2(const float* z, const float* codebooks, 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slots = 2 * (sms > 0 ? sms : 148);
         const size_t max_smem = (size_t)(9 * FPW + RVQ_CT) * RVQ_PITCH * sizeof(float);
-        const cudaError_t e = cudaFuncSetAttribute(rvq_encode_v2_kernel<FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(rvq_encode_kernel<FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)max_smem);
         if (e != cudaSuccess) { slots = 0; return e; }
     }
@@ -331,27 +202,15 @@ static cudaError_t launch_rvq_encode_v2(const float* z, const float* codebooks, 
     const int ft = warps * FPW;
     const size_t smem = (size_t)(ft + RVQ_CT) * RVQ_PITCH * sizeof(float);
     const unsigned grid = (unsigned)((frames + ft - 1) / ft);
-    rvq_encode_v2_kernel<FPW><<<grid, warps * 32, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx ? 1 : 0);
+    rvq_encode_kernel<FPW><<<grid, warps * 32, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx ? 1 : 0);
     return cudaGetLastError();
 }
 
 cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const float* ee, int size, int dim, long long frames,
                               int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
-    static const bool v2 = [] { const char* e = std::getenv("HILCODEC_RVQ_V2"); return e && e[0] == '1'; }();
-    if (v2 && dim == RVQ_DIM && frames > 0 && n > 0)
-        return launch_rvq_encode_v2(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx, st);
     if (dim != RVQ_DIM) return cudaErrorInvalidValue;
     if (frames == 0 || n == 0) return cudaSuccess;
-    static bool attr_set = false;
-    const size_t smem = (size_t)(RVQ_FT + RVQ_CT) * RVQ_PITCH * sizeof(float);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    const unsigned grid = (unsigned)((frames + RVQ_FT - 1) / RVQ_FT);
-    rvq_encode_kernel<<<grid, 256, smem, st>>>(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx ? 1 : 0);
-    return cudaGetLastError();
+    return launch_rvq_encode_big(z, codebooks, ee, size, frames, n, idx, qsum, drop_xx, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -362,8 +221,8 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
 // rebuilds the residual r = ((z - E_0[i_0]) - E_1[i_1]) ... in stage order, i.e. the same fp32 operations as above),
 // then scores ITS 128 codes of stage s with the same FMA order as above and leaves (best distance, index) per frame
 // in `part_out`.  A last launch (s == n) writes the final index and the dequantised sum.  n + 1 launches of ~4 us
-// instead of one of ~340 us; results are bit-identical to rvq_encode_kernel.
-// OFF by default (HILCODEC_RVQ_SPLIT=1): written after this round's GPU budget was spent -- compiled, not yet run.
+// instead of one of ~340 us; results are bit-identical to rvq_encode_kernel.  Default for <= 1024 frames since round 2
+// (one hil_music stream: 1.27 -> 0.88 ms per hop; HILCODEC_RVQ_SPLIT=0 keeps the one-kernel search for A/B runs).
 struct RvqCand { float d; int i; };
 
 __global__ void __launch_bounds__(256, 2)
@@ -496,7 +355,7 @@ rvq_stage_kernel(const float* __restrict__ z, const float* __restrict__ codebook
 }
 
 bool rvq_split_usable(int size, int dim, long long frames) {
-    static const bool on = [] { const char* e = std::getenv("HILCODEC_RVQ_SPLIT"); return e && e[0] == '1'; }();
+    static const bool on = [] { const char* e = std::getenv("HILCODEC_RVQ_SPLIT"); return !(e && e[0] == '0'); }();
     return on && dim == RVQ_DIM && frames > 0 && frames <= RVQ_SPLIT_MAX_FRAMES && (size + RVQ_CT - 1) / RVQ_CT <= RVQ_SPLIT_MAX_TILES;
 }
 

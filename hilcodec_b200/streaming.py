@@ -68,6 +68,11 @@ class _NativeCodec:
         # bumped by invalidate(): a StreamState remembers the generation it was created in and refuses to run
         # against a later one (its hil_state belongs to a model that has been replaced)
         self.generation = 0
+        # fp16-range guard (include/hilcodec_b200.h, hil_state_range_flag): after every module call read the state's
+        # "non-finite output" flag (one 4-byte D2H + stream sync) and, if set, repeat the call on the FP32 kernels.  The
+        # reference's fp32 convolutions have no |x| < 65504 limit; with this on, neither do the modules.  Set False
+        # to keep calls asynchronous (latency-critical loops); StreamState.step never checks (see range_overflow()).
+        self.check_range = True
 
     @property
     def _lib(self):
@@ -176,6 +181,27 @@ class _NativeCodec:
         return out
 
     # -- calls ---------------------------------------------------------------------------
+    def _guarded(self, state: int, dev: torch.device, call: tp.Callable[[], None],
+                 rollback: tp.Tuple[int, int] = (0, 0)) -> None:
+        """Run `call` (a closure over one C-ABI forward); if the range guard trips, undo the cache-generation advance
+        (`rollback` = (encoder, decoder) sides the call advances inside the state) and repeat it on the FP32 kernels."""
+        call()
+        if not self.check_range:
+            return
+        lib = self._lib
+        flag = C.c_int32(0)
+        _lib.check(lib.hil_state_range_flag(state, 1, _stream_ptr(dev), C.byref(flag)))
+        if not flag.value:
+            return
+        if any(rollback):
+            _lib.check(lib.hil_state_rollback(state, *rollback))
+        prev = lib.hil_set_exact_fp32(1)
+        try:
+            call()
+            _lib.check(lib.hil_state_range_flag(state, 1, _stream_ptr(dev), C.byref(flag)))
+        finally:
+            lib.hil_set_exact_fp32(prev)
+
     def _cache_io(self, which: int, caches: tp.Sequence[Tensor], batch: int, device: torch.device):
         shapes = self.cache_shapes(which, batch, device)
         if len(caches) != len(shapes):
@@ -208,8 +234,9 @@ class _NativeCodec:
             x = x.contiguous()
             ins, outs, pin, pout = self._cache_io(_lib.HIL_ENCODER, caches, B, dev)
             z = torch.empty(B, T // hop, self.cfg.dim, dtype=torch.float32, device=dev)
-            _lib.check(self._lib.hil_encode_caches(
-                self.model(dev), self.state(dev, B), x.data_ptr(), B, T, z.data_ptr(), pin, pout, _stream_ptr(dev)))
+            model, state = self.model(dev), self.state(dev, B)
+            self._guarded(state, dev, lambda: _lib.check(self._lib.hil_encode_caches(
+                model, state, x.data_ptr(), B, T, z.data_ptr(), pin, pout, _stream_ptr(dev))))
         return z, outs
 
     def encode_ragged(self, x: Tensor) -> Tensor:
@@ -224,8 +251,9 @@ class _NativeCodec:
         with torch.cuda.device(dev):
             x = x.contiguous()
             z = torch.empty(B, -(-T // self.cfg.hop), self.cfg.dim, dtype=torch.float32, device=dev)
-            _lib.check(self._lib.hil_encode_ragged(
-                self.model(dev), self.state(dev, B), x.data_ptr(), B, T, z.data_ptr(), _stream_ptr(dev)))
+            model, state = self.model(dev), self.state(dev, B)
+            self._guarded(state, dev, lambda: _lib.check(self._lib.hil_encode_ragged(
+                model, state, x.data_ptr(), B, T, z.data_ptr(), _stream_ptr(dev))))
         return z
 
     def decode(self, q: Tensor, caches: tp.Sequence[Tensor]) -> tp.Tuple[Tensor, tp.List[Tensor]]:
@@ -240,8 +268,9 @@ class _NativeCodec:
             q = q.contiguous()
             ins, outs, pin, pout = self._cache_io(_lib.HIL_DECODER, caches, B, dev)
             wav = torch.empty(B, 1, F * self.cfg.hop, dtype=torch.float32, device=dev)
-            _lib.check(self._lib.hil_decode_caches(
-                self.model(dev), self.state(dev, B), q.data_ptr(), B, F, wav.data_ptr(), pin, pout, _stream_ptr(dev)))
+            model, state = self.model(dev), self.state(dev, B)
+            self._guarded(state, dev, lambda: _lib.check(self._lib.hil_decode_caches(
+                model, state, q.data_ptr(), B, F, wav.data_ptr(), pin, pout, _stream_ptr(dev))))
         return wav, outs
 
     def rvq_encode(self, z: Tensor, n: int, with_sum: bool = False):
@@ -612,8 +641,8 @@ class HILCodec(nn.Module):
                 st = state.handle(B)
             idx = torch.empty(n, B, T // self.cfg.hop, dtype=torch.int64, device=dev)
             y = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
-            _lib.check(lib.hil_codec_forward(model, st, x.data_ptr(), B, T, n, None, idx.data_ptr(), y.data_ptr(),
-                                             _stream_ptr(dev)))
+            core._guarded(st, dev, lambda: _lib.check(lib.hil_codec_forward(
+                model, st, x.data_ptr(), B, T, n, None, idx.data_ptr(), y.data_ptr(), _stream_ptr(dev))), rollback=(1, 1))
         return idx, y
 
     def new_stream_state(self, batch: int, device: tp.Union[str, torch.device] = "cuda") -> "StreamState":
@@ -679,6 +708,15 @@ class StreamState:
             _lib.check(self._lib.hil_codec_forward_graph(self._core.model(self.device), self._h, xin.data_ptr(), B, T, n,
                                                          idx.data_ptr(), y.data_ptr(), _stream_ptr(self.device)))
         return idx, y
+
+    def range_overflow(self, clear: bool = True) -> bool:
+        """True if any step since the last (cleared) check produced a non-finite latent or PCM sample -- an activation
+        left the fp16 range of the tensor-core kernels (`hil_state_range_flag`; synchronises the stream).  `step` does not
+        check by itself: a streaming loop stays asynchronous and polls this when it wants to."""
+        self._check()
+        flag = C.c_int32(0)
+        _lib.check(self._lib.hil_state_range_flag(self._h, 1 if clear else 0, _stream_ptr(self.device), C.byref(flag)))
+        return bool(flag.value)
 
     def export(self) -> tp.Tuple[tp.List[Tensor], tp.List[Tensor]]:
         self._check()

@@ -98,6 +98,19 @@ int32_t hil_state_import_cache(hil_state* s, int32_t which, int32_t i, const flo
 void hil_state_destroy(hil_state* s);
 size_t hil_state_workspace_bytes(const hil_state* s);
 
+/* ---- fp16-range guard (no counterpart in the reference, whose fp32 convolutions have no such limit) -------
+ * The tensor-core kernels split every activation into two fp16 numbers, which needs |x| < 65504; beyond that the
+ * split is Inf / NaN and the affected latents / PCM samples come out NaN.  The last kernel of the encoder (L2 norm)
+ * and of the decoder (conv_post + tanh) set a sticky per-state device flag when they produce a non-finite value.
+ * hil_state_range_flag reads it (synchronises `stream`; clear != 0 resets it).  hil_set_exact_fp32(1) makes every later
+ * call of THIS thread run on the FP32 FFMA kernels (exact reference range, ~5x slower) until hil_set_exact_fp32(0);
+ * returns the previous setting.  hil_state_rollback undoes the cache-generation advance of the last hil_encode /
+ * hil_decode / hil_codec_forward on `s` (the previous generation is intact: caches ping-pong) so that the call can be
+ * repeated.  hil_codec_forward_host does all of this by itself; the Python modules do it unless check_range is False. */
+int32_t hil_state_range_flag(hil_state* s, int32_t clear, void* stream, int32_t* flag_out);
+int32_t hil_state_rollback(hil_state* s, int32_t encoder, int32_t decoder);
+int32_t hil_set_exact_fp32(int32_t on);
+
 /* ---- the four calls of the deployment flow (scripts/HILCodec Onnx.ipynb cell 3) --- */
 /* Encoder.forward streaming.py:482-517: wav [B,1,T] (T multiple of hop) -> z [B,T/hop,dim];
  * caches advance inside `s`. */
@@ -148,20 +161,26 @@ int32_t hil_unpack_indices(hil_model* m, const uint8_t* in_dev, int32_t B, int32
 /* kernels launched by this library since load (bench.py reports the per-step delta as gpu_launches) */
 uint64_t hil_launch_count(void);
 /* Per-kernel-category timing: between begin and end every launch is bracketed by CUDA events on
- * its stream.  Categories: 0 pointwise GEMM, 1 STFT GEMM, 2 depthwise conv, 3 transposed
- * depthwise, 4 conv_pre, 5 conv_post+tanh, 6 RVQ, 7 misc (wav concat, l2norm).
+ * its stream.  Categories: 0 pointwise GEMM of the narrow layers (1x1 / fused DWSBlock / fused upsampling with
+ * Cin, Cout < 384: HBM-bound), 1 STFT GEMM, 2 depthwise conv, 3 transposed depthwise, 4 conv_pre, 5 conv_post+tanh,
+ * 6 RVQ, 7 misc (wav concat, l2norm, ResBlock halo gather), 8 pointwise GEMM of the wide layers (Cin or Cout >= 384:
+ * bound by the tensor pipe and its operand stream), 9 fused whole-ResBlock kernel (C <= 128: HBM-bound).
  * end() synchronises the device and fills summed ms / algorithmic FLOPs / algorithmic bytes /
  * launch counts per category (arrays of HIL_PROFILE_CATEGORIES). */
 /* Kernel selection for A/B measurement (returns the previous mode).  Bit 0: 1 (default) = GEMMs and STFT on the
- * tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy), 0 = FP32 FFMA kernels everywhere.  Bit 2 set: do not
- * fuse DWS blocks.  Bit 3 set: use the experimental time-major kernel (gemm_tm.cu, activations through TMEM)
- * for plain 1x1 convs with Cout <= 192.  Bit 4 set (default): fp16-split tensor-core kernels (gemm_h.cu, kind::f16)
+ * tensor pipe (tcgen05, fp32-level accuracy from split operands), 0 = FP32 FFMA kernels everywhere.  Bit 2 set: do not
+ * fuse DWS blocks.  Bit 4 set (default): fp16-split tensor-core kernels (gemm_h.cu, kind::f16)
  * instead of 3xTF32.  Bit 5 set: do not fuse whole ResBlocks (gemm_rb.cu).  Bit 6 set: do not fuse the decoder's
  * upsampling layers (transposed depthwise conv -> 1x1). */
 int32_t hil_set_tensor_cores(int32_t mode);
-#define HIL_PROFILE_CATEGORIES 8
+#define HIL_PROFILE_CATEGORIES 10
 int32_t hil_profile_begin(void);
 int32_t hil_profile_end(double* ms, double* flops, double* bytes, int64_t* launches, int32_t n_cat);
+/* The launches of the last finished profile, in execution order: category, milliseconds, algorithmic FLOPs and bytes of
+ * each (any pointer may be NULL; at most `cap` entries are written).  Returns the number of launches recorded -- the
+ * same sequence an `ncu` launch list of the same step shows, which is how tools/summarize_launches.py attributes the
+ * measured DRAM traffic to layer classes. */
+int32_t hil_profile_launches(int32_t* cat, double* ms, double* flops, double* bytes, int32_t cap);
 
 /* ---- operator level: the reference's causal primitives, for per-kernel parity tests - */
 /* CausalConv1d.forward causal_layers.py:160-165, depthwise (groups=C).
@@ -187,7 +206,7 @@ int32_t hil_op_dws(const float* x, const float* w_pw_host, const float* w_dw, co
 /* ResBlock.forward streaming.py:252-275 with the residual scale folded into the second depthwise conv
  * (merge_scaling :240-250):  h[B,C,T] <- h + dw5_1(W1 * ELU(dw5_0(W0 * pre(h)) + b0)) + b1, in place.
  * c0/c1 [B,C,4] are the caches of the two depthwise convs (in -> out).  fused = 1: the one-kernel path
- * (C <= 256, C % 32 == 0, T >= 128; tmp1 receives the halo columns), fused = 0: two hil_op_dws-style launches
+ * (C <= 128, C % 32 == 0, T >= 128; tmp1 receives the halo columns), fused = 0: two hil_op_dws-style launches
  * through tmp1/tmp2 [B,C,T].  w0_host / w1_host are HOST [C,C,1] weights. */
 int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, const float* dw0_w, const float* dw0_b,
                         const float* dw1_w, const float* dw1_b, const float* c0_in, float* c0_out, const float* c1_in,
@@ -195,9 +214,8 @@ int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, co
                         int32_t fused, void* stream);
 /* Decoder upsampling layer, streaming.py:633-637: pre(x) -> CausalConvTranspose1d (causal_layers.py:183-188,
  * depthwise, kernel 2S, stride S, cache [B,K,1]) -> nn.Conv1d(k=1) + bias.  x [B,K,T_in] -> y [B,M,S*T_in].
- * fused = 1: one tensor-core kernel (S in {2,4,5,8}, K % 32 == 0, S*T_in >= 128, pre 0 or 2), fused = 2: the
- * transposed conv writes fp16 hi/lo planes into tmp and the 1x1 conv reads them by TMA (no conversion pass; the
- * wide decoder stages), fused = 0: hil_op_dwconv_transpose + hil_op_pointwise through tmp [B,K,S*T_in] (fp32).
+ * fused = 1: one tensor-core kernel (S in {2,4,5,8}, K % 32 == 0, S*T_in >= 128, pre 0 or 2),
+ * fused = 0: hil_op_dwconv_transpose + hil_op_pointwise through tmp [B,K,S*T_in] (fp32).
  * w_pw_host is a HOST [M,K,1] weight. */
 int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out, const float* w_up, const float* w_pw_host,
                         const float* bias, float* tmp, float* y, int32_t B, int32_t K, int32_t M, int32_t T_in, int32_t S,

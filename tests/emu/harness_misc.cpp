@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
         std::vector<float> y((size_t)B * T, -12345.f), co((size_t)B * C * 4, -12345.f);
         const int Tq = (T + 7) / 8, th = Tq >= 128 ? 128 : 32;
         emu_launch(max(1, (Tq + th - 1) / th), B, th, [&] {
-            conv_post_tanh_kernel<5>(x, (long long)C * Tp, Tp, ci, co.data(), w, bias, y.data(), C, T, pre, pre_scale, 1);
+            conv_post_tanh_kernel<5>(x, (long long)C * Tp, Tp, ci, co.data(), w, bias, y.data(), C, T, pre, pre_scale, 1, nullptr);
         });
         dump(argv[8], {{y.data(), y.size() * 4}, {co.data(), co.size() * 4}});
     } else if (mode == "l2norm") {
@@ -73,7 +73,7 @@ int main(int argc, char** argv) {
         std::vector<float> z((size_t)B * Fr * C, -12345.f);
         const long long total = (long long)B * Fr;
         emu_launch((unsigned)((total * 32 + 255) / 256), 1, 256, [&] {
-            l2norm_chlast_kernel(reinterpret_cast<const float*>(in.data()), (long long)C * Fp, Fp, z.data(), C, Fr, total, scale);
+            l2norm_chlast_kernel(reinterpret_cast<const float*>(in.data()), (long long)C * Fp, Fp, z.data(), C, Fr, total, scale, nullptr);
         });
         dump(argv[7], {{z.data(), z.size() * 4}});
     } else if (mode == "wavcat") {

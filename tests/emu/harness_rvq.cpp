@@ -1,8 +1,8 @@
-// Runs rvq.cu's one-kernel search (rvq_encode_kernel) and its per-stage variant (rvq_stage_kernel) -- source text
-// extracted into rvq_extracted.inc -- on the CPU emulation layer.
-// Also the large-batch v2 kernel (8 frames per warp, launcher-chosen warps per CTA; `slots` stands for 2 x SM count).
+// Runs rvq.cu's one-kernel search (rvq_encode_kernel<8>: 8 frames per warp, launcher-chosen warps per CTA; `slots`
+// stands for 2 x SM count) and its per-stage variant (rvq_stage_kernel) -- source text extracted into
+// rvq_extracted.inc -- on the CPU emulation layer.
 // argv: size frames n drop_xx in.bin out.bin slots;  in.bin = z[frames*128] codebooks[n*size*128] (float32);
-// out.bin = idx_mono idx_split idx_v2 [n*frames each] (int64) qsum_mono qsum_split qsum_v2 [frames*128 each] (float32)
+// out.bin = idx_mono idx_split [n*frames each] (int64) qsum_mono qsum_split [frames*128 each] (float32)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -31,7 +31,13 @@ int main(int argc, char** argv) {
     std::vector<int64_t> idx_a((size_t)n * frames, -1), idx_b((size_t)n * frames, -1);
     std::vector<float> q_a(z.size(), -1.f), q_b(z.size(), -1.f);
     const unsigned fblocks = (unsigned)((frames + RVQ_FT - 1) / RVQ_FT);
-    emu_launch(fblocks, 1, 256, [&] { rvq_encode_kernel(z.data(), cb.data(), ee.data(), size, frames, n, idx_a.data(), q_a.data(), drop_xx); });
+    {   // launch_rvq_encode_big
+        const int warps = rvq_v2_warps(frames, 8, slots), ft = warps * 8;
+        emu_launch((unsigned)((frames + ft - 1) / ft), 1, warps * 32, [&] {
+            rvq_encode_kernel<8>(z.data(), cb.data(), ee.data(), size, frames, n, idx_a.data(), q_a.data(), drop_xx);
+        });
+        std::fprintf(stderr, "one-kernel search: %d warps per CTA\n", warps);
+    }
     const int tiles = (size + RVQ_CT - 1) / RVQ_CT;
     std::vector<RvqCand> part[2];
     part[0].resize((size_t)frames * tiles); part[1].resize((size_t)frames * tiles);
@@ -40,22 +46,11 @@ int main(int argc, char** argv) {
             rvq_stage_kernel(z.data(), cb.data(), ee.data(), size, tiles, frames, s, n, idx_b.data(), q_b.data(),
                              part[(s + 1) & 1].data(), part[s & 1].data(), drop_xx);
         });
-    std::vector<int64_t> idx_c((size_t)n * frames, -1);
-    std::vector<float> q_c(z.size(), -1.f);
-    {   // launch_rvq_encode_v2
-        const int warps = rvq_v2_warps(frames, 8, slots), ft = warps * 8;
-        emu_launch((unsigned)((frames + ft - 1) / ft), 1, warps * 32, [&] {
-            rvq_encode_v2_kernel<8>(z.data(), cb.data(), ee.data(), size, frames, n, idx_c.data(), q_c.data(), drop_xx);
-        });
-        std::fprintf(stderr, "v2: %d warps per CTA\n", warps);
-    }
     f = std::fopen(argv[6], "wb");
     std::fwrite(idx_a.data(), 8, idx_a.size(), f);
     std::fwrite(idx_b.data(), 8, idx_b.size(), f);
-    std::fwrite(idx_c.data(), 8, idx_c.size(), f);
     std::fwrite(q_a.data(), 4, q_a.size(), f);
     std::fwrite(q_b.data(), 4, q_b.size(), f);
-    std::fwrite(q_c.data(), 4, q_c.size(), f);
     std::fclose(f);
     return 0;
 }

@@ -104,11 +104,15 @@ def test_dwconv_transpose(B, Cc, T, S, pre):
     (1, 128, 1024, 5, 0, True, False),
     (4, 192, 192, 1, 1, False, False),     # one column per stream
     (1, 256, 257, 129, 2, True, True),
-    # one stream, one hop (the streaming shapes; with HILCODEC_SKINNY=1 these run on gemm_skinny.cu)
+    # one stream, one hop (the streaming shapes: gemm_skinny.cu)
     (1, 768, 1536, 8, 2, True, True),
     (1, 1536, 128, 1, 0, False, False),
     (3, 384, 768, 40, 1, False, True),
     (64, 96, 96, 5, 1, True, False),
+    # 64 concurrent streams, one hop: 40-column chunks take the tensor-core tiles (one partly filled tile per clip)
+    (64, 256, 256, 40, 1, False, False),
+    (64, 384, 768, 40, 0, True, True),
+    (64, 512, 512, 8, 1, False, False),    # 512 columns: the skinny kernel's largest launch
 ])
 def test_pointwise(B, M, K, T, pre, bias, res):
     lib = _lib.load()
@@ -174,7 +178,10 @@ def test_stft_logmag(B, n_fft, hop, T):
     (1, 192, 248, False, 0),    # exactly two 124-column tiles
     (2, 384, 130, True, 1),     # multi row-tile, second tile nearly empty
     (2, 128, 75, False, 1),     # T not a multiple of 4 -> unfused FFMA + depthwise fallback
-    (4, 96, 8, True, 1),        # short chunk (streaming) fallback
+    (4, 96, 8, True, 1),        # short chunk (streaming): depthwise in the skinny GEMM's epilogue
+    (64, 256, 40, True, 1),     # 64 streams, one hop: fused tensor-core kernel on a 40-column chunk (44 of 128 tile columns)
+    (64, 384, 40, False, 2),
+    (33, 128, 36, True, 1),     # shortest chunk the tensor-core tiles take (T >= 32, B * T > 512)
 ])
 def test_dws_block(B, Cc, T, skip, pre):
     """DWSBlock (ELU -> 1x1 -> depthwise k5 + bias) plus the ResBlock's residual add."""
@@ -244,9 +251,8 @@ def _resblock_ref(x, w0, w1, d0w, d0b, d1w, d1b, c0, c1, pre, pre_scale):
     (1, 64, 1000, 2),     # encoder stage 0: half-empty m-block, ragged last tile, scaled ELU prologue
     (3, 128, 128, 1),     # shortest chunk the fused kernel takes: two tiles, the second one 8 columns wide
     (2, 128, 364, 1),     # three full tiles and a 4-column one
-    (1, 192, 1500, 1),    # decoder stage 2: two m-blocks, 64-column tiles (56 outputs each)
-    (2, 256, 300, 2),     # encoder stage 2: both m-blocks full
     (1, 32, 200, 1),
+    (4, 64, 500, 2),      # even batch at C = 64: the clip-pair form (block-diagonal weights, see hil_op_resblock)
 ])
 def test_resblock_fused(B, Cc, T, pre):
     """gemm_rb.cu (whole ResBlock in one kernel, h updated in place) against the fp64 reference and against the two
@@ -306,9 +312,7 @@ def test_upsample_fused(B, K, M, T_in, S, pre):
     assert y_ref.shape[2] == T
     xd, cd, wud, bd = x.cuda(), cache.cuda(), wu.cuda(), bias.cuda()
     outs = []
-    for fused in (1, 0, 2):   # one kernel / fp32 intermediate / fp16 hi-lo planes intermediate
-        if fused == 2 and T % 8 != 0:
-            continue
+    for fused in (1, 0):   # one kernel / transposed conv + 1x1 through the fp32 intermediate
         y = torch.zeros(B, M, T, device="cuda")
         co = torch.zeros(B, K, 1, device="cuda")
         tmp = torch.zeros(B, K, T, device="cuda")
@@ -321,5 +325,3 @@ def test_upsample_fused(B, K, M, T_in, S, pre):
         assert (y.double() - y_ref).abs().max().item() < 2e-5 * scale
         assert (co.double() - xin[:, :, -1:]).abs().max().item() < 1e-6
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5 * scale
-    if len(outs) == 3:   # same arithmetic as the fused kernel (same ELU, same products, same split)
-        assert (outs[0][0] - outs[2][0]).abs().max().item() < 1e-5 * scale

@@ -47,7 +47,8 @@ import ctypes as C
 from hilcodec_b200 import _lib
 
 lib = _lib.load()
-CATS = ["pointwise_gemm", "stft_gemm", "depthwise", "depthwise_transposed", "conv_pre", "conv_post_tanh", "rvq", "misc"]
+CATS = ["pointwise_gemm_narrow", "stft_gemm", "depthwise", "depthwise_transposed", "conv_pre", "conv_post_tanh", "rvq", "misc",
+        "pointwise_gemm_wide", "resblock_fused"]
 for B in (1, 64):
     x = (0.1 * torch.randn(B, 1, 320 * 80, device="cuda")).clamp(-1, 1)
     st = m.new_stream_state(B)

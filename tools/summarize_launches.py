@@ -5,6 +5,12 @@ profiles/dominant_kernel_traffic.json that bench.py reads for `roofline.traffic`
 
     python tools/summarize_launches.py gpurun_out/launches.csv --first K --count N --out profiles/NAME.csv \
         [--traffic-json profiles/dominant_kernel_traffic.json --dominant gemm_h_kernel,resblock]
+        [--manifest gpurun_out/manifest.json --workload music256 --class-json profiles/r2_traffic_by_class.json]
+
+`--manifest` is the launch-by-launch category list bench.py writes when HILCODEC_DUMP_LAUNCHES=<path> is set (the
+library's own record of the step, `hil_profile_launches`); the ncu launch list of the same step has the same launches in
+the same order, so zipping the two attributes the measured DRAM bytes to the layer classes bench.py reports rooflines
+for (`roofline.traffic`).
 """
 import argparse
 import collections
@@ -43,6 +49,9 @@ def main():
     ap.add_argument("--title", default="")
     ap.add_argument("--traffic-json")
     ap.add_argument("--dominant", default="gemm_h_kernel,resblock_kernel")
+    ap.add_argument("--manifest")
+    ap.add_argument("--workload", default="music256")
+    ap.add_argument("--class-json")
     a = ap.parse_args()
     rows = load(a.csv)
     rows = rows[a.first:a.first + a.count] if a.count else rows[a.first:]
@@ -77,6 +86,37 @@ def main():
                    "launches": len(dom), "source": (a.out or a.csv) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                    "dram_bytes_per_launch_avg": by / max(len(dom), 1), "dram_bytes_per_step": by},
                   open(a.traffic_json, "w"), indent=1)
+    if a.manifest and a.class_json:
+        by_class(rows, a.manifest, a.workload, a.class_json, (a.out or a.csv) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum)")
+
+
+def by_class(rows, manifest_path, workload, out_path, source):
+    man = json.load(open(manifest_path))["launches"]
+    # ncu sees every kernel (also cudaMemset2D etc. are not kernels: same count expected); align by count
+    if len(man) != len(rows):
+        raise SystemExit(f"manifest has {len(man)} launches, the ncu window {len(rows)}: adjust --first / --count")
+    agg = collections.OrderedDict()
+    for m, r in zip(man, rows):
+        g = agg.setdefault(m["cat"], {"launches": 0, "dram_bytes_per_step": 0.0, "us": 0.0, "algorithmic_bytes_per_step": 0.0,
+                                      "kernels": set()})
+        g["launches"] += 1
+        g["dram_bytes_per_step"] += r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0)
+        g["us"] += r.get("gpu__time_duration.sum", 0.0)
+        g["algorithmic_bytes_per_step"] += m["bytes"]
+        g["kernels"].add(r["name"])
+    try:
+        doc = json.load(open(out_path))
+    except Exception:
+        doc = {}
+    doc[workload] = {k: {"launches": g["launches"], "dram_bytes_per_step": g["dram_bytes_per_step"],
+                         "dram_bytes_per_launch_avg": g["dram_bytes_per_step"] / g["launches"],
+                         "algorithmic_bytes_per_step": g["algorithmic_bytes_per_step"],
+                         "ncu_us_per_step": g["us"], "kernels": sorted(g["kernels"]), "source": source}
+                     for k, g in agg.items()}
+    json.dump(doc, open(out_path, "w"), indent=1)
+    for k, v in doc[workload].items():
+        print(f"{k:24s} {v['launches']:3d} launches  {v['dram_bytes_per_step'] / 1e9:8.2f} GB DRAM  "
+              f"{v['algorithmic_bytes_per_step'] / 1e9:8.2f} GB algorithmic  {v['ncu_us_per_step'] / 1e3:7.2f} ms")
 
 
 if __name__ == "__main__":
