@@ -88,6 +88,7 @@ SIGNATURES = {
     "hil_op_dws": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _F, _P]),
     "hil_op_upsample": (_I, [_P] * 8 + [_I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "hil_op_resblock": (_I, [_P] * 13 + [_I, _I, _I, _I, _F, _I, _P]),
+    "hil_op_downsample": (_I, [_P] * 8 + [_I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "hil_op_stft_logmag": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
 }
 

@@ -216,6 +216,27 @@ static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs,
                       post_scale);
 }
 
+// Encoder downsampling pair (streaming.py:506-510): Scale -> ELU -> 1x1 (C -> 2C, no bias) -> causal depthwise conv (kernel
+// 2r, stride r) + bias.  One tensor-core kernel with the strided conv in its epilogue when usable (the [2C][T]
+// intermediate, the largest tensor of an encoder stage, never exists), else the two kernels through `tmp`.
+// mode bit 7 (128) of hil_set_tensor_cores or HILCODEC_FUSE_DOWNSAMPLE=0 keep the two launches.
+static bool g_fuse_down = []() { const char* e = std::getenv("HILCODEC_FUSE_DOWNSAMPLE"); return !(e && e[0] == '0'); }();
+static int32_t run_downsample(const PackedMat& W, const float* x, long long x_bs, int x_rs, int B, int T, int r, int pre,
+                              float pre_scale, const float* dw_w, const float* dw_b, const float* ci, float* co, float* tmp,
+                              float* Y, long long y_bs, int y_rs, bool allow_fused, cudaStream_t st) {
+    const int M = W.M, T2 = T / r;
+    if (allow_fused && tc_on() && g_use_h && g_fuse_dw && g_fuse_down && x != Y &&
+        gemm_h_down_usable(W, x, x_bs, x_rs, T, r, Y, y_bs, y_rs)) {
+        const double n = (double)B * T;
+        HIL_LAUNCH(gemm_cat(W), 2.0 * M * W.K * n + 4.0 * M * n, 4.0 * (n * W.K + (double)B * T2 * M) + 4.0 * M * W.K, st,
+                   launch_gemm_h_down(W, x, x_bs, x_rs, B, T, r, pre, pre_scale, dw_w, dw_b, ci, co, Y, y_bs, y_rs, st));
+        return HIL_OK;
+    }
+    const int Tp = pitch4(T);
+    HIL_TRY(run_gemm_linear(W, x, x_bs, x_rs, B, T, pre, pre_scale, nullptr, nullptr, tmp, (long long)M * Tp, Tp, st));
+    return run_dwconv(tmp, (long long)M * Tp, Tp, ci, co, dw_w, dw_b, nullptr, Y, y_bs, y_rs, B, M, T, 2 * r, r, PRE_NONE, 1.f, st);
+}
+
 // ResBlock.forward streaming.py:252-275 as ONE tensor-core kernel (+ the halo gather in front of it)
 static int32_t run_resblock(const PackedMat& W0, const PackedMat& W1, float* h, long long bs, int rs, int B, int T, int pre,
                             float pre_scale, const float* dw0_w, const float* dw0_b, const float* dw1_w, const float* dw1_b,
@@ -1066,15 +1087,20 @@ int32_t encode_impl(hil_model* m, const Buffers& w, const float* wav, int B, int
             ci += 2 * c.n_residual_enc;
         }
         // Scale -> ELU -> 1x1 (C -> 2C) -> strided depthwise (streaming.py:506-510)
-        HIL_TRY(run_gemm_linear(sg.down_pw, h, bs, Tp, B, Ts, PRE_SCALE_ELU, m->enc_post_scale, nullptr, nullptr, a1,
-                                2 * bs, Tp, st));
         const int Ts2 = Ts / sg.ratio, Tp2 = pitch4(Ts2);
         const int Lv = (T_valid + stride - 1) / stride;  // valid columns at this rate
-        if (Lv < Ts)
+        if (Lv < Ts) {   // ragged training-graph call: the strided conv's input is zero-extended (see above), two kernels
+            HIL_TRY(run_gemm_linear(sg.down_pw, h, bs, Tp, B, Ts, PRE_SCALE_ELU, m->enc_post_scale, nullptr, nullptr, a1,
+                                    2 * bs, Tp, st));
             HIL_CUDA(cudaMemset2DAsync(a1 + Lv, (size_t)Tp * sizeof(float), 0, (size_t)(Ts - Lv) * sizeof(float),
                                        (size_t)B * 2 * C, st));
-        HIL_TRY(run_dwconv(a1, 2 * bs, Tp, cin[ci], cout[ci], sg.down_w, sg.down_b, nullptr, h,
+            HIL_TRY(run_dwconv(a1, 2 * bs, Tp, cin[ci], cout[ci], sg.down_w, sg.down_b, nullptr, h,
                                (long long)2 * C * Tp2, Tp2, B, 2 * C, Ts, 2 * sg.ratio, sg.ratio, PRE_NONE, 1.f, st));
+        } else {         // h (rate Ts) -> a2 (rate Ts / r): the output cannot overwrite the input other tiles still read
+            HIL_TRY(run_downsample(sg.down_pw, h, bs, Tp, B, Ts, sg.ratio, PRE_SCALE_ELU, m->enc_post_scale, sg.down_w,
+                                   sg.down_b, cin[ci], cout[ci], a1, a2, (long long)2 * C * Tp2, Tp2, true, st));
+            std::swap(h, a2);
+        }
         ci += 1;
         C *= 2;
         Ts = Ts2;
@@ -1426,12 +1452,14 @@ int32_t hil_unpack_indices(hil_model* m, const uint8_t* in, int32_t B, int32_t F
 uint64_t hil_launch_count(void) { return g_prof.launches; }
 
 int32_t hil_set_tensor_cores(int32_t mode) {
-    const int32_t prev = (g_use_tc ? 1 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32) | (g_fuse_up ? 0 : 64);
+    const int32_t prev = (g_use_tc ? 1 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32) | (g_fuse_up ? 0 : 64) |
+                         (g_fuse_down ? 0 : 128);
     g_use_tc = (mode & 1) != 0;
     g_fuse_dw = (mode & 4) == 0;
     g_use_h = (mode & 16) != 0;
     g_fuse_rb = (mode & 32) == 0;
     g_fuse_up = (mode & 64) == 0;
+    g_fuse_down = (mode & 128) == 0;
     return prev;
 }
 
@@ -1639,6 +1667,33 @@ int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out,
         rc = run_upsample(pm, x, (long long)K * T_in, T_in, B, T_in, S, pre, pre_scale, w_up, cache_in, cache_out, bias, tmp,
                           y, (long long)M * T, T, fused != 0, st, true);
         g_fuse_up = keep;
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    HIL_TRY(rc);
+    HIL_CUDA(e2);
+    return HIL_OK;
+}
+
+int32_t hil_op_downsample(const float* x, const float* cache_in, float* cache_out, const float* w_pw_host, const float* w_dw,
+                          const float* b_dw, float* tmp, float* y, int32_t B, int32_t K, int32_t M, int32_t T, int32_t r,
+                          int32_t pre, float pre_scale, int32_t fused, void* stream) {
+    if (!x || !cache_in || !cache_out || !w_pw_host || !w_dw || !tmp || !y) return fail(HIL_ERR_INVALID, "null pointer");
+    if (r < 1 || T < r || T % r) return fail(HIL_ERR_INVALID, "T must be a positive multiple of the stride");
+    PackedMat pm;
+    float* dev = nullptr;
+    HIL_TRY(upload_packed(w_pw_host, M, K, choose_tm(M), false, &pm, &dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T2 = T / r;
+    int32_t rc;
+    if (fused && !(tc_on() && g_use_h && gemm_h_down_usable(pm, x, (long long)K * T, T, T, r, y, (long long)M * T2, T2)))
+        rc = fail(HIL_ERR_INVALID, "fused downsampling kernel not usable for this shape / mode");
+    else {
+        const bool keep = g_fuse_down;
+        g_fuse_down = true;
+        rc = run_downsample(pm, x, (long long)K * T, T, B, T, r, pre, pre_scale, w_dw, b_dw, cache_in, cache_out, tmp, y,
+                            (long long)M * T2, T2, fused != 0, st);
+        g_fuse_down = keep;
     }
     cudaError_t e2 = cudaStreamSynchronize(st);
     cudaFree(dev);

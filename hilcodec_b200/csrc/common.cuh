@@ -121,6 +121,13 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
                              float* cache_out, const float* skip, float* Y, long long y_bs, int y_rs, cudaStream_t st,
                              int post_elu = 0);
 
+// encoder downsampling pair: act -> 1x1 (no bias) -> causal strided depthwise conv (kernel 2r, stride r) + bias, one kernel
+bool gemm_h_down_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, int r, const float* Y,
+                        long long y_bs, int y_rs);
+cudaError_t launch_gemm_h_down(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int r, int pre,
+                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in, float* cache_out,
+                               float* Y, long long y_bs, int y_rs, cudaStream_t st);
+
 // upsampling layer: act -> causal transposed depthwise conv (stride S, kernel 2S) -> 1x1 conv + bias, one kernel
 bool gemm_h_up_usable(const PackedMat& W, const float* x, long long x_bs, int x_rs, int T_in, int S, int pre, const float* Y,
                       long long y_bs, int y_rs);

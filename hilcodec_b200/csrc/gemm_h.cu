@@ -64,6 +64,7 @@ constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
 constexpr int TMEM_COLS = 512;
+constexpr int NOUT_BYTES_MAX = HIL_OUT_BUFS * OUT_BYTES;   // the strided-depthwise epilogue stages a whole tile's outputs at once
 constexpr size_t SMEM_BYTES = 1024 + (size_t)6 * RAW_BYTES + (size_t)3 * OP_BYTES + 2 * OUT_BYTES + 256;   // 224 KB + slack in every configuration
 
 struct Params {
@@ -100,6 +101,17 @@ struct Params {
 template <int S>
 __device__ __forceinline__ int up_box_start(int tt) { return ((tt * BN) / S - 1) & ~3; }
 constexpr int up_ni(int S) { return ((BN / S + 2 + (BN % S ? 1 : 0)) + HIL_UP_NI_ALIGN - 1) & ~(HIL_UP_NI_ALIGN - 1); }
+
+// Fused encoder downsampling (kDs = stride r > 0): 1x1 conv -> causal STRIDED depthwise conv (kernel 2r, stride r), the
+// pair at the end of every encoder stage (streaming.py:506-510).  A tile's 128 pointwise columns are
+// [unused alignment padding | r columns of history | DS_STEP new columns]; every TMA box starts on a 16-byte boundary
+// (DS_HALO is a multiple of 4), tiles start on output boundaries (DS_STEP % r == 0) and write a multiple of 4 outputs
+// (16-byte rows for the TMA store): r = 2 / 4 / 5 -> 60 / 28 / 24 outputs from 124 / 116 / 128 of the 128 columns.
+// r = 8 (12 outputs from 104 columns, and a tensor-bound layer) stays on the two-kernel path.
+constexpr int ds_halo(int r) { return (r + 3) & ~3; }
+constexpr int ds_step(int r) { return ((BN - ds_halo(r)) / (4 * r)) * 4 * r; }
+constexpr int ds_nout(int r) { return ds_step(r) / r; }
+static_assert(ds_halo(2) + ds_step(2) == 124 && ds_halo(4) + ds_step(4) == 116 && ds_halo(5) + ds_step(5) == 128, "tile geometry");
 
 constexpr uint32_t IDESC_N128 = make_idesc_f16(BM, BN);
 constexpr uint32_t IDESC_N256 = make_idesc_f16(BM, 2 * BN);
@@ -198,7 +210,7 @@ __device__ __forceinline__ void load_up_taps(const float* wsm, int xw, int n_abs
 // (inside the box-to-box noise), fp16 hi/lo planes as the B operand with no transform pass (not faster: the operand
 // stream out of L2 paces the wide layers, not the transform), activation boxes shared by TMA multicast across 2-CTA
 // clusters (+5.7 % on the step: at cluster size 2 the multicast saves no L2 bandwidth and couples the two pipelines).
-template <bool kDw, int kUp = 0>
+template <bool kDw, int kUp = 0, int kDs = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
@@ -414,7 +426,91 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE), cb2 = pk2(c_big, c_big);
         long long it = 0;
         uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
-        if constexpr (!kDw) {
+        if constexpr (kDs > 0) {
+            // ---- fused strided depthwise epilogue: y[n] = b + sum_{k < 2r} w[k] * pw[(n - 1) r + k], pw[-r .. -1] = cache.
+            // A thread owns one channel row and walks the tile's columns once; input column j feeds output j / r with
+            // tap (j % r) + r and output j / r + 1 with tap j % r, so two running sums see the taps in the order
+            // k = 0 .. 2r - 1 of the stand-alone kernel (dwconv_strided4_kernel, conv.cu): bit-identical results.
+            constexpr int R = kDs, HALO = ds_halo(R), STEP = ds_step(R), NOUT = ds_nout(R), J0 = HALO - R;
+            static_assert(NOUT * 4 * BM <= NOUT_BYTES_MAX, "staging");
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int m_blk = (int)(tile % p.num_m);
+                const long long rest = tile / p.num_m;
+                const int tt = (int)(rest % p.tiles_t);
+                const int b = (int)(rest / p.tiles_t);
+                const int acc = (int)(it & 1);
+                const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+                const int m = m_blk * BM + row;
+                const bool row_ok = m < p.M;
+                float wk[2 * R];
+#pragma unroll
+                for (int k = 0; k < 2 * R; ++k) wk[k] = row_ok ? p.dw_w[m * 2 * R + k] * c_big : 0.f;
+                const float bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                const float c_inv = 1.0f / c_big;
+                const int tcol0 = tt * STEP - HALO;               // time of tile column 0
+                float hist[R];                                     // tile 0: the r pointwise outputs before the chunk
+#pragma unroll
+                for (int k = 0; k < R; ++k) hist[k] = (tt == 0 && row_ok) ? p.cache_in[((size_t)b * p.M + m) * R + k] * c_inv : 0.f;
+                const bool has_tail = row_ok && (tcol0 + HALO + STEP > p.T - R) && (tcol0 + HALO <= p.T - 1);
+                mbar_wait<64>(tfull_bar(acc), acc_ph);
+                tc_fence_after();
+                const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+                if (issuer) tma_wait_read<0>();                    // the previous tile's store has drained the staging buffer
+                epi_bar_sync();
+                const uint32_t orow = my_out + row * (NOUT * 4);
+                float a_cur = 0.f, a_next = 0.f;
+                float o4[4];
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t rb[32], rs[32];
+                    tmem_ld32(t_big + c * 32, rb);
+                    tmem_ld32(t_big + BN + c * 32, rs);
+                    tmem_ld_wait();
+                    if (c == BN / 32 - 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2)
+                        upk2(ffma2(pk2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), lo2,
+                                   pk2(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]))), v[j], v[j + 1]);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int j = c * 32 + i;                  // tile column (compile-time after unrolling)
+                        if (j < J0 || j >= HALO + STEP) continue;
+                        const int jj = j - J0;                     // 0 .. R + STEP - 1
+                        const int grp = jj / R - 1, ph = jj % R;   // group -1 = history, 0 .. NOUT-1 = outputs
+                        float x = v[i];
+                        if (grp < 0 && tt == 0) x = hist[ph];
+                        if (has_tail && grp >= 0) {                // new cache = pointwise outputs at times T-r .. T-1
+                            const int t = tcol0 + j;
+                            if (t >= p.T - R && t < p.T) p.cache_out[((size_t)b * p.M + m) * R + (t - (p.T - R))] = x * c_big;
+                        }
+                        if (grp >= 0) a_cur = fmaf(wk[ph + R], x, a_cur);
+                        if (grp < NOUT - 1) a_next = fmaf(wk[ph], x, a_next);
+                        if (ph == R - 1) {
+                            if (grp >= 0) {
+                                o4[grp & 3] = a_cur + bv;
+                                if ((grp & 3) == 3)
+                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (uint32_t)(grp - 3) * 4u),
+                                                 "f"(o4[0]), "f"(o4[1]), "f"(o4[2]), "f"(o4[3]) : "memory");
+                            }
+                            a_cur = a_next;
+                            a_next = 0.f;
+                        }
+                    }
+                }
+                fence_proxy_async();
+                epi_bar_sync();
+                if (issuer) {
+                    tma_store_3d(&map_y, my_out, tt * NOUT, m_blk * BM, b);
+                    tma_commit();
+                }
+            }
+            if (issuer) tma_wait_all();
+        } else if constexpr (!kDw) {
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
@@ -735,6 +831,66 @@ cudaError_t launch_gemm_h_up(const PackedMat& W, const float* x, long long x_bs,
     if (S == SS) return launch_up<SS>(W, x, x_bs, x_rs, B, T_in, pre, pre_scale, up_w, cache_in, cache_out, bias, Y, y_bs, y_rs, st);
     HIL_UP(2) HIL_UP(4) HIL_UP(5) HIL_UP(8)
 #undef HIL_UP
+    return cudaErrorInvalidValue;
+}
+
+// Encoder downsampling pair in one kernel: pre(x) -> 1x1 (K -> M, no bias) -> causal depthwise conv (kernel 2r, stride r) +
+// bias (streaming.py:506-510).  x [B][K][T] -> Y [B][M][T / r]; cache [B][M][r] = the last r pointwise outputs.
+bool gemm_h_down_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, int r, const float* Y,
+                        long long y_bs, int y_rs) {
+    if (!W.H_hi || !W.H_lo) return false;
+    if (r != 2 && r != 4 && r != 5) return false;
+    if (T < 128 || (T % r) != 0) return false;
+    if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
+    return true;
+}
+
+template <int R>
+static cudaError_t launch_down(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
+                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in, float* cache_out,
+                               float* Y, long long y_bs, int y_rs, cudaStream_t st) {
+    using namespace th;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<false, 0, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    CUtensorMap map_hi, map_lo, map_x, map_y;
+    int num_sms = 0;
+    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
+    if (e != cudaSuccess) return e;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)(T / R), (cuuint64_t)W.M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)ds_nout(R), BM, 1};
+        if (!tc::make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+    }
+    Params p{};
+    p.M = W.M; p.K = W.K; p.T = T; p.B = B;
+    p.num_m = (W.M + BM - 1) / BM;
+    p.t_step = ds_step(R); p.t_halo = ds_halo(R);
+    p.tiles_t = (T + p.t_step - 1) / p.t_step;
+    p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out;
+    p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
+    p.xform_sleep = tc::xform_sleep_env();
+    p.elu_poly = elu_poly_env();
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    gemm_h_kernel<false, 0, R><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_h_down(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int r, int pre,
+                               float pre_scale, const float* dw_w, const float* dw_b, const float* cache_in, float* cache_out,
+                               float* Y, long long y_bs, int y_rs, cudaStream_t st) {
+    if (B == 0 || T == 0) return cudaSuccess;
+#define HIL_DOWN(RR) \
+    if (r == RR) return launch_down<RR>(W, X, x_bs, x_rs, B, T, pre, pre_scale, dw_w, dw_b, cache_in, cache_out, Y, y_bs, y_rs, st);
+    HIL_DOWN(2) HIL_DOWN(4) HIL_DOWN(5)
+#undef HIL_DOWN
     return cudaErrorInvalidValue;
 }
 

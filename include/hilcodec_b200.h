@@ -171,7 +171,8 @@ uint64_t hil_launch_count(void);
  * tensor pipe (tcgen05, fp32-level accuracy from split operands), 0 = FP32 FFMA kernels everywhere.  Bit 2 set: do not
  * fuse DWS blocks.  Bit 4 set (default): fp16-split tensor-core kernels (gemm_h.cu, kind::f16)
  * instead of 3xTF32.  Bit 5 set: do not fuse whole ResBlocks (gemm_rb.cu).  Bit 6 set: do not fuse the decoder's
- * upsampling layers (transposed depthwise conv -> 1x1). */
+ * upsampling layers (transposed depthwise conv -> 1x1).  Bit 7 set: do not fuse the encoder's downsampling pairs
+ * (1x1 -> strided depthwise conv). */
 int32_t hil_set_tensor_cores(int32_t mode);
 #define HIL_PROFILE_CATEGORIES 10
 int32_t hil_profile_begin(void);
@@ -220,6 +221,14 @@ int32_t hil_op_resblock(float* h, const float* w0_host, const float* w1_host, co
 int32_t hil_op_upsample(const float* x, const float* cache_in, float* cache_out, const float* w_up, const float* w_pw_host,
                         const float* bias, float* tmp, float* y, int32_t B, int32_t K, int32_t M, int32_t T_in, int32_t S,
                         int32_t pre, float pre_scale, int32_t fused, void* stream);
+/* Encoder downsampling pair, streaming.py:506-510: pre(x) -> nn.Conv1d(k=1, K -> M, no bias) -> CausalConv1d
+ * (causal_layers.py:160-165, depthwise, kernel 2r, stride r, cache [B,M,r]) + bias.  x [B,K,T] (T % 4 == 0 for the dense
+ * rows of this entry) -> y [B,M,T/r] (T/r % 4 == 0).  fused = 1: one tensor-core kernel with the strided conv in its
+ * epilogue (r in {2,4,5}, T >= 128), fused = 0: hil_op_pointwise + hil_op_dwconv through tmp [B,M,T].
+ * w_pw_host is a HOST [M,K,1] weight; w_dw [M,1,2r], b_dw [M]|NULL are device pointers. */
+int32_t hil_op_downsample(const float* x, const float* cache_in, float* cache_out, const float* w_pw_host, const float* w_dw,
+                          const float* b_dw, float* tmp, float* y, int32_t B, int32_t K, int32_t M, int32_t T, int32_t r,
+                          int32_t pre, float pre_scale, int32_t fused, void* stream);
 /* CausalSTFT.forward causal_layers.py:135-144 + clamp/log streaming.py:351:
  * wav_window [B,1,(T-1)*hop+n_fft], w_host [2F,1,n_fft] HOST -> y [B,F,T] = log(max(|STFT|,1e-5)). */
 int32_t hil_op_stft_logmag(const float* wav_window, const float* w_host, float* y, int32_t B, int32_t n_fft, int32_t hop,

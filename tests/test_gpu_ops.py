@@ -325,3 +325,47 @@ def test_upsample_fused(B, K, M, T_in, S, pre):
         assert (y.double() - y_ref).abs().max().item() < 2e-5 * scale
         assert (co.double() - xin[:, :, -1:]).abs().max().item() < 1e-6
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5 * scale
+
+
+@pytest.mark.parametrize("B,K,M,T,r,pre", [
+    (2, 64, 128, 2400, 2, 2),     # encoder stage 0: 64 -> 128, stride 2 (20 tiles of 120 columns per clip)
+    (1, 128, 256, 1200, 4, 2),    # stage 1: stride 4, two row tiles
+    (2, 256, 512, 600, 5, 2),     # stage 2: stride 5 (tile = 8 halo + 120 new columns), four row tiles
+    (3, 64, 128, 136, 2, 1),      # ragged: second tile 16 columns wide
+    (1, 32, 64, 240, 4, 0),       # half-empty row tile, no activation, last tile partly past the end
+    (2, 96, 192, 200, 5, 2),
+])
+def test_downsample_fused(B, K, M, T, r, pre):
+    """Encoder downsampling pair (act -> 1x1 -> causal strided depthwise conv + bias) as one tensor-core kernel, against
+    the fp64 reference and the two-kernel path (same FMA order in the depthwise window: the two CUDA paths agree to the
+    last bits of the 1x1 result, which the same GEMM mainloop produces)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(K + 13 * r + T)
+    x = torch.randn(B, K, T, generator=g)
+    wp = (torch.randn(M, K, 1, generator=g) / K ** 0.5).contiguous()
+    wd = torch.randn(M, 1, 2 * r, generator=g) / (2 * r) ** 0.5
+    bd = torch.randn(M, generator=g)
+    cache = torch.randn(B, M, r, generator=g)
+    pw = F.conv1d(_pre_ref(x, pre, 0.7745967).double(), wp.double())
+    xin = torch.cat((cache.double(), pw), 2)
+    y_ref = F.conv1d(xin, wd.double(), bd.double(), stride=r, groups=M)
+    T2 = T // r
+    assert y_ref.shape[2] == T2
+    if T % 4 or T2 % 4:
+        pytest.skip("dense-row operator entry needs T % 4 == 0 and (T / r) % 4 == 0")
+    xd, cd, wdd, bdd = x.cuda(), cache.cuda(), wd.cuda(), bd.cuda()
+    outs = []
+    for fused in (1, 0):
+        y = torch.zeros(B, M, T2, device="cuda")
+        co = torch.zeros(B, M, r, device="cuda")
+        tmp = torch.zeros(B, M, T, device="cuda")
+        _lib.check(lib.hil_op_downsample(_ptr(xd), _ptr(cd), _ptr(co), _ptr(wp), _ptr(wdd), _ptr(bdd), _ptr(tmp), _ptr(y),
+                                         B, K, M, T, r, pre, 0.7745967, fused, _stream()))
+        torch.cuda.synchronize()
+        outs.append((y.cpu(), co.cpu()))
+    scale = max(1.0, y_ref.abs().max().item())
+    for y, co in outs:
+        assert (y.double() - y_ref).abs().max().item() < 2e-5 * scale
+        assert (co.double() - xin[:, :, -r:]).abs().max().item() < 1e-5
+    assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0] - outs[1][0]).abs().max()
+    assert torch.equal(outs[0][1], outs[1][1])
