@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 namespace hil {
 
 enum Pre { PRE_NONE = 0, PRE_ELU = 1, PRE_SCALE_ELU = 2 };
@@ -56,7 +58,11 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Chunk lengths the per-clip 128-column tensor-core tiles are used for: T >= 64, or -- many concurrent streams fed a
 // hop at a time -- T >= 32 once the launch has more columns than the skinny-N FP32 kernel takes (one partly filled tile
 // per clip still beats the FP32 pipes there; config 4 with 64 streams: the 40-column layers).
-static inline bool tc_chunk_ok(int B, int T) { return T >= 64 || (T >= 32 && (long long)B * T > 512); }
+// HILCODEC_TC_MIN_COLS=<n> moves the column threshold (A/B knob; 0 = every chunk of >= 32 samples).
+static inline bool tc_chunk_ok(int B, int T) {
+    static const long long min_cols = []() { const char* e = std::getenv("HILCODEC_TC_MIN_COLS"); return e ? std::atoll(e) : 512LL; }();
+    return T >= 64 || (T >= 32 && (long long)B * T > min_cols);
+}
 static inline int pitch4(int t) { return (t + 3) & ~3; }
 
 // A weight matrix W[M][K] repacked k-major for the GEMM kernels: A[Kp][Mp], zero padded.

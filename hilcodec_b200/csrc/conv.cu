@@ -442,11 +442,79 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, long long x_b
     }
 }
 
+// Short chunks (streaming: T = 320 per hop): the kernel above gives a thread 8 outputs and ALL C channels, which for one
+// stream is 40 threads walking 96 channels one dependent load after the other (~100 us per hop, 10 % of a streaming
+// frame).  Here a block is 32 time lanes x 8 channel slices: slice s sums channels s, s + 8, ... for 4 outputs per
+// lane, the 8 partial sums are added in slice order (deterministic), then bias + tanh.
+template <int K>
+__global__ void conv_post_tanh_small_kernel(const float* __restrict__ x, long long x_bs, int x_rs,
+                                            const float* __restrict__ cache_in, float* __restrict__ cache_out,
+                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                            float* __restrict__ y, int C, int T, int pre, float pre_scale,
+                                            int* __restrict__ nonfinite) {
+    constexpr int P = K - 1, NO = 4, SL = 8;
+    __shared__ float part[SL][32 * NO];
+    const int b = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
+    const int t0 = (blockIdx.x * 32 + tx) * NO;
+    const float* xb = x + b * x_bs;
+    const float* cb = cache_in + (size_t)b * C * P;
+    float a[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) a[o] = 0.f;
+    if (t0 < T) {
+        for (int c = ty; c < C; c += SL) {
+            const float* xr = xb + (long long)c * x_rs;
+            float xin[P + NO];   // xin index j <-> time t0 - P + j
+#pragma unroll
+            for (int j = 0; j < P + NO; ++j) {
+                const int t = t0 - P + j;
+                xin[j] = t < 0 ? cb[c * P + P + t] : (t < T ? apply_act_ex2(xr[t], pre, pre_scale) : 0.f);
+            }
+            float wk[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) wk[k] = __ldg(w + c * K + k);
+#pragma unroll
+            for (int o = 0; o < NO; ++o)
+#pragma unroll
+                for (int k = 0; k < K; ++k) a[o] = fmaf(wk[k], xin[o + k], a[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) part[ty][tx * NO + o] = a[o];
+    __syncthreads();
+    if (ty == 0 && t0 < T) {
+        const float bv = bias ? bias[0] : 0.f;
+        bool bad = false;
+        for (int o = 0; o < NO && t0 + o < T; ++o) {
+            float sum = part[0][tx * NO + o];
+#pragma unroll
+            for (int sl = 1; sl < SL; ++sl) sum += part[sl][tx * NO + o];
+            const float v = tanhf(sum + bv);
+            bad |= !(fabsf(v) <= 1.0f);
+            y[(size_t)b * T + t0 + o] = v;
+        }
+        if (bad && nonfinite) *nonfinite = 1;
+    }
+    if (blockIdx.x == 0) {
+        for (int i = ty * 32 + tx; i < C * P; i += 32 * SL) {
+            const int c = i / P, jj = i - c * P;
+            const int j = T + jj;   // index into xin = cat(cache, act(x)) of length P + T
+            cache_out[(size_t)b * C * P + i] = j < P ? cb[c * P + j] : apply_act_ex2(xb[(long long)c * x_rs + (j - P)], pre, pre_scale);
+        }
+    }
+}
+
 cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                                   const float* w, const float* bias, float* y, int B, int C, int T, int K, int pre,
                                   float pre_scale, int* nonfinite, cudaStream_t st) {
     if (K != 5) return cudaErrorInvalidValue;
     if (B == 0) return cudaSuccess;
+    if ((long long)B * T <= 64LL * 1024) {   // few output samples: spread the channel sum over the block
+        dim3 grid((T + 127) / 128, B), block(32, 8);
+        conv_post_tanh_small_kernel<5><<<grid, block, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, y, C, T, pre,
+                                                               pre_scale, nonfinite);
+        return cudaGetLastError();
+    }
     const int Tq = (T + 7) / 8;
     const int threads = Tq >= 128 ? 128 : 32;
     const int vec = ((x_rs & 3) == 0) && ((x_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);

@@ -64,7 +64,6 @@ constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
 constexpr int TMEM_COLS = 512;
-constexpr int NOUT_BYTES_MAX = HIL_OUT_BUFS * OUT_BYTES;   // the strided-depthwise epilogue stages a whole tile's outputs at once
 constexpr size_t SMEM_BYTES = 1024 + (size_t)6 * RAW_BYTES + (size_t)3 * OP_BYTES + 2 * OUT_BYTES + 256;   // 224 KB + slack in every configuration
 
 struct Params {
@@ -111,6 +110,7 @@ constexpr int up_ni(int S) { return ((BN / S + 2 + (BN % S ? 1 : 0)) + HIL_UP_NI
 constexpr int ds_halo(int r) { return (r + 3) & ~3; }
 constexpr int ds_step(int r) { return ((BN - ds_halo(r)) / (4 * r)) * 4 * r; }
 constexpr int ds_nout(int r) { return ds_step(r) / r; }
+constexpr int ds_n1(int r) { return ((ds_nout(r) / 2 + 3) / 4) * 4; }   // outputs in the first of the two store halves
 static_assert(ds_halo(2) + ds_step(2) == 124 && ds_halo(4) + ds_step(4) == 116 && ds_halo(5) + ds_step(5) == 128, "tile geometry");
 
 constexpr uint32_t IDESC_N128 = make_idesc_f16(BM, BN);
@@ -431,8 +431,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             // A thread owns one channel row and walks the tile's columns once; input column j feeds output j / r with
             // tap (j % r) + r and output j / r + 1 with tap j % r, so two running sums see the taps in the order
             // k = 0 .. 2r - 1 of the stand-alone kernel (dwconv_strided4_kernel, conv.cu): bit-identical results.
+            // The tile's NOUT outputs leave in two halves (N1 | N2, both multiples of 4) through the two staging buffers,
+            // so the TMA store of one half drains while the other half is computed (a single store per tile, waited for
+            // before the next tile may touch the buffer, made this epilogue 3x slower than the kernel pair it replaces).
             constexpr int R = kDs, HALO = ds_halo(R), STEP = ds_step(R), NOUT = ds_nout(R), J0 = HALO - R;
-            static_assert(NOUT * 4 * BM <= NOUT_BYTES_MAX, "staging");
+            constexpr int N1 = ds_n1(R), N2 = NOUT - N1;
+            static_assert(N1 % 4 == 0 && N2 % 4 == 0 && N1 * 4 * BM <= OUT_BYTES && N2 * 4 * BM <= OUT_BYTES && OUT_BUFS >= 2, "staging");
+            const uint32_t buf_a = my_out, buf_b = my_out + OUT_BYTES;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
@@ -451,13 +456,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 float hist[R];                                     // tile 0: the r pointwise outputs before the chunk
 #pragma unroll
                 for (int k = 0; k < R; ++k) hist[k] = (tt == 0 && row_ok) ? p.cache_in[((size_t)b * p.M + m) * R + k] * c_inv : 0.f;
-                const bool has_tail = row_ok && (tcol0 + HALO + STEP > p.T - R) && (tcol0 + HALO <= p.T - 1);
+                // the tile whose new columns hold times T-r .. T-1 (T % r == 0 and STEP % r == 0: all of them or none)
+                const int j_tail = p.T - R - tcol0;
+                const bool tail_tile = j_tail >= HALO && j_tail < HALO + STEP;
                 mbar_wait<64>(tfull_bar(acc), acc_ph);
                 tc_fence_after();
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
-                if (issuer) tma_wait_read<0>();                    // the previous tile's store has drained the staging buffer
+                if (issuer) tma_wait_read<0>();                    // the previous tile's stores have drained both buffers
                 epi_bar_sync();
-                const uint32_t orow = my_out + row * (NOUT * 4);
                 float a_cur = 0.f, a_next = 0.f;
                 float o4[4];
 #pragma unroll
@@ -467,6 +473,31 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     tmem_ld32(t_big + BN + c * 32, rs);
                     tmem_ld_wait();
                     if (c == BN / 32 - 1) {
+                        if (tail_tile) {   // new cache = pointwise outputs at times T-r .. T-1, re-read from TMEM (one tile per clip)
+                            // 8 columns from the 4-column boundary below j_tail (TMEM loads of this library always
+                            // start on one), then a compile-time-indexed select of the r values
+                            const int jb = j_tail & ~3, off = j_tail & 3;
+                            uint32_t cb[8], cs[8];
+                            {
+                                uint32_t t0[4], t1[4], u0[4], u1[4];
+                                tmem_ld4(t_big + jb, t0);
+                                tmem_ld4(t_big + jb + 4, t1);
+                                tmem_ld4(t_big + BN + jb, u0);
+                                tmem_ld4(t_big + BN + jb + 4, u1);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) { cb[k] = t0[k]; cb[4 + k] = t1[k]; cs[k] = u0[k]; cs[4 + k] = u1[k]; }
+                            }
+                            if (row_ok) {
+#pragma unroll
+                                for (int k = 0; k < R; ++k) {
+                                    const uint32_t bg = off == 0 ? cb[k] : off == 1 ? cb[k + 1] : off == 2 ? cb[k + 2] : cb[k + 3];
+                                    const uint32_t sm = off == 0 ? cs[k] : off == 1 ? cs[k + 1] : off == 2 ? cs[k + 2] : cs[k + 3];
+                                    p.cache_out[((size_t)b * p.M + m) * R + k] =
+                                        fmaf(__uint_as_float(sm), 1.0f / LO_SCALE, __uint_as_float(bg)) * c_big;
+                                }
+                            }
+                        }
                         tc_fence_before();
                         mbar_arrive(tempty_bar(acc));
                     }
@@ -477,25 +508,31 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                                    pk2(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]))), v[j], v[j + 1]);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        constexpr int dummy = 0; (void)dummy;
                         const int j = c * 32 + i;                  // tile column (compile-time after unrolling)
                         if (j < J0 || j >= HALO + STEP) continue;
                         const int jj = j - J0;                     // 0 .. R + STEP - 1
                         const int grp = jj / R - 1, ph = jj % R;   // group -1 = history, 0 .. NOUT-1 = outputs
                         float x = v[i];
                         if (grp < 0 && tt == 0) x = hist[ph];
-                        if (has_tail && grp >= 0) {                // new cache = pointwise outputs at times T-r .. T-1
-                            const int t = tcol0 + j;
-                            if (t >= p.T - R && t < p.T) p.cache_out[((size_t)b * p.M + m) * R + (t - (p.T - R))] = x * c_big;
-                        }
                         if (grp >= 0) a_cur = fmaf(wk[ph + R], x, a_cur);
                         if (grp < NOUT - 1) a_next = fmaf(wk[ph], x, a_next);
                         if (ph == R - 1) {
                             if (grp >= 0) {
                                 o4[grp & 3] = a_cur + bv;
-                                if ((grp & 3) == 3)
-                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (uint32_t)(grp - 3) * 4u),
-                                                 "f"(o4[0]), "f"(o4[1]), "f"(o4[2]), "f"(o4[3]) : "memory");
+                                if ((grp & 3) == 3) {
+                                    const uint32_t dst = grp < N1 ? buf_a + row * (N1 * 4) + (uint32_t)(grp - 3) * 4u
+                                                                  : buf_b + row * (N2 * 4) + (uint32_t)(grp - N1 - 3) * 4u;
+                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o4[0]), "f"(o4[1]),
+                                                 "f"(o4[2]), "f"(o4[3]) : "memory");
+                                }
+                                if (grp == N1 - 1) {               // first half complete: hand it to the TMA engine
+                                    fence_proxy_async();
+                                    epi_bar_sync();
+                                    if (issuer) {
+                                        tma_store_3d(&map_y, buf_a, tt * NOUT, m_blk * BM, b);
+                                        tma_commit();
+                                    }
+                                }
                             }
                             a_cur = a_next;
                             a_next = 0.f;
@@ -505,7 +542,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 fence_proxy_async();
                 epi_bar_sync();
                 if (issuer) {
-                    tma_store_3d(&map_y, my_out, tt * NOUT, m_blk * BM, b);
+                    tma_store_3d(&map_y28, buf_b, tt * NOUT + N1, m_blk * BM, b);
                     tma_commit();
                 }
             }
@@ -857,15 +894,18 @@ static cudaError_t launch_down(const PackedMat& W, const float* X, long long x_b
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    CUtensorMap map_hi, map_lo, map_x, map_y;
+    CUtensorMap map_hi, map_lo, map_x, map_y, map_y2;
     int num_sms = 0;
     cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
     if (e != cudaSuccess) return e;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)(T / R), (cuuint64_t)W.M, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)ds_nout(R), BM, 1};
-        if (!tc::make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+        const cuuint32_t box1[3] = {(cuuint32_t)ds_n1(R), BM, 1};
+        const cuuint32_t box2[3] = {(cuuint32_t)(ds_nout(R) - ds_n1(R)), BM, 1};
+        if (!tc::make_map(&map_y, Y, 3, dims, strides, box1, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+            !tc::make_map(&map_y2, Y, 3, dims, strides, box2, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return cudaErrorInvalidValue;
     }
     Params p{};
     p.M = W.M; p.K = W.K; p.T = T; p.B = B;
@@ -879,7 +919,7 @@ static cudaError_t launch_down(const PackedMat& W, const float* X, long long x_b
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    gemm_h_kernel<false, 0, R><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    gemm_h_kernel<false, 0, R><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y2, p);
     return cudaGetLastError();
 }
 

@@ -220,7 +220,10 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
 // (picks the best of the per-tile candidates the previous launch left in `part_in`, lowest code index on ties, and
 // rebuilds the residual r = ((z - E_0[i_0]) - E_1[i_1]) ... in stage order, i.e. the same fp32 operations as above),
 // then scores ITS 128 codes of stage s with the same FMA order as above and leaves (best distance, index) per frame
-// in `part_out`.  A last launch (s == n) writes the final index and the dequantised sum.  n + 1 launches of ~4 us
+// in `part_out`.  The residual entering stage s and the running dequantised sum are handed from launch to launch through
+// two ping-pong scratch rows per frame (launch s reads side (s-1) & 1, its tile-0 CTA writes side s & 1), so every
+// launch does ONE gather (round 2: rebuilding both from z with s gathers per launch made the chain O(n^2) dependent
+// L2 round trips, 180 us of a 880 us streaming hop).  A last launch (s == n) writes the final index and the sum.  n + 1 launches of ~4 us
 // instead of one of ~340 us; results are bit-identical to rvq_encode_kernel.  Default for <= 1024 frames since round 2
 // (one hil_music stream: 1.27 -> 0.88 ms per hop; HILCODEC_RVQ_SPLIT=0 keeps the one-kernel search for A/B runs).
 struct RvqCand { float d; int i; };
@@ -228,10 +231,17 @@ struct RvqCand { float d; int i; };
 __global__ void __launch_bounds__(256, 2)
 rvq_stage_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee, int size,
                  int tiles, long long frames, int s, int n, int64_t* __restrict__ idx, float* __restrict__ qsum,
-                 const RvqCand* __restrict__ part_in, RvqCand* __restrict__ part_out, int drop_xx) {
+                 const RvqCand* __restrict__ part_in, RvqCand* __restrict__ part_out, float* __restrict__ rq_scratch,
+                 int drop_xx) {
     extern __shared__ __align__(16) float smem[];
     float* R = smem;                              // [RVQ_FT][RVQ_PITCH]
     float* E = smem + RVQ_FT * RVQ_PITCH;         // [RVQ_CT][RVQ_PITCH]
+    // rq_scratch: [2 sides][residual | qsum][RVQ_SPLIT_MAX_FRAMES][RVQ_DIM]
+    const size_t side = (size_t)2 * RVQ_SPLIT_MAX_FRAMES * RVQ_DIM;
+    const float* r_in = rq_scratch + (size_t)((s - 1) & 1) * side;
+    const float* q_in = r_in + (size_t)RVQ_SPLIT_MAX_FRAMES * RVQ_DIM;
+    float* r_out = rq_scratch + (size_t)(s & 1) * side;
+    float* q_out = r_out + (size_t)RVQ_SPLIT_MAX_FRAMES * RVQ_DIM;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long f0 = (long long)blockIdx.y * RVQ_FT;
@@ -245,24 +255,28 @@ rvq_stage_kernel(const float* __restrict__ z, const float* __restrict__ codebook
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fr < frames) {
-            r = *reinterpret_cast<const float4*>(z + fr * RVQ_DIM + lane * 4);
-            for (int j = 0; j < s; ++j) {
-                int bi;
-                if (j < s - 1) {
-                    bi = (int)idx[(size_t)j * frames + fr];
-                } else {
-                    float bd = -INFINITY;
-                    bi = 0x7fffffff;
-                    for (int t = 0; t < tiles; ++t) {       // ascending code ranges: strict > keeps the first maximum
-                        const RvqCand c = part_in[(size_t)fr * tiles + t];
-                        if (c.d > bd || (c.d == bd && c.i < bi)) { bd = c.d; bi = c.i; }
-                    }
-                    if (bi < 0 || bi >= size) bi = 0;       // all-NaN row, as above
-                    if (tile == 0 && lane == 0) idx[(size_t)j * frames + fr] = bi;
+            // residual / sum entering stage s-1 (z / 0 for the first stage), then stage s-1's code: the same fp32
+            // operations in the same order as the one-kernel search
+            const bool first = s <= 1;
+            r = *reinterpret_cast<const float4*>((first ? z : r_in) + fr * RVQ_DIM + lane * 4);
+            if (!first) q = *reinterpret_cast<const float4*>(q_in + fr * RVQ_DIM + lane * 4);
+            if (s > 0) {
+                const int j = s - 1;
+                float bd = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int t = 0; t < tiles; ++t) {       // ascending code ranges: strict > keeps the first maximum
+                    const RvqCand c = part_in[(size_t)fr * tiles + t];
+                    if (c.d > bd || (c.d == bd && c.i < bi)) { bd = c.d; bi = c.i; }
                 }
+                if (bi < 0 || bi >= size) bi = 0;       // all-NaN row, as above
+                if (tile == 0 && lane == 0) idx[(size_t)j * frames + fr] = bi;
                 const float4 e = *reinterpret_cast<const float4*>(codebooks + ((size_t)j * size + bi) * RVQ_DIM + lane * 4);
                 r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y); r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
                 q.x = __fadd_rn(q.x, e.x); q.y = __fadd_rn(q.y, e.y); q.z = __fadd_rn(q.z, e.z); q.w = __fadd_rn(q.w, e.w);
+                if (tile == 0 && !last) {
+                    *reinterpret_cast<float4*>(r_out + fr * RVQ_DIM + lane * 4) = r;
+                    *reinterpret_cast<float4*>(q_out + fr * RVQ_DIM + lane * 4) = q;
+                }
             }
             if (last && tile == 0 && qsum) *reinterpret_cast<float4*>(qsum + fr * RVQ_DIM + lane * 4) = q;
         }
@@ -359,8 +373,9 @@ bool rvq_split_usable(int size, int dim, long long frames) {
     return on && dim == RVQ_DIM && frames > 0 && frames <= RVQ_SPLIT_MAX_FRAMES && (size + RVQ_CT - 1) / RVQ_CT <= RVQ_SPLIT_MAX_TILES;
 }
 
-// scratch: 2 * RVQ_SPLIT_MAX_FRAMES * RVQ_SPLIT_MAX_TILES candidates (rvq_split_scratch_bytes())
-size_t rvq_split_scratch_bytes() { return (size_t)2 * RVQ_SPLIT_MAX_FRAMES * RVQ_SPLIT_MAX_TILES * sizeof(RvqCand); }
+// scratch (rvq_split_scratch_bytes()): 2 * RVQ_SPLIT_MAX_FRAMES * RVQ_SPLIT_MAX_TILES candidates, then the residual / sum rows
+static size_t rvq_split_cand_bytes() { return (size_t)2 * RVQ_SPLIT_MAX_FRAMES * RVQ_SPLIT_MAX_TILES * sizeof(RvqCand); }
+size_t rvq_split_scratch_bytes() { return rvq_split_cand_bytes() + (size_t)4 * RVQ_SPLIT_MAX_FRAMES * RVQ_DIM * sizeof(float); }
 
 cudaError_t launch_rvq_encode_split(const float* z, const float* codebooks, const float* ee, int size, int dim,
                                     long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, void* scratch,
@@ -381,7 +396,9 @@ cudaError_t launch_rvq_encode_split(const float* z, const float* codebooks, cons
     for (int s = 0; s <= n; ++s) {
         const dim3 grid(s == n ? 1 : tiles, fblocks);
         rvq_stage_kernel<<<grid, 256, smem, st>>>(z, codebooks, ee, size, tiles, frames, s, n, idx, qsum, part[(s + 1) & 1],
-                                                  part[s & 1], drop_xx ? 1 : 0);
+                                                  part[s & 1],
+                                                  reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + rvq_split_cand_bytes()),
+                                                  drop_xx ? 1 : 0);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -13,6 +13,8 @@
 //     and TMA loads it; for hop 1 / 2 (row stride not a multiple of 16 bytes) the transform
 //     warps gather the windows through L1 and write the swizzled tile themselves;
 //   * the epilogue stores F rows per 128 accumulator rows (box 32 x 64).
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace hil {
@@ -38,6 +40,7 @@ struct Params {
     int num_m, tiles_t;
     long long total_tiles;
     int gather;          // 1: transform warps build B from global memory (hop % 4 != 0)
+    int exact_log;       // 1: logf (HILCODEC_STFT_LOGF=1), 0: lg2.approx * ln 2
     const float* wav;    // window base (first sample of the window of frame 0)
     long long w_bs;      // batch stride of wav
 };
@@ -246,7 +249,11 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
                         const float a = even ? mine[i] : mine[16 + i];   // own component of the column this lane evaluates
                         const float ss = __fadd_rn(__fmul_rn(a, a), __fmul_rn(recv, recv));
-                        o[e] = 0.5f * logf(fmaxf(ss, 1e-10f));
+                        // 0.5 * ln(ss) = lg2(ss) * (ln 2 / 2).  lg2.approx: absolute error <= 2^-22 on [0.5, 2), <= 2 ulp elsewhere,
+                        // i.e. fp32 rounding level like logf -- at 2 issue slots instead of ~25: ncu showed this epilogue
+                        // (128 x 128 logarithms per tile on four warps), not the MMAs, bounds the high-rate stages
+                        const float sc = fmaxf(ss, 1e-10f);
+                        o[e] = p.exact_log ? 0.5f * logf(sc) : __log2f(sc) * 0.34657359027997264f;
                     }
                     const uint32_t chunk = (uint32_t)(even ? j4 : 4 + j4);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + ((chunk ^ sw) << 4)), "f"(o[0]),
@@ -325,6 +332,8 @@ cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_
     p.tiles_t = (T + BN - 1) / BN;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
     p.gather = gather; p.wav = wav; p.w_bs = w_bs;
+    static const int exact_log = []() { const char* e = std::getenv("HILCODEC_STFT_LOGF"); return (e && e[0] == '1') ? 1 : 0; }();
+    p.exact_log = exact_log;
     const int num_sms = device_sm_count();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     stft_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);

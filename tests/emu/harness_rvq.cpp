@@ -39,12 +39,13 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "one-kernel search: %d warps per CTA\n", warps);
     }
     const int tiles = (size + RVQ_CT - 1) / RVQ_CT;
+    std::vector<float> rq((size_t)4 * RVQ_SPLIT_MAX_FRAMES * RVQ_DIM, -7.f);   // residual / sum hand-over rows
     std::vector<RvqCand> part[2];
     part[0].resize((size_t)frames * tiles); part[1].resize((size_t)frames * tiles);
     for (int s = 0; s <= n; ++s)   // launch_rvq_encode_split
         emu_launch(s == n ? 1 : tiles, fblocks, 256, [&] {
             rvq_stage_kernel(z.data(), cb.data(), ee.data(), size, tiles, frames, s, n, idx_b.data(), q_b.data(),
-                             part[(s + 1) & 1].data(), part[s & 1].data(), drop_xx);
+                             part[(s + 1) & 1].data(), part[s & 1].data(), rq.data(), drop_xx);
         });
     f = std::fopen(argv[6], "wb");
     std::fwrite(idx_a.data(), 8, idx_a.size(), f);
