@@ -281,6 +281,38 @@ def cpu_stream_run(model_name, n_q, streams, hop, budget_s, threads_list=None):
     return r
 
 
+def reference_on_gpu_run(ctx, model_name, n_q, samples, clips, reps=5):
+    """Second, stated baseline: the reference's OWN classes moved to the same B200 with
+    `.cuda()`, i.e. stock PyTorch -> cuDNN / cuBLAS in fp32 (TF32 off, as the parity bars need), one-shot on a sub-batch
+    of the workload.  Not the `--impl reference` arm (that one is the CPU path BASELINE.json names)."""
+    import torch
+
+    from oracle import ref_shim
+
+    if not ref_shim.deploy_available():
+        return None
+    cfg, w, wdesc = load_weights(model_name)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = ref_shim.build_reference_model(w, n_q).to(ctx.dev)
+    x = synth(clips, samples, 1234).to(ctx.dev)
+    for _ in range(2):
+        ref_shim.reference_forward(model, x, n_q)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ref_shim.reference_forward(model, x, n_q)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    del model, x
+    torch.cuda.empty_cache()
+    return {"value": clips * (samples // cfg.hop) / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "clips": clips,
+            "what": f"the reference's streaming.py classes .cuda() (torch {torch.__version__}, cuDNN / cuBLAS fp32, TF32 off), "
+                    f"{clips} x {samples} one-shot, {reps} timed calls, {wdesc}"}
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -666,12 +698,19 @@ def run_batch(ctx, wl, steps, warmup, with_cpu, cpu_budget=None):
     if world == 1 and with_cpu:
         r = cpu_reference_run(model_name, n_q, samples, steps=4, warmup=1, budget_s=cpu_budget or 40.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            g = reference_on_gpu_run(ctx, model_name, n_q, samples, clips=min(B, 32))
+            if g:
+                line["reference_on_same_gpu"] = g
+        except Exception as e:   # informative extra: never takes the line down
+            line["reference_on_same_gpu"] = {"error": f"{type(e).__name__}: {e}"}
     return line
 
 
 def condensed(line):
     keep = ("value", "unit", "ms_per_step", "ms_per_hop", "x_realtime_per_stream", "rtf_x_realtime", "e2e", "roofline",
-            "cpu_baseline", "gpu_launches", "gpu_launches_per_hop", "config", "data", "steps", "warmup")
+            "cpu_baseline", "reference_on_same_gpu", "gpu_launches", "gpu_launches_per_hop", "config", "data", "steps",
+            "warmup")
     return {k: line[k] for k in keep if k in line}
 
 

@@ -55,15 +55,14 @@ __device__ __forceinline__ float apply_act_fast(float x, int mode, float s) {
 }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-// Chunk lengths the per-clip 128-column tensor-core tiles are used for: T >= 64, or -- many concurrent streams fed a
-// hop at a time -- T >= 32 once the launch has more columns than the skinny-N FP32 kernel takes (one partly filled tile
-// per clip still beats the FP32 pipes there; config 4 with 64 streams: the 40-column layers).
-// HILCODEC_TC_MIN_COLS=<n> moves the column threshold (A/B knob; 0 = every chunk of >= 32 samples).
-static inline bool tc_chunk_ok(int B, int T) {
-    static const long long min_cols = []() { const char* e = std::getenv("HILCODEC_TC_MIN_COLS"); return e ? std::atoll(e) : 512LL; }();
-    return T >= 64 || (T >= 32 && (long long)B * T > min_cols);
-}
 static inline int pitch4(int t) { return (t + 3) & ~3; }
+// Chunk lengths the per-clip 128-column tensor-core tiles are used for: T >= 32.  Measured in round 2 (hil_music, hop 320):
+// giving the 40-column layers of a hop one partly filled tile per clip instead of the FP32 kernels takes one stream from
+// 0.80 to 0.67 ms per hop and 64 streams from 2.9 to 2.1 ms.  HILCODEC_TC_MIN_T=<n> moves the threshold (A/B knob).
+static inline bool tc_chunk_ok(int /*B*/, int T) {
+    static const int min_t = []() { const char* e = std::getenv("HILCODEC_TC_MIN_T"); return e ? std::atoi(e) : 32; }();
+    return T >= (min_t < 8 ? 8 : min_t);
+}
 
 // A weight matrix W[M][K] repacked k-major for the GEMM kernels: A[Kp][Mp], zero padded.
 struct PackedMat {

@@ -58,6 +58,50 @@ def test_onnx_runner_reproduces_reference_artefacts(tmp_path):
     assert np.abs(out.astype(np.int32) - g["wav_out"][:frames * 320].astype(np.int32)).max() <= 2
 
 
+@pytest.mark.skipif(not W.have_pretrained("hil_speech"), reason="published weights not extracted")
+def test_onnx_runner_cache_npz_protocol(tmp_path, capsys):
+    """`e_in{i}` / `d_in{i}` dicts seeded from `{name}_cache_{enc,dec}.npz` (test_onnx.py:73, 80-81, 121, 133-134): the
+    zero caches the runner writes have the reference's names and shapes, a run seeded from them equals a run without
+    the files, and NON-zero caches (the state after the first half of a clip) resume the stream exactly."""
+    from scipy.io import wavfile
+
+    g = np.load(os.path.join(GOLDEN, "speech_kat.npz"))
+    d = str(tmp_path)
+    assert onnx_runner.main(["-n", "hil_speech", "--save-cache", "--outdir", d]) == 0
+    ce, cd = np.load(os.path.join(d, "hil_speech_cache_enc.npz")), np.load(os.path.join(d, "hil_speech_cache_dec.npz"))
+    assert ce.files == [f"e_in{i}" for i in range(22)] and cd.files == [f"d_in{i}" for i in range(30)]
+    assert ce["e_in0"].shape == (1, 1, 1023) and cd["d_in0"].shape == (1, 1536, 4) and not ce["e_in5"].any()
+    frames = 40
+    wavfile.write(os.path.join(d, "a.wav"), 24000, g["wav_in"][:frames * 320])
+    wavfile.write(os.path.join(d, "b.wav"), 24000, g["wav_in"][frames * 320:2 * frames * 320])
+    assert onnx_runner.main(["-n", "hil_speech", "-q", "8", "-t", "2", "--enc", "--dec", "--input", os.path.join(d, "a.wav"),
+                             "--outdir", d]) == 0
+    out = capsys.readouterr().out
+    assert "wav length: " in out and "encoder: " in out and "decoder: " in out and "rtf: " in out and "(↑)" in out
+    qa = np.load(os.path.join(d, "hil_speech_quantized.npy"))
+    assert np.array_equal(qa, g["indices"][:, :, :frames])
+    # second half, seeded with the caches left by the first half
+    m = S.HILCodec.from_pretrained("hil_speech").cuda()
+    x = torch.from_numpy(g["wav_in"][:frames * 320].astype(np.float32) / 32768).view(1, 1, -1).cuda()
+    e, dcache = m.initialize_cache(x)
+    z, e = m.encoder(x, *e)
+    _, dcache = m.decoder(m.dequantizer(m.quantizer(z, 8), 8), *dcache)
+    d2 = os.path.join(d, "resume")
+    os.makedirs(d2)
+    np.savez(os.path.join(d2, "hil_speech_cache_enc.npz"), **{f"e_in{i}": c.cpu().numpy() for i, c in enumerate(e)})
+    np.savez(os.path.join(d2, "hil_speech_cache_dec.npz"), **{f"d_in{i}": c.cpu().numpy() for i, c in enumerate(dcache)})
+    assert onnx_runner.main(["-n", "hil_speech", "-q", "8", "--enc", "--dec", "--input", os.path.join(d, "b.wav"),
+                             "--outdir", d2, "--cache-dir", d2]) == 0
+    qb = np.load(os.path.join(d2, "hil_speech_quantized.npy"))
+    assert np.array_equal(qb, g["indices"][:, :, frames:2 * frames])
+    _, outb = wavfile.read(os.path.join(d2, "hil_speech_output.wav"))
+    assert np.abs(outb.astype(np.int32) - g["wav_out"][frames * 320:2 * frames * 320].astype(np.int32)).max() <= 2
+    # wrong shapes / missing names are errors, not silent zeros
+    np.savez(os.path.join(d2, "hil_speech_cache_enc.npz"), e_in0=np.zeros((1, 1, 5), np.float32))
+    with pytest.raises(KeyError):
+        onnx_runner.main(["-n", "hil_speech", "--enc", "--input", os.path.join(d, "b.wav"), "--outdir", d2])
+
+
 def test_training_graph_signatures():
     cfg = W.HIL_MUSIC
     w = W.random_weights(cfg, 6)

@@ -119,3 +119,23 @@ def test_training_graph_adapter_surface_without_gpu():
         models.HILCodec(d.deploy, graph="onnx")
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 1, 333))
+
+
+def test_onnx_runner_report_and_cache_names():
+    """Host logic of the test_onnx.py-compatible runner: the timing lines (test_onnx.py:41-47) and the cache tensor
+    names of the exported graphs (`e_in0..21`, `d_in0..29`), which the reference's own cache files carry."""
+    import numpy as np
+
+    from hilcodec_b200 import onnx_runner
+    from oracle import ref_shim
+
+    text = onnx_runner.report(24000 * 5, 24000, 3.2, 9.0)
+    assert "wav length: 5.0 s" in text
+    assert "encoder: 3.2 s / rtf: 1.5625 (↑)" in text and "decoder: 9.0 s / rtf: 0.5556 (↑)" in text
+    assert "decoder" not in onnx_runner.report(24000, 24000, 1.0, 0.0)
+    assert onnx_runner.cache_names("enc", 3) == ["e_in0", "e_in1", "e_in2"]
+    assert onnx_runner.cache_names("dec", 2) == ["d_in0", "d_in1"]
+    if ref_shim.available():
+        for side, n in (("enc", 22), ("dec", 30)):
+            ref = np.load(os.path.join(ref_shim.REF, "onnx", f"hil_music_cache_{side}.npz"))
+            assert sorted(ref.files, key=lambda k: int(k.split("in")[1])) == onnx_runner.cache_names(side, n)
