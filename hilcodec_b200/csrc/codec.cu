@@ -295,7 +295,9 @@ static int32_t run_rvq_encode(const float* z, const float* cb, const float* ee, 
                               int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
     HIL_LAUNCH(CAT_RVQ, 2.0 * frames * (double)n * size * dim,
                4.0 * frames * dim * (qsum ? 2 : 1) + 8.0 * frames * n + 4.0 * (double)n * size * dim, st,
-               launch_rvq_encode(z, cb, ee, size, dim, frames, n, idx, qsum, drop_xx, st));
+               rvq_cluster_usable(size, dim, frames)   // few frames (streaming): one cluster launch, bit-identical
+                   ? launch_rvq_encode_cluster(z, cb, ee, size, dim, frames, n, idx, qsum, drop_xx, st)
+                   : launch_rvq_encode(z, cb, ee, size, dim, frames, n, idx, qsum, drop_xx, st));
     return HIL_OK;
 }
 static int32_t run_rvq_decode(const int64_t* idx, const float* cb, int size, int dim, long long frames, int n, float* q,
@@ -1274,9 +1276,15 @@ int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav, int32_t 
     const int ge = s->enc_gen, gd = s->dec_gen;
     HIL_TRY(encode_impl(m, w, wav, B, T, z, s->enc_c[ge].data(), s->enc_c[ge ^ 1].data(), st));
     s->enc_gen = ge ^ 1;
-    if (rvq_split_usable(m->cfg.codebook_size, m->cfg.dim, (long long)B * F)) {
-        // streaming: n + 1 short launches instead of one CTA walking every stage (HILCODEC_RVQ_SPLIT=1)
-        const long long fr = (long long)B * F;
+    const long long fr = (long long)B * F;
+    if (rvq_cluster_usable(m->cfg.codebook_size, m->cfg.dim, fr)) {
+        // streaming: all n stages in one launch of (code tiles)-CTA clusters (rvq.cu)
+        HIL_LAUNCH(CAT_RVQ, 2.0 * fr * (double)n * m->cfg.codebook_size * m->cfg.dim,
+                   8.0 * fr * m->cfg.dim + 8.0 * fr * n + 4.0 * (double)n * m->cfg.codebook_size * m->cfg.dim, st,
+                   launch_rvq_encode_cluster(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, fr, n, idx, w.q,
+                                             m->graph == HIL_GRAPH_TRAIN, st));
+    } else if (rvq_split_usable(m->cfg.codebook_size, m->cfg.dim, fr)) {
+        // n + 1 short launches instead of one CTA walking every stage (HILCODEC_RVQ_CLUSTER=0)
         g_prof.launches += n;  // HIL_LAUNCH below counts one
         HIL_LAUNCH(CAT_RVQ, 2.0 * fr * (double)n * m->cfg.codebook_size * m->cfg.dim,
                    8.0 * fr * m->cfg.dim + 8.0 * fr * n + 4.0 * (double)n * m->cfg.codebook_size * m->cfg.dim, st,

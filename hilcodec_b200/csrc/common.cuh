@@ -195,6 +195,11 @@ size_t rvq_split_scratch_bytes();
 cudaError_t launch_rvq_encode_split(const float* z, const float* codebooks, const float* ee, int size, int dim,
                                     long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, void* scratch,
                                     cudaStream_t st);
+// few-frame variant in ONE launch: a cluster of (code tiles) CTAs per 32 frames, candidates exchanged through distributed
+// shared memory; HILCODEC_RVQ_CLUSTER=0 disables
+bool rvq_cluster_usable(int size, int dim, long long frames);
+cudaError_t launch_rvq_encode_cluster(const float* z, const float* codebooks, const float* ee, int size, int dim,
+                                      long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st);
 cudaError_t launch_rvq_decode(const int64_t* idx, const float* codebooks, int size, int dim, long long frames, int n,
                               float* q, cudaStream_t st);
 

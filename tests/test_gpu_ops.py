@@ -135,8 +135,11 @@ def test_pointwise(B, M, K, T, pre, bias, res):
     torch.cuda.synchronize()
     err = (y.cpu().double() - y64).abs().max().item()
     ref_err = (y_ref.double() - y64).abs().max().item()
-    # as accurate as the CPU fp32 result is (both are fp32 accumulations in different orders)
-    assert err <= max(4 * ref_err, 2e-6), (err, ref_err)
+    # As accurate as the CPU fp32 result is (both are fp32 accumulations in different orders), plus what the tensor
+    # pipe's accumulator costs: tcgen05.mma adds each k16 step into the fp32 TMEM accumulator with TRUNCATION, a bias
+    # that grows linearly with K (measured on the B200: 4.8e-6 at K = 768, 8.5e-6 at K = 1536 for O(1) outputs, i.e.
+    # ~K * 6e-9; the FP32 kernels that take the short chunks stay at the CPU's level).  DESIGN.md section 5.
+    assert err <= max(4 * ref_err, 2e-6, 8e-9 * K), (err, ref_err)
 
 
 @pytest.mark.parametrize("B,n_fft,hop,T", [(2, 64, 1, 640), (2, 128, 2, 320), (1, 256, 8, 75),
@@ -369,3 +372,37 @@ def test_downsample_fused(B, K, M, T, r, pre):
         assert (co.double() - xin[:, :, -r:]).abs().max().item() < 1e-5
     assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0] - outs[1][0]).abs().max()
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("size,frames,n,train", [(1024, 1, 12, False), (1024, 64, 12, False), (1024, 75, 8, True),
+                                                  (1024, 1000, 3, False), (200, 33, 2, False), (64, 5, 4, True)])
+def test_rvq_few_frame_variants_bit_identical(size, frames, n, train, monkeypatch):
+    """The streaming RVQ paths (one cluster launch with DSMEM candidate exchange; n + 1 per-stage launches) against the
+    one-kernel search: same indices and the same dequantised sum, bit for bit, including exact ties."""
+    import subprocess, sys, json, os
+    code = r"""
+import json, sys, torch
+sys.path.insert(0, %r)
+from hilcodec_b200 import streaming as S, weights as W, _lib
+size, frames, n, train = %d, %d, %d, %d
+cfg = W.CodecConfig(num_quantizers=n, codebook_size=size)
+g = torch.Generator().manual_seed(size + frames)
+cbs = {f"quantizer.layers.{i}.embed": (torch.randn(size, 128, generator=g) * 0.7 ** i).numpy() for i in range(n)}
+cbs["quantizer.layers.0.embed"][7] = cbs["quantizer.layers.0.embed"][3]
+core = S._NativeCodec(cfg, _lib.HIL_GRAPH_TRAIN if train else _lib.HIL_GRAPH_DEPLOY)
+core.set_weights(cbs)
+z = torch.nn.functional.normalize(torch.randn(1, frames, 128, generator=g), dim=2) * 128 ** 0.5
+z[0, 0] = torch.from_numpy(cbs["quantizer.layers.0.embed"][3])
+idx, q = core.rvq_encode(z.cuda(), n, with_sum=True)
+torch.cuda.synchronize()
+print(json.dumps({"idx": idx.cpu().flatten().tolist(), "q": q.cpu().flatten().tolist()}))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), size, frames, n, int(train))
+    outs = {}
+    for name, env in (("cluster", {}), ("one_kernel", {"HILCODEC_RVQ_CLUSTER": "0"})):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                           env={**os.environ, **env})
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert outs["cluster"]["idx"] == outs["one_kernel"]["idx"]
+    assert outs["cluster"]["q"] == outs["one_kernel"]["q"]
+    assert outs["cluster"]["idx"][0] == 3          # frame 0 IS code 3 of stage 0; its exact copy (code 7) must lose

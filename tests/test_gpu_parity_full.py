@@ -80,12 +80,12 @@ def _check_against_oracle(m, p, x, n_q, o, what):
                 for b in ill:
                     if b0 <= b < b0 + 8:
                         z64s[b] = z64[b - b0]
-        tail = 2.0 * e_cpu.max().item()
+        tail = 4.0 * e_cpu.max().item()
         for b in ill:
             e_gpu = (zc[b].double() - z64s[b]).abs().max().item()
             cond[b] = (e_gpu, e_cpu[b].item())
             assert e_gpu <= max(TOL, 8.0 * e_cpu[b].item(), tail), \
-                (what, "clip", b, "cuda vs fp64", e_gpu, "reference fp32 vs fp64", e_cpu[b].item(), "batch tail x2", tail)
+                (what, "clip", b, "cuda vs fp64", e_gpu, "reference fp32 vs fp64", e_cpu[b].item(), "batch tail x4", tail)
         cond["reference_fp32_vs_fp64_over_batch"] = (f"max {e_cpu.max().item():.2e}", f"median {e_cpu.median().item():.2e}")
     good = torch.ones(x.shape[0], dtype=torch.bool)
     good[ill] = False
