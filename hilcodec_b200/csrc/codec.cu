@@ -1134,7 +1134,15 @@ int32_t decode_impl(hil_model* m, const Buffers& w, const float* q, int B, int F
     {
         const int Tp = pitch4(Ts);
         const long long bs = (long long)C * Tp;
-        HIL_TRY(run_gemm_chlast_in(m->dec_pre_pw, q, B, Ts, nullptr, a1, bs, Tp, st));
+        if (tc_on() && g_use_h && (long long)B * Ts >= 2048 && gemm_h_usable(m->dec_pre_pw, a2, (long long)c.dim * Tp, Tp, Ts, nullptr, a1, bs, Tp, B)) {
+            // batches: transpose the channel-last latents once (a few MB) and run the 128 -> C 1x1 conv on the tensor pipe
+            // (the FP32 kernel that reads channel-last input directly took 240 us of the 256-clip step)
+            HIL_LAUNCH(CAT_MISC, 0.0, 8.0 * B * c.dim * (double)Ts, st,
+                       launch_chlast_to_ncw(q, a2, B, c.dim, Ts, (long long)c.dim * Tp, Tp, st));
+            HIL_TRY(run_gemm_linear(m->dec_pre_pw, a2, (long long)c.dim * Tp, Tp, B, Ts, PRE_NONE, 1.f, nullptr, nullptr, a1, bs, Tp, st));
+        } else {
+            HIL_TRY(run_gemm_chlast_in(m->dec_pre_pw, q, B, Ts, nullptr, a1, bs, Tp, st));
+        }
         // the ELU in front of the first upsampling layer (streaming.py:633) is applied when storing
         HIL_TRY(run_dwconv(a1, bs, Tp, cin[ci], cout[ci], m->dec_pre_dw_w, m->dec_pre_dw_b, nullptr, h, bs, Tp, B, C,
                            Ts, 5, 1, PRE_NONE, 1.f, st, PRE_ELU, 1.f));

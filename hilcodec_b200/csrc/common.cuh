@@ -179,6 +179,8 @@ cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
 cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                                   const float* w, const float* bias, float* y, int B, int C, int T, int K, int pre,
                                   float pre_scale, int* nonfinite, cudaStream_t st);
+// q [B][F][C] -> y [B][C][pitch]
+cudaError_t launch_chlast_to_ncw(const float* q, float* y, int B, int C, int F, long long y_bs, int y_rs, cudaStream_t st);
 // z[b][f][c] = x[b][c][f] / max(||x[b][:,f]||, 1e-12) * scale
 // nonfinite (may be null): set to 1 when a latent / PCM sample comes out NaN or Inf
 cudaError_t launch_l2norm_chlast(const float* x, long long x_bs, int x_rs, float* z, int B, int C, int F, float scale,

@@ -524,6 +524,32 @@ cudaError_t launch_conv_post_tanh(const float* x, long long x_bs, int x_rs, cons
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ channel-last -> NCW
+// q [B][F][C] (the dequantised latents, streaming.py:157) -> y [B][C][pitch]: lets the decoder's first 1x1 conv run on the
+// tensor-core GEMM (which reads NCW boxes by TMA) for batches; 32 x 32 tiles through shared memory, both sides coalesced.
+__global__ void chlast_to_ncw_kernel(const float* __restrict__ q, float* __restrict__ y, int C, int F, long long y_bs, int y_rs) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* qb = q + (size_t)b * F * C;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int f = f0 + r, c = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (f < F && c < C) ? qb[(size_t)f * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, f = f0 + threadIdx.x;
+        if (c < C && f < F) y[b * y_bs + (long long)c * y_rs + f] = tile[threadIdx.x][r];
+    }
+}
+
+cudaError_t launch_chlast_to_ncw(const float* q, float* y, int B, int C, int F, long long y_bs, int y_rs, cudaStream_t st) {
+    if (B == 0 || F == 0) return cudaSuccess;
+    if (B > 65535) return cudaErrorInvalidValue;
+    dim3 grid((F + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    chlast_to_ncw_kernel<<<grid, block, 0, st>>>(q, y, C, F, y_bs, y_rs);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ L2 norm + channel-last
 // L2Norm.forward streaming.py:284-285 then x.transpose(1,2) (:517).  One warp per (b, f).
 __global__ void l2norm_chlast_kernel(const float* __restrict__ x, long long x_bs, int x_rs, float* __restrict__ z,

@@ -31,7 +31,8 @@ constexpr int NUM_THREADS = 512;
 constexpr int NUM_XFORM = 256;
 constexpr int NUM_EPI = 128;
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256;
+constexpr int SPAN_FLOATS = 512;                 // gather mode: (BN - 1) * hop + n_fft samples of one tile (hop 1 / 2: 191 / 382)
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256 + 2 * SPAN_FLOATS * 4;
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0);  // A and B both K-major
 constexpr uint32_t IDESC_N256 = make_idesc(BM, 2 * BN, 0);
 
@@ -39,7 +40,7 @@ struct Params {
     int M, F, K, T, B, hop;
     int num_m, tiles_t;
     long long total_tiles;
-    int gather;          // 1: transform warps build B from global memory (hop % 4 != 0)
+    int gather;          // transform warps build B themselves (hop % 4 != 0): 1 from a staged span, 2 from global memory
     int exact_log;       // 1: logf (HILCODEC_STFT_LOGF=1), 0: lg2.approx * ln 2
     const float* wav;    // window base (first sample of the window of frame 0)
     long long w_bs;      // batch stride of wav
@@ -59,6 +60,7 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     auto tempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
     const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    float* span_base = reinterpret_cast<float*>(gen_base + (bars - base) + 256);   // 2 x SPAN_FLOATS (gather mode)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.K / BK;
@@ -152,10 +154,26 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int xt = threadIdx.x - 256;
         int s = 0;
         uint32_t ph = 0;
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        uint32_t tcount = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
             const long long rest = tile / p.num_m;
             const int tt = (int)(rest % p.tiles_t);
             const int b = (int)(rest / p.tiles_t);
+            // Gather mode (hop 1 / 2: the im2col rows are not 16-byte aligned, no tensor map): the tile's 128 windows
+            // overlap almost completely -- B[t][k] = wav[(t0 + t) * hop + k] -- so its whole operand comes from ONE span
+            // of (BN - 1) * hop + n_fft samples.  Stage the span in shared memory with coalesced loads (double-buffered
+            // by tile parity, one barrier of the 8 transform warps per tile) and build the k-blocks from it; the
+            // per-k-block scalar global gathers this replaces were what the high-rate stages waited on (ncu: long
+            // scoreboard on the first use of every gathered value).
+            float* span = span_base + (tcount & 1u) * SPAN_FLOATS;
+            if (p.gather == 1) {
+                const int span_len = (BN - 1) * p.hop + p.K;
+                const long long g0 = (long long)tt * BN * p.hop;                      // first sample of the tile's first window
+                const long long g_end = (long long)(p.T - 1) * p.hop + p.K;            // samples the clip's windows cover
+                const float* src = p.wav + (long long)b * p.w_bs + g0;
+                for (int i = xt; i < span_len; i += NUM_XFORM) span[i] = (g0 + i < g_end) ? __ldg(src + i) : 0.f;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(full_bar(s), ph);   // also: the slot is free (the producer waited for its MMAs)
                 float4* bh = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 2 * TILE_BYTES);
@@ -168,8 +186,13 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const int tg = tt * BN + t;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (tg < p.T) {
-                            const float* src = p.wav + (long long)b * p.w_bs + (long long)tg * p.hop + kb * BK + k4 * 4;
-                            v.x = __ldg(src); v.y = __ldg(src + 1); v.z = __ldg(src + 2); v.w = __ldg(src + 3);
+                            if (p.gather == 1) {
+                                const float* src = span + t * p.hop + kb * BK + k4 * 4;
+                                v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+                            } else {   // span too long for the staging buffer (never with the published strides)
+                                const float* src = p.wav + (long long)b * p.w_bs + (long long)tg * p.hop + kb * BK + k4 * 4;
+                                v.x = __ldg(src); v.y = __ldg(src + 1); v.z = __ldg(src + 2); v.w = __ldg(src + 3);
+                            }
                         }
                         float4 l;
                         l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
@@ -331,7 +354,7 @@ cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_
     p.num_m = (Wdft.M + BM - 1) / BM;
     p.tiles_t = (T + BN - 1) / BN;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
-    p.gather = gather; p.wav = wav; p.w_bs = w_bs;
+    p.gather = gather ? (((BN - 1) * hop + Wdft.K <= SPAN_FLOATS) ? 1 : 2) : 0; p.wav = wav; p.w_bs = w_bs;
     static const int exact_log = []() { const char* e = std::getenv("HILCODEC_STFT_LOGF"); return (e && e[0] == '1') ? 1 : 0; }();
     p.exact_log = exact_log;
     const int num_sms = device_sm_count();
