@@ -1,4 +1,5 @@
-// CausalSTFT + magnitude + clamp + log on the tensor pipe (tcgen05, 3xTF32).
+// CausalSTFT + magnitude + clamp + log on the tensor pipe (tcgen05; fp16 hi/lo splits by default, 3xTF32 with
+// HILCODEC_GEMM=tf32).
 //
 //   S[2F][t] = sum_k Wdft[2F][k] * wav[t*hop + k],  y[f][t] = log(max(sqrt(re_f^2 + im_f^2), 1e-5))
 //
@@ -14,18 +15,28 @@
 //     warps gather the windows through L1 and write the swizzled tile themselves;
 //   * the epilogue stores F rows per 128 accumulator rows (box 32 x 64).
 #include <cstdlib>
+#include <cstring>
 
-#include "tc_ptx.cuh"
+#include "h_split.cuh"
 
 namespace hil {
 namespace stft {
 
 using namespace tc;
+using th::LO_SCALE;
 
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+// kH = true (fp16 hi/lo splits, same number format and MMA pattern as gemm_h.cu: twice the tf32 rate): a stage is
+// A_hi | A_lo | B_hi | B_lo as K-major fp16 tiles (128 rows x 32 k = 64-byte rows, SWIZZLE_64B, 8 KB each) + the raw fp32
+// window tile the TMA delivers (16 KB) = 48 KB, four stages
+constexpr int H_TILE = BM * BK * 2;              // 8 KB
+constexpr int H_STAGE_BYTES = 4 * H_TILE + TILE_BYTES;
+constexpr int H_STAGES = 4;
+constexpr uint32_t IDESC_H_N128 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);        // f16 x f16 -> f32, A and B K-major
+constexpr uint32_t IDESC_H_N256 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 constexpr int OUT_BYTES = 64 * 32 * 4;           // 64 bins x 32 columns
 constexpr int NUM_THREADS = 512;
 constexpr int NUM_XFORM = 256;
@@ -33,6 +44,7 @@ constexpr int NUM_EPI = 128;
 constexpr int TMEM_COLS = 512;
 constexpr int SPAN_FLOATS = 512;                 // gather mode: (BN - 1) * hop + n_fft samples of one tile (hop 1 / 2: 191 / 382)
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256 + 2 * SPAN_FLOATS * 4;
+static_assert((size_t)H_STAGES * H_STAGE_BYTES <= (size_t)STAGES * STAGE_BYTES, "the fp16 configuration fits the same allocation");
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0);  // A and B both K-major
 constexpr uint32_t IDESC_N256 = make_idesc(BM, 2 * BN, 0);
 
@@ -44,14 +56,21 @@ struct Params {
     int exact_log;       // 1: logf (HILCODEC_STFT_LOGF=1), 0: lg2.approx * ln 2
     const float* wav;    // window base (first sample of the window of frame 0)
     long long w_bs;      // batch stride of wav
+    float c_big;         // kH: 2^-s of the DFT basis' fp16 scaling (gemm_h.cu)
 };
 
+template <bool kH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const Params p) {
+    constexpr int STAGES = kH ? H_STAGES : stft::STAGES;
+    constexpr int STAGE_BYTES = kH ? H_STAGE_BYTES : stft::STAGE_BYTES;
+    constexpr int A_BYTES = kH ? H_TILE : TILE_BYTES;            // one A plane of a stage
+    constexpr int B_OFF = 2 * A_BYTES;                           // B_hi of a stage
+    constexpr int RAW_OFF = kH ? 4 * H_TILE : 2 * TILE_BYTES;    // where the TMA puts the fp32 window tile (kH: behind the fp16 tiles)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t out_base = base + STAGES * STAGE_BYTES;
+    const uint32_t out_base = base + stft::STAGES * stft::STAGE_BYTES;
     const uint32_t bars = out_base + 2 * OUT_BYTES;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto xform_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -106,10 +125,10 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait<32>(empty_bar(s), ph ^ 1);
                     const uint32_t st = base + s * STAGE_BYTES;
-                    mbar_arrive_expect_tx(full_bar(s), p.gather ? 2 * TILE_BYTES : 3 * TILE_BYTES);
+                    mbar_arrive_expect_tx(full_bar(s), 2 * A_BYTES + (p.gather ? 0 : TILE_BYTES));
                     tma_load_2d(&map_a_hi, st, full_bar(s), kb * BK, m_blk * BM);
-                    tma_load_2d(&map_a_lo, st + TILE_BYTES, full_bar(s), kb * BK, m_blk * BM);
-                    if (!p.gather) tma_load_3d(&map_x, st + 2 * TILE_BYTES, full_bar(s), kb * BK, tt * BN, b);
+                    tma_load_2d(&map_a_lo, st + A_BYTES, full_bar(s), kb * BK, m_blk * BM);
+                    if (!p.gather) tma_load_3d(&map_x, st + RAW_OFF, full_bar(s), kb * BK, tt * BN, b);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -132,15 +151,26 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(xform_bar(s), ph);
                 tc_fence_after();
                 if (lane == 0) {
+                    // B_hi (rows 0..127) and B_lo (rows 128..255) are adjacent K-major tiles: one N = 256 MMA
+                    // computes A_hi*[B_hi | B_lo] into [big | small], a second N = 128 MMA adds A_lo*B_hi.
+                    if constexpr (kH) {
 #pragma unroll
-                    for (int j = 0; j < BK / 8; ++j) {
-                        // B_hi (rows 0..127) and B_lo (rows 128..255) are adjacent K-major tiles: one N = 256 MMA
-                        // computes A_hi*[B_hi | B_lo] into [big | small], a second N = 128 MMA adds A_lo*B_hi.
-                        const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
-                        const uint64_t a_lo = make_desc(st + TILE_BYTES + j * 32, 16, 1024, 2);
-                        const uint64_t b_hl = make_desc(st + 2 * TILE_BYTES + j * 32, 16, 1024, 2);
-                        umma_tf32(d_big, a_hi, b_hl, IDESC_N256, (kb | j) != 0);
-                        umma_tf32(d_small, a_lo, b_hl, IDESC, 1);
+                        for (int j = 0; j < BK / 16; ++j) {   // 64-byte rows, SWIZZLE_64B: 8-row groups 512 B apart, +32 B per k16
+                            const uint64_t a_hi = make_desc(st + j * 32, 16, 512, 4);
+                            const uint64_t a_lo = make_desc(st + A_BYTES + j * 32, 16, 512, 4);
+                            const uint64_t b_hl = make_desc(st + B_OFF + j * 32, 16, 512, 4);
+                            th::umma_f16(d_big, a_hi, b_hl, IDESC_H_N256, (kb | j) != 0);
+                            th::umma_f16(d_small, a_lo, b_hl, IDESC_H_N128, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BK / 8; ++j) {
+                            const uint64_t a_hi = make_desc(st + j * 32, 16, 1024, 2);
+                            const uint64_t a_lo = make_desc(st + TILE_BYTES + j * 32, 16, 1024, 2);
+                            const uint64_t b_hl = make_desc(st + 2 * TILE_BYTES + j * 32, 16, 1024, 2);
+                            umma_tf32(d_big, a_hi, b_hl, IDESC_N256, (kb | j) != 0);
+                            umma_tf32(d_small, a_lo, b_hl, IDESC, 1);
+                        }
                     }
                     umma_commit(empty_bar(s));
                     if (kb == nkb - 1) umma_commit(tfull_bar(acc));
@@ -176,6 +206,40 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(full_bar(s), ph);   // also: the slot is free (the producer waited for its MMAs)
+                if constexpr (kH) {
+                    // fp32 window tile (TMA, 128-byte rows, SWIZZLE_128B) or gathered values -> fp16 hi / lo tiles
+                    // (64-byte rows, SWIZZLE_64B: 16-byte chunk c of row t sits at chunk c ^ ((t >> 1) & 3))
+                    const float4* raw = reinterpret_cast<const float4*>(gen_base + s * STAGE_BYTES + RAW_OFF);
+                    uint8_t* bhi = gen_base + s * STAGE_BYTES + B_OFF;
+#pragma unroll
+                    for (int i = 0; i < TILE_BYTES / 16 / NUM_XFORM; ++i) {
+                        const int item = xt + i * NUM_XFORM;
+                        const int t = item >> 3;
+                        int k4;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.gather) {
+                            k4 = item & 7;
+                            const int tg = tt * BN + t;
+                            if (tg < p.T) {
+                                if (p.gather == 1) {
+                                    const float* src = span + t * p.hop + kb * BK + k4 * 4;
+                                    v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+                                } else {
+                                    const float* src = p.wav + (long long)b * p.w_bs + (long long)tg * p.hop + kb * BK + k4 * 4;
+                                    v.x = __ldg(src); v.y = __ldg(src + 1); v.z = __ldg(src + 2); v.w = __ldg(src + 3);
+                                }
+                            }
+                        } else {
+                            k4 = (item & 7) ^ (t & 7);   // the float4 at physical index `item` holds k = 4 * k4 .. 4 * k4 + 3 of row t
+                            v = raw[item];
+                        }
+                        uint32_t h01, h23, l01, l23;
+                        th::split4<PRE_NONE>(v, 1.0f, h01, h23, l01, l23);
+                        const uint32_t off = (uint32_t)t * 64u + ((((uint32_t)k4 >> 1) ^ (((uint32_t)t >> 1) & 3u)) << 4) + ((uint32_t)k4 & 1u) * 8u;
+                        *reinterpret_cast<uint2*>(bhi + off) = make_uint2(h01, h23);
+                        *reinterpret_cast<uint2*>(bhi + H_TILE + off) = make_uint2(l01, l23);
+                    }
+                } else {
                 float4* bh = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 2 * TILE_BYTES);
                 float4* bl = reinterpret_cast<float4*>(gen_base + s * STAGE_BYTES + 3 * TILE_BYTES);
                 if (p.gather) {
@@ -211,6 +275,7 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         l.z = tf32_rna(v.z - tf32_trunc(v.z)); l.w = tf32_rna(v.w - tf32_trunc(v.w));
                         bl[idx] = l;
                     }
+                }
                 }
                 fence_proxy_async();
                 mbar_arrive(xform_bar(s));
@@ -260,7 +325,9 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 // bottleneck of the whole kernel).
                 float mine[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mine[j] = __uint_as_float(rb[j]) + __uint_as_float(rs[j]);
+                for (int j = 0; j < 32; ++j)
+                    mine[j] = kH ? fmaf(__uint_as_float(rs[j]), 1.0f / LO_SCALE, __uint_as_float(rb[j])) * p.c_big
+                                 : __uint_as_float(rb[j]) + __uint_as_float(rs[j]);
                 const uint32_t orow = obuf + frow * 128;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -305,6 +372,16 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
 }  // namespace stft
 
+// HILCODEC_GEMM=tf32 (the switch of the pointwise GEMMs) also keeps this kernel on 3xTF32
+static bool stft_use_h() {
+    static const bool v = []() {
+        const char* e = std::getenv("HILCODEC_GEMM");
+        const char* f = std::getenv("HILCODEC_STFT");   // HILCODEC_STFT=tf32: this kernel only (A/B knob)
+        return !(e && std::strcmp(e, "tf32") == 0) && !(f && std::strcmp(f, "tf32") == 0);
+    }();
+    return v;
+}
+
 bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
                     int y_rs) {
     if (!Wdft.A_hi || !Wdft.A_lo) return false;
@@ -320,13 +397,23 @@ cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_
     if (B == 0 || T == 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(stft_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    const bool use_h = stft_use_h() && Wdft.H_hi && Wdft.H_lo;
     const int F = Wdft.M / 2;
     CUtensorMap map_hi, map_lo, map_x, map_y;
-    {
+    if (use_h) {   // fp16 hi / lo planes of the basis, K-major, 64-byte rows (as gemm_h.cu's A operand)
+        const cuuint64_t dims[2] = {(cuuint64_t)Wdft.Kp32, (cuuint64_t)Wdft.Mp128};
+        const cuuint64_t strides[1] = {(cuuint64_t)Wdft.Kp32 * 2};
+        const cuuint32_t box[2] = {BK, BM};
+        if (!make_map_dt(&map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Wdft.H_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !make_map_dt(&map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Wdft.H_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+            return cudaErrorInvalidValue;
+    } else {
         const cuuint64_t dims[2] = {(cuuint64_t)Wdft.Kp32, (cuuint64_t)Wdft.Mp128};
         const cuuint64_t strides[1] = {(cuuint64_t)Wdft.Kp32 * 4};
         const cuuint32_t box[2] = {BK, BM};
@@ -357,9 +444,11 @@ cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_
     p.gather = gather ? (((BN - 1) * hop + Wdft.K <= SPAN_FLOATS) ? 1 : 2) : 0; p.wav = wav; p.w_bs = w_bs;
     static const int exact_log = []() { const char* e = std::getenv("HILCODEC_STFT_LOGF"); return (e && e[0] == '1') ? 1 : 0; }();
     p.exact_log = exact_log;
+    p.c_big = Wdft.h_inv_scale;
     const int num_sms = device_sm_count();
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    stft_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
+    if (use_h) stft_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
+    else stft_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, p);
     return cudaGetLastError();
 }
 
