@@ -13,7 +13,7 @@ with no data-path collective -- clips are independent.
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the launch stream, inputs resident in HBM, max
 over ranks; `e2e` goes through the C-ABI host-buffer call (`hil_codec_forward_host`: pinned-host H2D, forward, D2H of
 indices + PCM, stream sync).  At N = 1 with no --workload the same line also carries `other_workloads`: configs[1]
-(speech64) and configs[3] (stream1 / stream64: hil_music fed hop by hop, GPU-resident caches), each with its own value /
+(speech64), configs[0] (speech1: the single clip the CPU reference is quoted on) and configs[3] (stream1 / stream64: hil_music fed hop by hop, GPU-resident caches), each with its own value /
 e2e / roofline / cpu_baseline.  `--workload X` runs only X.
 
 CPU legs (`cpu_baseline`, `--impl reference`): the reference's OWN classes (models/hilcodec/streaming.py, unmodified
@@ -43,6 +43,7 @@ WORKLOADS = {
     # name: (model, clips per GPU, samples, n_q, BASELINE.json config it is)
     "music256": ("hil_music", 256, 24000, 12, "configs[2]: hil_music, batch=256x24000 @24 kHz, n_q=12"),
     "speech64": ("hil_speech", 64, 24000, 8, "configs[1]: hil_speech, batch=64x24000 @24 kHz, n_q=8"),
+    "speech1": ("hil_speech", 1, 24000, 8, "configs[0]: hil_speech, 1 utterance x 24000 @24 kHz, n_q=8 (the CPU reference's case)"),
     # streaming: `clips` concurrent streams fed hop by hop, one step = 75 hops = 1 s of audio per stream
     "stream1": ("hil_music", 1, 24000, 12, "configs[3]: hil_music streaming, hop 320, per-frame causal cache, 1 stream"),
     "stream64": ("hil_music", 64, 24000, 12, "configs[3]: hil_music streaming, hop 320, per-frame causal cache, 64 streams"),
@@ -211,8 +212,9 @@ class CpuCodec:
             return time.perf_counter() - t0
 
 
-def cpu_reference_run(model_name, n_q, samples, steps, warmup, budget_s):
-    """One-shot batches on all host threads, on a bounded sample of the workload."""
+def cpu_reference_run(model_name, n_q, samples, steps, warmup, budget_s, clips=None):
+    """One-shot batches on all host threads, on a bounded sample of the workload (`clips`: the workload's batch size;
+    sub-batches larger than it are not tried, so configs[0] is timed as the single clip it is)."""
     import torch
 
     cores = host_cores()
@@ -229,11 +231,13 @@ def cpu_reference_run(model_name, n_q, samples, steps, warmup, budget_s):
     # probe a few sub-batch sizes and give the reference its best one
     best_b, best_rate = 1, 0.0
     for b in (1, 2, 4, 8):
+        if clips is not None and b > clips:
+            break
         t = run(synth(b, samples, 90 + b))
         if b / t > best_rate:
             best_b, best_rate = b, b / t
     total_steps = max(1, steps + warmup)
-    reps = int(max(1, min(256 // best_b, budget_s / total_steps * best_rate / best_b)))
+    reps = int(max(1, min((clips or 256) // best_b, budget_s / total_steps * best_rate / best_b)))
     batch = reps * best_b
     xs = [synth(best_b, samples, 1234 + i) for i in range(reps)]
 
@@ -326,7 +330,7 @@ def main_reference(args):
         cfgd = {"workload": desc, "model": model_name, "streams": clips, "hop": hop, "n_q": n_q,
                 "note": "CPU: bounded number of sequential hops, scaled to a 75-hop step"}
     else:
-        r = cpu_reference_run(model_name, n_q, samples, args.steps, args.warmup, budget_s=150.0)
+        r = cpu_reference_run(model_name, n_q, samples, args.steps, args.warmup, budget_s=150.0, clips=clips)
         ms_step = r["ms_per_step"]
         cfgd = {"workload": desc, "model": model_name, "clips_per_step": r["batch"], "samples": samples, "n_q": n_q,
                 "note": "CPU: bounded sample of the workload per step"}
@@ -672,7 +676,9 @@ def run_batch(ctx, wl, steps, warmup, with_cpu, cpu_budget=None):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": f"synthetic 0.1*randn audio, {wdesc}",
         "config": {"workload": desc, "model": model_name, "clips_per_gpu": B, "samples": T, "n_q": n_q,
                    "sharding": f"batch-sharded x{world}, no data-path collective",
-                   "l2": "no explicit flush: one step streams >10 GB of activations through the 126 MB L2"},
+                   "l2": ("no explicit flush: one step streams >10 GB of activations through the 126 MB L2" if B >= 32 else
+                          "no flush: a single clip's activations and the ~50 MB of weights fit the 126 MB L2, as they would "
+                          "in a service that keeps the model loaded")},
         "rtf_x_realtime": value / 75.0,
         "model_tflops": value * FLOP_PER_FRAME[model_name] / 1e12,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * 4,
@@ -696,7 +702,7 @@ def run_batch(ctx, wl, steps, warmup, with_cpu, cpu_budget=None):
     if gather:
         line["gather"] = gather
     if world == 1 and with_cpu:
-        r = cpu_reference_run(model_name, n_q, samples, steps=4, warmup=1, budget_s=cpu_budget or 40.0)
+        r = cpu_reference_run(model_name, n_q, samples, steps=4, warmup=1, budget_s=cpu_budget or 40.0, clips=B)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         try:
             g = reference_on_gpu_run(ctx, model_name, n_q, samples, clips=min(B, 32))
@@ -723,7 +729,7 @@ def main_ours(args):
     if line is not None and args.workload is None and ctx.world == 1 and not args.no_other_workloads:
         # the other BASELINE configs that fit one GPU, in the same contract (shorter runs: they are not the headline)
         others = {}
-        for name, st in (("speech64", 10), ("stream1", 4), ("stream64", 4)):
+        for name, st in (("speech64", 10), ("speech1", 10), ("stream1", 4), ("stream64", 4)):
             try:
                 r = (run_stream if name.startswith("stream") else run_batch)(ctx, name, st, 3, with_cpu, cpu_budget=14.0)
                 others[name] = condensed(r)

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -110,6 +111,9 @@ static bool g_use_tc = std::getenv("HILCODEC_DISABLE_TC") == nullptr;  // tensor
 static thread_local bool tl_exact_fp32 = false;
 static inline bool tc_on() { return g_use_tc && !tl_exact_fp32; }
 static bool g_fuse_dw = std::getenv("HILCODEC_DISABLE_DWS_FUSION") == nullptr;
+// residual-VQ search of batches on the tensor cores (run_rvq_tc); mode bit 8 (256) of hil_set_tensor_cores or
+// HILCODEC_RVQ_TC=0 keep the FFMA search
+static bool g_rvq_tc = []() { const char* e = std::getenv("HILCODEC_RVQ_TC"); return !(e && e[0] == '0'); }();
 // fp16-split tensor-core kernel (gemm_h.cu, kind::f16 at twice the tf32 rate, decoupled load / operand rings):
 // mode bit 4 (16) of hil_set_tensor_cores, or HILCODEC_GEMM=tf32 to fall back to gemm_tc.cu.
 static bool g_use_h = []() { const char* e = std::getenv("HILCODEC_GEMM"); return !(e && std::strcmp(e, "tf32") == 0); }();
@@ -376,6 +380,15 @@ struct hil_model {
     // quantizer
     const float* codebooks = nullptr;  // [n_q][size][dim]
     float* ee = nullptr;               // [n_q][size]
+    // tensor-core batch search (run_rvq_tc): every codebook also as a GEMM operand, max_c |e_c|^2 per stage for the
+    // near-tie bound, and a model-owned scratch (k-major residuals / sums + one stage of dot products) that calls on
+    // different streams hand to each other through an event
+    std::vector<hil::PackedMat> cb_mat;
+    std::vector<float> ee_max;
+    float* rvq_tc_scratch = nullptr;
+    size_t rvq_tc_floats = 0;
+    cudaEvent_t rvq_tc_ev = nullptr;
+    std::mutex rvq_tc_mu;
 
     std::vector<std::vector<int64_t>> enc_cache_shape, dec_cache_shape;  // [C, len]
     int hop = 1;
@@ -733,6 +746,21 @@ int32_t hil_model_finalize(hil_model* m) {
         if (t) std::memcpy(b.arena.buf.data() + cb_off + cb_elems * i, t->data.data(), cb_elems * sizeof(float));
     }
     const size_t ee_off = b.arena.alloc((size_t)c.codebook_size * c.num_quantizers);
+    if (m->has_vq && b.missing.empty()) {
+        m->cb_mat.assign(c.num_quantizers, hil::PackedMat());
+        m->ee_max.assign(c.num_quantizers, 0.f);
+        for (int i = 0; i < c.num_quantizers; ++i) {
+            const HostTensor* t = b.get(N("quantizer.layers.%d.embed", i), {c.codebook_size, c.dim});
+            b.pack(t->data.data(), c.codebook_size, c.dim, choose_tm(c.codebook_size), false, &m->cb_mat[i]);
+            double mx = 0.0;
+            for (int r = 0; r < c.codebook_size; ++r) {
+                double ss = 0.0;
+                for (int k = 0; k < c.dim; ++k) ss += (double)t->data[(size_t)r * c.dim + k] * t->data[(size_t)r * c.dim + k];
+                mx = std::max(mx, ss);
+            }
+            m->ee_max[i] = (float)mx;
+        }
+    }
 
     if (!b.missing.empty()) return fail(HIL_ERR_MISSING, "tensor not set: " + b.missing);
 
@@ -764,6 +792,8 @@ int32_t hil_model_finalize(hil_model* m) {
 
 static void free_model(hil_model* m) {
     if (m->arena) cudaFree(m->arena);
+    if (m->rvq_tc_ev) { cudaEventSynchronize(m->rvq_tc_ev); cudaEventDestroy(m->rvq_tc_ev); }
+    if (m->rvq_tc_scratch) cudaFree(m->rvq_tc_scratch);
     delete m;
 }
 
@@ -1248,6 +1278,77 @@ int32_t hil_decode(hil_model* m, hil_state* s, const float* q, int32_t B, int32_
     return HIL_OK;
 }
 
+// Batch search on the tensor cores (rvq.cu, rvq_tc_select_kernel): per stage one fp32-accurate GEMM
+// [size x 128] . [128 x frames] for the dot products and one decision / residual-update kernel that re-scores near
+// ties with the exact FFMA expression, so the result is bit-identical to the one-kernel search at ~1/3 of its time
+// (config 3: 19 200 frames x 12 stages).  HILCODEC_RVQ_TC=0 keeps the FFMA search; chunks of <= 32 768 frames bound
+// the scratch (one stage of dot products = 4 KB per frame).
+constexpr long long RVQ_TC_MIN_FRAMES = 2048, RVQ_TC_CHUNK = 32768;
+
+static bool rvq_tc_usable(const hil_model* m, long long frames, cudaStream_t st) {
+    if (!g_rvq_tc || !tc_on() || !g_use_h || frames < RVQ_TC_MIN_FRAMES || m->cb_mat.empty()) return false;
+    if (m->cfg.dim != 128 || m->cfg.codebook_size % 128 != 0 || !m->cb_mat[0].H_hi) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+    return true;
+}
+
+static int32_t run_rvq_tc(hil_model* m, const float* z, long long frames, int n, int64_t* idx, float* qsum,
+                          cudaStream_t st) {
+    const int size = m->cfg.codebook_size, dim = m->cfg.dim;
+    const bool drop_xx = m->graph == HIL_GRAPH_TRAIN;
+    const long long chunk = std::min(frames, RVQ_TC_CHUNK);
+    const long long pitch = (chunk + 127) / 128 * 128;
+    const size_t need = (size_t)(size + 2 * dim) * pitch;
+    std::lock_guard<std::mutex> lock(m->rvq_tc_mu);
+    if (!m->rvq_tc_ev) HIL_CUDA(cudaEventCreateWithFlags(&m->rvq_tc_ev, cudaEventDisableTiming));
+    if (m->rvq_tc_floats < need) {
+        HIL_CUDA(cudaEventSynchronize(m->rvq_tc_ev));   // the previous user of the old buffer
+        if (m->rvq_tc_scratch) cudaFree(m->rvq_tc_scratch);
+        m->rvq_tc_scratch = nullptr; m->rvq_tc_floats = 0;
+        HIL_CUDA(cudaMalloc(&m->rvq_tc_scratch, need * sizeof(float)));
+        HIL_CUDA(cudaMemsetAsync(m->rvq_tc_scratch, 0, need * sizeof(float), st));   // columns past the last frame stay finite
+        m->rvq_tc_floats = need;
+    }
+    HIL_CUDA(cudaStreamWaitEvent(st, m->rvq_tc_ev, 0));
+    float* Rk = m->rvq_tc_scratch;
+    float* Qk = Rk + (size_t)dim * pitch;
+    float* Y = Qk + (size_t)dim * pitch;
+    for (long long c0 = 0; c0 < frames; c0 += chunk) {
+        const long long fc = std::min(chunk, frames - c0);
+        // z rows [fc][128] -> k-major residuals (32 x 32 tiles, at most 65 535 x 32 frames per launch)
+        HIL_LAUNCH(CAT_RVQ, 0.0, 8.0 * fc * dim, st,
+                   launch_chlast_to_ncw(z + (size_t)c0 * dim, Rk, 1, dim, (int)fc, (long long)dim * pitch, (int)pitch, st));
+        for (int s = 0; s < n; ++s) {
+            const PackedMat& W = m->cb_mat[s];
+            // one "clip" per 128-frame tile: X = columns [128 t, 128 t + 128) of Rk, Y block t = [size][128]
+            const int tiles = (int)((fc + 127) / 128);
+            if (!gemm_h_usable(W, Rk, 128, (int)pitch, 128, nullptr, Y, (long long)size * 128, 128, tiles))
+                return fail(HIL_ERR_STATE, "rvq: codebook GEMM not launchable");
+            HIL_LAUNCH(CAT_RVQ, 2.0 * fc * size * dim, 4.0 * fc * dim + 4.0 * size * dim + 4.0 * fc * size, st,
+                       launch_gemm_h(W, Rk, 128, (int)pitch, tiles, 128, PRE_NONE, 1.f, nullptr, nullptr, Y,
+                                     (long long)size * 128, 128, st));
+            HIL_LAUNCH(CAT_RVQ, 4.0 * fc * size, 4.0 * fc * size + (qsum ? 20.0 : 12.0) * fc * dim + 8.0 * fc, st,
+                       launch_rvq_tc_select(Y, Rk, qsum ? Qk : nullptr, m->codebooks + (size_t)s * size * dim,
+                                            m->ee + (size_t)s * size, size, pitch, fc, s == 0,
+                                            idx + (size_t)s * frames + c0, m->ee_max[s], drop_xx, nullptr, st));
+        }
+        if (qsum)
+            HIL_LAUNCH(CAT_RVQ, 0.0, 8.0 * fc * dim, st,
+                       launch_kmajor_to_rows(Qk, pitch, qsum + (size_t)c0 * dim, dim, fc, st));
+    }
+    HIL_CUDA(cudaEventRecord(m->rvq_tc_ev, st));
+    return HIL_OK;
+}
+
+// the search for `frames` latents: tensor-core GEMM + decision kernel for batches, FFMA kernels otherwise
+static int32_t rvq_encode_any(hil_model* m, const float* z, long long frames, int n, int64_t* idx, float* qsum,
+                              cudaStream_t st) {
+    if (rvq_tc_usable(m, frames, st)) return run_rvq_tc(m, z, frames, n, idx, qsum, st);
+    return run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, frames, n, idx, qsum,
+                          m->graph == HIL_GRAPH_TRAIN, st);
+}
+
 int32_t hil_rvq_encode(hil_model* m, const float* z, int32_t B, int32_t F, int32_t n, int64_t* idx, float* qsum,
                        void* stream) {
     if (!m || !m->finalized) return fail(HIL_ERR_STATE, "model not finalized");
@@ -1255,8 +1356,7 @@ int32_t hil_rvq_encode(hil_model* m, const float* z, int32_t B, int32_t F, int32
     if (!m->has_vq) return fail(HIL_ERR_STATE, "model has no codebooks");
     // assert 1 <= n <= len(self.layers)  (models/hilcodec/vector_quantize.py:213)
     if (n < 1 || n > m->cfg.num_quantizers) return fail(HIL_ERR_INVALID, "n must satisfy 1 <= n <= num_quantizers");
-    HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, qsum,
-                               m->graph == HIL_GRAPH_TRAIN, (cudaStream_t)stream));
+    HIL_TRY(rvq_encode_any(m, z, (long long)B * F, n, idx, qsum, (cudaStream_t)stream));
     return HIL_OK;
 }
 
@@ -1299,8 +1399,7 @@ int32_t hil_codec_forward(hil_model* m, hil_state* s, const float* wav, int32_t 
                    launch_rvq_encode_split(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, fr, n, idx, w.q,
                                            m->graph == HIL_GRAPH_TRAIN, s->rvq_scratch, st));
     } else {
-        HIL_TRY(run_rvq_encode(z, m->codebooks, m->ee, m->cfg.codebook_size, m->cfg.dim, (long long)B * F, n, idx, w.q,
-                               m->graph == HIL_GRAPH_TRAIN, st));
+        HIL_TRY(rvq_encode_any(m, z, fr, n, idx, w.q, st));
     }
     HIL_TRY(decode_impl(m, w, w.q, B, F, wav_out, s->dec_c[gd].data(), s->dec_c[gd ^ 1].data(), st));
     s->dec_gen = gd ^ 1;
@@ -1469,7 +1568,8 @@ uint64_t hil_launch_count(void) { return g_prof.launches; }
 
 int32_t hil_set_tensor_cores(int32_t mode) {
     const int32_t prev = (g_use_tc ? 1 : 0) | (g_fuse_dw ? 0 : 4) | (g_use_h ? 16 : 0) | (g_fuse_rb ? 0 : 32) | (g_fuse_up ? 0 : 64) |
-                         (g_fuse_down ? 0 : 128);
+                         (g_fuse_down ? 0 : 128) | (g_rvq_tc ? 0 : 256);
+    g_rvq_tc = (mode & 256) == 0;
     g_use_tc = (mode & 1) != 0;
     g_fuse_dw = (mode & 4) == 0;
     g_use_h = (mode & 16) != 0;

@@ -194,6 +194,11 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
 // few-frame (streaming) variant: one launch per stage over (code tiles) x (frame blocks); HILCODEC_RVQ_SPLIT=0 disables
 bool rvq_split_usable(int size, int dim, long long frames);
 size_t rvq_split_scratch_bytes();
+// tensor-core batch search (rvq.cu): per-stage decision kernel on the GEMM's dot products + the final transpose
+cudaError_t launch_rvq_tc_select(const float* Y, float* Rk, float* Qk, const float* cb, const float* ees, int size,
+                                 long long pitch, long long frames, int first, int64_t* idx, float ee_max, bool drop_xx,
+                                 unsigned int* rescored, cudaStream_t st);
+cudaError_t launch_kmajor_to_rows(const float* x, long long pitch, float* y, int C, long long F, cudaStream_t st);
 cudaError_t launch_rvq_encode_split(const float* z, const float* codebooks, const float* ee, int size, int dim,
                                     long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, void* scratch,
                                     cudaStream_t st);

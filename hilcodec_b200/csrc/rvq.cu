@@ -214,6 +214,207 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Tensor-core search for BATCHES (round 2; codec.cu run_rvq_tc).  Per stage the 2 * frames * size * 128 FLOP of dot
+// products are ONE fp32-accurate tensor-core GEMM (gemm_h.cu, the same kernel as the 1x1 convolutions):
+//     Y[f / 128][c][f % 128] = sum_k E_s[c][k] * Rk[k][f]      Rk = the residuals, k-major [128][pitch]; the GEMM is
+//                                                                launched with one "clip" per 128-frame tile, so the
+//                                                                dot products of a tile are one contiguous 512 KB block
+// and the kernel below turns Y into the stage's indices with the EXACT arithmetic of rvq_encode_kernel wherever the
+// tensor-core value could change the decision: v[c] = 2 Y[c][f] - ee[c] is scanned for the best and
+// second-best code; when they are closer than tau (a bound on |v - exact| + the FFMA chain's own rounding, 20x the
+// observed error) every code within tau of the best is re-scored with the sequential-k fp32 FMA chain and the
+// reference's -((xx - 2 dot) + ee) expression, first index winning ties -- so indices, residuals and sums are
+// bit-identical to the one-kernel search (tests/test_gpu_ops.py, test_kernel_emulation.py).  The residual update and
+// the running dequantised sum are the same fp32 subtract / add per element, in stage order, on the k-major copies.
+constexpr int RVQ_TC_TILE = 128;   // frames per Y block = the GEMM's column tile
+
+__global__ void __launch_bounds__(256)
+rvq_tc_select_kernel(const float* __restrict__ Y, float* __restrict__ Rk, float* __restrict__ Qk,
+                     const float* __restrict__ cb, const float* __restrict__ ees, int size, long long pitch,
+                     long long frames, int first, int64_t* __restrict__ idx, float ee_max, int drop_xx,
+                     unsigned int* __restrict__ rescored) {
+    // CTA = 32 frames (lane = frame, so every row access is one 128-byte line) x 8 warps; warp w owns residual dims
+    // 16w .. 16w+15 and scans codes [w * size/8, (w+1) * size/8)
+    __shared__ float sm_p[32][33];
+    __shared__ float sm_xx[32], sm_lim[32];
+    __shared__ float sm_v1[8][32], sm_v2[8][32];
+    __shared__ int sm_i1[8][32];
+    __shared__ int sm_idx[32], sm_flag[32];
+    __shared__ int sm_nflag;
+    __shared__ float sm_wd[8];
+    __shared__ int sm_wi[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long f0 = (long long)blockIdx.x * 32;
+    const bool live = f0 + lane < frames;
+    const long long f = live ? f0 + lane : frames - 1;   // idle lanes read a valid column and write nothing
+    // dot products of frame f, tile-major: Y[f / 128][code][f % 128] (one 512 KB block per 128 frames)
+    const float* y = Y + (f / RVQ_TC_TILE) * (long long)size * RVQ_TC_TILE + (f % RVQ_TC_TILE);
+
+    // |r|^2 with rvq_encode_kernel's association: partials over 4 dims, then the xor-butterfly tree
+    float rv[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rv[4 * j + i] = Rk[(long long)(16 * w + 4 * j + i) * pitch + f];
+        float q = __fmul_rn(rv[4 * j], rv[4 * j]);
+        q = fmaf(rv[4 * j + 1], rv[4 * j + 1], q);
+        q = fmaf(rv[4 * j + 2], rv[4 * j + 2], q);
+        q = fmaf(rv[4 * j + 3], rv[4 * j + 3], q);
+        sm_p[4 * w + j][lane] = q;
+    }
+    if (threadIdx.x == 0) sm_nflag = 0;
+    __syncthreads();
+    if (w == 0) {
+        float p[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l) p[l] = sm_p[l][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int l = 0; l < o; ++l) p[l] = __fadd_rn(p[l], p[l + o]);
+        sm_xx[lane] = p[0];
+    }
+
+    {   // best and second-best of v[c] = 2 Y[c][f] - ee[c] over this warp's codes (ascending: the first maximum wins);
+        // 16 independent loads are issued before their compare chain
+        const int cpw = (size + 7) / 8;
+        const int c_lo = w * cpw, c_hi = min(size, c_lo + cpw);
+        float v1 = -INFINITY, v2 = -INFINITY;
+        int i1 = 0x7fffffff;
+        for (int c = c_lo; c < c_hi; c += 16) {
+            float yv[16], ev[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int cc = min(c + u, c_hi - 1);
+                yv[u] = y[(long long)cc * RVQ_TC_TILE];
+                ev[u] = __ldg(ees + cc);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const float v = fmaf(2.f, yv[u], -ev[u]);
+                if (c + u < c_hi) {
+                    if (v > v1) { v2 = v1; v1 = v; i1 = c + u; }
+                    else if (v > v2) v2 = v;
+                }
+            }
+        }
+        sm_v1[w][lane] = v1; sm_v2[w][lane] = v2; sm_i1[w][lane] = i1;
+    }
+    __syncthreads();
+    if (w == 0) {
+        float v1 = -INFINITY, v2 = -INFINITY;
+        int i1 = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float a1 = sm_v1[u][lane], a2 = sm_v2[u][lane];
+            if (a1 > v1) { v2 = fmaxf(v1, a2); v1 = a1; i1 = sm_i1[u][lane]; }
+            else v2 = fmaxf(v2, a1);
+        }
+        const float tau = 4e-5f * (sm_xx[lane] + ee_max);
+        if (live && !(v1 - v2 >= tau)) {   // near tie (or NaN): decided below with the exact expression
+            const int slot = atomicAdd(&sm_nflag, 1);
+            sm_flag[slot] = lane;
+            sm_lim[lane] = v1 - tau;
+        }
+        sm_idx[lane] = i1;
+    }
+    __syncthreads();
+
+    const int nflag = sm_nflag;
+    for (int q = 0; q < nflag; ++q) {
+        const int fl = sm_flag[q];
+        const float lim = sm_lim[fl];
+        const float xs = drop_xx ? 0.f : sm_xx[fl];
+        const float* yq = Y + ((f0 + fl) / RVQ_TC_TILE) * (long long)size * RVQ_TC_TILE + ((f0 + fl) % RVQ_TC_TILE);
+        const float* r = Rk + f0 + fl;
+        float bd = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = threadIdx.x; c < size; c += 256) {
+            const float v = fmaf(2.f, yq[(long long)c * RVQ_TC_TILE], -__ldg(ees + c));
+            if (v < lim) continue;
+            const float4* e = reinterpret_cast<const float4*>(cb + (size_t)c * RVQ_DIM);
+            float dot = 0.f;   // the sequential-k FMA chain of rvq_encode_kernel
+            for (int k4 = 0; k4 < RVQ_DIM / 4; ++k4) {
+                const float4 e4 = __ldg(e + k4);
+                dot = fmaf(r[(long long)(4 * k4) * pitch], e4.x, dot);
+                dot = fmaf(r[(long long)(4 * k4 + 1) * pitch], e4.y, dot);
+                dot = fmaf(r[(long long)(4 * k4 + 2) * pitch], e4.z, dot);
+                dot = fmaf(r[(long long)(4 * k4 + 3) * pitch], e4.w, dot);
+            }
+            const float d = -__fadd_rn(__fsub_rn(xs, __fmul_rn(2.f, dot)), __ldg(ees + c));
+            if (d > bd) { bd = d; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { sm_wd[w] = bd; sm_wi[w] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int u = 1; u < 8; ++u)
+                if (sm_wd[u] > bd || (sm_wd[u] == bd && sm_wi[u] < bi)) { bd = sm_wd[u]; bi = sm_wi[u]; }
+            sm_idx[fl] = bi;
+            if (rescored) atomicAdd(rescored, 1u);
+        }
+        __syncthreads();
+    }
+
+    int i1 = sm_idx[lane];
+    if (i1 < 0 || i1 >= size) i1 = 0;
+    if (live) {
+        const float4* e = reinterpret_cast<const float4*>(cb + (size_t)i1 * RVQ_DIM + 16 * w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 e4 = __ldg(e + j);
+            const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long o = (long long)(16 * w + 4 * j + i) * pitch + f;
+                Rk[o] = __fsub_rn(rv[4 * j + i], ev[i]);
+                if (Qk) Qk[o] = __fadd_rn(first ? 0.f : Qk[o], ev[i]);
+            }
+        }
+        if (w == 0) idx[f] = i1;
+    }
+}
+
+cudaError_t launch_rvq_tc_select(const float* Y, float* Rk, float* Qk, const float* cb, const float* ees, int size,
+                                 long long pitch, long long frames, int first, int64_t* idx, float ee_max, bool drop_xx,
+                                 unsigned int* rescored, cudaStream_t st) {
+    if (frames == 0) return cudaSuccess;
+    rvq_tc_select_kernel<<<(unsigned)((frames + 31) / 32), 256, 0, st>>>(Y, Rk, Qk, cb, ees, size, pitch, frames, first,
+                                                                         idx, ee_max, drop_xx ? 1 : 0, rescored);
+    return cudaGetLastError();
+}
+
+// k-major [C][pitch] -> rows [F][C] (the dequantised sum back in the layout the decoder and the callers read)
+__global__ void kmajor_to_rows_kernel(const float* __restrict__ x, long long pitch, float* __restrict__ y, int C, long long F) {
+    __shared__ float tile[32][33];
+    const long long f0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int c = c0 + rr;
+        const long long f = f0 + threadIdx.x;
+        tile[rr][threadIdx.x] = (c < C && f < F) ? x[(long long)c * pitch + f] : 0.f;
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const long long f = f0 + rr;
+        const int c = c0 + threadIdx.x;
+        if (f < F && c < C) y[f * C + c] = tile[threadIdx.x][rr];
+    }
+}
+
+cudaError_t launch_kmajor_to_rows(const float* x, long long pitch, float* y, int C, long long F, cudaStream_t st) {
+    if (F == 0) return cudaSuccess;
+    dim3 grid((unsigned)((F + 31) / 32), (C + 31) / 32), block(32, 8);
+    kmajor_to_rows_kernel<<<grid, block, 0, st>>>(x, pitch, y, C, F);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Split variant for FEW frames (streaming: one frame per stream and hop).  The kernel above gives 32 frames to one
 // CTA, which then walks all n stages x 8 code tiles alone (~3.5 us per tile => ~340 us for n = 12 however few frames
 // there are).  Here stage s is ONE launch of (code tiles) x (frame blocks) CTAs: every CTA first finishes stage s-1

@@ -172,7 +172,8 @@ uint64_t hil_launch_count(void);
  * fuse DWS blocks.  Bit 4 set (default): fp16-split tensor-core kernels (gemm_h.cu, kind::f16)
  * instead of 3xTF32.  Bit 5 set: do not fuse whole ResBlocks (gemm_rb.cu).  Bit 6 set: do not fuse the decoder's
  * upsampling layers (transposed depthwise conv -> 1x1).  Bit 7 set: do not fuse the encoder's downsampling pairs
- * (1x1 -> strided depthwise conv). */
+ * (1x1 -> strided depthwise conv).  Bit 8 set: residual-VQ search of batches (>= 2048 frames) on the FFMA kernel
+ * instead of the tensor-core GEMM + decision kernel (bit-identical results). */
 int32_t hil_set_tensor_cores(int32_t mode);
 #define HIL_PROFILE_CATEGORIES 10
 int32_t hil_profile_begin(void);

@@ -1,8 +1,12 @@
 // Runs rvq.cu's one-kernel search (rvq_encode_kernel<8>: 8 frames per warp, launcher-chosen warps per CTA; `slots`
 // stands for 2 x SM count) and its per-stage variant (rvq_stage_kernel) -- source text extracted into
 // rvq_extracted.inc -- on the CPU emulation layer.
+// The batch variant's decision kernel (rvq_tc_select_kernel) runs on dot products computed here in fp64 and then
+// perturbed by +-2e-6 |e||r| (twice the tensor-core GEMM's error bound), so its near-tie re-scoring is what keeps the
+// indices equal.
 // argv: size frames n drop_xx in.bin out.bin slots;  in.bin = z[frames*128] codebooks[n*size*128] (float32);
-// out.bin = idx_mono idx_split [n*frames each] (int64) qsum_mono qsum_split [frames*128 each] (float32)
+// out.bin = idx_mono idx_split idx_tc [n*frames each] (int64) qsum_mono qsum_split qsum_tc [frames*128 each] (float32)
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -47,11 +51,48 @@ int main(int argc, char** argv) {
             rvq_stage_kernel(z.data(), cb.data(), ee.data(), size, tiles, frames, s, n, idx_b.data(), q_b.data(),
                              part[(s + 1) & 1].data(), part[s & 1].data(), rq.data(), drop_xx);
         });
+    // run_rvq_tc: k-major residuals / sums, one "GEMM" + one decision launch per stage
+    std::vector<int64_t> idx_c((size_t)n * frames, -1);
+    std::vector<float> q_c(z.size(), -1.f);
+    {
+        const long long pitch = (frames + 127) / 128 * 128;
+        std::vector<float> Rk((size_t)RVQ_DIM * pitch, 0.f), Qk((size_t)RVQ_DIM * pitch, -3.f), Y((size_t)size * pitch, 0.f);
+        for (long long fr = 0; fr < frames; ++fr)
+            for (int k = 0; k < RVQ_DIM; ++k) Rk[(size_t)k * pitch + fr] = z[(size_t)fr * RVQ_DIM + k];
+        unsigned rescored = 0;
+        uint32_t lcg = 12345u;
+        for (int s = 0; s < n; ++s) {
+            const float* cbs = cb.data() + (size_t)s * size * RVQ_DIM;
+            float ee_max = 0.f;
+            for (int c = 0; c < size; ++c) ee_max = std::fmax(ee_max, ee[(size_t)s * size + c]);
+            for (long long fr = 0; fr < frames; ++fr) {
+                double rr = 0.0;
+                for (int k = 0; k < RVQ_DIM; ++k) rr += (double)Rk[(size_t)k * pitch + fr] * Rk[(size_t)k * pitch + fr];
+                for (int c = 0; c < size; ++c) {
+                    double dot = 0.0;
+                    for (int k = 0; k < RVQ_DIM; ++k) dot += (double)cbs[(size_t)c * RVQ_DIM + k] * Rk[(size_t)k * pitch + fr];
+                    lcg = lcg * 1664525u + 1013904223u;
+                    const double noise = ((double)(lcg >> 8) / 8388608.0 - 1.0) * 2e-6 *
+                                         std::sqrt(rr * (double)ee[(size_t)s * size + c]);
+                    Y[((size_t)(fr / RVQ_TC_TILE) * size + c) * RVQ_TC_TILE + fr % RVQ_TC_TILE] = (float)(dot + noise);
+                }
+            }
+            emu_launch((unsigned)((frames + 31) / 32), 1, 256, [&] {
+                rvq_tc_select_kernel(Y.data(), Rk.data(), Qk.data(), cbs, ee.data() + (size_t)s * size, size, pitch, frames,
+                                     s == 0, idx_c.data() + (size_t)s * frames, ee_max, drop_xx, &rescored);
+            });
+        }
+        for (long long fr = 0; fr < frames; ++fr)   // kmajor_to_rows_kernel
+            for (int k = 0; k < RVQ_DIM; ++k) q_c[(size_t)fr * RVQ_DIM + k] = Qk[(size_t)k * pitch + fr];
+        std::fprintf(stderr, "tensor-core variant: %u of %lld decisions re-scored\n", rescored, (long long)n * frames);
+    }
     f = std::fopen(argv[6], "wb");
     std::fwrite(idx_a.data(), 8, idx_a.size(), f);
     std::fwrite(idx_b.data(), 8, idx_b.size(), f);
+    std::fwrite(idx_c.data(), 8, idx_c.size(), f);
     std::fwrite(q_a.data(), 4, q_a.size(), f);
     std::fwrite(q_b.data(), 4, q_b.size(), f);
+    std::fwrite(q_c.data(), 4, q_c.size(), f);
     std::fclose(f);
     return 0;
 }

@@ -213,32 +213,6 @@ def test_dws_block(B, Cc, T, skip, pre):
     assert (co.cpu().double() - xin[:, :, -4:]).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("B,M,K,T,pre,bias,res", [(2, 64, 64, 1024, 0, False, False), (2, 96, 96, 2000, 1, True, True),
-                                                  (1, 192, 192, 900, 2, False, False), (2, 128, 1024, 76, 0, True, False)])
-def test_pointwise_time_major_kernel_matches_channel_major(B, M, K, T, pre, bias, res):
-    """The experimental time-major tensor-core kernel (activations through TMEM, TS-mode MMA) does the same
-    3xTF32 arithmetic as the default kernel (only the issue order of the two cross terms differs)."""
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + K)
-    x = torch.randn(B, K, T, generator=g).cuda()
-    w = (torch.randn(M, K, 1, generator=g) / K ** 0.5).contiguous()
-    b = torch.randn(M, generator=g).cuda() if bias else None
-    r = torch.randn(B, M, T, generator=g).cuda() if res else None
-    outs = []
-    prev = lib.hil_set_tensor_cores(1)
-    try:
-        for mode in (1, 9):
-            lib.hil_set_tensor_cores(mode)
-            y = torch.empty(B, M, T, device="cuda")
-            _lib.check(lib.hil_op_pointwise(_ptr(x), _ptr(w), _ptr(b), _ptr(r), _ptr(y), B, M, K, T, pre, 0.8660254,
-                                            _stream()))
-            torch.cuda.synchronize()
-            outs.append(y.cpu())
-    finally:
-        lib.hil_set_tensor_cores(prev)
-    assert (outs[0] - outs[1]).abs().max().item() < 1e-5 * max(1.0, outs[0].abs().max().item())
-
-
 def _resblock_ref(x, w0, w1, d0w, d0b, d1w, d1b, c0, c1, pre, pre_scale):
     """ResBlock.forward streaming.py:252-275 (merged scaling) in fp64, with both depthwise caches."""
     C = x.shape[1]
@@ -373,6 +347,45 @@ def test_downsample_fused(B, K, M, T, r, pre):
         assert (co.double() - xin[:, :, -r:]).abs().max().item() < 1e-5
     assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0] - outs[1][0]).abs().max()
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("size,B,F,n,train", [(1024, 4, 600, 12, False), (1024, 32, 75, 8, True), (256, 1, 2048, 3, False),
+                                               (1024, 2, 17000, 2, False)])
+def test_rvq_tensor_core_search_bit_identical(size, B, F, n, train):
+    """Batches (>= 2048 frames) run the search as one fp32-accurate tensor-core GEMM per stage plus a decision kernel
+    that re-scores near ties with the FFMA expression (rvq.cu rvq_tc_select_kernel): indices and dequantised sums
+    must equal the one-kernel FFMA search bit for bit -- exact ties, realistic latents drawn near codebook rows (small
+    margins in the later stages), and more than one 32 768-frame chunk."""
+    from hilcodec_b200 import streaming as S, weights as W, _lib
+    lib = _lib.load()
+    cfg = W.CodecConfig(num_quantizers=n, codebook_size=size)
+    g = torch.Generator().manual_seed(size + F)
+    cbs = {f"quantizer.layers.{i}.embed": (torch.randn(size, 128, generator=g) * 0.6 ** i).numpy() for i in range(n)}
+    cbs["quantizer.layers.0.embed"][7] = cbs["quantizer.layers.0.embed"][3]
+    cbs["quantizer.layers.0.embed"][130] = cbs["quantizer.layers.0.embed"][3]
+    core = S._NativeCodec(cfg, _lib.HIL_GRAPH_TRAIN if train else _lib.HIL_GRAPH_DEPLOY)
+    core.set_weights(cbs)
+    z = torch.nn.functional.normalize(torch.randn(B, F, 128, generator=g), dim=2) * 128 ** 0.5
+    # a quarter of the frames are sums of codebook rows plus a little noise: the later stages see residuals that are tiny
+    # against the codebook scale, where margins are smallest
+    pick = torch.randint(0, size, (n, B, F // 4), generator=g)
+    acc = sum(torch.from_numpy(cbs[f"quantizer.layers.{i}.embed"])[pick[i]] for i in range(n))
+    z[:, : F // 4] = acc + 1e-3 * torch.randn(B, F // 4, 128, generator=g)
+    z[0, 0] = torch.from_numpy(cbs["quantizer.layers.0.embed"][3])   # an exact three-way tie: the first index wins
+    z = z.cuda()
+    prev = lib.hil_set_tensor_cores(1 | 16)
+    try:
+        idx_tc, q_tc = core.rvq_encode(z, n, with_sum=True)
+        only_idx = core.rvq_encode(z, n)
+        lib.hil_set_tensor_cores(1 | 16 | 256)
+        idx_ff, q_ff = core.rvq_encode(z, n, with_sum=True)
+        torch.cuda.synchronize()
+    finally:
+        lib.hil_set_tensor_cores(prev)
+    assert torch.equal(idx_tc, idx_ff)
+    assert torch.equal(only_idx, idx_ff)
+    assert torch.equal(q_tc, q_ff)
+    assert idx_tc[0, 0, 0].item() == 3
 
 
 @pytest.mark.parametrize("size,frames,n,train", [(1024, 1, 12, False), (1024, 64, 12, False), (1024, 75, 8, True),

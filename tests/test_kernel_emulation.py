@@ -195,7 +195,9 @@ def rvq_exe(tmp_path_factory):
     mono = _function(src, src.index("template <int FPW>\n__global__ void __launch_bounds__(288, 2)\nrvq_encode_kernel("))
     stage = _function(src, src.index("__global__ void __launch_bounds__(256, 2)\nrvq_stage_kernel("))
     warps = _function(src, src.index("int rvq_v2_warps("))
-    text = consts + mono + "\nstruct RvqCand { float d; int i; };\n" + stage + "\n" + warps
+    select = "constexpr int RVQ_TC_TILE = 128;\n" + _function(
+        src, src.index("__global__ void __launch_bounds__(256)\nrvq_tc_select_kernel("))
+    text = consts + mono + "\nstruct RvqCand { float d; int i; };\n" + stage + "\n" + warps + "\n" + select
     assert text.count("extern __shared__ __align__(16) float smem[];") == 2
     text = text.replace("extern __shared__ __align__(16) float smem[];", "float* smem = g_dyn_smem;")
     return _build(str(tmp_path_factory.mktemp("emu_rvq")), "rvq", "rvq_extracted.inc", text, "harness_rvq.cpp")
@@ -204,8 +206,8 @@ def rvq_exe(tmp_path_factory):
 @pytest.mark.parametrize("size,frames,n,drop_xx,slots", [(1024, 5, 3, 0, 296), (256, 40, 4, 1, 2), (200, 33, 2, 0, 1),
                                                           (128, 100, 2, 0, 1)])
 def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx, slots):
-    """The one-kernel search (1, 3, 5 and 8 warps per CTA in these cases) against the oracle; the per-stage variant
-    bit-identical to it."""
+    """The one-kernel search (1, 3, 5 and 8 warps per CTA in these cases) against the oracle; the per-stage variant and
+    the tensor-core variant's decision kernel bit-identical to it."""
     from oracle import hilcodec_oracle as O
 
     g = torch.Generator().manual_seed(size + frames)
@@ -224,8 +226,12 @@ def test_rvq_kernels_source_on_cpu(rvq_exe, tmp_path, size, frames, n, drop_xx, 
     ni = n * frames * 8
     idx_a = raw[:ni].view(np.int64).reshape(n, frames)
     idx_b = raw[ni:2 * ni].view(np.int64).reshape(n, frames)
-    q = raw[2 * ni:].view(np.float32).reshape(2, frames, 128)
+    idx_c = raw[2 * ni:3 * ni].view(np.int64).reshape(n, frames)
+    q = raw[3 * ni:].view(np.float32).reshape(3, frames, 128)
     assert np.array_equal(idx_a, idx_b) and np.array_equal(q[0], q[1])  # split == one-kernel, bit for bit
+    # the batch variant's decision kernel on perturbed dot products (stand-in for the tensor-core GEMM): also bit for bit
+    assert np.array_equal(idx_a, idx_c) and np.array_equal(q[0], q[2])
+    assert "re-scored" in r.stderr and int(r.stderr.split("tensor-core variant: ")[1].split()[0]) >= 1
     assert not (idx_a[0] == 7).any() and not (idx_a[0] == 130).any()
     assert idx_a[0, 0] == 3  # frame 0 IS code 3 of stage 0 (set below): its two exact copies must lose
     p = {f"quantizer.layers.{i}.embed": c for i, c in enumerate(cbs)}
