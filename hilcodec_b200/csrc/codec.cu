@@ -1287,7 +1287,7 @@ constexpr long long RVQ_TC_MIN_FRAMES = 2048, RVQ_TC_CHUNK = 32768;
 
 static bool rvq_tc_usable(const hil_model* m, long long frames, cudaStream_t st) {
     if (!g_rvq_tc || !tc_on() || !g_use_h || frames < RVQ_TC_MIN_FRAMES || m->cb_mat.empty()) return false;
-    if (m->cfg.dim != 128 || m->cfg.codebook_size % 128 != 0 || !m->cb_mat[0].H_hi) return false;
+    if (m->cfg.dim != 128 || m->cfg.codebook_size % 128 != 0 || m->cfg.codebook_size > 2048 || !m->cb_mat[0].H_hi) return false;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
     return true;

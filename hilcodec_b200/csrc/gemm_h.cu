@@ -28,7 +28,9 @@
 // Per k-block two k16 steps of { A_hi x [B_hi | B_lo] (N = 256) -> [big | small]; A_lo x B_hi (N = 128) ->
 // small }.  Epilogues are the ones of gemm_tc.cu (TMEM -> registers -> swizzled staging -> TMA store /
 // reduce-add; optional fused causal depthwise k5).
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include <cuda_fp16.h>
 
@@ -77,6 +79,18 @@ struct Params {
     const float* bias;
     int reduce_add;         // 1: Y += tile (TMA reduce), 0: Y = tile
     int xform_sleep;        // ns of back-off in the transform warps' barrier polls (0 = spin)
+    // resident weights (K <= 192): the CTA's weight rows (all k-blocks, hi + lo) are loaded ONCE and stay in shared
+    // memory for every tile it computes -- the grid is a multiple of num_m, so a CTA never changes its row block.  The
+    // kernel is otherwise bound by the L2 -> SM operand stream (16 KB of weights + 16 KB of activations per k-block);
+    // this halves it.  The operand ring then has `nop` = 2 stages (one per transform group) and the tiles live in their
+    // A halves (k-blocks 0, 1), in the third operand stage (k-blocks 2, 3) and in the top two raw stages (k-blocks 4,
+    // 5), which leaves `nraw` = 4 raw stages.  Both ring depths stay multiples of the number of transform groups: a
+    // stage shared by two groups is ambiguous under mbarrier parity waits (TMA loads complete out of order).
+    int a_res, nraw, nop;
+    // HILCODEC_TRACE=1 (tools/gpu/trace_gemm.py): per-CTA cycle counters of where each warp role waits, 16 per CTA:
+    // 0 MMA<-tempty 1 MMA<-a_full 2 MMA<-b_ready 3 MMA total | 4 xform<-raw_full 5 xform<-op_empty 6 xform total |
+    // 7 epi<-tfull 8 epi total 9 epi<-store drain | 10 Xprod<-raw_empty 11 Xprod total | 12 Aprod<-op_empty | 13 tiles
+    unsigned long long* trace;
     int post_elu;           // fused DWS only: store ELU(y) (the consumer then needs no activation prologue)
     int t_step, t_halo;     // tile tt covers columns [tt * t_step - t_halo, ... + BN)
     const float* dw_w;      // [M][5]
@@ -239,6 +253,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + BK - 1) / BK;
+    const int nraw = p.nraw, nop = p.nop;
+    auto a_res_addr = [&](int kb) {   // resident weight tile of k-block kb (hi, then lo at + A_TILE)
+        return kb < 2 ? op_base + kb * OP_BYTES
+             : kb < 4 ? op_base + 2 * OP_BYTES + (kb - 2) * 2 * A_TILE
+                      : raw_base + (RAW_STAGES - 1 - (kb - 4)) * RAW_BYTES;
+    };
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi);
         prefetch_tmap(&map_a_lo);
@@ -276,12 +296,16 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         if (lane == 0) {
             int r = 0;
             uint32_t ph = 0;
+            long long tr_w = 0;
+            const long long tr_s = p.trace ? clock64() : 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const long long rest = tile / p.num_m;
                 const int tt = (int)(rest % p.tiles_t);
                 const int b = (int)(rest / p.tiles_t);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    const long long tr0 = p.trace ? clock64() : 0;
                     mbar_wait<32>(raw_empty(r), ph ^ 1);
+                    if (p.trace) tr_w += clock64() - tr0;
                     if constexpr (kUp > 0) {   // low-rate box: the inputs of the tile's columns and the one before
                         constexpr uint32_t XB = BK * up_ni(kUp) * 4, WB = BK * 2 * kUp * 4;   // activation box, tap slice
                         mbar_arrive_expect_tx(raw_full(r), XB + WB);
@@ -291,19 +315,29 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                         mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
                         tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
                     }
-                    if (++r == RAW_STAGES) { r = 0; ph ^= 1; }
+                    if (++r == nraw) { r = 0; ph ^= 1; }
                 }
             }
+            if (p.trace) { p.trace[blockIdx.x * 16 + 10] = tr_w; p.trace[blockIdx.x * 16 + 11] = clock64() - tr_s; }
         }
     } else if (warp == 3) {
         // ===================================================================== A producer (op ring)
-        if (lane == 0) {
+        if (lane == 0 && p.a_res) {
+            const int m_blk = (int)(blockIdx.x % p.num_m);   // == tile % num_m for every tile of this CTA
+            mbar_arrive_expect_tx(a_full(0), (uint32_t)nkb * 2 * A_TILE);
+            for (int kb = 0; kb < nkb; ++kb) {
+                tma_load_2d(&map_a_hi, a_res_addr(kb), a_full(0), kb * BK, m_blk * BM);
+                tma_load_2d(&map_a_lo, a_res_addr(kb) + A_TILE, a_full(0), kb * BK, m_blk * BM);
+            }
+        } else if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int m_blk = (int)(tile % p.num_m);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    const long long tr0 = p.trace ? clock64() : 0;
                     mbar_wait<32>(op_empty(s), ph ^ 1);
+                    if (p.trace) p.trace[blockIdx.x * 16 + 12] += clock64() - tr0;
                     const uint32_t st = op_base + s * OP_BYTES;
                     mbar_arrive_expect_tx(a_full(s), 2 * A_TILE);
                     tma_load_2d(&map_a_hi, st, a_full(s), kb * BK, m_blk * BM);
@@ -317,17 +351,26 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         int s = 0;
         uint32_t ph = 0;
         long long it = 0;
+        long long tr_e = 0, tr_a = 0, tr_b = 0;
+        const long long tr_s = p.trace ? clock64() : 0;
+        if (p.a_res) mbar_wait(a_full(0), 0);
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int acc = (int)(it & 1);
             const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+            long long tr0 = p.trace ? clock64() : 0;
             mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+            if (p.trace) tr_e += clock64() - tr0;
             tc_fence_after();
             const uint32_t d_big = tmem_base + acc * 2 * BN;
             const uint32_t d_small = d_big + BN;
             for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t st = op_base + s * OP_BYTES;
-                mbar_wait(a_full(s), ph);
+                const uint32_t sa = p.a_res ? a_res_addr(kb) : st;
+                tr0 = p.trace ? clock64() : 0;
+                if (!p.a_res) mbar_wait(a_full(s), ph);
+                if (p.trace) { const long long t1 = clock64(); tr_a += t1 - tr0; tr0 = t1; }
                 mbar_wait(b_ready(s), ph);
+                if (p.trace) tr_b += clock64() - tr0;
                 tc_fence_after();
                 if (lane == 0) {
 #pragma unroll
@@ -336,8 +379,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                         //   64-byte swizzle row.
                         // B (MN-major, SWIZZLE_128B): 64-column panels B_PANEL apart (LBO) -- B_hi p0, p1, B_lo p0,
                         //   p1 back to back -- 8-k-row atoms 1024 B apart (SBO); one k16 step = 2 atoms = 2 KB.
-                        const uint64_t a_hi = make_desc(st + j * 32, 16, 512, 4);
-                        const uint64_t a_lo = make_desc(st + A_TILE + j * 32, 16, 512, 4);
+                        const uint64_t a_hi = make_desc(sa + j * 32, 16, 512, 4);
+                        const uint64_t a_lo = make_desc(sa + A_TILE + j * 32, 16, 512, 4);
                         const uint64_t b_hl = make_desc(st + 2 * A_TILE + j * 2048, B_PANEL, 1024, 2);
                         umma_f16(d_big, a_hi, b_hl, IDESC_N256, (kb | j) != 0);
                         umma_f16(d_small, a_lo, b_hl, IDESC_N128, 1);
@@ -346,8 +389,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     if (kb == nkb - 1) umma_commit(tfull_bar(acc));
                 }
                 __syncwarp();
-                if (++s == OP_STAGES) { s = 0; ph ^= 1; }
+                if (++s == nop) { s = 0; ph ^= 1; }
             }
+        }
+        if (p.trace && lane == 0) {
+            unsigned long long* tr = p.trace + blockIdx.x * 16;
+            tr[0] = tr_e; tr[1] = tr_a; tr[2] = tr_b; tr[3] = clock64() - tr_s; tr[13] = it;
         }
     } else if (warp >= XW0) {
         // ===================================================================== transform: raw fp32 -> B_hi / B_lo fp16
@@ -361,6 +408,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const uint32_t chunk = (uint32_t)((lane >> 1) & 7);  // 16-byte chunk (8 columns) inside the 128-byte row
         const uint32_t half8 = (uint32_t)(lane & 1) * 8u;
         uint32_t n = 0;                                    // k-blocks seen by this CTA (all tiles)
+        long long tr_r = 0, tr_o = 0;
+        const long long tr_s = p.trace ? clock64() : 0;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             [[maybe_unused]] const int m_blk = (int)(tile % p.num_m);
             [[maybe_unused]] const long long rest = tile / p.num_m;
@@ -368,10 +417,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             [[maybe_unused]] const int b = (int)(rest / p.tiles_t);
             for (int kb = 0; kb < nkb; ++kb, ++n) {
                 if ((int)(n % XG) != xg) continue;
-                const int r = (int)(n % RAW_STAGES), s = (int)(n % OP_STAGES);
-                const uint32_t rph = (n / RAW_STAGES) & 1u, sph = (n / OP_STAGES) & 1u;
+                const int r = (int)(n % (uint32_t)nraw), s = (int)(n % (uint32_t)nop);
+                const uint32_t rph = (n / (uint32_t)nraw) & 1u, sph = (n / (uint32_t)nop) & 1u;
+                long long tr0 = p.trace ? clock64() : 0;
                 mbar_wait_ns(raw_full(r), rph, p.xform_sleep);
+                if (p.trace) { const long long t1 = clock64(); tr_r += t1 - tr0; tr0 = t1; }
                 mbar_wait_ns(op_empty(s), sph ^ 1, p.xform_sleep);
+                if (p.trace) tr_o += clock64() - tr0;
                 const uint32_t bhi = op_base + s * OP_BYTES + 2 * A_TILE + panel * B_PANEL;
                 if constexpr (kUp > 0) {
                     const float* raw = reinterpret_cast<const float*>(gen_base + (raw_base - base) + r * RAW_BYTES);
@@ -414,6 +466,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 }
             }
         }
+        if (p.trace && xw == 0 && lane == 0) {
+            unsigned long long* tr = p.trace + blockIdx.x * 16;
+            tr[4] = tr_r; tr[5] = tr_o; tr[6] = clock64() - tr_s;
+        }
     } else if (warp >= 4 && warp < 8) {
         // ===================================================================== epilogue
         const int q = warp & 3;                             // TMEM lane quarter of this warp
@@ -426,6 +482,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE), cb2 = pk2(c_big, c_big);
         long long it = 0;
         uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
+        long long tr_f = 0, tr_d = 0;
+        const long long tr_s = p.trace ? clock64() : 0;
         if constexpr (kDs > 0) {
             // ---- fused strided depthwise epilogue: y[n] = b + sum_{k < 2r} w[k] * pw[(n - 1) r + k], pw[-r .. -1] = cache.
             // A thread owns one channel row and walks the tile's columns once; input column j feeds output j / r with
@@ -555,7 +613,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const int b = (int)(rest / p.tiles_t);
                 const int acc = (int)(it & 1);
                 const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+                const long long tr0 = p.trace ? clock64() : 0;
                 mbar_wait<64>(tfull_bar(acc), acc_ph);
+                if (p.trace) tr_f += clock64() - tr0;
                 tc_fence_after();
                 const int m = m_blk * BM + row;
                 const float bv = (m < p.M && p.bias) ? p.bias[m] : 0.f;
@@ -566,8 +626,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c, ++g) {
                     const uint32_t obuf = my_out + (g % NOUT) * OUT_BYTES;
+                    const long long tr1 = p.trace ? clock64() : 0;
                     if (issuer) tma_wait_read<NOUT - 1>();          // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
+                    if (p.trace) tr_d += clock64() - tr1;
                     uint32_t rb[32], rs[32];
                     tmem_ld32(t_big + c * 32, rb);
                     tmem_ld32(t_big + BN + c * 32, rs);
@@ -627,7 +689,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     const float4 cv = *reinterpret_cast<const float4*>(p.cache_in + ((size_t)b * p.M + m) * 4);
                     carry[0] = cv.x * c_inv; carry[1] = cv.y * c_inv; carry[2] = cv.z * c_inv; carry[3] = cv.w * c_inv;
                 }
+                const long long tr0 = p.trace ? clock64() : 0;
                 mbar_wait<64>(tfull_bar(acc), acc_ph);
+                if (p.trace) tr_f += clock64() - tr0;
                 tc_fence_after();
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
 #pragma unroll 1
@@ -658,8 +722,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                                 p.cache_out[((size_t)b * p.M + m) * 4 + (t - (p.T - 4))] = v[4 + j] * c_big;
                         }
                     }
+                    const long long tr1 = p.trace ? clock64() : 0;
                     if (issuer) tma_wait_read<NOUT - 1>();   // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
+                    if (p.trace) tr_d += clock64() - tr1;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float o[4];
@@ -696,6 +762,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 }
             }
             if (issuer) tma_wait_all();
+        }
+        if (p.trace && issuer) {
+            unsigned long long* tr = p.trace + blockIdx.x * 16;
+            tr[7] = tr_f; tr[8] = clock64() - tr_s; tr[9] = tr_d;
         }
     }
 
@@ -755,6 +825,52 @@ static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs,
     return cudaSuccess;
 }
 
+// weight residency (Params::a_res): on unless HILCODEC_A_RESIDENT=0, for K <= 192 and a grid that is a multiple of num_m
+static unsigned long long* g_trace_buf = nullptr;
+static bool trace_on() {
+    static const bool on = []() { const char* e = std::getenv("HILCODEC_TRACE"); return e && e[0] == '1'; }();
+    return on;
+}
+// HILCODEC_TRACE=1: synchronise after the launch and print the per-role wait cycles averaged over the CTAs
+static void trace_report(const th::Params& p, unsigned grid, const char* what, cudaStream_t st) {
+    if (!trace_on() || !g_trace_buf) return;
+    cudaStreamSynchronize(st);
+    std::vector<unsigned long long> h((size_t)grid * 16);
+    cudaMemcpy(h.data(), g_trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
+    double a[16] = {0};
+    for (unsigned c = 0; c < grid; ++c)
+        for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)c * 16 + i] / grid;
+    const double kbs = a[13] * ((p.K + th::BK - 1) / th::BK);
+    std::fprintf(stderr,
+                 "[trace] %s M=%d K=%d T=%d B=%d a_res=%d tiles/CTA=%.1f | per k-block: total %.0f | MMA waits: tempty %.0f a_full %.0f "
+                 "b_ready %.0f | xform: raw_full %.0f op_empty %.0f of %.0f | epi: tfull %.0f drain %.0f of %.0f | Xprod: raw_empty %.0f of "
+                 "%.0f | Aprod: op_empty %.0f\n",
+                 what, p.M, p.K, p.T, p.B, p.a_res, a[13], a[3] / kbs, a[0] / kbs, a[1] / kbs, a[2] / kbs, 2 * a[4] / kbs, 2 * a[5] / kbs,
+                 2 * a[6] / kbs, a[7] / kbs, a[9] / kbs, a[8] / kbs, a[10] / kbs, a[11] / kbs, a[12] / kbs);
+}
+
+static unsigned plan_grid(th::Params& p, int num_sms) {
+    using namespace th;
+    if (trace_on()) {
+        if (!g_trace_buf) cudaMalloc(&g_trace_buf, 1024 * 16 * sizeof(unsigned long long));
+        cudaMemset(g_trace_buf, 0, 1024 * 16 * sizeof(unsigned long long));
+        p.trace = g_trace_buf;
+    }
+    static const bool on = []() { const char* e = std::getenv("HILCODEC_A_RESIDENT"); return !(e && e[0] == '0'); }();
+    const int nkb = (p.K + BK - 1) / BK;
+    unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    p.a_res = 0;
+    p.nraw = RAW_STAGES;
+    p.nop = OP_STAGES;
+    if (on && RAW_STAGES == 6 && OP_STAGES == 3 && XG == 2 && nkb <= 6 && grid >= (unsigned)p.num_m) {
+        grid = grid / p.num_m * p.num_m;
+        p.a_res = 1;
+        p.nraw = nkb > 4 ? 4 : 6;
+        p.nop = 2;
+    }
+    return grid;
+}
+
 static cudaError_t seed_residual(const float* R, float* Y, long long y_bs, int y_rs, int B, int M, int T, cudaStream_t st) {
     for (int b = 0; b < B; ++b) {   // out-of-place residual: seed Y with R, then accumulate in place
         cudaError_t e = cudaMemcpy2DAsync(Y + (long long)b * y_bs, (size_t)y_rs * 4, R + (long long)b * y_bs, (size_t)y_rs * 4,
@@ -792,8 +908,9 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
-    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    const unsigned grid = plan_grid(p, num_sms);
     gemm_h_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    trace_report(p, grid, "pointwise", st);
     return cudaGetLastError();
 }
 
@@ -855,8 +972,9 @@ static cudaError_t launch_up(const PackedMat& W, const float* x, long long x_bs,
     p.elu_poly = 0;
     p.t_in = T_in; p.up_w = up_w; p.up_ci = ci; p.up_co = co;
     const int num_sms = tc::device_sm_count();
-    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    const unsigned grid = plan_grid(p, num_sms);
     gemm_h_kernel<false, S><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y, p);
+    trace_report(p, grid, "upsample", st);
     return cudaGetLastError();
 }
 
@@ -918,7 +1036,7 @@ static cudaError_t launch_down(const PackedMat& W, const float* X, long long x_b
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
-    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    const unsigned grid = plan_grid(p, num_sms);
     gemm_h_kernel<false, 0, R><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y2, p);
     return cudaGetLastError();
 }
@@ -970,8 +1088,9 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
     p.xform_sleep = tc::xform_sleep_env();
     p.elu_poly = elu_poly_env();
-    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    const unsigned grid = plan_grid(p, num_sms);
     gemm_h_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, map_x, map_y, map_y28, p);
+    trace_report(p, grid, "dws", st);
     return cudaGetLastError();
 }
 

@@ -227,8 +227,9 @@ cudaError_t launch_rvq_encode(const float* z, const float* codebooks, const floa
 // bit-identical to the one-kernel search (tests/test_gpu_ops.py, test_kernel_emulation.py).  The residual update and
 // the running dequantised sum are the same fp32 subtract / add per element, in stage order, on the k-major copies.
 constexpr int RVQ_TC_TILE = 128;   // frames per Y block = the GEMM's column tile
+constexpr int RVQ_TC_CPW = 256;    // codes per warp of the decision kernel: codebooks of <= 2048 codes
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 rvq_tc_select_kernel(const float* __restrict__ Y, float* __restrict__ Rk, float* __restrict__ Qk,
                      const float* __restrict__ cb, const float* __restrict__ ees, int size, long long pitch,
                      long long frames, int first, int64_t* __restrict__ idx, float ee_max, int drop_xx,
@@ -236,6 +237,7 @@ rvq_tc_select_kernel(const float* __restrict__ Y, float* __restrict__ Rk, float*
     // CTA = 32 frames (lane = frame, so every row access is one 128-byte line) x 8 warps; warp w owns residual dims
     // 16w .. 16w+15 and scans codes [w * size/8, (w+1) * size/8)
     __shared__ float sm_p[32][33];
+    __shared__ float sm_ee[8][RVQ_TC_CPW];
     __shared__ float sm_xx[32], sm_lim[32];
     __shared__ float sm_v1[8][32], sm_v2[8][32];
     __shared__ int sm_i1[8][32];
@@ -276,22 +278,20 @@ rvq_tc_select_kernel(const float* __restrict__ Y, float* __restrict__ Rk, float*
     }
 
     {   // best and second-best of v[c] = 2 Y[c][f] - ee[c] over this warp's codes (ascending: the first maximum wins);
-        // 16 independent loads are issued before their compare chain
+        // 8 independent loads are issued before their compare chain; the warp's |e|^2 values sit in shared memory
         const int cpw = (size + 7) / 8;
         const int c_lo = w * cpw, c_hi = min(size, c_lo + cpw);
+        for (int i = lane; i < c_hi - c_lo; i += 32) sm_ee[w][i] = __ldg(ees + c_lo + i);
+        __syncwarp();
         float v1 = -INFINITY, v2 = -INFINITY;
         int i1 = 0x7fffffff;
-        for (int c = c_lo; c < c_hi; c += 16) {
-            float yv[16], ev[16];
+        for (int c = c_lo; c < c_hi; c += 8) {
+            float yv[8];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int cc = min(c + u, c_hi - 1);
-                yv[u] = y[(long long)cc * RVQ_TC_TILE];
-                ev[u] = __ldg(ees + cc);
-            }
+            for (int u = 0; u < 8; ++u) yv[u] = y[(long long)min(c + u, c_hi - 1) * RVQ_TC_TILE];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const float v = fmaf(2.f, yv[u], -ev[u]);
+            for (int u = 0; u < 8; ++u) {
+                const float v = fmaf(2.f, yv[u], -sm_ee[w][min(c + u - c_lo, RVQ_TC_CPW - 1)]);
                 if (c + u < c_hi) {
                     if (v > v1) { v2 = v1; v1 = v; i1 = c + u; }
                     else if (v > v2) v2 = v;

@@ -195,8 +195,8 @@ def rvq_exe(tmp_path_factory):
     mono = _function(src, src.index("template <int FPW>\n__global__ void __launch_bounds__(288, 2)\nrvq_encode_kernel("))
     stage = _function(src, src.index("__global__ void __launch_bounds__(256, 2)\nrvq_stage_kernel("))
     warps = _function(src, src.index("int rvq_v2_warps("))
-    select = "constexpr int RVQ_TC_TILE = 128;\n" + _function(
-        src, src.index("__global__ void __launch_bounds__(256)\nrvq_tc_select_kernel("))
+    select = "constexpr int RVQ_TC_TILE = 128;\nconstexpr int RVQ_TC_CPW = 256;\n" + _function(
+        src, src.index("__global__ void __launch_bounds__(256, 5)\nrvq_tc_select_kernel("))
     text = consts + mono + "\nstruct RvqCand { float d; int i; };\n" + stage + "\n" + warps + "\n" + select
     assert text.count("extern __shared__ __align__(16) float smem[];") == 2
     text = text.replace("extern __shared__ __align__(16) float smem[];", "float* smem = g_dyn_smem;")
