@@ -42,31 +42,29 @@ namespace th {
 using namespace tc;
 
 constexpr int BM = 128, BN = 128, BK = 32;
-#ifndef HIL_XFORM_GROUPS
-#define HIL_XFORM_GROUPS 2
-#endif
-constexpr int XG = HIL_XFORM_GROUPS;              // k-blocks the transform warps convert concurrently
-// A transform group waits for "the previous use of my operand stage has been consumed" by mbarrier parity, which is
-// only unambiguous while a group cannot run two uses ahead: either XG <= 2 (its own waits on the stages in between
-// imply it) or one operand stage per group (XG == OP_STAGES).  XG = 4 therefore takes 4 + 4 stages instead of 6 + 3.
-#ifndef HIL_OUT_BUFS
-#define HIL_OUT_BUFS 2
-#endif
-constexpr int OUT_BUFS = HIL_OUT_BUFS;            // epilogue staging buffers; 4 trades two raw stages for them
-constexpr int RAW_STAGES = (XG == 4 || OUT_BUFS == 4) ? 4 : 6;
-constexpr int OP_STAGES = XG == 4 ? 4 : 3;
-static_assert(XG == 1 || XG == 2 || XG == OP_STAGES, "see the parity note above");
+constexpr int XG = 2;                             // k-blocks the transform warps convert concurrently (two groups of 4 warps)
+constexpr int OUT_BUFS = 2;                       // epilogue staging buffers
+// Three rings of 16 KB stages.  Every depth is a multiple of XG: a stage is then always filled for, and released by,
+// the same transform group -- the groups wait by mbarrier parity, which is ambiguous for a stage shared by two groups
+// (TMA loads complete out of order).  Stage s of the weight ring and stage s of the operand ring are filled for the same
+// k-block and released together.
+constexpr int RAW_STAGES = 4;                     // fp32 activation boxes from TMA
+constexpr int A_STAGES = 4;                       // weight tiles A_hi | A_lo
+constexpr int OP_STAGES = 4;                      // converted activations B_hi | B_lo
+static_assert(A_STAGES == OP_STAGES, "stage s of both rings is one unit: one ready barrier, one release");
 constexpr int RAW_BYTES = BK * BN * 4;            // 16 KB fp32 activation box
 constexpr int A_TILE = BM * BK * 2;               // 8 KB
 constexpr int B_TILE = BK * BN * 2;               // 8 KB
-constexpr int OP_BYTES = 2 * A_TILE + 2 * B_TILE; // 32 KB: A_hi, A_lo, B_hi, B_lo
+constexpr int A_STAGE = 2 * A_TILE;               // 16 KB: A_hi | A_lo
+constexpr int OP_BYTES = 2 * B_TILE;              // 16 KB: B_hi panels | B_lo panels
 constexpr int B_PANEL = 8 * 128 * (BK / 8);       // 4 KB: 64 columns x 32 k (4 swizzle atoms of 8 k-rows x 128 B)
 constexpr int NUM_THREADS = 512;
 constexpr int NUM_XFORM_WARPS = 8;
 constexpr int NUM_EPI = 128;
 constexpr int OUT_BYTES = BM * 32 * 4;            // 16 KB: one 128-row x 32-column output chunk
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)6 * RAW_BYTES + (size_t)3 * OP_BYTES + 2 * OUT_BYTES + 256;   // 224 KB + slack in every configuration
+constexpr size_t SMEM_BYTES = 1024 + (size_t)RAW_STAGES * RAW_BYTES + (size_t)A_STAGES * A_STAGE + (size_t)OP_STAGES * OP_BYTES +
+                              OUT_BUFS * OUT_BYTES + 256;   // 224 KB + slack
 
 struct Params {
     int M, K, T, B;
@@ -82,14 +80,14 @@ struct Params {
     // resident weights (K <= 192): the CTA's weight rows (all k-blocks, hi + lo) are loaded ONCE and stay in shared
     // memory for every tile it computes -- the grid is a multiple of num_m, so a CTA never changes its row block.  The
     // kernel is otherwise bound by the L2 -> SM operand stream (16 KB of weights + 16 KB of activations per k-block);
-    // this halves it.  The operand ring then has `nop` = 2 stages (one per transform group) and the tiles live in their
-    // A halves (k-blocks 0, 1), in the third operand stage (k-blocks 2, 3) and in the top two raw stages (k-blocks 4,
-    // 5), which leaves `nraw` = 4 raw stages.  Both ring depths stay multiples of the number of transform groups: a
-    // stage shared by two groups is ambiguous under mbarrier parity waits (TMA loads complete out of order).
+    // this halves it.  The tiles live in the four stages of the weight ring (k-blocks 0 .. 3) and, for K > 128, in the
+    // top two stages of the operand ring (k-blocks 4, 5), which then has `nop` = 2 stages, one per transform group.
     int a_res, nraw, nop;
-    // HILCODEC_TRACE=1 (tools/gpu/trace_gemm.py): per-CTA cycle counters of where each warp role waits, 16 per CTA:
+    int probe;              // MMA issuer probes the next stage's barrier early (HILCODEC_MMA_PROBE=0: A/B off)
+    // HILCODEC_TRACE=1 (tools/gpu/trace_gemm.py): per-CTA cycle counters of where each warp role waits, 24 per CTA:
     // 0 MMA<-tempty 1 MMA<-a_full 2 MMA<-b_ready 3 MMA total | 4 xform<-raw_full 5 xform<-op_empty 6 xform total |
-    // 7 epi<-tfull 8 epi total 9 epi<-store drain | 10 Xprod<-raw_empty 11 Xprod total | 12 Aprod<-op_empty | 13 tiles
+    // 7 epi<-tfull 8 epi total 9 epi<-store drain | 10 Xprod<-raw_empty 11 Xprod total | 12 Aprod<-a_empty | 13 tiles |
+    // 14 epi tcgen05.ld + wait 15 epi depthwise taps + staging stores (fused DWS epilogue only) | 16 MMA issue 17 commits
     unsigned long long* trace;
     int post_elu;           // fused DWS only: store ELU(y) (the consumer then needs no activation prologue)
     int t_step, t_halo;     // tile tt covers columns [tt * t_step - t_halo, ... + BN)
@@ -238,26 +236,30 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t raw_base = base;
-    const uint32_t op_base = raw_base + RAW_STAGES * RAW_BYTES;
+    const uint32_t a_base = raw_base + RAW_STAGES * RAW_BYTES;
+    const uint32_t op_base = a_base + A_STAGES * A_STAGE;
     const uint32_t out_base = op_base + OP_STAGES * OP_BYTES;
     const uint32_t bars = out_base + NOUT * OUT_BYTES;
+    // One `ready` barrier per operand stage collects the weight tile's TMA bytes AND the transform group's arrivals, and
+    // one tcgen05.commit (`op_empty`) releases both halves: the single MMA-issuing thread is what paces this kernel
+    // (HILCODEC_TRACE=1: ~180 cycles per mbarrier wait, ~100 per commit, ~70 per MMA on its serial path), so every
+    // wait / commit it does not execute is time the tensor pipe gets.
+    constexpr int NB0 = 2 * RAW_STAGES + 2 * OP_STAGES + 1;
     auto raw_full = [&](int r) { return bars + 8u * r; };
     auto raw_empty = [&](int r) { return bars + 8u * (RAW_STAGES + r); };
-    auto a_full = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };
-    auto b_ready = [&](int s) { return bars + 8u * (2 * RAW_STAGES + OP_STAGES + s); };
-    auto op_empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + s); };
-    auto tfull_bar = [&](int a) { return bars + 8u * (2 * RAW_STAGES + 3 * OP_STAGES + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (2 * RAW_STAGES + 3 * OP_STAGES + 2 + a); };
-    const uint32_t tmem_slot = bars + 8u * (2 * RAW_STAGES + 3 * OP_STAGES + 4);
+    auto ready = [&](int s) { return bars + 8u * (2 * RAW_STAGES + s); };
+    auto op_empty = [&](int s) { return bars + 8u * (2 * RAW_STAGES + OP_STAGES + s); };
+    const uint32_t ares_bar = bars + 8u * (2 * RAW_STAGES + 2 * OP_STAGES);   // resident weights loaded
+    auto tfull_bar = [&](int a) { return bars + 8u * (NB0 + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (NB0 + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (NB0 + 4);
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + BK - 1) / BK;
     const int nraw = p.nraw, nop = p.nop;
     auto a_res_addr = [&](int kb) {   // resident weight tile of k-block kb (hi, then lo at + A_TILE)
-        return kb < 2 ? op_base + kb * OP_BYTES
-             : kb < 4 ? op_base + 2 * OP_BYTES + (kb - 2) * 2 * A_TILE
-                      : raw_base + (RAW_STAGES - 1 - (kb - 4)) * RAW_BYTES;
+        return kb < A_STAGES ? a_base + kb * A_STAGE : op_base + (OP_STAGES - 1 - (kb - A_STAGES)) * OP_BYTES;
     };
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi);
@@ -271,10 +273,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             mbar_init(raw_empty(r), XW_PER_G);
         }
         for (int s = 0; s < OP_STAGES; ++s) {
-            mbar_init(a_full(s), 1);
-            mbar_init(b_ready(s), XW_PER_G);
+            mbar_init(ready(s), XW_PER_G + (p.a_res ? 0 : 1));   // transform warps (+ the weight producer's expect_tx)
             mbar_init(op_empty(s), 1);
         }
+        mbar_init(ares_bar, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), NUM_EPI);
@@ -318,16 +320,16 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     if (++r == nraw) { r = 0; ph ^= 1; }
                 }
             }
-            if (p.trace) { p.trace[blockIdx.x * 16 + 10] = tr_w; p.trace[blockIdx.x * 16 + 11] = clock64() - tr_s; }
+            if (p.trace) { p.trace[blockIdx.x * 24 + 10] = tr_w; p.trace[blockIdx.x * 24 + 11] = clock64() - tr_s; }
         }
     } else if (warp == 3) {
         // ===================================================================== A producer (op ring)
         if (lane == 0 && p.a_res) {
             const int m_blk = (int)(blockIdx.x % p.num_m);   // == tile % num_m for every tile of this CTA
-            mbar_arrive_expect_tx(a_full(0), (uint32_t)nkb * 2 * A_TILE);
+            mbar_arrive_expect_tx(ares_bar, (uint32_t)nkb * 2 * A_TILE);
             for (int kb = 0; kb < nkb; ++kb) {
-                tma_load_2d(&map_a_hi, a_res_addr(kb), a_full(0), kb * BK, m_blk * BM);
-                tma_load_2d(&map_a_lo, a_res_addr(kb) + A_TILE, a_full(0), kb * BK, m_blk * BM);
+                tma_load_2d(&map_a_hi, a_res_addr(kb), ares_bar, kb * BK, m_blk * BM);
+                tma_load_2d(&map_a_lo, a_res_addr(kb) + A_TILE, ares_bar, kb * BK, m_blk * BM);
             }
         } else if (lane == 0) {
             int s = 0;
@@ -337,11 +339,11 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 for (int kb = 0; kb < nkb; ++kb) {
                     const long long tr0 = p.trace ? clock64() : 0;
                     mbar_wait<32>(op_empty(s), ph ^ 1);
-                    if (p.trace) p.trace[blockIdx.x * 16 + 12] += clock64() - tr0;
-                    const uint32_t st = op_base + s * OP_BYTES;
-                    mbar_arrive_expect_tx(a_full(s), 2 * A_TILE);
-                    tma_load_2d(&map_a_hi, st, a_full(s), kb * BK, m_blk * BM);
-                    tma_load_2d(&map_a_lo, st + A_TILE, a_full(s), kb * BK, m_blk * BM);
+                    if (p.trace) p.trace[blockIdx.x * 24 + 12] += clock64() - tr0;
+                    const uint32_t st = a_base + s * A_STAGE;
+                    mbar_arrive_expect_tx(ready(s), 2 * A_TILE);
+                    tma_load_2d(&map_a_hi, st, ready(s), kb * BK, m_blk * BM);
+                    tma_load_2d(&map_a_lo, st + A_TILE, ready(s), kb * BK, m_blk * BM);
                     if (++s == OP_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -351,9 +353,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         int s = 0;
         uint32_t ph = 0;
         long long it = 0;
-        long long tr_e = 0, tr_a = 0, tr_b = 0;
+        long long tr_e = 0, tr_a = 0, tr_b = 0, tr_i = 0, tr_c = 0;
         const long long tr_s = p.trace ? clock64() : 0;
-        if (p.a_res) mbar_wait(a_full(0), 0);
+        if (p.a_res) mbar_wait(ares_bar, 0);
+        bool pre_ok = false;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int acc = (int)(it & 1);
             const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
@@ -365,36 +368,43 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             const uint32_t d_small = d_big + BN;
             for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t st = op_base + s * OP_BYTES;
-                const uint32_t sa = p.a_res ? a_res_addr(kb) : st;
+                const uint32_t at = p.a_res ? a_res_addr(kb) : a_base + s * A_STAGE;
                 tr0 = p.trace ? clock64() : 0;
-                if (!p.a_res) mbar_wait(a_full(s), ph);
-                if (p.trace) { const long long t1 = clock64(); tr_a += t1 - tr0; tr0 = t1; }
-                mbar_wait(b_ready(s), ph);
+                if (!pre_ok) mbar_wait(ready(s), ph);
                 if (p.trace) tr_b += clock64() - tr0;
                 tc_fence_after();
+                // probe the NEXT stage (non-blocking test_wait) before issuing this one's MMAs: the barrier round trip (~100 cycles on the
+                // issuer's serial path) overlaps the issue below, and in steady state the transform is a stage ahead
+                int s2 = s + 1;
+                uint32_t ph2 = ph;
+                if (s2 == nop) { s2 = 0; ph2 ^= 1; }
+                pre_ok = p.probe && mbar_test_wait(ready(s2), ph2);
                 if (lane == 0) {
+                    const long long ti0 = p.trace ? clock64() : 0;
 #pragma unroll
                     for (int j = 0; j < BK / 16; ++j) {
                         // A (K-major, SWIZZLE_64B): 8-row groups 512 B apart; +32 B walks one k16 step inside the
                         //   64-byte swizzle row.
                         // B (MN-major, SWIZZLE_128B): 64-column panels B_PANEL apart (LBO) -- B_hi p0, p1, B_lo p0,
                         //   p1 back to back -- 8-k-row atoms 1024 B apart (SBO); one k16 step = 2 atoms = 2 KB.
-                        const uint64_t a_hi = make_desc(sa + j * 32, 16, 512, 4);
-                        const uint64_t a_lo = make_desc(sa + A_TILE + j * 32, 16, 512, 4);
-                        const uint64_t b_hl = make_desc(st + 2 * A_TILE + j * 2048, B_PANEL, 1024, 2);
+                        const uint64_t a_hi = make_desc(at + j * 32, 16, 512, 4);
+                        const uint64_t a_lo = make_desc(at + A_TILE + j * 32, 16, 512, 4);
+                        const uint64_t b_hl = make_desc(st + j * 2048, B_PANEL, 1024, 2);
                         umma_f16(d_big, a_hi, b_hl, IDESC_N256, (kb | j) != 0);
                         umma_f16(d_small, a_lo, b_hl, IDESC_N128, 1);
                     }
+                    const long long ti1 = p.trace ? clock64() : 0;
                     umma_commit(op_empty(s));
                     if (kb == nkb - 1) umma_commit(tfull_bar(acc));
+                    if (p.trace) { tr_i += ti1 - ti0; tr_c += clock64() - ti1; }
                 }
                 __syncwarp();
-                if (++s == nop) { s = 0; ph ^= 1; }
+                s = s2; ph = ph2;
             }
         }
         if (p.trace && lane == 0) {
-            unsigned long long* tr = p.trace + blockIdx.x * 16;
-            tr[0] = tr_e; tr[1] = tr_a; tr[2] = tr_b; tr[3] = clock64() - tr_s; tr[13] = it;
+            unsigned long long* tr = p.trace + blockIdx.x * 24;
+            tr[0] = tr_e; tr[1] = tr_a; tr[2] = tr_b; tr[3] = clock64() - tr_s; tr[13] = it; tr[16] = tr_i; tr[17] = tr_c;
         }
     } else if (warp >= XW0) {
         // ===================================================================== transform: raw fp32 -> B_hi / B_lo fp16
@@ -408,6 +418,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const uint32_t chunk = (uint32_t)((lane >> 1) & 7);  // 16-byte chunk (8 columns) inside the 128-byte row
         const uint32_t half8 = (uint32_t)(lane & 1) * 8u;
         uint32_t n = 0;                                    // k-blocks seen by this CTA (all tiles)
+        // ring positions of this group's next k-block (n = xg, xg + XG, ...): advanced by XG with wrap-around, the
+        // parity flips on every wrap (the depths are multiples of XG or, for the operand ring, at least XG)
+        int r = xg % nraw, s = xg % nop;
+        uint32_t rph = 0, sph = 0;
         long long tr_r = 0, tr_o = 0;
         const long long tr_s = p.trace ? clock64() : 0;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -417,14 +431,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             [[maybe_unused]] const int b = (int)(rest / p.tiles_t);
             for (int kb = 0; kb < nkb; ++kb, ++n) {
                 if ((int)(n % XG) != xg) continue;
-                const int r = (int)(n % (uint32_t)nraw), s = (int)(n % (uint32_t)nop);
-                const uint32_t rph = (n / (uint32_t)nraw) & 1u, sph = (n / (uint32_t)nop) & 1u;
                 long long tr0 = p.trace ? clock64() : 0;
                 mbar_wait_ns(raw_full(r), rph, p.xform_sleep);
                 if (p.trace) { const long long t1 = clock64(); tr_r += t1 - tr0; tr0 = t1; }
                 mbar_wait_ns(op_empty(s), sph ^ 1, p.xform_sleep);
                 if (p.trace) tr_o += clock64() - tr0;
-                const uint32_t bhi = op_base + s * OP_BYTES + 2 * A_TILE + panel * B_PANEL;
+                const uint32_t bhi = op_base + s * OP_BYTES + panel * B_PANEL;
                 if constexpr (kUp > 0) {
                     const float* raw = reinterpret_cast<const float*>(gen_base + (raw_base - base) + r * RAW_BYTES);
                     const float* ci = p.up_ci + (size_t)b * p.K;
@@ -461,13 +473,15 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(b_ready(s));
+                    mbar_arrive(ready(s));
                     mbar_arrive(raw_empty(r));
                 }
+                r += XG; if (r >= nraw) { r -= nraw; rph ^= 1u; }
+                s += XG; if (s >= nop) { s -= nop; sph ^= 1u; }
             }
         }
         if (p.trace && xw == 0 && lane == 0) {
-            unsigned long long* tr = p.trace + blockIdx.x * 16;
+            unsigned long long* tr = p.trace + blockIdx.x * 24;
             tr[4] = tr_r; tr[5] = tr_o; tr[6] = clock64() - tr_s;
         }
     } else if (warp >= 4 && warp < 8) {
@@ -482,7 +496,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE), cb2 = pk2(c_big, c_big);
         long long it = 0;
         uint32_t g = 0;                                      // running chunk counter -> staging buffer parity
-        long long tr_f = 0, tr_d = 0;
+        long long tr_f = 0, tr_d = 0, tr_l = 0, tr_c = 0;
         const long long tr_s = p.trace ? clock64() : 0;
         if constexpr (kDs > 0) {
             // ---- fused strided depthwise epilogue: y[n] = b + sum_{k < 2r} w[k] * pw[(n - 1) r + k], pw[-r .. -1] = cache.
@@ -698,9 +712,11 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 for (int c = 0; c < n_chunks; ++c, ++g) {
                     const uint32_t obuf = my_out + (g % NOUT) * OUT_BYTES;
                     uint32_t rb[32], rs[32];
+                    const long long tr2 = p.trace ? clock64() : 0;
                     tmem_ld32(t_big + c * 32, rb);
                     tmem_ld32(t_big + BN + c * 32, rs);
                     tmem_ld_wait();
+                    if (p.trace) tr_l += clock64() - tr2;
                     if (c == n_chunks - 1) {
                         tc_fence_before();
                         mbar_arrive(tempty_bar(acc));
@@ -726,6 +742,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     if (issuer) tma_wait_read<NOUT - 1>();   // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
                     if (p.trace) tr_d += clock64() - tr1;
+                    const long long tr3 = p.trace ? clock64() : 0;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float o[4];
@@ -750,6 +767,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                                      : "memory");
                     }
                     carry[0] = v[32]; carry[1] = v[33]; carry[2] = v[34]; carry[3] = v[35];
+                    if (p.trace) tr_c += clock64() - tr3;
                     fence_proxy_async();
                     epi_bar_sync();
                     if (issuer) {
@@ -764,8 +782,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             if (issuer) tma_wait_all();
         }
         if (p.trace && issuer) {
-            unsigned long long* tr = p.trace + blockIdx.x * 16;
-            tr[7] = tr_f; tr[8] = clock64() - tr_s; tr[9] = tr_d;
+            unsigned long long* tr = p.trace + blockIdx.x * 24;
+            tr[7] = tr_f; tr[8] = clock64() - tr_s; tr[9] = tr_d; tr[14] = tr_l; tr[15] = tr_c;
         }
     }
 
@@ -835,38 +853,39 @@ static bool trace_on() {
 static void trace_report(const th::Params& p, unsigned grid, const char* what, cudaStream_t st) {
     if (!trace_on() || !g_trace_buf) return;
     cudaStreamSynchronize(st);
-    std::vector<unsigned long long> h((size_t)grid * 16);
+    std::vector<unsigned long long> h((size_t)grid * 24);
     cudaMemcpy(h.data(), g_trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
-    double a[16] = {0};
+    double a[24] = {0};
     for (unsigned c = 0; c < grid; ++c)
-        for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)c * 16 + i] / grid;
+        for (int i = 0; i < 24; ++i) a[i] += (double)h[(size_t)c * 24 + i] / grid;
     const double kbs = a[13] * ((p.K + th::BK - 1) / th::BK);
     std::fprintf(stderr,
                  "[trace] %s M=%d K=%d T=%d B=%d a_res=%d tiles/CTA=%.1f | per k-block: total %.0f | MMA waits: tempty %.0f a_full %.0f "
                  "b_ready %.0f | xform: raw_full %.0f op_empty %.0f of %.0f | epi: tfull %.0f drain %.0f of %.0f | Xprod: raw_empty %.0f of "
-                 "%.0f | Aprod: op_empty %.0f\n",
+                 "%.0f | Aprod: a_empty %.0f | epi detail: tmem_ld %.0f taps+sts %.0f | MMA issue %.0f commit %.0f\n",
                  what, p.M, p.K, p.T, p.B, p.a_res, a[13], a[3] / kbs, a[0] / kbs, a[1] / kbs, a[2] / kbs, 2 * a[4] / kbs, 2 * a[5] / kbs,
-                 2 * a[6] / kbs, a[7] / kbs, a[9] / kbs, a[8] / kbs, a[10] / kbs, a[11] / kbs, a[12] / kbs);
+                 2 * a[6] / kbs, a[7] / kbs, a[9] / kbs, a[8] / kbs, a[10] / kbs, a[11] / kbs, a[12] / kbs, a[14] / kbs, a[15] / kbs, a[16] / kbs, a[17] / kbs);
 }
 
 static unsigned plan_grid(th::Params& p, int num_sms) {
     using namespace th;
     if (trace_on()) {
-        if (!g_trace_buf) cudaMalloc(&g_trace_buf, 1024 * 16 * sizeof(unsigned long long));
-        cudaMemset(g_trace_buf, 0, 1024 * 16 * sizeof(unsigned long long));
+        if (!g_trace_buf) cudaMalloc(&g_trace_buf, 1024 * 24 * sizeof(unsigned long long));
+        cudaMemset(g_trace_buf, 0, 1024 * 24 * sizeof(unsigned long long));
         p.trace = g_trace_buf;
     }
     static const bool on = []() { const char* e = std::getenv("HILCODEC_A_RESIDENT"); return !(e && e[0] == '0'); }();
     const int nkb = (p.K + BK - 1) / BK;
     unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    static const bool probe = []() { const char* e = std::getenv("HILCODEC_MMA_PROBE"); return !(e && e[0] == '0'); }();
+    p.probe = probe ? 1 : 0;
     p.a_res = 0;
     p.nraw = RAW_STAGES;
     p.nop = OP_STAGES;
-    if (on && RAW_STAGES == 6 && OP_STAGES == 3 && XG == 2 && nkb <= 6 && grid >= (unsigned)p.num_m) {
+    if (on && nkb <= A_STAGES + 2 && grid >= (unsigned)p.num_m) {
         grid = grid / p.num_m * p.num_m;
         p.a_res = 1;
-        p.nraw = nkb > 4 ? 4 : 6;
-        p.nop = 2;
+        p.nop = nkb > A_STAGES ? OP_STAGES - 2 : OP_STAGES;   // k-blocks 4, 5 live in the top two operand stages
     }
     return grid;
 }

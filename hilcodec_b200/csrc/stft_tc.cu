@@ -93,7 +93,7 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(xform_bar(s), NUM_XFORM);
+            mbar_init(xform_bar(s), NUM_XFORM / 32);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -147,7 +147,8 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t d_small = d_big + BN;
             for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t st = base + s * STAGE_BYTES;
-                mbar_wait(full_bar(s), ph);
+                // one wait per k-block on the issuer's serial path: every transform thread waited for full_bar(s) (the
+                // weight tile's TMA bytes included) before it arrived on xform_bar(s), so this wait covers both
                 mbar_wait(xform_bar(s), ph);
                 tc_fence_after();
                 if (lane == 0) {
@@ -278,7 +279,8 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
                 }
                 fence_proxy_async();
-                mbar_arrive(xform_bar(s));
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive(xform_bar(s));   // one arrival per warp (8, not 256, per k-block)
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }

@@ -33,6 +33,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a while when the phase is still pending; test_wait never does).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a protocol bug becomes a trapped kernel (launch error) instead of a hung GPU.
 // Roles with long waits (producer, epilogue) back off with nanosleep so their polling does not
 // take issue slots from the transform warps sharing the scheduler.
