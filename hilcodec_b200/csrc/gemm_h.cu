@@ -295,7 +295,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     if (warp == 0) {
         // ===================================================================== X producer (raw ring)
-        if (lane == 0) {
+        if (elect_one()) {
             int r = 0;
             uint32_t ph = 0;
             long long tr_w = 0;
@@ -324,14 +324,15 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
     } else if (warp == 3) {
         // ===================================================================== A producer (op ring)
-        if (lane == 0 && p.a_res) {
+        const bool leader = elect_one();
+        if (leader && p.a_res) {
             const int m_blk = (int)(blockIdx.x % p.num_m);   // == tile % num_m for every tile of this CTA
             mbar_arrive_expect_tx(ares_bar, (uint32_t)nkb * 2 * A_TILE);
             for (int kb = 0; kb < nkb; ++kb) {
                 tma_load_2d(&map_a_hi, a_res_addr(kb), ares_bar, kb * BK, m_blk * BM);
                 tma_load_2d(&map_a_lo, a_res_addr(kb) + A_TILE, ares_bar, kb * BK, m_blk * BM);
             }
-        } else if (lane == 0) {
+        } else if (leader) {
             int s = 0;
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -379,7 +380,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 uint32_t ph2 = ph;
                 if (s2 == nop) { s2 = 0; ph2 ^= 1; }
                 pre_ok = p.probe && mbar_test_wait(ready(s2), ph2);
-                if (lane == 0) {
+                if (elect_one()) {
                     const long long ti0 = p.trace ? clock64() : 0;
 #pragma unroll
                     for (int j = 0; j < BK / 16; ++j) {
@@ -488,7 +489,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         // ===================================================================== epilogue
         const int q = warp & 3;                             // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                      // row inside the 128-row tile = TMEM lane
-        const bool issuer = (q == 0 && lane == 0);
+        // TMA stores / waits of the epilogue: warp q == 0's elected lane (elect.sync picks the same lane every time for the
+        // same mask, so the thread that commits a bulk group is the one that waits for it)
+        [[maybe_unused]] const bool issuer = (q == 0 && lane == 0);
         const uint32_t my_out = out_base;
         auto epi_bar_sync = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
         const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
@@ -534,7 +537,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 mbar_wait<64>(tfull_bar(acc), acc_ph);
                 tc_fence_after();
                 const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
-                if (issuer) tma_wait_read<0>();                    // the previous tile's stores have drained both buffers
+                if (q == 0 && elect_one()) tma_wait_read<0>();                    // the previous tile's stores have drained both buffers
                 epi_bar_sync();
                 float a_cur = 0.f, a_next = 0.f;
                 float o4[4];
@@ -600,7 +603,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                                 if (grp == N1 - 1) {               // first half complete: hand it to the TMA engine
                                     fence_proxy_async();
                                     epi_bar_sync();
-                                    if (issuer) {
+                                    if (q == 0 && elect_one()) {
                                         tma_store_3d(&map_y, buf_a, tt * NOUT, m_blk * BM, b);
                                         tma_commit();
                                     }
@@ -613,12 +616,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 }
                 fence_proxy_async();
                 epi_bar_sync();
-                if (issuer) {
+                if (q == 0 && elect_one()) {
                     tma_store_3d(&map_y28, buf_b, tt * NOUT + N1, m_blk * BM, b);
                     tma_commit();
                 }
             }
-            if (issuer) tma_wait_all();
+            if (q == 0 && elect_one()) tma_wait_all();
         } else if constexpr (!kDw) {
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int m_blk = (int)(tile % p.num_m);
@@ -641,7 +644,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 for (int c = 0; c < n_chunks; ++c, ++g) {
                     const uint32_t obuf = my_out + (g % NOUT) * OUT_BYTES;
                     const long long tr1 = p.trace ? clock64() : 0;
-                    if (issuer) tma_wait_read<NOUT - 1>();          // the store that used this buffer two chunks ago has drained it
+                    if (q == 0 && elect_one()) tma_wait_read<NOUT - 1>();          // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
                     if (p.trace) tr_d += clock64() - tr1;
                     uint32_t rb[32], rs[32];
@@ -668,14 +671,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     }
                     fence_proxy_async();
                     epi_bar_sync();
-                    if (issuer) {
+                    if (q == 0 && elect_one()) {
                         if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
                         else tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
                         tma_commit();
                     }
                 }
             }
-            if (issuer) tma_wait_all();
+            if (q == 0 && elect_one()) tma_wait_all();
         } else {
             // ---- fused DWS epilogue (see gemm_tc.cu): the tile holds 128 pointwise columns for times
             // [t0-4, t0+124); each thread owns one channel row and slides the 5-tap window along it in registers.
@@ -739,7 +742,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                         }
                     }
                     const long long tr1 = p.trace ? clock64() : 0;
-                    if (issuer) tma_wait_read<NOUT - 1>();   // the store that used this buffer two chunks ago has drained it
+                    if (q == 0 && elect_one()) tma_wait_read<NOUT - 1>();   // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
                     if (p.trace) tr_d += clock64() - tr1;
                     const long long tr3 = p.trace ? clock64() : 0;
@@ -770,7 +773,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     if (p.trace) tr_c += clock64() - tr3;
                     fence_proxy_async();
                     epi_bar_sync();
-                    if (issuer) {
+                    if (q == 0 && elect_one()) {
                         const CUtensorMap* mp = c == 0 ? &map_y28 : &map_y;
                         const int tc0 = c == 0 ? tcol0 + p.t_halo : tcol0 + c * 32;
                         if (p.reduce_add) tma_reduce_add_3d(mp, obuf, tc0, m_blk * BM, b);
@@ -779,7 +782,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     }
                 }
             }
-            if (issuer) tma_wait_all();
+            if (q == 0 && elect_one()) tma_wait_all();
         }
         if (p.trace && issuer) {
             unsigned long long* tr = p.trace + blockIdx.x * 24;

@@ -194,7 +194,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
 
     if (warp == 0) {
         // ===================================================================== X producer: [own columns | halo] boxes
-        if (lane == 0) {
+        if (elect_one()) {
             int r = 0;
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -212,7 +212,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
         }
     } else if (warp == 3) {
         // ===================================================================== weight producer (same order as the MMA issuer)
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             auto pieces = [&](const CUtensorMap* mh, const CUtensorMap* ml) {
@@ -241,7 +241,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             for (int mb = 0; mb < p.num_m; ++mb) {
                 mbar_wait(a_full(sa), pha);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t ast = a_base + sa * A_PIECE;
                     const uint32_t d_big = d_base + mb * 2 * BN;
 #pragma unroll
@@ -265,11 +265,11 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(b_ready(sb), phb);
                 issue_kblock(b_base + sb * G::B_STAGE, tmem_base, kb);
-                if (lane == 0) umma_commit(b_empty(sb));
+                if (elect_one()) umma_commit(b_empty(sb));
                 __syncwarp();
                 if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
             }
-            if (lane == 0) umma_commit(d1_full);
+            if (elect_one()) umma_commit(d1_full);
             __syncwarp();
         };
         auto g2 = [&](uint32_t it) {   // D2 = W1 * B2(tile it); D2 is free once E2 of tile it-1 has read it
@@ -277,7 +277,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
             mbar_wait(d2_empty, (it & 1) ^ 1);
             tc_fence_after();
             for (int kb = 0; kb < nkb; ++kb) issue_kblock(b2_base + kb * G::B_STAGE, tmem_base + 256, kb);
-            if (lane == 0) umma_commit(d2_full);
+            if (elect_one()) umma_commit(d2_full);
             __syncwarp();
         };
         for (uint32_t it = 0; it < n_my; ++it) {
@@ -429,7 +429,9 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
         // ===================================================================== epilogue E2: D2 -> dw1 -> h += (TMA reduce-add)
         const int q = warp - 4;
         const int row = q * 32 + lane;                      // row inside an m-block = TMEM lane
-        const bool issuer = (q == 0 && lane == 0);
+        // TMA stores / waits of the epilogue: warp q == 0's elected lane (elect.sync picks the same lane every time for the
+        // same mask, so the thread that commits a bulk group is the one that waits for it)
+        [[maybe_unused]] const bool issuer = (q == 0 && lane == 0);
         const uint32_t sw = (uint32_t)(row & 7);
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE);
         const float c_big1 = p.c_big1, c_inv1 = 1.0f / p.c_big1;
@@ -500,7 +502,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                         tc_fence_before();
                         mbar_arrive(d2_empty);
                     }
-                    if (issuer) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
+                    if (q == 0 && elect_one()) tma_wait_read<1>();   // the store that used this buffer two chunks ago has drained it
                     epi_bar_sync();
                     if (warp_ok) {
 #pragma unroll
@@ -524,7 +526,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                     }
                     fence_proxy_async();
                     epi_bar_sync();
-                    if (issuer) {
+                    if (q == 0 && elect_one()) {
                         if (c == 0) tma_reduce_add_3d(&map_y24, obuf, tcol0 + HALO, mb * BM, b);
                         else tma_reduce_add_3d(&map_y, obuf, tcol0 + c * 32, mb * BM, b);
                         tma_commit();
@@ -532,7 +534,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_a0_hi, const __grid_cons
                 }
             }
         }
-        if (issuer) tma_wait_all();
+        if (q == 0 && elect_one()) tma_wait_all();
     }
 
     tc_fence_before();

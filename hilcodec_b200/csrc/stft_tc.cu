@@ -114,7 +114,7 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (warp == 0) {
         // ===================================================================== TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -151,7 +151,7 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 // weight tile's TMA bytes included) before it arrived on xform_bar(s), so this wait covers both
                 mbar_wait(xform_bar(s), ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     // B_hi (rows 0..127) and B_lo (rows 128..255) are adjacent K-major tiles: one N = 256 MMA
                     // computes A_hi*[B_hi | B_lo] into [big | small], a second N = 128 MMA adds A_lo*B_hi.
                     if constexpr (kH) {
@@ -289,7 +289,9 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int q = warp - 4;
         const int row = q * 32 + lane;            // accumulator row: 2f (re) / 2f+1 (im)
         const int frow = row >> 1;                // bin inside the tile's 64
-        const bool issuer = (q == 0 && lane == 0);
+        // TMA stores / waits of the epilogue: warp q == 0's elected lane (elect.sync picks the same lane every time for the
+        // same mask, so the thread that commits a bulk group is the one that waits for it)
+        [[maybe_unused]] const bool issuer = (q == 0 && lane == 0);
         const bool even = (lane & 1) == 0;
         const uint32_t sw = (uint32_t)(frow & 7);
         long long it = 0;
@@ -309,7 +311,7 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll 1
             for (int c = 0; c < n_chunks; ++c, ++g) {
                 const uint32_t obuf = out_base + (g & 1) * OUT_BYTES;
-                if (issuer) tma_wait_read<1>();
+                if (q == 0 && elect_one()) tma_wait_read<1>();
                 epi_bar_sync();
                 uint32_t rb[32], rs[32];
                 tmem_ld32(t_big + c * 32, rb);
@@ -354,13 +356,13 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
                 fence_proxy_async();
                 epi_bar_sync();
-                if (issuer) {
+                if (q == 0 && elect_one()) {
                     tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * 64, b);
                     tma_commit();
                 }
             }
         }
-        if (issuer) tma_wait_all();
+        if (q == 0 && elect_one()) tma_wait_all();
     }
 
     tc_fence_before();

@@ -33,6 +33,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// One elected lane of a converged warp (elect.sync): ptxas then knows the guarded region runs on a single thread and emits
+// the tcgen05 / uniform-datapath instructions inside it directly, instead of the "elect, execute, loop while any thread is
+// left" waterfall it wraps around each of them under a generic `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 // Non-blocking probe (try_wait may suspend the thread for a while when the phase is still pending; test_wait never does).
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;

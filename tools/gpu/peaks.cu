@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int mode, int iters) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: no per-instruction waterfall around the tcgen05 ops (as the kernels issue them)
             const bool f16 = mode <= 2;
             // K-major A (SWIZZLE_64B for fp16 as in gemm_h.cu, SWIZZLE_128B for tf32), MN-major / K-major B as the kernels use them
             const uint64_t a = f16 ? make_desc(base, 16, 512, 4) : make_desc(base, 16, 1024, 2);
