@@ -52,9 +52,17 @@ def main():
     ap.add_argument("--manifest")
     ap.add_argument("--workload", default="music256")
     ap.add_argument("--class-json")
+    ap.add_argument("--last-step", action="store_true",
+                    help="take the LAST --count (or manifest length) launches of this library: torch's own kernels "
+                         "(at::, cub::, ...) are dropped first, so the window is the profiled step bench.py ran last")
     a = ap.parse_args()
     rows = load(a.csv)
-    rows = rows[a.first:a.first + a.count] if a.count else rows[a.first:]
+    if a.last_step:
+        rows = [r for r in rows if not re.search(r"\bat::|at_cuda_detail|cub::|elementwise_kernel|vectorized_|distribution_|Memset|memset", r["name"])]
+        n = a.count or (len(json.load(open(a.manifest))["launches"]) if a.manifest else 0)
+        rows = rows[-n:] if n else rows
+    else:
+        rows = rows[a.first:a.first + a.count] if a.count else rows[a.first:]
     agg = collections.OrderedDict()
     for r in rows:
         g = agg.setdefault(r["name"], {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0, "tensor": 0.0})
