@@ -16,18 +16,20 @@
 // The 2^11 scale keeps both lo parts in the normal fp16 range, so nothing is lost to fp16
 // subnormals; all scalings are powers of two (exact).
 //
-// Pipeline (one persistent CTA per SM, 128 x 128 output tile, BK = 32, 512 threads).  The ablation in
-// profiles/r1_gemm_tc_ablation.md showed gemm_tc.cu is bound by the LATENCY of one serial chain per
-// smem stage (HBM load -> transform -> MMA -> release, 3 stages in flight), so here the rings are
-// decoupled:
-//   raw ring  (6 x 16 KB): fp32 activation boxes [32 k][128 t] straight from TMA (no swizzle)
-//   op ring   (3 x 32 KB): A_hi | A_lo (fp16, K-major, SWIZZLE_64B, TMA from the pre-split weights)
-//                          B_hi | B_lo (fp16, MN-major, SWIZZLE_128B, written by the transform warps)
+// Pipeline (one persistent CTA per SM, 128 x 128 output tile, BK = 32, 512 threads), three rings of 16 KB stages:
+//   raw ring     (4): fp32 activation boxes [32 k][128 t] straight from TMA (no swizzle)
+//   weight ring  (4): A_hi | A_lo (fp16, K-major, SWIZZLE_64B, TMA from the pre-split weights) -- or, for K <= 192, the
+//                     CTA's weight rows resident for the whole kernel (Params::a_res)
+//   operand ring (4): B_hi | B_lo (fp16, MN-major, SWIZZLE_128B, written by the transform warps)
 // warp 0  X producer (TMA)      warp 3  A producer (TMA)      warp 1  MMA issuer
-// warp 2  TMEM allocator        warps 4-7 epilogue            warps 8-15 transform (ELU prologue + split)
+// warp 2  TMEM allocator        warps 4-7 epilogue            warps 8-15 transform (ELU prologue + split), two groups
 // Per k-block two k16 steps of { A_hi x [B_hi | B_lo] (N = 256) -> [big | small]; A_lo x B_hi (N = 128) ->
-// small }.  Epilogues are the ones of gemm_tc.cu (TMEM -> registers -> swizzled staging -> TMA store /
-// reduce-add; optional fused causal depthwise k5).
+// small }.  The MMA-issuing thread is the resource everything else waits for (HILCODEC_TRACE=1),
+// so its serial path is kept minimal: ONE ready barrier per stage (weight bytes + transform arrivals), ONE commit, the
+// next stage probed with mbarrier.test_wait before the current MMAs go out, and every single-thread region guarded by
+// elect.sync (a generic `if (lane == 0)` makes ptxas wrap each tcgen05 / TMA instruction in an elect-and-loop waterfall).
+// Epilogues are the ones of gemm_tc.cu (TMEM -> registers -> swizzled staging -> TMA store / reduce-add; optional fused
+// causal depthwise k5, fused strided depthwise, fused transposed-depthwise prologue).
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
