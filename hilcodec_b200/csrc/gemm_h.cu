@@ -515,6 +515,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             constexpr int N1 = ds_n1(R), N2 = NOUT - N1;
             static_assert(N1 % 4 == 0 && N2 % 4 == 0 && N1 * 4 * BM <= OUT_BYTES && N2 * 4 * BM <= OUT_BYTES && OUT_BUFS >= 2, "staging");
             const uint32_t buf_a = my_out, buf_b = my_out + OUT_BYTES;
+            float wk[2 * R], bv = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2 * R; ++k) wk[k] = 0.f;
+            int m_taps = -1;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
@@ -524,10 +528,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
                 const int m = m_blk * BM + row;
                 const bool row_ok = m < p.M;
-                float wk[2 * R];
+                if (m != m_taps) {
 #pragma unroll
-                for (int k = 0; k < 2 * R; ++k) wk[k] = row_ok ? p.dw_w[m * 2 * R + k] * c_big : 0.f;
-                const float bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                    for (int k = 0; k < 2 * R; ++k) wk[k] = row_ok ? p.dw_w[m * 2 * R + k] * c_big : 0.f;
+                    bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                    m_taps = m;
+                }
                 const float c_inv = 1.0f / c_big;
                 const int tcol0 = tt * STEP - HALO;               // time of tile column 0
                 float hist[R];                                     // tile 0: the r pointwise outputs before the chunk
@@ -625,6 +631,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             }
             if (q == 0 && elect_one()) tma_wait_all();
         } else if constexpr (!kDw) {
+            float bv = 0.f;
+            int m_bias = -1;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
@@ -637,7 +645,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 if (p.trace) tr_f += clock64() - tr0;
                 tc_fence_after();
                 const int m = m_blk * BM + row;
-                const float bv = (m < p.M && p.bias) ? p.bias[m] : 0.f;
+                if (m != m_bias) { bv = (m < p.M && p.bias) ? p.bias[m] : 0.f; m_bias = m; }
                 const f32x2 bv2 = pk2(bv, bv);
                 const int t0 = tt * BN;
                 const int n_chunks = min(BN / 32, (p.T - t0 + 31) / 32);
@@ -684,6 +692,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         } else {
             // ---- fused DWS epilogue (see gemm_tc.cu): the tile holds 128 pointwise columns for times
             // [t0-4, t0+124); each thread owns one channel row and slides the 5-tap window along it in registers.
+            float wk[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, bv = 0.f;
+            int m_taps = -1;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
@@ -695,10 +705,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const bool row_ok = m < p.M;
                 // The window slides over u = (big + small * 2^-11) = pointwise / c_big, with the taps pre-multiplied
                 // by c_big (powers of two: the products are unchanged); the caches hold true-scale values.
-                float wk[5];
+                if (m != m_taps) {   // taps and bias of this row: global loads on the epilogue's critical path, so only
+                                     // when the row changes (never, when the CTA keeps its row block: resident weights)
 #pragma unroll
-                for (int k = 0; k < 5; ++k) wk[k] = row_ok ? p.dw_w[m * 5 + k] * c_big : 0.f;
-                const float bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                    for (int k = 0; k < 5; ++k) wk[k] = row_ok ? p.dw_w[m * 5 + k] * c_big : 0.f;
+                    bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                    m_taps = m;
+                }
                 const float c_inv = 1.0f / c_big;
                 const int tcol0 = tt * p.t_step - p.t_halo;       // time of tile column 0
                 const int n_chunks = min(BN / 32, (p.T - tcol0 + 31) / 32);
