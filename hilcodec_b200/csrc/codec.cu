@@ -194,10 +194,10 @@ static int32_t run_dwconv(const float* x, long long x_bs, int x_rs, const float*
 static int32_t run_dws(const PackedMat& W, const float* X, long long bs, int rs, int B, int T, int pre, float pre_scale,
                        const float* dw_w, const float* dw_b, const float* ci, float* co, const float* skip, int post,
                        float post_scale, float* tmp, float* Y, cudaStream_t st) {
-    const bool hcore = g_use_h && gemm_h_usable(W, X, bs, rs, T, skip, Y, bs, rs, B);
+    const bool hcore = g_use_h && gemm_h_dw_usable(W, X, bs, rs, T, skip, Y, bs, rs, B);
     // store-side ELU (post == PRE_ELU, no skip) exists in the fp16-split kernel only
     const bool post_ok = post == PRE_NONE || (post == PRE_ELU && !skip && hcore);
-    if (tc_on() && g_fuse_dw && post_ok && gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs, B)) {
+    if (tc_on() && g_fuse_dw && post_ok && (hcore || gemm_tc_usable(W, X, bs, rs, T, skip, Y, bs, rs, B))) {
         const double n = (double)B * T;
         HIL_LAUNCH(gemm_cat(W), 2.0 * W.M * W.K * n + 10.0 * W.M * n,
                    4.0 * n * (W.K + W.M * (skip ? 2 : 1)) + 4.0 * W.M * W.K, st,

@@ -64,6 +64,17 @@ static inline bool tc_chunk_ok(int /*B*/, int T) {
     return T >= (min_t < 8 ? 8 : min_t);
 }
 
+// Flat tiles for SHORT chunks of MANY clips (concurrent streams: 64 streams x 8 samples): a 128-column tile is
+// 128 / T whole clips, gathered by a {T, B, K} tensor map whose box is {T, 128 / T, 32} -- TMA does the flattening, the
+// shared-memory image is the same [32 k][128 columns] box the kernel always sees.  Before round 2's last step these
+// layers (the WIDEST of a hop: 512 - 1536 channels at 8 or 1 samples per stream) ran on the FP32 skinny kernels: 65 % of
+// a 64-stream hop.  HILCODEC_TC_FLAT=0 keeps them there; fewer than `min` flat columns stay on the skinny kernels too.
+static inline bool tc_flat_ok(int B, int T) {
+    static const int min_cols = []() { const char* e = std::getenv("HILCODEC_TC_FLAT"); return e ? std::atoi(e) : 128; }();
+    if (min_cols <= 0) return false;
+    return (T == 4 || T == 8 || T == 16) && (long long)B * T >= min_cols;
+}
+
 // A weight matrix W[M][K] repacked k-major for the GEMM kernels: A[Kp][Mp], zero padded.
 struct PackedMat {
     const float* A = nullptr;  // device, [Kp][Mp] for the FFMA kernels
@@ -118,6 +129,8 @@ cudaError_t launch_gemm_tc(const PackedMat& W, const float* X, long long x_bs, i
 // ---- gemm_h.cu: the same two contracts with fp16 hi/lo splits (tcgen05 kind::f16, 2x the tf32 rate)
 bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
                    long long y_bs, int y_rs, int B = 1);
+bool gemm_h_dw_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
+                      long long y_bs, int y_rs, int B = 1);
 cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, int pre,
                           float pre_scale, const float* bias, const float* R, float* Y, long long y_bs, int y_rs,
                           cudaStream_t st);

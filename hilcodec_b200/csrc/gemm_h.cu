@@ -85,6 +85,7 @@ struct Params {
     // this halves it.  The tiles live in the four stages of the weight ring (k-blocks 0 .. 3) and, for K > 128, in the
     // top two stages of the operand ring (k-blocks 4, 5), which then has `nop` = 2 stages, one per transform group.
     int a_res, nraw, nop;
+    int flat_t, flat_b;     // flat tiles (tc_flat_ok): samples per clip and number of clips; T = flat_b * flat_t columns, B = 1
     int probe;              // MMA issuer probes the next stage's barrier early (HILCODEC_MMA_PROBE=0: A/B off)
     // HILCODEC_TRACE=1 (tools/gpu/trace_gemm.py): per-CTA cycle counters of where each warp role waits, 24 per CTA:
     // 0 MMA<-tempty 1 MMA<-a_full 2 MMA<-b_ready 3 MMA total | 4 xform<-raw_full 5 xform<-op_empty 6 xform total |
@@ -317,7 +318,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                         bulk_load(raw_base + r * RAW_BYTES + XB, p.up_w + (size_t)kb * BK * 2 * kUp, WB, raw_full(r));
                     } else {
                         mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
-                        tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
+                        if (p.flat_t)   // {t, clip, k}: the tile's 128 / T clips, all their samples
+                            tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), 0, tt * (BN / p.flat_t), kb * BK);
+                        else
+                            tma_load_3d(&map_x, raw_base + r * RAW_BYTES, raw_full(r), tt * p.t_step - p.t_halo, kb * BK, b);
                     }
                     if (++r == nraw) { r = 0; ph ^= 1; }
                 }
@@ -496,7 +500,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         [[maybe_unused]] const bool issuer = (q == 0 && lane == 0);
         const uint32_t my_out = out_base;
         auto epi_bar_sync = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
-        const uint32_t sw = (uint32_t)(row & 7);            // 128B-swizzle phase of this row
+        // 128B-swizzle phase of this row; flat tiles stage unswizzled (a SWIZZLE_128B tensor map whose box is only
+        // 32 bytes wide faults on the store: tools/gpu/tma_flat_test.cu)
+        const uint32_t sw = p.flat_t ? 0u : (uint32_t)(row & 7);
         const float c_big = p.c_big;                        // 2^-s; c_small = c_big * 2^-11
         const f32x2 lo2 = pk2(1.0f / LO_SCALE, 1.0f / LO_SCALE), cb2 = pk2(c_big, c_big);
         long long it = 0;
@@ -682,8 +688,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     fence_proxy_async();
                     epi_bar_sync();
                     if (q == 0 && elect_one()) {
-                        if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
-                        else tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * BM, b);
+                        // flat tiles: the chunk's 32 columns are 32 / T whole clips of the {t, clip, m} map
+                        const int c0 = p.flat_t ? 0 : t0 + c * 32;
+                        const int c1 = p.flat_t ? (t0 + c * 32) / p.flat_t : m_blk * BM;
+                        const int c2 = p.flat_t ? m_blk * BM : b;
+                        if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, c0, c1, c2);
+                        else tma_store_3d(&map_y, obuf, c0, c1, c2);
                         tma_commit();
                     }
                 }
@@ -694,6 +704,91 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             // [t0-4, t0+124); each thread owns one channel row and slides the 5-tap window along it in registers.
             float wk[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, bv = 0.f;
             int m_taps = -1;
+            if (p.flat_t) {
+                // ---- flat tiles (8 samples per clip: 16 whole clips per tile, 4 per 32-column chunk).  Every clip's window
+                // starts from ITS cache (times -4 .. -1) and every column is an output, so there is no halo column and
+                // no carry between chunks: out[t] = b + sum_k w[k] * v[t + k], v = [cache | 8 pointwise values].
+                constexpr int TT = 8, CPC = 32 / TT;
+                for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                    const int m_blk = (int)(tile % p.num_m);
+                    const int tt = (int)(tile / p.num_m);
+                    const int acc = (int)(it & 1);
+                    const uint32_t acc_ph = (uint32_t)((it >> 1) & 1);
+                    const int m = m_blk * BM + row;
+                    const bool row_ok = m < p.M;
+                    if (m != m_taps) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) wk[k] = row_ok ? p.dw_w[m * 5 + k] * c_big : 0.f;
+                        bv = (row_ok && p.dw_b) ? p.dw_b[m] : 0.f;
+                        m_taps = m;
+                    }
+                    const float c_inv = 1.0f / c_big;
+                    const int clip0 = tt * (BN / TT);                 // first clip of the tile
+                    const int n_chunks = min(BN / 32, (p.flat_b - clip0 + CPC - 1) / CPC);
+                    mbar_wait<64>(tfull_bar(acc), acc_ph);
+                    tc_fence_after();
+                    const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN;
+#pragma unroll 1
+                    for (int c = 0; c < n_chunks; ++c, ++g) {
+                        const uint32_t obuf = my_out + (g % NOUT) * OUT_BYTES;
+                        float4 cv[CPC];                               // the 4 clips' caches: loads in flight under the TMEM read
+#pragma unroll
+                        for (int j = 0; j < CPC; ++j) {
+                            const int clip = clip0 + c * CPC + j;
+                            cv[j] = (row_ok && clip < p.flat_b)
+                                        ? *reinterpret_cast<const float4*>(p.cache_in + ((size_t)clip * p.M + m) * 4)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        uint32_t rb[32], rs[32];
+                        tmem_ld32(t_big + c * 32, rb);
+                        tmem_ld32(t_big + BN + c * 32, rs);
+                        tmem_ld_wait();
+                        if (c == n_chunks - 1) {
+                            tc_fence_before();
+                            mbar_arrive(tempty_bar(acc));
+                        }
+                        if (q == 0 && elect_one()) tma_wait_read<NOUT - 1>();
+                        epi_bar_sync();
+#pragma unroll
+                        for (int j = 0; j < CPC; ++j) {
+                            float v[4 + TT];
+                            v[0] = cv[j].x * c_inv; v[1] = cv[j].y * c_inv; v[2] = cv[j].z * c_inv; v[3] = cv[j].w * c_inv;
+#pragma unroll
+                            for (int i = 0; i < TT; i += 2)
+                                upk2(ffma2(pk2(__uint_as_float(rs[j * TT + i]), __uint_as_float(rs[j * TT + i + 1])), lo2,
+                                           pk2(__uint_as_float(rb[j * TT + i]), __uint_as_float(rb[j * TT + i + 1]))),
+                                     v[4 + i], v[5 + i]);
+                            const int clip = clip0 + c * CPC + j;
+                            if (row_ok && clip < p.flat_b)   // new cache = the clip's last 4 pointwise values, true scale
+                                *reinterpret_cast<float4*>(p.cache_out + ((size_t)clip * p.M + m) * 4) =
+                                    make_float4(v[TT] * c_big, v[TT + 1] * c_big, v[TT + 2] * c_big, v[TT + 3] * c_big);
+#pragma unroll
+                            for (int h = 0; h < TT / 4; ++h) {
+                                float o[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float a = bv;
+#pragma unroll
+                                    for (int k = 0; k < 5; ++k) a = fmaf(wk[k], v[h * 4 + e + k], a);
+                                    o[e] = a;
+                                }
+                                if (p.post_elu) elu4(o[0], o[1], o[2], o[3]);
+                                const uint32_t dst = obuf + row * 128 + ((((uint32_t)(j * (TT / 4) + h)) ^ sw) << 4);
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                                             "f"(o[3])
+                                             : "memory");
+                            }
+                        }
+                        fence_proxy_async();
+                        epi_bar_sync();
+                        if (q == 0 && elect_one()) {
+                            if (p.reduce_add) tma_reduce_add_3d(&map_y, obuf, 0, clip0 + c * CPC, m_blk * BM);
+                            else tma_store_3d(&map_y, obuf, 0, clip0 + c * CPC, m_blk * BM);
+                            tma_commit();
+                        }
+                    }
+                }
+            } else
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int m_blk = (int)(tile % p.num_m);
                 const long long rest = tile / p.num_m;
@@ -820,11 +915,18 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
                    long long y_bs, int y_rs, int B) {
     if (!W.H_hi || !W.H_lo) return false;
-    if (!tc_chunk_ok(B, T)) return false;  // short chunks (streaming) go to the flattened-column FP32 kernels
+    // short chunks: flat tiles when there are enough clips (tc_flat_ok), else the flattened-column FP32 kernels
+    if (!tc_chunk_ok(B, T) && !tc_flat_ok(B, T)) return false;
     if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
     if (R && (reinterpret_cast<uintptr_t>(R) & 15)) return false;
     return true;
+}
+
+// the fused DWSBlock kernel: per-clip tiles, or flat tiles at 8 samples per clip
+bool gemm_h_dw_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
+                      long long y_bs, int y_rs, int B) {
+    return gemm_h_usable(W, X, x_bs, x_rs, T, R, Y, y_bs, y_rs, B) && (tc_chunk_ok(B, T) || T == 8);
 }
 
 static int elu_poly_env() {
@@ -833,7 +935,7 @@ static int elu_poly_env() {
 }
 
 static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs, int x_rs, int B, int T, CUtensorMap* map_hi,
-                             CUtensorMap* map_lo, CUtensorMap* map_x, int* num_sms_out) {
+                             CUtensorMap* map_lo, CUtensorMap* map_x, int* num_sms_out, bool flat = false) {
     using namespace th;
     static bool attr_set = false;
     if (!attr_set) {
@@ -852,13 +954,36 @@ static cudaError_t th_common(const PackedMat& W, const float* X, long long x_bs,
             !tc::make_map_dt(map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W.H_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
             return cudaErrorInvalidValue;
     }
-    {
+    if (flat) {   // {t, clip, k}: a box is 128 / T whole clips x 32 k; its shared-memory image is the usual [32 k][128 columns]
+        const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)W.K};
+        const cuuint64_t strides[2] = {(cuuint64_t)x_bs * 4, (cuuint64_t)x_rs * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)T, (cuuint32_t)(BN / T), BK};
+        if (!tc::make_map(map_x, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+    } else {
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.K, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)x_rs * 4, (cuuint64_t)x_bs * 4};
         const cuuint32_t box[3] = {BN, BK, 1};
         if (!tc::make_map(map_x, X, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
     }
     return cudaSuccess;
+}
+
+// output map of a flat launch: {t, clip, m}, one store = 32 / T whole clips x 128 rows (a [128][32] staging chunk)
+static bool flat_map_y(CUtensorMap* map_y, float* Y, long long y_bs, int y_rs, int B, int T, int M) {
+    using namespace th;
+    const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)M};
+    const cuuint64_t strides[2] = {(cuuint64_t)y_bs * 4, (cuuint64_t)y_rs * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)T, (cuuint32_t)(32 / T), BM};
+    return tc::make_map(map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+// tile bookkeeping of a flat launch: the kernel sees ONE clip of B * T columns
+static void flat_params(th::Params& p, int B, int T) {
+    using namespace th;
+    p.flat_t = T; p.flat_b = B;
+    p.T = B * T; p.B = 1;
+    p.t_step = BN; p.t_halo = 0;
+    p.tiles_t = (p.T + BN - 1) / BN;
+    p.total_tiles = (long long)p.num_m * p.tiles_t;
 }
 
 // weight residency (Params::a_res): on unless HILCODEC_A_RESIDENT=0, for K <= 192 and a grid that is a multiple of num_m
@@ -923,9 +1048,12 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     if (B == 0 || T == 0) return cudaSuccess;
     CUtensorMap map_hi, map_lo, map_x, map_y;
     int num_sms = 0;
-    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
+    const bool flat = !tc_chunk_ok(B, T);
+    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms, flat);
     if (e != cudaSuccess) return e;
-    {
+    if (flat) {
+        if (!flat_map_y(&map_y, Y, y_bs, y_rs, B, T, W.M)) return cudaErrorInvalidValue;
+    } else {
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
         const cuuint32_t box[3] = {32, BM, 1};
@@ -941,6 +1069,7 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.t_step = BN; p.t_halo = 0;
     p.tiles_t = (T + p.t_step - 1) / p.t_step;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    if (flat) flat_params(p, B, T);
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
     p.xform_sleep = tc::xform_sleep_env();
@@ -1097,9 +1226,14 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     if (B == 0 || T == 0) return cudaSuccess;
     CUtensorMap map_hi, map_lo, map_x, map_y, map_y28;
     int num_sms = 0;
-    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms);
+    const bool flat = !tc_chunk_ok(B, T);
+    if (flat && T != 8) return cudaErrorInvalidValue;   // the flat epilogue is written for 8 samples per clip
+    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms, flat);
     if (e != cudaSuccess) return e;
-    {
+    if (flat) {
+        if (!flat_map_y(&map_y, Y, y_bs, y_rs, B, T, W.M)) return cudaErrorInvalidValue;
+        map_y28 = map_y;
+    } else {
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
         const cuuint32_t box[3] = {32, BM, 1};
@@ -1118,6 +1252,7 @@ cudaError_t launch_gemm_h_dw(const PackedMat& W, const float* X, long long x_bs,
     p.t_step = BN - 4; p.t_halo = 4;
     p.tiles_t = (T + p.t_step - 1) / p.t_step;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    if (flat) flat_params(p, B, T);
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f;
     p.dw_w = dw_w; p.dw_b = dw_b; p.cache_in = cache_in; p.cache_out = cache_out;
     p.reduce_add = skip ? 1 : 0;

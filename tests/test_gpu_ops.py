@@ -109,6 +109,12 @@ def test_dwconv_transpose(B, Cc, T, S, pre):
     (1, 1536, 128, 1, 0, False, False),
     (3, 384, 768, 40, 1, False, True),
     (64, 96, 96, 5, 1, True, False),
+    # flat tiles (128 / T whole clips per tile) for short chunks of many streams
+    (64, 1024, 512, 8, 0, True, False),
+    (64, 768, 1536, 8, 2, True, True),
+    (50, 256, 257, 8, 1, False, True),    # odd K, clips not a multiple of 16
+    (40, 192, 384, 4, 1, True, False),    # 4 samples per clip: 32 clips per tile
+    (9, 128, 96, 16, 0, False, True),     # 16 samples per clip, 144 columns: second tile nearly empty
     # 64 concurrent streams, one hop: 40-column chunks take the tensor-core tiles (one partly filled tile per clip)
     (64, 256, 256, 40, 1, False, False),
     (64, 384, 768, 40, 0, True, True),
@@ -186,6 +192,11 @@ def test_stft_logmag(B, n_fft, hop, T):
     (64, 256, 40, True, 1),     # 64 streams, one hop: fused tensor-core kernel on a 40-column chunk (44 of 128 tile columns)
     (64, 384, 40, False, 2),
     (33, 128, 36, True, 1),     # shortest chunk the tensor-core tiles take (T >= 32, B * T > 512)
+    # flat tiles: 16 whole 8-sample clips per 128-column tile ({t, clip, k} tensor map), every clip's window from its cache
+    (64, 768, 8, True, 0),      # decoder stage 1 at 64 streams: unit 1 of a ResBlock (in-place residual)
+    (64, 512, 8, False, 2),     # encoder stage 3: unit 0 (pre-scale + ELU prologue)
+    (37, 192, 8, True, 1),      # clips not a multiple of 4 / 16: partly filled last chunk and tile
+    (16, 256, 8, False, 1),     # exactly one tile
 ])
 def test_dws_block(B, Cc, T, skip, pre):
     """DWSBlock (ELU -> 1x1 -> depthwise k5 + bias) plus the ResBlock's residual add."""
