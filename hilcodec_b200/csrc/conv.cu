@@ -87,7 +87,8 @@ __global__ void dwconv_kernel(const float* __restrict__ x, long long x_bs, int x
                               long long y_bs, int y_rs, int C, int T, int T_out, int pre, float pre_scale, int post,
                               float post_scale) {
     constexpr int P = K - S;
-    const int c = blockIdx.y, b = blockIdx.z;
+    const int c = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;   // blockDim.y > 1: short chunks, many rows per CTA
+    if (c >= C) return;
     const float* xr = x + b * x_bs + (long long)c * x_rs;
     const float* ci = cache_in + ((size_t)b * C + c) * P;
     float wk[K];
@@ -120,7 +121,8 @@ __global__ void dwconv5_kernel(const float* __restrict__ x, long long x_bs, int 
                                const float* __restrict__ bias, const float* skip, float* y,
                                long long y_bs, int y_rs, int C, int T, int pre, float pre_scale, int post,
                                float post_scale) {
-    const int c = blockIdx.y, b = blockIdx.z;
+    const int c = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;   // blockDim.y > 1: short chunks, many rows per CTA
+    if (c >= C) return;
     const float* xr = x + b * x_bs + (long long)c * x_rs;
     const float* ci = cache_in + ((size_t)b * C + c) * 4;
     float wk[5];
@@ -187,7 +189,8 @@ __global__ void dwconv_strided4_kernel(const float* __restrict__ x, long long x_
     constexpr int P4 = (P + 3) & ~3;
     constexpr int D = P4 - P;
     constexpr int NV = (P4 + 4 * S) / 4;
-    const int c = blockIdx.y, b = blockIdx.z;
+    const int c = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;   // blockDim.y > 1: short chunks, many rows per CTA
+    if (c >= C) return;
     const float* xr = x + b * x_bs + (long long)c * x_rs;
     const float* ci = cache_in + ((size_t)b * C + c) * P;
     float wk[K];
@@ -249,6 +252,20 @@ __global__ void dwconv_strided4_kernel(const float* __restrict__ x, long long x_
     }
 }
 
+// Block shape of the depthwise kernels: threads along time x channel rows per CTA.  Long chunks: 32 / 128 time threads, one
+// row.  Short chunks (streaming: 1 - 8 samples per row) used to launch one 32-thread CTA per (channel, clip) with one or two
+// live threads -- 98 304 CTAs and 54 us for 1536 channels x 64 streams; now a CTA covers 128 / tx rows.
+static inline dim3 dw_block(int time_threads, int min_tx) {
+    if (time_threads >= 128) return dim3(128, 1);
+    if (time_threads > 16) return dim3(32, 1);
+    int tx = 1;
+    while (tx < time_threads || tx < min_tx) tx <<= 1;
+    return dim3(tx, 128 / tx);
+}
+static inline dim3 dw_grid(int time_threads, dim3 block, int C, int B) {
+    return dim3(min((time_threads + (int)block.x - 1) / (int)block.x, 512), (C + (int)block.y - 1) / (int)block.y, B);
+}
+
 cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float* cache_in, float* cache_out,
                           const float* w, const float* bias, const float* skip, float* y, long long y_bs, int y_rs,
                           int B, int C, int T, int K, int S, int pre, float pre_scale, int post, float post_scale,
@@ -263,16 +280,14 @@ cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float*
                          (skip == nullptr || (reinterpret_cast<uintptr_t>(skip) & 15) == 0);
     if (K == 5 && S == 1 && aligned) {
         const int Tq = (T + 3) / 4;
-        const int threads = Tq >= 128 ? 128 : 32;
-        dim3 grid(min((Tq + threads - 1) / threads, 512), C, B);
+        const dim3 threads = dw_block(Tq, 4), grid = dw_grid(Tq, threads, C, B);
         dwconv5_kernel<<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y, y_bs, y_rs, C, T,
                                                  pre, pre_scale, post, post_scale);
         return cudaGetLastError();
     }
     if (aligned && K == 2 * S && T % S == 0 && T_out >= 16) {
         const int Tq = (T_out + 3) / 4;
-        const int threads = Tq >= 128 ? 128 : 32;
-        dim3 grid(min((Tq + threads - 1) / threads, 512), C, B);
+        const dim3 threads = dw_block(Tq, P), grid = dw_grid(Tq, threads, C, B);
 #define HIL_DWS4(KK, SS)                                                                                                  \
     if (K == KK && S == SS) {                                                                                            \
         dwconv_strided4_kernel<KK, SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y,   \
@@ -283,8 +298,7 @@ cudaError_t launch_dwconv(const float* x, long long x_bs, int x_rs, const float*
         HIL_DWS4(4, 2) HIL_DWS4(8, 4) HIL_DWS4(10, 5) HIL_DWS4(16, 8)
 #undef HIL_DWS4
     }
-    const int threads = T_out >= 128 ? 128 : 32;
-    dim3 grid(min((T_out + threads - 1) / threads, 512), C, B);
+    const dim3 threads = dw_block(T_out, P), grid = dw_grid(T_out, threads, C, B);
 #define HIL_DW(KK, SS)                                                                                              \
     if (K == KK && S == SS) {                                                                                       \
         dwconv_kernel<KK, SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, bias, skip, y, y_bs, \
@@ -306,7 +320,8 @@ template <int S>
 __global__ void dwconvT_kernel(const float* __restrict__ x, long long x_bs, int x_rs, const float* __restrict__ cache_in,
                                float* __restrict__ cache_out, const float* __restrict__ w, float* __restrict__ y,
                                long long y_bs, int y_rs, int C, int T, int pre, float pre_scale, int vec) {
-    const int c = blockIdx.y, b = blockIdx.z;
+    const int c = blockIdx.y * blockDim.y + threadIdx.y, b = blockIdx.z;   // blockDim.y > 1: short chunks, many rows per CTA
+    if (c >= C) return;
     const float* xr = x + b * x_bs + (long long)c * x_rs;
     const float cprev = cache_in[(size_t)b * C + c];
     float wc[2 * S];
@@ -357,8 +372,9 @@ cudaError_t launch_dwconv_transpose(const float* x, long long x_bs, int x_rs, co
     const int vec = ((x_rs & 3) == 0) && ((x_bs & 3) == 0) && ((y_rs & 3) == 0) && ((y_bs & 3) == 0) &&
                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
     const int Tq = (T + 3) / 4;
-    const int threads = Tq >= 128 ? 128 : 32;
-    dim3 grid(max(1, min((Tq + threads - 1) / threads, 512)), C, B);
+    const dim3 threads = dw_block(Tq, 1);
+    dim3 grid = dw_grid(Tq, threads, C, B);
+    if (grid.x < 1) grid.x = 1;
 #define HIL_DWT(SS)                                                                                                  \
     if (S == SS) {                                                                                                   \
         dwconvT_kernel<SS><<<grid, threads, 0, st>>>(x, x_bs, x_rs, cache_in, cache_out, w, y, y_bs, y_rs, C, T, pre, \

@@ -912,11 +912,16 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 }  // namespace th
 
 // ------------------------------------------------------------------------------- host side
+// samples per clip a flat launch uses: T itself, or 4 for shorter rows whose pitch is 4
+static inline int flat_t_of(int T, int x_rs, int y_rs) { return (T < 4 && x_rs == 4 && y_rs == 4) ? 4 : T; }
+
 bool gemm_h_usable(const PackedMat& W, const float* X, long long x_bs, int x_rs, int T, const float* R, const float* Y,
                    long long y_bs, int y_rs, int B) {
     if (!W.H_hi || !W.H_lo) return false;
-    // short chunks: flat tiles when there are enough clips (tc_flat_ok), else the flattened-column FP32 kernels
-    if (!tc_chunk_ok(B, T) && !tc_flat_ok(B, T)) return false;
+    // short chunks: flat tiles when there are enough clips (tc_flat_ok), else the flattened-column FP32 kernels.  Rows of
+    // 1 - 3 samples stored with pitch 4 (every activation buffer of the codec) run as 4-sample clips: the pad columns
+    // are computed and stored like any other and never read.
+    if (!tc_chunk_ok(B, T) && !tc_flat_ok(B, flat_t_of(T, x_rs, y_rs))) return false;
     if ((x_rs & 3) || (x_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
     if (R && (reinterpret_cast<uintptr_t>(R) & 15)) return false;
@@ -1049,10 +1054,11 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     CUtensorMap map_hi, map_lo, map_x, map_y;
     int num_sms = 0;
     const bool flat = !tc_chunk_ok(B, T);
-    cudaError_t e = th_common(W, X, x_bs, x_rs, B, T, &map_hi, &map_lo, &map_x, &num_sms, flat);
+    const int Tf = flat ? flat_t_of(T, x_rs, y_rs) : T;   // samples per clip as the flat maps see them (pad columns included)
+    cudaError_t e = th_common(W, X, x_bs, x_rs, B, Tf, &map_hi, &map_lo, &map_x, &num_sms, flat);
     if (e != cudaSuccess) return e;
     if (flat) {
-        if (!flat_map_y(&map_y, Y, y_bs, y_rs, B, T, W.M)) return cudaErrorInvalidValue;
+        if (!flat_map_y(&map_y, Y, y_bs, y_rs, B, Tf, W.M)) return cudaErrorInvalidValue;
     } else {
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)W.M, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
@@ -1069,7 +1075,7 @@ cudaError_t launch_gemm_h(const PackedMat& W, const float* X, long long x_bs, in
     p.t_step = BN; p.t_halo = 0;
     p.tiles_t = (T + p.t_step - 1) / p.t_step;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
-    if (flat) flat_params(p, B, T);
+    if (flat) flat_params(p, B, Tf);
     p.pre = pre; p.pre_scale = (pre == PRE_SCALE_ELU) ? pre_scale : 1.0f; p.bias = bias; p.reduce_add = R ? 1 : 0;
     p.c_big = W.h_inv_scale; p.c_small = W.h_inv_scale * (1.0f / LO_SCALE);
     p.xform_sleep = tc::xform_sleep_env();

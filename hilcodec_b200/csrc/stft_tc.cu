@@ -387,9 +387,11 @@ static bool stft_use_h() {
 }
 
 bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
-                    int y_rs) {
+                    int y_rs, int B) {
     if (!Wdft.A_hi || !Wdft.A_lo) return false;
-    if (T < 64 || (Wdft.K % 32) != 0) return false;
+    // >= 64 windows per clip, or >= 32 when there are more columns than the skinny FP32 kernel takes (64 streams x 40
+    // windows: one partly filled 128-window tile per clip instead of gemm.cu, 43 -> ~12 us)
+    if ((T < 64 && !(T >= 32 && (long long)B * T > 512)) || (Wdft.K % 32) != 0) return false;
     if ((w_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
     if ((reinterpret_cast<uintptr_t>(wav) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
     return true;

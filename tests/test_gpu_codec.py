@@ -250,6 +250,37 @@ def test_full_size_properties_config2():
     assert bad == 0 or worst < 1e-5, (bad, worst)
 
 
+@pytest.mark.parametrize("name,n_q,streams", [("hil_music", 12, 64), ("hil_speech", 8, 40)])
+def test_many_streams_hop_by_hop_matches_one_shot(name, n_q, streams):
+    """Config 4 with many concurrent streams, one 320-sample hop per call.  At >= 16 streams the 8-sample layers of a hop
+    (the widest of the model) run on flat tensor-core tiles (128 / 8 whole clips per tile: gemm_h.cu `flat_t`), the
+    40-window STFT on the tensor-core STFT kernel, the short depthwise rows many per CTA.  The hop-by-hop result must be
+    the one-shot result of the same audio: indices equal up to fp64 near ties, PCM within the bar on every stream whose
+    indices all agree."""
+    cfg = W.CONFIGS[name]
+    w = W.load_pretrained(name) if W.have_pretrained(name) else W.random_weights(cfg, 4)
+    m = _model(w, n_q)
+    hops = 8
+    x = synth_wav(streams, 320 * hops, seed=77).cuda()
+    idx, y = m.codec_forward(x, n_q)
+    ce, _ = m.initialize_cache(x)
+    z, _ = m.encoder(x, *ce)
+    st = m.new_stream_state(streams)
+    ids, ys = [], []
+    for h in range(hops):
+        i2, y2 = m.codec_forward(x[:, :, 320 * h:320 * (h + 1)], n_q, state=st)
+        ids.append(i2)
+        ys.append(y2)
+    idc, yc = torch.cat(ids, 2), torch.cat(ys, 2)
+    assert torch.isfinite(yc).all()
+    assert (idc == idx).float().mean().item() > 0.995
+    bad, worst = index_report(oracle_cfg(n_q), params(w), z, idx, idc.cpu(), n_q)
+    assert bad == 0 or worst < 1e-5, (bad, worst)
+    rows_equal = (idc == idx).all(dim=0).all(dim=1)          # streams whose every index agrees
+    assert rows_equal.float().mean().item() > 0.8
+    assert (yc[rows_equal] - y[rows_equal]).abs().max().item() < TOL
+
+
 def test_full_size_properties_config3():
     """BASELINE config 3 size (hil_music, 256 x 24000, n_q = 12: the bench workload, 19 200 frames per step): batch
     rows are independent of the batch they ride in, outputs are finite and bounded by tanh, ||z_t|| = sqrt(128),

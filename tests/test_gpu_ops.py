@@ -149,7 +149,7 @@ def test_pointwise(B, M, K, T, pre, bias, res):
     assert err <= max(4 * ref_err, 2e-6, 1.2e-8 * K), (err, ref_err)
 
 
-@pytest.mark.parametrize("B,n_fft,hop,T", [(2, 64, 1, 640), (2, 128, 2, 320), (1, 256, 8, 75),
+@pytest.mark.parametrize("B,n_fft,hop,T", [(2, 64, 1, 640), (2, 128, 2, 320), (1, 256, 8, 75), (64, 256, 8, 40),
                                             (2, 512, 40, 15), (2, 1024, 320, 3), (1, 1024, 320, 1),
                                             # tensor-core kernel (T >= 64, 16-byte aligned rows)
                                             (2, 64, 1, 1000), (2, 128, 2, 500), (2, 256, 8, 300),
