@@ -163,7 +163,7 @@ static int32_t run_gemm_chlast_in(const PackedMat& W, const float* Q, int B, int
 static int32_t run_gemm_stft_logmag(const PackedMat& Wd, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
                                     long long y_bs, int y_rs, cudaStream_t st) {
     const double n = (double)B * T;
-    const bool tcore = tc_on() && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs, B);
+    const bool tcore = tc_on() && stft_tc_usable(Wd, wav, w_bs, T, Y, y_bs, y_rs, B, hop);
     HIL_LAUNCH(CAT_GEMM_STFT, 2.0 * Wd.M * Wd.K * n, 4.0 * (n * hop + n * (Wd.M / 2)) + 4.0 * Wd.M * Wd.K, st,
                tcore ? launch_stft_tc(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)
                : gemm_skinny_usable(Wd, B, T) ? launch_gemm_skinny_stft_logmag(Wd, wav, w_bs, hop, B, T, Y, y_bs, y_rs, st)

@@ -169,7 +169,7 @@ cudaError_t launch_gemm_tc_dw(const PackedMat& W, const float* X, long long x_bs
 
 // ---- stft_tc.cu: launch_gemm_stft_logmag on the tensor pipe
 bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
-                    int y_rs, int B = 1);
+                    int y_rs, int B = 1, int hop = 1);
 cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_bs, int hop, int B, int T, float* Y,
                            long long y_bs, int y_rs, cudaStream_t st);
 

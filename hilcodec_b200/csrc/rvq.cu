@@ -585,16 +585,20 @@ __device__ __forceinline__ void rvq_cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// FPW = frames per warp (1, 2 or 4): a CTA covers 8 * FPW frames.  Few frames (64 concurrent streams = 64 frames per hop)
+// are spread over more clusters with FPW = 1 instead of leaving 3 of 4 frame slots per warp to two clusters.
+template <int FPW>
 __global__ void __launch_bounds__(256, 1)
 rvq_cluster_kernel(const float* __restrict__ z, const float* __restrict__ codebooks, const float* __restrict__ ee, int size,
                    int tiles, long long frames, int n, int64_t* __restrict__ idx, float* __restrict__ qsum, int drop_xx) {
+    constexpr int FT = 8 * FPW;                             // frames per CTA
     extern __shared__ __align__(16) float smem[];
-    float* R = smem;                                        // [RVQ_FT][RVQ_PITCH]
-    float* E0 = smem + RVQ_FT * RVQ_PITCH;                  // 2 x [RVQ_CT][RVQ_PITCH]
-    RvqCand* cand = reinterpret_cast<RvqCand*>(E0 + 2 * RVQ_CT * RVQ_PITCH);   // [2 parities][tiles][RVQ_FT]
+    float* R = smem;                                        // [FT][RVQ_PITCH]
+    float* E0 = smem + FT * RVQ_PITCH;                  // 2 x [RVQ_CT][RVQ_PITCH]
+    RvqCand* cand = reinterpret_cast<RvqCand*>(E0 + 2 * RVQ_CT * RVQ_PITCH);   // [2 parities][tiles][FT]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long f0 = (long long)blockIdx.y * RVQ_FT;
+    const long long f0 = (long long)blockIdx.y * FT;
     const int tile = blockIdx.x;                            // = rank in the cluster (cluster dims (tiles, 1, 1))
     const int c0 = tile * RVQ_CT;
 
@@ -611,13 +615,13 @@ rvq_cluster_kernel(const float* __restrict__ z, const float* __restrict__ codebo
     };
 
     prefetch(0);
-    float4 q[4];
+    float4 q[FPW];
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {                           // residual rows of this warp's 4 frames (lane owns 4 dims)
-        const long long fr = f0 + warp * 4 + f;
+    for (int f = 0; f < FPW; ++f) {                           // residual rows of this warp's 4 frames (lane owns 4 dims)
+        const long long fr = f0 + warp * FPW + f;
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fr < frames) r = *reinterpret_cast<const float4*>(z + fr * RVQ_DIM + lane * 4);
-        *reinterpret_cast<float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]) = r;
+        *reinterpret_cast<float4*>(&R[(warp * FPW + f) * RVQ_PITCH + lane * 4]) = r;
         q[f] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     rvq_cluster_sync();                                     // every CTA of the cluster is resident before any DSMEM store
@@ -629,30 +633,30 @@ rvq_cluster_kernel(const float* __restrict__ z, const float* __restrict__ codebo
         const float* E = E0 + (size_t)(s & 1) * RVQ_CT * RVQ_PITCH;
         const float* ees = ee + (size_t)s * size;
 
-        float xx[4];
+        float xx[FPW];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            const float4 v = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]);
+        for (int f = 0; f < FPW; ++f) {
+            const float4 v = *reinterpret_cast<const float4*>(&R[(warp * FPW + f) * RVQ_PITCH + lane * 4]);
             float p = __fmul_rn(v.x, v.x);
             p = fmaf(v.y, v.y, p); p = fmaf(v.z, v.z, p); p = fmaf(v.w, v.w, p);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
             xx[f] = drop_xx ? 0.f : p;
         }
-        float dot[4][4];
+        float dot[FPW][4];
 #pragma unroll
-        for (int f = 0; f < 4; ++f)
+        for (int f = 0; f < FPW; ++f)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dot[f][j] = 0.f;
 #pragma unroll 4
         for (int k4 = 0; k4 < RVQ_DIM / 4; ++k4) {
-            float4 r4[4], e4[4];
+            float4 r4[FPW], e4[4];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) r4[f] = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + k4 * 4]);
+            for (int f = 0; f < FPW; ++f) r4[f] = *reinterpret_cast<const float4*>(&R[(warp * FPW + f) * RVQ_PITCH + k4 * 4]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) e4[j] = *reinterpret_cast<const float4*>(&E[(lane + 32 * j) * RVQ_PITCH + k4 * 4]);
 #pragma unroll
-            for (int f = 0; f < 4; ++f)
+            for (int f = 0; f < FPW; ++f)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float d = dot[f][j];
@@ -663,25 +667,25 @@ rvq_cluster_kernel(const float* __restrict__ z, const float* __restrict__ codebo
                     dot[f][j] = d;
                 }
         }
-        float best[4];
-        int besti[4];
+        float best[FPW];
+        int besti[FPW];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) { best[f] = -INFINITY; besti[f] = 0x7fffffff; }
+        for (int f = 0; f < FPW; ++f) { best[f] = -INFINITY; besti[f] = 0x7fffffff; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int code = c0 + lane + 32 * j;
             if (code < size) {
                 const float e2 = ees[code];
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
+                for (int f = 0; f < FPW; ++f) {
                     const float d = -__fadd_rn(__fsub_rn(xx[f], __fmul_rn(2.f, dot[f][j])), e2);
                     if (d > best[f]) { best[f] = d; besti[f] = code; }
                 }
             }
         }
-        RvqCand* cs = cand + (size_t)(s & 1) * tiles * RVQ_FT;   // this stage's mailbox: [tiles][RVQ_FT]
+        RvqCand* cs = cand + (size_t)(s & 1) * tiles * FT;   // this stage's mailbox: [tiles][FT]
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
+        for (int f = 0; f < FPW; ++f) {
             float bd = best[f];
             int bi = besti[f];
 #pragma unroll
@@ -692,7 +696,7 @@ rvq_cluster_kernel(const float* __restrict__ z, const float* __restrict__ codebo
             }
             // lane t < tiles delivers this CTA's candidate for the frame into CTA t's mailbox
             if (lane < tiles) {
-                const uint32_t local = rvq_smem_u32(&cs[tile * RVQ_FT + warp * 4 + f]);
+                const uint32_t local = rvq_smem_u32(&cs[tile * FT + warp * FPW + f]);
                 uint32_t remote;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(lane));
                 asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(remote), "r"(__float_as_uint(bd)), "r"(bi) : "memory");
@@ -700,38 +704,38 @@ rvq_cluster_kernel(const float* __restrict__ z, const float* __restrict__ codebo
         }
         rvq_cluster_sync();                                 // all candidates of stage s have landed everywhere
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            const long long fr = f0 + warp * 4 + f;
+        for (int f = 0; f < FPW; ++f) {
+            const long long fr = f0 + warp * FPW + f;
             float bd = -INFINITY;
             int bi = 0x7fffffff;
             for (int t = 0; t < tiles; ++t) {               // ascending code ranges: strict > keeps the first maximum
-                const RvqCand c = cs[t * RVQ_FT + warp * 4 + f];
+                const RvqCand c = cs[t * FT + warp * FPW + f];
                 if (c.d > bd || (c.d == bd && c.i < bi)) { bd = c.d; bi = c.i; }
             }
             if (bi < 0 || bi >= size) bi = 0;               // all-NaN row, as in the one-kernel search
             if (fr < frames) {
                 if (tile == 0 && lane == 0) idx[(size_t)s * frames + fr] = bi;
                 const float4 e = *reinterpret_cast<const float4*>(codebooks + ((size_t)s * size + bi) * RVQ_DIM + lane * 4);
-                float4 r = *reinterpret_cast<const float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]);
+                float4 r = *reinterpret_cast<const float4*>(&R[(warp * FPW + f) * RVQ_PITCH + lane * 4]);
                 r.x = __fsub_rn(r.x, e.x); r.y = __fsub_rn(r.y, e.y); r.z = __fsub_rn(r.z, e.z); r.w = __fsub_rn(r.w, e.w);
                 q[f].x = __fadd_rn(q[f].x, e.x); q[f].y = __fadd_rn(q[f].y, e.y);
                 q[f].z = __fadd_rn(q[f].z, e.z); q[f].w = __fadd_rn(q[f].w, e.w);
-                *reinterpret_cast<float4*>(&R[(warp * 4 + f) * RVQ_PITCH + lane * 4]) = r;
+                *reinterpret_cast<float4*>(&R[(warp * FPW + f) * RVQ_PITCH + lane * 4]) = r;
             }
         }
         __syncwarp();                                       // this warp's R rows are rewritten before it reads them again
     }
     if (tile == 0 && qsum) {
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            const long long fr = f0 + warp * 4 + f;
+        for (int f = 0; f < FPW; ++f) {
+            const long long fr = f0 + warp * FPW + f;
             if (fr < frames) *reinterpret_cast<float4*>(qsum + fr * RVQ_DIM + lane * 4) = q[f];
         }
     }
 }
 
-static size_t rvq_cluster_smem(int tiles) {
-    return (size_t)(RVQ_FT + 2 * RVQ_CT) * RVQ_PITCH * sizeof(float) + (size_t)2 * tiles * RVQ_FT * sizeof(RvqCand);
+static size_t rvq_cluster_smem(int tiles, int ft) {
+    return (size_t)(ft + 2 * RVQ_CT) * RVQ_PITCH * sizeof(float) + (size_t)2 * tiles * ft * sizeof(RvqCand);
 }
 
 // HILCODEC_RVQ_CLUSTER=0 keeps the per-stage launches (A/B knob)
@@ -741,16 +745,15 @@ bool rvq_cluster_usable(int size, int dim, long long frames) {
     return on && dim == RVQ_DIM && frames > 0 && frames <= RVQ_SPLIT_MAX_FRAMES && tiles >= 1 && tiles <= 8;
 }
 
-cudaError_t launch_rvq_encode_cluster(const float* z, const float* codebooks, const float* ee, int size, int dim,
+template <int FPW>
+static cudaError_t launch_cluster_fpw(const float* z, const float* codebooks, const float* ee, int size, int tiles,
                                       long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
-    if (dim != RVQ_DIM) return cudaErrorInvalidValue;
-    if (frames == 0 || n == 0) return cudaSuccess;
-    const int tiles = (size + RVQ_CT - 1) / RVQ_CT;
-    const size_t smem = rvq_cluster_smem(tiles);
+    constexpr int FT = 8 * FPW;
+    const size_t smem = rvq_cluster_smem(tiles, FT);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rvq_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)rvq_cluster_smem(8));
+        cudaError_t e = cudaFuncSetAttribute(rvq_cluster_kernel<FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)rvq_cluster_smem(8, FT));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -758,13 +761,27 @@ cudaError_t launch_rvq_encode_cluster(const float* z, const float* codebooks, co
     cudaLaunchAttribute attr{};
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = (unsigned)tiles; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.gridDim = dim3((unsigned)tiles, (unsigned)((frames + RVQ_FT - 1) / RVQ_FT));
+    cfg.gridDim = dim3((unsigned)tiles, (unsigned)((frames + FT - 1) / FT));
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, rvq_cluster_kernel, z, codebooks, ee, size, tiles, frames, n, idx, qsum, drop_xx ? 1 : 0);
+    return cudaLaunchKernelEx(&cfg, rvq_cluster_kernel<FPW>, z, codebooks, ee, size, tiles, frames, n, idx, qsum,
+                              drop_xx ? 1 : 0);
+}
+
+cudaError_t launch_rvq_encode_cluster(const float* z, const float* codebooks, const float* ee, int size, int dim,
+                                      long long frames, int n, int64_t* idx, float* qsum, bool drop_xx, cudaStream_t st) {
+    if (dim != RVQ_DIM) return cudaErrorInvalidValue;
+    if (frames == 0 || n == 0) return cudaSuccess;
+    const int tiles = (size + RVQ_CT - 1) / RVQ_CT;
+    // frames per warp: as few as keeps the launch at <= 16 clusters (128 CTAs of 148 SMs); HILCODEC_RVQ_FPW=<1|2|4> forces
+    static const int forced = []() { const char* e = std::getenv("HILCODEC_RVQ_FPW"); return e ? std::atoi(e) : 0; }();
+    const int fpw = forced ? forced : (frames <= 128 ? 1 : frames <= 256 ? 2 : 4);
+    if (fpw == 1) return launch_cluster_fpw<1>(z, codebooks, ee, size, tiles, frames, n, idx, qsum, drop_xx, st);
+    if (fpw == 2) return launch_cluster_fpw<2>(z, codebooks, ee, size, tiles, frames, n, idx, qsum, drop_xx, st);
+    return launch_cluster_fpw<4>(z, codebooks, ee, size, tiles, frames, n, idx, qsum, drop_xx, st);
 }
 
 bool rvq_split_usable(int size, int dim, long long frames) {

@@ -57,6 +57,7 @@ struct Params {
     const float* wav;    // window base (first sample of the window of frame 0)
     long long w_bs;      // batch stride of wav
     float c_big;         // kH: 2^-s of the DFT basis' fp16 scaling (gemm_h.cu)
+    int flat_t;          // flat tiles (gemm_h.cu): windows per clip, 128 / flat_t whole clips per tile; T = all flat columns, B = 1
 };
 
 template <bool kH>
@@ -128,7 +129,10 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_arrive_expect_tx(full_bar(s), 2 * A_BYTES + (p.gather ? 0 : TILE_BYTES));
                     tma_load_2d(&map_a_hi, st, full_bar(s), kb * BK, m_blk * BM);
                     tma_load_2d(&map_a_lo, st + A_BYTES, full_bar(s), kb * BK, m_blk * BM);
-                    if (!p.gather) tma_load_3d(&map_x, st + RAW_OFF, full_bar(s), kb * BK, tt * BN, b);
+                    if (!p.gather) {
+                        if (p.flat_t) tma_load_3d(&map_x, st + RAW_OFF, full_bar(s), kb * BK, 0, tt * (BN / p.flat_t));
+                        else tma_load_3d(&map_x, st + RAW_OFF, full_bar(s), kb * BK, tt * BN, b);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -293,7 +297,7 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // same mask, so the thread that commits a bulk group is the one that waits for it)
         [[maybe_unused]] const bool issuer = (q == 0 && lane == 0);
         const bool even = (lane & 1) == 0;
-        const uint32_t sw = (uint32_t)(frow & 7);
+        const uint32_t sw = p.flat_t ? 0u : (uint32_t)(frow & 7);   // flat tiles stage unswizzled (see gemm_h.cu)
         long long it = 0;
         uint32_t g = 0;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -357,7 +361,8 @@ stft_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 fence_proxy_async();
                 epi_bar_sync();
                 if (q == 0 && elect_one()) {
-                    tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * 64, b);
+                    if (p.flat_t) tma_store_3d(&map_y, obuf, 0, (t0 + c * 32) / p.flat_t, m_blk * 64);
+                    else tma_store_3d(&map_y, obuf, t0 + c * 32, m_blk * 64, b);
                     tma_commit();
                 }
             }
@@ -386,12 +391,21 @@ static bool stft_use_h() {
     return v;
 }
 
+// windows per clip of a flat launch (0: not flat): short chunks of many streams, as in gemm_h.cu -- T itself, or 4 for
+// 1 - 3 windows when the output rows have pitch 4 (the windows past the clip's last one are out of the tensor map's
+// bounds and load as zeros)
+static inline int stft_flat_t(int T, int y_rs, int B) {
+    const int tf = (T < 4 && y_rs == 4) ? 4 : T;
+    return (T < 32 && tc_flat_ok(B, tf)) ? tf : 0;
+}
+
 bool stft_tc_usable(const PackedMat& Wdft, const float* wav, long long w_bs, int T, const float* Y, long long y_bs,
-                    int y_rs, int B) {
+                    int y_rs, int B, int hop) {
     if (!Wdft.A_hi || !Wdft.A_lo) return false;
     // >= 64 windows per clip, or >= 32 when there are more columns than the skinny FP32 kernel takes (64 streams x 40
     // windows: one partly filled 128-window tile per clip instead of gemm.cu, 43 -> ~12 us)
-    if ((T < 64 && !(T >= 32 && (long long)B * T > 512)) || (Wdft.K % 32) != 0) return false;
+    if ((Wdft.K % 32) != 0) return false;
+    if (T < 64 && !(T >= 32 && (long long)B * T > 512) && !((hop % 4) == 0 && stft_flat_t(T, y_rs, B))) return false;
     if ((w_bs & 3) || (y_rs & 3) || (y_bs & 3)) return false;
     if ((reinterpret_cast<uintptr_t>(wav) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15)) return false;
     return true;
@@ -428,15 +442,26 @@ cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_
             return cudaErrorInvalidValue;
     }
     int gather = (hop % 4) != 0;
+    const int flat_t = (T < 32 && !gather) ? stft_flat_t(T, y_rs, B) : 0;
+    if (T < 32 && !flat_t) return cudaErrorInvalidValue;
     if (!gather) {
-        // im2col as a tensor map with overlapping rows: row t = wav[t*hop .. t*hop + n_fft)
+        // im2col as a tensor map with overlapping rows: row t = wav[t*hop .. t*hop + n_fft); a flat box is 128 / flat_t
+        // whole clips x their windows: the same [128 windows][32 k] image
         const cuuint64_t dims[3] = {(cuuint64_t)Wdft.K, (cuuint64_t)T, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)hop * 4, (cuuint64_t)w_bs * 4};
-        const cuuint32_t box[3] = {BK, BN, 1};
-        if (!make_map(&map_x, wav, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) gather = 1;
+        const cuuint32_t box[3] = {BK, flat_t ? (cuuint32_t)flat_t : BN, flat_t ? (cuuint32_t)(BN / flat_t) : 1u};
+        if (!make_map(&map_x, wav, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) {
+            if (flat_t) return cudaErrorInvalidValue;
+            gather = 1;
+        }
     }
     if (gather) map_x = map_hi;  // unused placeholder
-    {
+    if (flat_t) {   // {t, clip, f}: one store = 32 / flat_t whole clips x 64 bins, staged unswizzled
+        const cuuint64_t dims[3] = {(cuuint64_t)flat_t, (cuuint64_t)B, (cuuint64_t)F};
+        const cuuint64_t strides[2] = {(cuuint64_t)y_bs * 4, (cuuint64_t)y_rs * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)flat_t, (cuuint32_t)(32 / flat_t), 64};
+        if (!make_map(&map_y, Y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+    } else {
         const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)y_rs * 4, (cuuint64_t)y_bs * 4};
         const cuuint32_t box[3] = {32, 64, 1};
@@ -447,6 +472,11 @@ cudaError_t launch_stft_tc(const PackedMat& Wdft, const float* wav, long long w_
     p.num_m = (Wdft.M + BM - 1) / BM;
     p.tiles_t = (T + BN - 1) / BN;
     p.total_tiles = (long long)p.num_m * p.tiles_t * B;
+    if (flat_t) {
+        p.flat_t = flat_t; p.T = B * flat_t; p.B = 1;
+        p.tiles_t = (p.T + BN - 1) / BN;
+        p.total_tiles = (long long)p.num_m * p.tiles_t;
+    }
     p.gather = gather ? (((BN - 1) * hop + Wdft.K <= SPAN_FLOATS) ? 1 : 2) : 0; p.wav = wav; p.w_bs = w_bs;
     static const int exact_log = []() { const char* e = std::getenv("HILCODEC_STFT_LOGF"); return (e && e[0] == '1') ? 1 : 0; }();
     p.exact_log = exact_log;

@@ -150,6 +150,7 @@ def test_pointwise(B, M, K, T, pre, bias, res):
 
 
 @pytest.mark.parametrize("B,n_fft,hop,T", [(2, 64, 1, 640), (2, 128, 2, 320), (1, 256, 8, 75), (64, 256, 8, 40),
+                                            (64, 512, 40, 8), (37, 512, 40, 8), (48, 1024, 320, 4),   # flat tiles: whole clips per tile
                                             (2, 512, 40, 15), (2, 1024, 320, 3), (1, 1024, 320, 1),
                                             # tensor-core kernel (T >= 64, 16-byte aligned rows)
                                             (2, 64, 1, 1000), (2, 128, 2, 500), (2, 256, 8, 300),
@@ -400,7 +401,8 @@ def test_rvq_tensor_core_search_bit_identical(size, B, F, n, train):
 
 
 @pytest.mark.parametrize("size,frames,n,train", [(1024, 1, 12, False), (1024, 64, 12, False), (1024, 75, 8, True),
-                                                  (1024, 1000, 3, False), (200, 33, 2, False), (64, 5, 4, True)])
+                                                  (1024, 1000, 3, False), (200, 33, 2, False), (64, 5, 4, True),
+                                                  (1024, 200, 4, False)])   # 1 / 2 / 4 frames per warp: <= 128 / <= 256 / more
 def test_rvq_few_frame_variants_bit_identical(size, frames, n, train, monkeypatch):
     """The streaming RVQ paths (one cluster launch with DSMEM candidate exchange; n + 1 per-stage launches) against the
     one-kernel search: same indices and the same dequantised sum, bit for bit, including exact ties."""
