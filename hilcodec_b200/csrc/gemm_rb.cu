@@ -562,13 +562,19 @@ __global__ void halo_gather_kernel(const float* __restrict__ h, long long bs, in
 }  // namespace rb
 
 // ------------------------------------------------------------------------------- host side
-static int rb_bn(int) { return 128; }
+// 128 < C <= 256: two 128-row blocks per 64-column tile (HILCODEC_RB_WIDE=1; measured slower than two fused-DWS launches in
+// round 1, re-measured after the issuer work of round 2)
+static bool rb_wide_on() {
+    static const bool on = []() { const char* e = std::getenv("HILCODEC_RB_WIDE"); return e && e[0] == '1'; }();
+    return on;
+}
+static int rb_bn(int C) { return C > 128 ? 64 : 128; }
 
 bool resblock_h_usable(const PackedMat& W0, const PackedMat& W1, const float* h, long long bs, int rs, int T) {
     const int C = W0.M;
     if (W0.K != C || W1.M != C || W1.K != C) return false;
     if (!W0.H_hi || !W0.H_lo || !W1.H_hi || !W1.H_lo) return false;
-    if (C < 32 || C > 128 || (C & 31)) return false;
+    if (C < 32 || C > (rb_wide_on() ? 256 : 128) || (C & 31)) return false;
     if (T < 128) return false;                    // short chunks (streaming) keep the two-kernel path
     if ((rs & 3) || (bs & 3) || (reinterpret_cast<uintptr_t>(h) & 15)) return false;
     return true;
@@ -655,6 +661,9 @@ cudaError_t launch_resblock_h(const PackedMat& W0, const PackedMat& W1, float* h
                               const float* c0_in, float* c0_out, const float* c1_in, float* c1_out, const float* halo,
                               cudaStream_t st) {
     if (B == 0 || T == 0) return cudaSuccess;
+    if (W0.M > 128)
+        return launch_rb<64>(W0, W1, h, bs, rs, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in, c1_out,
+                             halo, st);
     return launch_rb<128>(W0, W1, h, bs, rs, B, T, pre, pre_scale, dw0_w, dw0_b, dw1_w, dw1_b, c0_in, c0_out, c1_in, c1_out,
                           halo, st);
 }
