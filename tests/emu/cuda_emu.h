@@ -36,6 +36,7 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline float fmaxf(float a, float b) { return std::fmax(a, b); }
+inline float fminf(float a, float b) { return std::fmin(a, b); }
 // compiled with -ffp-contract=off: these stay separately rounded operations
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
