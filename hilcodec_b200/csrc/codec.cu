@@ -1048,7 +1048,7 @@ int32_t res_block(const Dws* u, float* h, float* a1, float* a2, int B, int C, in
     const long long bs = (long long)C * Tp;
     const int pre0 = pre_scale == 1.0f ? PRE_ELU : PRE_SCALE_ELU;
     // one kernel per ResBlock for C <= 128 (the 64-column two-m-block variant for 128 < C <= 256 measured slower than
-    // two fused-DWS launches in round 1 and was removed)
+    // two fused-DWS launches in round 1 and again after round 2's issuer work: opt-in, HILCODEC_RB_WIDE=1)
     static const bool pair_ok = []() { const char* e = std::getenv("HILCODEC_RB_PAIR"); return !(e && e[0] == '0'); }();
     if (tc_on() && g_use_h && g_fuse_dw && g_fuse_rb && pair_ok && (B & 1) == 0 && u[0].pw2.H_hi && u[1].pw2.H_hi &&
         resblock_h_usable(u[0].pw2, u[1].pw2, h, 2 * bs, Tp, Ts))

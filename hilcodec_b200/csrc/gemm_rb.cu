@@ -20,8 +20,8 @@
 //
 // Geometry: C <= 128: one 128-row m-block, BN = 128: an accumulator (big | small) fills 256 TMEM columns, D1 and D2
 // fill the 512.  (The kernel stays templated on BN; the two-m-block BN = 64 instantiation for 128 < C <= 256
-// re-streamed both weight matrices from L2 for every 56 outputs, measured slower than two fused-DWS launches in
-// round 1 and is no longer built.)
+// re-streams both weight matrices from L2 for every 56 outputs and issues half-width MMAs: measured slower than two
+// fused-DWS launches in round 1 and again at the end of round 2 (+2.3 ms per step), so it is opt-in: HILCODEC_RB_WIDE=1.)
 // Warp roles (512 threads, 1 CTA/SM): 0 X producer (TMA), 1 MMA issuer, 2 TMEM allocator, 3 weight producer
 // (TMA, W0 then W1 pieces through one ring), 8-15 workers: transform (ELU + split of the input tile) and E1, two warps
 // per TMEM lane quarter; 4-7 epilogue E2.  E2 of tile i overlaps the transform / G1 / E1 of tile i+1.
