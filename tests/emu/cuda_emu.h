@@ -64,21 +64,30 @@ template <class T> inline T __shfl_xor_sync(unsigned, T v, int o) {
     return r;
 }
 
-// run `kernel()` for every CTA of the grid (CTAs one after the other, the threads of a CTA concurrently)
-template <class F> void emu_launch(unsigned gx, unsigned gy, unsigned threads, F kernel, unsigned gz = 1) {
+struct dim3 {
+    unsigned x = 1, y = 1, z = 1;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+// run `kernel()` for every CTA of the grid (CTAs one after the other, the threads of a CTA concurrently); `rows` > 1 makes
+// the block two-dimensional: blockDim = (threads, rows), thread t of the CTA is (t % threads, t / threads)
+template <class F> void emu_launch(unsigned gx, unsigned gy, unsigned threads, F kernel, unsigned gz = 1, unsigned rows = 1) {
     gridDim = {gx, gy, gz};
-    blockDim = {threads, 1, 1};
+    blockDim = {threads, rows, 1};
+    const unsigned tx = threads;
+    threads *= rows;
     for (unsigned bz = 0; bz < gz; ++bz)
     for (unsigned by = 0; by < gy; ++by)
         for (unsigned bx = 0; bx < gx; ++bx) {
             std::barrier<> cta((std::ptrdiff_t)threads);
             emu::cta_bar = &cta;
             emu::warp_bar.clear();
-            for (unsigned w = 0; w < threads / 32; ++w) emu::warp_bar.push_back(std::make_unique<std::barrier<>>(32));
+            for (unsigned w = 0; w < (threads + 31) / 32; ++w)
+                emu::warp_bar.push_back(std::make_unique<std::barrier<>>((std::ptrdiff_t)(threads - 32 * w < 32 ? threads - 32 * w : 32)));
             std::vector<std::thread> ts;
             for (unsigned t = 0; t < threads; ++t)
                 ts.emplace_back([=, &kernel] {
-                    threadIdx = {t, 0, 0};
+                    threadIdx = {t % tx, t / tx, 0};
                     blockIdx = {bx, by, bz};
                     kernel();
                     emu::cta_bar->arrive_and_drop();               // a thread that returned no longer takes part

@@ -1,5 +1,6 @@
 // Runs conv.cu's causal depthwise kernels (source text extracted into conv_extracted.inc) on the CPU emulation layer
-// with the launch geometry of launch_dwconv / launch_dwconv_transpose.
+// with the launch geometry of launch_dwconv / launch_dwconv_transpose (dw_block / dw_grid, extracted too: short rows run
+// many per CTA with a two-dimensional block).
 // argv: mode K S B C T pre pre_scale has_bias has_skip post post_scale in.bin out.bin
 //   mode 0 dwconv_kernel<K,S>   1 dwconv5_kernel   2 dwconv_strided4_kernel<K,S>   3 dwconvT_kernel<S> (K = 2S)
 // rows are pitched to a multiple of 4 floats.  in.bin = x[B*C*Tp] cache[B*C*P] w[C*K] bias[C]? skip[B*C*Top]?
@@ -36,28 +37,31 @@ int main(int argc, char** argv) {
     const float* skip = has_skip ? w + nw + (has_bias ? C : 0) : nullptr;
     std::vector<float> y(ny, -12345.f), co(nc, -12345.f);
     const long long x_bs = (long long)C * Tp, y_bs = (long long)C * Top;
-    auto grid_x = [](int n, int threads) { return (unsigned)max(1, min((n + threads - 1) / threads, 512)); };
+    // geometry of the launchers: block = dw_block(time threads, min threads along time), grid = dw_grid(...)
+    auto launch = [&](int time_threads, int min_tx, auto kernel) {
+        const dim3 block = dw_block(time_threads, min_tx);
+        dim3 grid = dw_grid(time_threads, block, C, B);
+        if (grid.x < 1) grid.x = 1;
+        std::fprintf(stderr, "block (%u, %u) grid (%u, %u, %u)\n", block.x, block.y, grid.x, grid.y, grid.z);
+        emu_launch(grid.x, grid.y, block.x, kernel, grid.z, block.y);
+    };
 #define ARGS x, x_bs, Tp, ci, co.data(), w, bias, skip, y.data(), y_bs, Top, C, T
     if (mode == 1) {
-        const int Tq = (T + 3) / 4, th = Tq >= 128 ? 128 : 32;
-        emu_launch(grid_x(Tq, th), C, th, [&] { dwconv5_kernel(ARGS, pre, pre_scale, post, post_scale); }, B);
+        launch((T + 3) / 4, 4, [&] { dwconv5_kernel(ARGS, pre, pre_scale, post, post_scale); });
     } else if (mode == 0 || mode == 2) {
-        const int n = mode == 2 ? (T_out + 3) / 4 : T_out, th = n >= 128 ? 128 : 32;
-        const unsigned gx = grid_x(n, th);
+        const int n = mode == 2 ? (T_out + 3) / 4 : T_out;
 #define RUN(KK, SS)                                                                                                      \
     if (K == KK && S == SS) {                                                                                            \
-        if (mode == 2) emu_launch(gx, C, th, [&] { dwconv_strided4_kernel<KK, SS>(ARGS, T_out, pre, pre_scale, post, post_scale); }, B); \
-        else emu_launch(gx, C, th, [&] { dwconv_kernel<KK, SS>(ARGS, T_out, pre, pre_scale, post, post_scale); }, B);   \
+        if (mode == 2) launch(n, P, [&] { dwconv_strided4_kernel<KK, SS>(ARGS, T_out, pre, pre_scale, post, post_scale); }); \
+        else launch(n, P, [&] { dwconv_kernel<KK, SS>(ARGS, T_out, pre, pre_scale, post, post_scale); });               \
     }
         RUN(4, 2) RUN(8, 4) RUN(10, 5) RUN(16, 8)
         if (K == 5 && S == 1 && mode == 0)
-            emu_launch(gx, C, th, [&] { dwconv_kernel<5, 1>(ARGS, T_out, pre, pre_scale, post, post_scale); }, B);
+            launch(n, P, [&] { dwconv_kernel<5, 1>(ARGS, T_out, pre, pre_scale, post, post_scale); });
 #undef RUN
     } else if (mode == 3) {
-        const int Tq = (T + 3) / 4, th = Tq >= 128 ? 128 : 32;
-        const unsigned gx = grid_x(Tq, th);
 #define RUNT(SS) \
-    if (S == SS) emu_launch(gx, C, th, [&] { dwconvT_kernel<SS>(x, x_bs, Tp, ci, co.data(), w, y.data(), y_bs, Top, C, T, pre, pre_scale, 1); }, B);
+    if (S == SS) launch((T + 3) / 4, 1, [&] { dwconvT_kernel<SS>(x, x_bs, Tp, ci, co.data(), w, y.data(), y_bs, Top, C, T, pre, pre_scale, 1); });
         RUNT(2) RUNT(4) RUNT(5) RUNT(8)
 #undef RUNT
     } else {

@@ -259,7 +259,7 @@ def conv_exe(tmp_path_factory):
     parts = []
     for sig in ("template <int K, int S>\n__global__ void dwconv_kernel(", "__global__ void dwconv5_kernel(",
                 "template <int K, int S>\n__global__ void dwconv_strided4_kernel(",
-                "template <int S>\n__global__ void dwconvT_kernel("):
+                "template <int S>\n__global__ void dwconvT_kernel(", "static inline dim3 dw_block(", "static inline dim3 dw_grid("):
         parts.append(_function(src, src.index(sig)))
     act = ("inline float apply_act_fast(float x, int mode, float s) {\n"
            "    if (mode == PRE_NONE) return x;\n    if (mode == PRE_SCALE_ELU) x = x * s;\n"
@@ -288,6 +288,11 @@ def _pitched(t):
     (2, 8, 4, 1, 2, 72, 0, True, False, 0),    # 18 outputs: ragged last group of 4
     (2, 10, 5, 1, 2, 600, 0, True, True, 1),   # stride 5: unaligned history
     (2, 16, 8, 1, 2, 600, 0, False, False, 0),
+    # short rows (streaming): many rows per CTA, two-dimensional blocks (dw_block)
+    (1, 5, 1, 3, 70, 8, 1, True, True, 0),      # k5: 2 time threads -> block (4, 32), 70 channels over 3 CTAs
+    (1, 5, 1, 2, 40, 1, 0, True, False, 1),     # one sample per row
+    (0, 16, 8, 2, 20, 8, 2, True, False, 0),    # stride 8: one output per row, 8 cache values -> block (8, 16)
+    (0, 10, 5, 3, 33, 40, 0, False, False, 0),  # 8 outputs per row
 ])
 def test_depthwise_kernels_source_on_cpu(conv_exe, tmp_path, mode, K, S, B, C, T, pre, bias, skip, post):
     """CausalConv1d.forward causal_layers.py:160-165 (depthwise) through the three kernels of conv.cu."""
@@ -320,7 +325,8 @@ def test_depthwise_kernels_source_on_cpu(conv_exe, tmp_path, mode, K, S, B, C, T
     assert np.abs(co - xin[:, :, -P:].numpy()).max() < 1e-6
 
 
-@pytest.mark.parametrize("S,B,C,T,pre", [(2, 2, 3, 40, 2), (4, 1, 2, 1, 0), (5, 1, 2, 37, 1), (8, 2, 2, 600, 2)])
+@pytest.mark.parametrize("S,B,C,T,pre", [(2, 2, 3, 40, 2), (4, 1, 2, 1, 0), (5, 1, 2, 37, 1), (8, 2, 2, 600, 2),
+                                          (8, 3, 150, 1, 1), (5, 2, 70, 8, 2)])   # short rows: 128 / 64 rows per CTA
 def test_transposed_depthwise_kernel_source_on_cpu(conv_exe, tmp_path, S, B, C, T, pre):
     """CausalConvTranspose1d.forward causal_layers.py:183-188 (depthwise, k = 2s) with its one-sample cache."""
     g = torch.Generator().manual_seed(S * 10 + T)
