@@ -5,6 +5,7 @@
 //   convpost B C T pre pre_scale in.bin out.bin      in = x[B*C*Tp] cache[B*C*4] w[C*5] bias[1]; out = y[B*T] cache_out[B*C*4]
 //   l2norm   B C F scale in.bin out.bin              in = x[B*C*Fp]; out = z[B*F*C]
 //   wavcat   B T P in.bin out.bin                    in = x[B*T] cache[B*P]; out = wav_ext[B*Wp] cache_out[B*P]
+//   transp   B C F in.bin out.bin                    in = q[B*F*C]; out = y[B*C*Fp] (chlast_to_ncw), then rows[F*C] of batch 0 back (kmajor_to_rows)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -84,6 +85,17 @@ int main(int argc, char** argv) {
         std::vector<float> ext((size_t)B * Wp, -12345.f), co((size_t)B * P, -12345.f);
         emu_launch(min((P + T + 255) / 256, 1024), B, 256, [&] { wavcat_kernel(x, ci, co.data(), ext.data(), Wp, T, P); });
         dump(argv[6], {{ext.data(), ext.size() * 4}, {co.data(), co.size() * 4}});
+    } else if (mode == "transp") {
+        const int B = atoi(argv[2]), C = atoi(argv[3]), F = atoi(argv[4]);
+        auto in = slurp(argv[5]);
+        const float* q = reinterpret_cast<const float*>(in.data());
+        const int Fp = (F + 3) & ~3;
+        std::vector<float> y((size_t)B * C * Fp, 0.f), rows((size_t)F * C, -1.f);
+        // launch_chlast_to_ncw: grid (F/32, C/32, B), block (32, 8)
+        emu_launch((F + 31) / 32, (C + 31) / 32, 32, [&] { chlast_to_ncw_kernel(q, y.data(), C, F, (long long)C * Fp, Fp); }, B, 8);
+        // launch_kmajor_to_rows on batch 0's [C][Fp] block: grid (F/32, C/32), block (32, 8)
+        emu_launch((F + 31) / 32, (C + 31) / 32, 32, [&] { kmajor_to_rows_kernel(y.data(), Fp, rows.data(), C, F); }, 1, 8);
+        dump(argv[6], {{y.data(), y.size() * 4}, {rows.data(), rows.size() * 4}});
     } else {
         return 4;
     }

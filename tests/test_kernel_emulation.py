@@ -438,9 +438,12 @@ def misc_exe(tmp_path_factory):
     bitp = open(os.path.join(CSRC, "bitpack.cu")).read()
     parts = [_function(conv, conv.index(sig)) for sig in (
         "__global__ void wavcat_kernel(", "template <int K>\n__global__ void conv_pre_kernel(",
-        "template <int K>\n__global__ void conv_post_tanh_kernel(", "__global__ void l2norm_chlast_kernel(")]
+        "template <int K>\n__global__ void conv_post_tanh_kernel(", "__global__ void l2norm_chlast_kernel(",
+        "__global__ void chlast_to_ncw_kernel(")]
     parts += [_function(bitp, bitp.index(sig)) for sig in ("__global__ void pack_indices_kernel(",
                                                            "__global__ void unpack_indices_kernel(")]
+    rvq = open(os.path.join(CSRC, "rvq.cu")).read()
+    parts.append(_function(rvq, rvq.index("__global__ void kmajor_to_rows_kernel(")))
     text = "\n".join(parts)
     assert text.count("extern __shared__ float sw[];") == 2
     text = text.replace("extern __shared__ float sw[];", "float* sw = g_dyn_smem;")
@@ -459,6 +462,19 @@ def _misc(exe, tmp, args, arrays):
     r = subprocess.run([exe] + [str(a) for a in args] + [fin, fout], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     return np.fromfile(fout, np.uint8)
+
+
+@pytest.mark.parametrize("B,C,F", [(2, 128, 75), (1, 128, 33), (3, 40, 5)])
+def test_layout_transposes_source_on_cpu(misc_exe, tmp_path, B, C, F):
+    """chlast_to_ncw (latents [B, F, C] -> NCW rows, the decoder input / the tensor-core RVQ's k-major residuals) and
+    kmajor_to_rows (its inverse for one block): 32 x 32 tiles through shared memory, two-dimensional blocks."""
+    g = torch.Generator().manual_seed(B * 100 + F)
+    q = torch.randn(B, F, C, generator=g)
+    raw = _misc(misc_exe, str(tmp_path), ["transp", B, C, F], [q.numpy()]).view(np.float32)
+    Fp = (F + 3) // 4 * 4
+    y = raw[:B * C * Fp].reshape(B, C, Fp)
+    assert np.array_equal(y[:, :, :F], q.transpose(1, 2).numpy())
+    assert np.array_equal(raw[B * C * Fp:].reshape(F, C), q[0].numpy())
 
 
 @pytest.mark.parametrize("n,frames", [(8, 300), (12, 129), (1, 5), (3, 77)])
