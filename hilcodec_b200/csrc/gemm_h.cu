@@ -168,13 +168,24 @@ __device__ __forceinline__ void xform_rows_up(const float* raw, const float (&wr
         const float* xr = raw + kr * NI + li;
         float ea = xr[-1], eb = xr[0], ec = kNeedC ? xr[1] : 0.f;
         if (kPre != PRE_NONE) {
-            ea = ea * s; eb = eb * s; ec = ec * s;
-            const float ta = ex2_approx(ea * 1.4426950408889634f) - 1.0f, tb = ex2_approx(eb * 1.4426950408889634f) - 1.0f;
-            ea = ea > 0.f ? ea : ta;
+            eb = eb * s; ec = ec * s;
+            const float tb = ex2_approx(eb * 1.4426950408889634f) - 1.0f;
             eb = eb > 0.f ? eb : tb;
             if (kNeedC) {
                 const float tcv = ex2_approx(ec * 1.4426950408889634f) - 1.0f;
                 ec = ec > 0.f ? ec : tcv;
+            }
+            // The input before this lane's first one is the previous lane's last one (S = 4: its `eb`, S = 2: its `ec`):
+            // take its activated value by shuffle instead of evaluating the ELU a second time (same instructions on the
+            // same number: identical bits); lane 0 takes it from the box.
+            constexpr bool kShare = (S == 4 || S == 2);
+            const float up = kShare ? __shfl_up_sync(0xffffffffu, S == 4 ? eb : ec, 1) : 0.f;
+            if (kShare && lane > 0) {
+                ea = up;
+            } else {
+                ea = ea * s;
+                const float ta = ex2_approx(ea * 1.4426950408889634f) - 1.0f;
+                ea = ea > 0.f ? ea : ta;
             }
         }
         if (i0 == 0) ea = k < K ? __ldg(ci + k) : 0.f;       // x[-1] is the cache (already activated)
